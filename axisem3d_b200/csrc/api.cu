@@ -1,0 +1,1200 @@
+// api.cu -- host side of the C-ABI (include/axisem3d_b200.h): collects the solver objects the reference's
+// Mesh::release would construct, flattens them into SoA device arrays at ax3d_finalize_setup, and launches the
+// kernels of kernels.cuh for the Domain step verbs.  No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/axisem3d_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef AX3D_WITH_NCCL
+#include <nccl.h>
+#endif
+
+static thread_local std::string g_last_error;
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            throw std::runtime_error(std::string("ax3d::cuda || ") + cudaGetErrorString(e_) + " || " #call);  \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T> &h) {
+        alloc(h.size());
+        if (n) CK(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void zero() {
+        if (n) CK(cudaMemset(p, 0, n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+// ------------------------------------------------------------------------------------------ host descriptors
+struct HPoint {
+    int kind;   // 0 solid, 1 fluid, 2 solid-fluid
+    int nr, nu;
+    bool axial, fluid_surf;
+    std::vector<float> im_s, im_f;       // inverse mass (1 or nr entries)
+    int n_sf = 0;
+    std::vector<float> n_un, n_as;       // SF coupling (3 or 3*nr entries, column-major nr x 3)
+    int s_idx = -1, f_idx = -1;
+    size_t s_off = 0, f_off = 0;
+};
+struct HAtt {
+    int kind = ATT_NONE, nsls = 0, do_kappa = 0;
+    std::vector<float> alpha, beta, gamma, dkappa, dmu;
+};
+struct HElem {
+    bool fluid;
+    int pt[AX_NPE];
+    double geom[5 * AX_NPE];
+    double theta[AX_NPE];
+    bool axial;
+    int law, rows, nr, nu, ncoef;
+    std::vector<float> coef;
+    HAtt att;
+    int cls = -1, idx = -1;   // class and index inside the class after finalize
+};
+struct HSource {
+    int elem;
+    int nrow[AX_NPE];
+    std::vector<float> force;
+};
+
+enum { CLS_S1D = 0, CLS_F1D = 1, CLS_S3D = 2, CLS_F3D = 3, NCLS = 4 };
+
+struct Chunk {   // a run of 3D elements of one class whose spectra fit the scratch ring together
+    int cls;
+    int w_begin, w_count;       // grad/quad work items
+    int f_begin, f_count;       // fft work items
+    size_t fft_smem;
+};
+
+struct ax3d_domain {
+    int device = 0;
+    bool finalized = false;
+    cudaStream_t stream = nullptr;
+    double G_GLL[25], G_GLJ[25];
+    bool have_g = false;
+    std::vector<HPoint> points;
+    std::vector<HElem> elems;
+    std::vector<HSource> sources;
+    long long launches = 0;
+    long long work = 0;
+    double alg_bytes[3] = {0, 0, 0};
+
+    // ---- device: points
+    size_t ns = 0, nf = 0;            // solid / fluid point counts
+    size_t s_len = 0, f_len = 0;      // field lengths (float2)
+    DevBuf<float2> s_field[4], f_field[4];
+    DevBuf<unsigned> s_off, f_off;
+    DevBuf<int> s_nu, f_nu, s_nr, f_nr, s_row_point, f_row_point, s_row_start, f_row_start;
+    DevBuf<unsigned char> s_flags, f_flags;
+    DevBuf<float> s_invmass, f_invmass;
+    PointTab s_tab{}, f_tab{};
+    std::vector<Mass3DItem> h_m3d_s, h_m3d_f;
+    DevBuf<Mass3DItem> m3d_s, m3d_f;
+    size_t m3d_smem_s = 0, m3d_smem_f = 0;
+    DevBuf<float> impool;
+    // ---- plans
+    std::vector<FftPlan> h_plans;
+    std::vector<std::vector<int>> h_perm;
+    std::map<int, int> plan_of_n;
+    DevBuf<FftPlan> plans;
+    DevBuf<float2> twpool;
+    // ---- elements
+    std::vector<ElemDesc> h_desc[NCLS];
+    DevBuf<ElemDesc> desc[NCLS];
+    DevBuf<float> geom, coef, attpar, attstate3d;
+    DevBuf<float2> attstate1d;
+    DevBuf<int> w_elem[NCLS], w_a0[NCLS];
+    int n_work[NCLS] = {0, 0, 0, 0};
+    DevBuf<FftItem> fft_items[NCLS];
+    std::vector<Chunk> chunks;
+    DevBuf<float2> scratch;
+    // ---- source, solid-fluid
+    DevBuf<unsigned> src_off;
+    DevBuf<float2> src_val;
+    int n_src = 0;
+    DevBuf<unsigned> sf_s_off, sf_f_off;
+    DevBuf<int> sf_nu, sf_row_point, sf_row_start;
+    DevBuf<float> sf_cpl;
+    SFTab sf_tab{};
+    std::vector<SF3DItem> h_sf3d;
+    DevBuf<SF3DItem> sf3d;
+    DevBuf<float> sf3d_pool;
+    size_t sf3d_smem = 0;
+    // ---- halo
+    int rank = 0, nproc = 1;
+    std::vector<int> neigh_rank;
+    std::vector<std::vector<int>> neigh_pts;
+    std::vector<size_t> neigh_begin;   // offsets into the packed buffers (float2)
+    DevBuf<unsigned> halo_idx;
+    DevBuf<float2> halo_send, halo_recv;
+    bool have_uid = false;
+    unsigned char uid[128];
+#ifdef AX3D_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+    // ---- misc
+    DevBuf<int> bad_flag;
+    bool timers = false;
+    double timer_ms[4] = {0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // receivers (scratch for ax3d_record_ground_motion)
+    DevBuf<RecvItem> rec_items;
+    DevBuf<float> rec_w, rec_out;
+    float *rec_host = nullptr;
+    size_t rec_cap = 0;
+    // run_steps
+    DevBuf<float> stf_dev;
+};
+
+static void fail(const std::string &m) { throw std::runtime_error(m); }
+
+// ------------------------------------------------------------------------------------------ FFT plans
+static std::vector<int> choose_radices(int N) {
+    std::vector<int> r;
+    int n = N, e = 0;
+    while (n % 2 == 0) { n /= 2; ++e; }
+    // odd factors first for the DIF order: the LAST DIF stage (stride-1 butterflies, worst bank pattern) should be a
+    // power of two only when nothing else is available
+    std::vector<int> pow2;
+    while (e >= 4) { pow2.push_back(16); e -= 4; }
+    if (e == 3) pow2.push_back(8);
+    else if (e == 2) pow2.push_back(4);
+    else if (e == 1) pow2.push_back(2);
+    std::vector<int> odd;
+    const int ps[5] = {13, 11, 7, 5, 3};
+    for (int p : ps)
+        while (n % p == 0) { odd.push_back(p); n /= p; }
+    if (n != 1) fail("ax3d::plan || Nr = " + std::to_string(N) + " has a prime factor > 13 (not a lucky number, PreloopFFTW.cpp:59-99)");
+    r = pow2;
+    r.insert(r.end(), odd.begin(), odd.end());
+    if ((int)r.size() > AX_MAX_STAGES) fail("ax3d::plan || too many FFT stages");
+    if (r.empty()) r.push_back(1);
+    return r;
+}
+
+static int get_plan(ax3d_domain *d, int N) {
+    auto it = d->plan_of_n.find(N);
+    if (it != d->plan_of_n.end()) return it->second;
+    FftPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.N = N;
+    std::vector<int> rad = choose_radices(N);
+    if (rad.size() == 1 && rad[0] == 1) {
+        pl.nstages = 0;
+    } else {
+        pl.nstages = (int)rad.size();
+        for (int s = 0; s < pl.nstages; ++s) pl.radix[s] = rad[s];
+    }
+    // perm[pos] = n : sample index stored at position pos after the DIF transform
+    std::vector<int> perm(N);
+    for (int k = 0; k < N; ++k) {
+        int kk = k, pos = 0, stride = N;
+        for (int s = 0; s < pl.nstages; ++s) {
+            stride /= pl.radix[s];
+            pos += (kk % pl.radix[s]) * stride;
+            kk /= pl.radix[s];
+        }
+        perm[pos] = k;
+    }
+    int id = (int)d->h_plans.size();
+    d->h_plans.push_back(pl);
+    d->h_perm.push_back(perm);
+    d->plan_of_n[N] = id;
+    return id;
+}
+
+// ------------------------------------------------------------------------------------------ setup helpers
+static void check_open(ax3d_domain *d) {
+    if (!d) fail("ax3d || null domain");
+    if (d->finalized) fail("Domain::add || setup already finalized");
+}
+static void check_final(ax3d_domain *d) {
+    if (!d) fail("ax3d || null domain");
+    if (!d->finalized) fail("Domain || ax3d_finalize_setup has not been called");
+}
+
+static void set_mass(std::vector<float> &dst, int nr, int n, const float *im, const char *who) {
+    if (n != 1 && n != nr) fail(std::string(who) + " || Mass3D::checkCompatibility || Incompatible size.");
+    dst.assign(im, im + n);
+}
+
+static int add_point(ax3d_domain *d, int kind, int nr, int axial, int n_s, const float *im_s, int n_f, const float *im_f,
+                     int fluid_surf, int n_sf, const float *n_un, const float *n_as) {
+    check_open(d);
+    if (nr < 1) fail("Point::Point || nr must be positive");
+    HPoint p;
+    p.kind = kind;
+    p.nr = nr;
+    p.nu = nr / 2;
+    p.axial = axial != 0;
+    p.fluid_surf = fluid_surf != 0;
+    if (kind == 0 || kind == 2) set_mass(p.im_s, nr, n_s, im_s, "SolidPoint::SolidPoint");
+    if (kind == 1 || kind == 2) set_mass(p.im_f, nr, n_f, im_f, "FluidPoint::FluidPoint");
+    if (kind == 2) {
+        if (n_sf != 1 && n_sf != nr) fail("SFCoupling3D::checkCompatibility || Incompatible size.");
+        p.n_sf = n_sf;
+        p.n_un.assign(n_un, n_un + 3 * n_sf);
+        p.n_as.assign(n_as, n_as + 3 * n_sf);
+    }
+    d->points.push_back(std::move(p));
+    return (int)d->points.size() - 1;
+}
+
+static void common_elem(ax3d_domain *d, HElem &e, const int tags[25], const double *geom, int axial, bool fluid) {
+    check_open(d);
+    e.fluid = fluid;
+    e.axial = axial != 0;
+    int nr = -1;
+    for (int i = 0; i < AX_NPE; ++i) {
+        int t = tags[i];
+        if (t < 0 || t >= (int)d->points.size()) fail("Element::Element || invalid point tag");
+        const HPoint &p = d->points[t];
+        if (fluid && p.kind == 0) fail("Point::scatterDisplToElement || Incompatible point type.");
+        if (!fluid && p.kind == 1) fail("Point::scatterDisplToElement || Incompatible point type.");
+        e.pt[i] = t;
+        nr = std::max(nr, p.nr);
+    }
+    e.nr = nr;
+    e.nu = nr / 2;
+    memcpy(e.geom, geom, sizeof(e.geom));
+}
+
+// ------------------------------------------------------------------------------------------ finalize
+static int pick_ppb(int N, int npair) {
+    const char *env = getenv("AX3D_FFT_SMEM_KB");
+    const double budget = (env ? atof(env) : 48.0) * 1024.0;
+    int ppb = (int)((budget / (8.0 * N) - 1.0) / npair);
+    const int choices[9] = {25, 13, 9, 7, 5, 4, 3, 2, 1};
+    for (int c : choices)
+        if (ppb >= c) return c;
+    return 1;
+}
+
+static void finalize(ax3d_domain *d) {
+    check_open(d);
+    if (!d->have_g) fail("Gradient::setGMat || ax3d_set_gmat has not been called");
+    CK(cudaSetDevice(d->device));
+    // ---------------- constants
+    {
+        float G[2][25];
+        for (int i = 0; i < 25; ++i) {
+            G[0][i] = (float)d->G_GLL[i];
+            G[1][i] = (float)d->G_GLJ[i];
+        }
+        CK(cudaMemcpyToSymbol(c_G, G, sizeof(G)));
+        float hc[17][16], hs[17][16];
+        memset(hc, 0, sizeof(hc));
+        memset(hs, 0, sizeof(hs));
+        for (int R = 1; R <= 16; ++R)
+            for (int k = 0; k < R && k < 16; ++k) {
+                hc[R][k] = (float)cos(2.0 * M_PI * k / R);
+                hs[R][k] = (float)sin(2.0 * M_PI * k / R);
+            }
+        CK(cudaMemcpyToSymbol(c_cos, hc, sizeof(hc)));
+        CK(cudaMemcpyToSymbol(c_sin, hs, sizeof(hs)));
+    }
+    // ---------------- points
+    std::vector<unsigned> so, fo;
+    std::vector<int> snu, fnu, snr, fnr, srp, frp, srs, frs;
+    std::vector<unsigned char> sfl, ffl;
+    std::vector<float> sim, fim, impool;
+    size_t s_len = 0, f_len = 0;
+    double bytes_pts = 0;
+    for (size_t t = 0; t < d->points.size(); ++t) {
+        HPoint &p = d->points[t];
+        const int M = p.nu + 1;
+        d->work += M;
+        if (p.kind == 0 || p.kind == 2) {
+            p.s_idx = (int)so.size();
+            p.s_off = s_len;
+            so.push_back((unsigned)s_len);
+            snu.push_back(p.nu);
+            snr.push_back(p.nr);
+            srs.push_back((int)srp.size());
+            for (int a = 0; a < M; ++a) srp.push_back(p.s_idx);
+            const bool m3 = p.im_s.size() > 1;
+            sfl.push_back((unsigned char)((p.axial ? 1 : 0) | (m3 ? 4 : 0)));
+            sim.push_back(m3 ? 1.f : p.im_s[0]);
+            if (m3) {
+                Mass3DItem it;
+                it.point = p.s_idx;
+                it.plan_id = get_plan(d, p.nr);
+                it.im_off = (long long)impool.size();
+                const std::vector<int> &perm = d->h_perm[it.plan_id];
+                for (int pos = 0; pos < p.nr; ++pos) impool.push_back(p.im_s[perm[pos]]);
+                d->h_m3d_s.push_back(it);
+                d->m3d_smem_s = std::max(d->m3d_smem_s, (size_t)3 * p.nr * sizeof(float2));
+            }
+            s_len += (size_t)3 * M;
+            bytes_pts += 192.0 * M + (m3 ? 4.0 * p.nr : 4.0);
+        }
+        if (p.kind == 1 || p.kind == 2) {
+            p.f_idx = (int)fo.size();
+            p.f_off = f_len;
+            fo.push_back((unsigned)f_len);
+            fnu.push_back(p.nu);
+            fnr.push_back(p.nr);
+            frs.push_back((int)frp.size());
+            for (int a = 0; a < M; ++a) frp.push_back(p.f_idx);
+            const bool m3 = p.im_f.size() > 1;
+            ffl.push_back((unsigned char)((p.axial ? 1 : 0) | (p.fluid_surf ? 2 : 0) | (m3 ? 4 : 0)));
+            fim.push_back(m3 ? 1.f : p.im_f[0]);
+            if (m3) {
+                Mass3DItem it;
+                it.point = p.f_idx;
+                it.plan_id = get_plan(d, p.nr);
+                it.im_off = (long long)impool.size();
+                const std::vector<int> &perm = d->h_perm[it.plan_id];
+                for (int pos = 0; pos < p.nr; ++pos) impool.push_back(p.im_f[perm[pos]]);
+                d->h_m3d_f.push_back(it);
+                d->m3d_smem_f = std::max(d->m3d_smem_f, (size_t)2 * p.nr * sizeof(float2));
+            }
+            f_len += (size_t)M;
+            bytes_pts += 64.0 * M + (m3 ? 4.0 * p.nr : 4.0);
+        }
+    }
+    if (s_len >= (1ull << 31) || f_len >= (1ull << 31)) fail("ax3d::finalize || field arrays exceed 2^31 complex entries per GPU");
+    d->ns = so.size();
+    d->nf = fo.size();
+    d->s_len = s_len;
+    d->f_len = f_len;
+    for (int k = 0; k < 4; ++k) {
+        d->s_field[k].alloc(s_len);
+        d->s_field[k].zero();
+        d->f_field[k].alloc(f_len);
+        d->f_field[k].zero();
+    }
+    d->s_off.upload(so); d->f_off.upload(fo);
+    d->s_nu.upload(snu); d->f_nu.upload(fnu);
+    d->s_nr.upload(snr); d->f_nr.upload(fnr);
+    d->s_row_point.upload(srp); d->f_row_point.upload(frp);
+    d->s_row_start.upload(srs); d->f_row_start.upload(frs);
+    d->s_flags.upload(sfl); d->f_flags.upload(ffl);
+    d->s_invmass.upload(sim); d->f_invmass.upload(fim);
+    d->s_tab = PointTab{d->s_off.p, d->s_nu.p, d->s_nr.p, d->s_flags.p, d->s_invmass.p, d->s_row_point.p, d->s_row_start.p, (int)srp.size()};
+    d->f_tab = PointTab{d->f_off.p, d->f_nu.p, d->f_nr.p, d->f_flags.p, d->f_invmass.p, d->f_row_point.p, d->f_row_start.p, (int)frp.size()};
+    d->alg_bytes[0] = bytes_pts;
+
+    // ---------------- elements: classify, sort 3D classes by Nr (descending) for load balance / chunking
+    std::vector<int> order[NCLS];
+    for (size_t e = 0; e < d->elems.size(); ++e) {
+        HElem &E = d->elems[e];
+        const bool is3d = E.rows > 1;
+        E.cls = E.fluid ? (is3d ? CLS_F3D : CLS_F1D) : (is3d ? CLS_S3D : CLS_S1D);
+        order[E.cls].push_back((int)e);
+    }
+    for (int c : {CLS_S3D, CLS_F3D})
+        std::stable_sort(order[c].begin(), order[c].end(), [&](int a, int b) { return d->elems[a].nr > d->elems[b].nr; });
+
+    std::vector<float> geom, coef, attpar;
+    size_t att1d_len = 0, att3d_len = 0;
+    double bytes_el = 0;
+    const char *env_sc = getenv("AX3D_SCRATCH_MB");
+    const size_t scratch_cap = (size_t)((env_sc ? atof(env_sc) : 64.0) * 1024.0 * 1024.0 / sizeof(float2));
+    size_t scratch_need = 0;
+
+    for (int c = 0; c < NCLS; ++c) {
+        const bool fluid = (c == CLS_F1D || c == CLS_F3D), is3d = (c == CLS_S3D || c == CLS_F3D);
+        const int npair = fluid ? 2 : 3;
+        std::vector<int> w_elem, w_a0;
+        std::vector<FftItem> fitems;
+        Chunk ch{c, 0, 0, 0, 0, 0};
+        size_t ch_scratch = 0;
+        auto close_chunk = [&]() {
+            if (ch.w_count > 0) d->chunks.push_back(ch);
+            ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0};
+            ch_scratch = 0;
+        };
+        for (size_t k = 0; k < order[c].size(); ++k) {
+            HElem &E = d->elems[order[c][k]];
+            E.idx = (int)k;
+            ElemDesc D;
+            memset(&D, 0, sizeof(D));
+            D.nr = E.nr;
+            D.nu = E.nu;
+            D.nyq = (E.nr % 2 == 0) ? 1 : 0;
+            D.axial = E.axial ? 1 : 0;
+            D.law = E.law;
+            D.tiso = (!fluid && E.law != AX3D_ISO) ? 1 : 0;
+            D.is3d = is3d ? 1 : 0;
+            D.att_kind = E.att.kind;
+            D.nsls = E.att.nsls;
+            D.do_kappa = E.att.do_kappa;
+            const int M = E.nu + 1, N = E.nr;
+            for (int i = 0; i < AX_NPE; ++i) {
+                const HPoint &p = d->points[E.pt[i]];
+                D.pt_off[i] = (unsigned)(fluid ? p.f_off : p.s_off);
+                D.pt_stride[i] = p.nu + 1;
+                D.pt_nlive[i] = p.nu - ((p.nr % 2 == 0) ? 1 : 0) + 1;
+            }
+            D.geom_off = (long long)geom.size();
+            for (int i = 0; i < 5 * AX_NPE; ++i) geom.push_back((float)E.geom[i]);
+            if (D.tiso) {
+                D.trig_off = (long long)geom.size();
+                for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)sin(E.theta[i]));
+                for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)cos(E.theta[i]));
+                for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)sin(2.0 * E.theta[i]));
+                for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)cos(2.0 * E.theta[i]));
+            }
+            D.coef_off = (long long)coef.size();
+            const std::vector<int> *perm = nullptr;
+            if (is3d) {
+                D.plan_id = get_plan(d, N);
+                perm = &d->h_perm[D.plan_id];
+                for (int kc = 0; kc < E.ncoef; ++kc)
+                    for (int p = 0; p < AX_NPE; ++p)
+                        for (int pos = 0; pos < N; ++pos) coef.push_back(E.coef[((size_t)kc * AX_NPE + p) * N + (*perm)[pos]]);
+            } else {
+                coef.insert(coef.end(), E.coef.begin(), E.coef.end());
+            }
+            if (E.att.kind != ATT_NONE) {
+                const int P = E.att.kind == ATT_CG4 ? 4 : AX_NPE;
+                D.att_par_off = (long long)attpar.size();
+                attpar.insert(attpar.end(), E.att.alpha.begin(), E.att.alpha.end());
+                attpar.insert(attpar.end(), E.att.beta.begin(), E.att.beta.end());
+                attpar.insert(attpar.end(), E.att.gamma.begin(), E.att.gamma.end());
+                const int rows = is3d ? N : 1;
+                // three * dkappa, dmu, two * dmu in Real (Attenuation3D_Full.cpp:11-12)
+                for (int which = 0; which < 3; ++which)
+                    for (int q = 0; q < P; ++q)
+                        for (int pos = 0; pos < rows; ++pos) {
+                            const int j = is3d ? (*perm)[pos] : 0;
+                            const float dk = E.att.dkappa[(size_t)q * rows + j], dm = E.att.dmu[(size_t)q * rows + j];
+                            attpar.push_back(which == 0 ? 3.f * dk : which == 1 ? dm : 2.f * dm);
+                        }
+                const size_t cells = (size_t)(E.att.nsls + 1) * 6 * P * (is3d ? N : M);
+                if (is3d) { D.att_state_off = (long long)att3d_len; att3d_len += cells; }
+                else { D.att_state_off = (long long)att1d_len; att1d_len += cells; }
+            }
+            // algorithmic bytes
+            {
+                const double nin = fluid ? 1 : 3;
+                double b = 2.0 * 200.0 * nin * M + 500.0 + (D.tiso ? 400.0 : 0.0);
+                b += (is3d ? 100.0 * N : 100.0) * E.ncoef;
+                if (E.att.kind != ATT_NONE) {
+                    const int P = E.att.kind == ATT_CG4 ? 4 : AX_NPE;
+                    const double R = is3d ? 4.0 * N : 8.0 * M;
+                    b += 2.0 * (E.att.nsls + 1) * 6 * P * R + 2.0 * P * (is3d ? 4.0 * N : 4.0);
+                }
+                bytes_el += b;
+            }
+            if (is3d) {
+                D.ppb = pick_ppb(N, npair);
+                const size_t need = (size_t)npair * AX_NPE * N;
+                if (need > scratch_cap && ch.w_count > 0) close_chunk();
+                if (ch_scratch + need > scratch_cap && ch.w_count > 0) close_chunk();
+                D.scratch_off = (long long)ch_scratch;
+                ch_scratch += need;
+                scratch_need = std::max(scratch_need, ch_scratch);
+                for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); ch.w_count++; }
+                for (int p0 = 0; p0 < AX_NPE; p0 += D.ppb) { fitems.push_back(FftItem{(int)k, p0}); ch.f_count++; }
+                ch.fft_smem = std::max(ch.fft_smem, (size_t)(npair * D.ppb + 1) * N * sizeof(float2));
+            } else {
+                for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); }
+            }
+            d->h_desc[c].push_back(D);
+        }
+        if (is3d) close_chunk();
+        d->desc[c].upload(d->h_desc[c]);
+        d->w_elem[c].upload(w_elem);
+        d->w_a0[c].upload(w_a0);
+        d->n_work[c] = (int)w_elem.size();
+        d->fft_items[c].upload(fitems);
+    }
+    d->geom.upload(geom);
+    d->coef.upload(coef);
+    d->attpar.upload(attpar);
+    d->attstate1d.alloc(att1d_len); d->attstate1d.zero();
+    d->attstate3d.alloc(att3d_len); d->attstate3d.zero();
+    d->scratch.alloc(scratch_need);
+    d->alg_bytes[1] = bytes_el;
+
+    // ---------------- sources: flatten to (offset, value)
+    {
+        std::vector<unsigned> off;
+        std::vector<float2> val;
+        for (const HSource &s : d->sources) {
+            const HElem &E = d->elems[s.elem];
+            size_t pos = 0;
+            for (int i = 0; i < AX_NPE; ++i) {
+                const HPoint &p = d->points[E.pt[i]];
+                if (p.s_idx < 0) fail("Point::addToStiff || Incompatible point type.");
+                const int nrow = s.nrow[i], keep = std::min(nrow, p.nu + 1);
+                for (int c = 0; c < 3; ++c)
+                    for (int a = 0; a < keep; ++a) {
+                        off.push_back((unsigned)(p.s_off + (size_t)c * (p.nu + 1) + a));
+                        val.push_back(make_float2(s.force[2 * (pos + (size_t)c * nrow + a)], s.force[2 * (pos + (size_t)c * nrow + a) + 1]));
+                    }
+                pos += (size_t)3 * nrow;
+            }
+        }
+        d->n_src = (int)off.size();
+        d->src_off.upload(off);
+        d->src_val.upload(val);
+    }
+    // ---------------- solid-fluid points
+    {
+        std::vector<unsigned> a, b;
+        std::vector<int> nu, rp, rs;
+        std::vector<float> cpl, pool;
+        for (const HPoint &p : d->points) {
+            if (p.kind != 2) continue;
+            if (p.n_sf == 1) {
+                const int q = (int)a.size();
+                a.push_back((unsigned)p.s_off);
+                b.push_back((unsigned)p.f_off);
+                nu.push_back(p.nu);
+                rs.push_back((int)rp.size());
+                for (int k = 0; k <= p.nu; ++k) rp.push_back(q);
+                cpl.push_back(p.n_un[0]); cpl.push_back(p.n_un[2]);
+                cpl.push_back(p.n_as[0]); cpl.push_back(p.n_as[2]);
+            } else {
+                SF3DItem it;
+                it.s_off = (unsigned)p.s_off;
+                it.f_off = (unsigned)p.f_off;
+                it.nu = p.nu;
+                it.plan_id = get_plan(d, p.nr);
+                it.n_off = (long long)pool.size();
+                const std::vector<int> &perm = d->h_perm[it.plan_id];
+                for (int c = 0; c < 3; ++c)
+                    for (int pos = 0; pos < p.nr; ++pos) pool.push_back(p.n_un[(size_t)c * p.nr + perm[pos]]);
+                for (int c = 0; c < 3; ++c)
+                    for (int pos = 0; pos < p.nr; ++pos) pool.push_back(p.n_as[(size_t)c * p.nr + perm[pos]]);
+                d->h_sf3d.push_back(it);
+                d->sf3d_smem = std::max(d->sf3d_smem, (size_t)3 * p.nr * sizeof(float2));
+            }
+        }
+        d->sf_s_off.upload(a); d->sf_f_off.upload(b); d->sf_nu.upload(nu);
+        d->sf_row_point.upload(rp); d->sf_row_start.upload(rs); d->sf_cpl.upload(cpl);
+        d->sf_tab = SFTab{d->sf_s_off.p, d->sf_f_off.p, d->sf_nu.p, d->sf_cpl.p, d->sf_row_point.p, d->sf_row_start.p, (int)rp.size()};
+        d->sf3d.upload(d->h_sf3d);
+        d->sf3d_pool.upload(pool);
+    }
+    // ---------------- Mass3D + plans
+    d->m3d_s.upload(d->h_m3d_s);
+    d->m3d_f.upload(d->h_m3d_f);
+    d->impool.upload(impool);
+    {
+        std::vector<float2> tw;
+        for (FftPlan &pl : d->h_plans) {
+            pl.tw_off = (int)tw.size();
+            for (int k = 0; k < pl.N; ++k) {
+                const double a = 2.0 * M_PI * k / pl.N;
+                tw.push_back(make_float2((float)cos(a), (float)sin(a)));
+            }
+        }
+        d->twpool.upload(tw);
+        d->plans.upload(d->h_plans);
+    }
+    // ---------------- halo index lists
+    {
+        std::vector<unsigned> idx;
+        d->neigh_begin.clear();
+        double hb = 0;
+        for (size_t n = 0; n < d->neigh_pts.size(); ++n) {
+            d->neigh_begin.push_back(idx.size());
+            for (int t : d->neigh_pts[n]) {
+                if (t < 0 || t >= (int)d->points.size()) fail("Domain::setMessaging || invalid point tag");
+                const HPoint &p = d->points[t];
+                // SolidFluidPoint::feedBuffer: solid block then fluid block (SolidFluidPoint.cpp:76-79)
+                if (p.s_idx >= 0)
+                    for (int k = 0; k < 3 * (p.nu + 1); ++k) idx.push_back((unsigned)(p.s_off + k));
+                if (p.f_idx >= 0)
+                    for (int k = 0; k < p.nu + 1; ++k) idx.push_back((unsigned)(p.f_off + k) | 0x80000000u);
+            }
+        }
+        d->neigh_begin.push_back(idx.size());
+        hb = 16.0 * idx.size();
+        d->halo_idx.upload(idx);
+        d->halo_send.alloc(idx.size());
+        d->halo_recv.alloc(idx.size());
+        d->alg_bytes[2] = hb;
+    }
+    d->bad_flag.alloc(1);
+    CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&d->ev0));
+    CK(cudaEventCreate(&d->ev1));
+    // opt in to large dynamic shared memory
+    size_t fmax = 0;
+    for (const Chunk &ch : d->chunks) fmax = std::max(fmax, ch.fft_smem);
+    if (fmax > 220 * 1024) fail("ax3d::finalize || Nr too large for the single-CTA FFT stage (needs > 220 KB shared memory)");
+    if (fmax > 48 * 1024) {
+        CK(cudaFuncSetAttribute(k_fft3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
+        CK(cudaFuncSetAttribute(k_fft3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
+    }
+    if (d->m3d_smem_s > 48 * 1024) CK(cudaFuncSetAttribute(k_mass3d<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->m3d_smem_s));
+    if (d->m3d_smem_f > 48 * 1024) CK(cudaFuncSetAttribute(k_mass3d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->m3d_smem_f));
+    if (d->sf3d_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_sf_couple3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->sf3d_smem));
+#ifdef AX3D_WITH_NCCL
+    if (d->nproc > 1 && d->have_uid) {
+        ncclUniqueId id;
+        memcpy(&id, d->uid, sizeof(id) < 128 ? sizeof(id) : 128);
+        ncclResult_t r = ncclCommInitRank(&d->comm, d->nproc, id, d->rank);
+        if (r != ncclSuccess) fail(std::string("XMPI::initialize || ncclCommInitRank: ") + ncclGetErrorString(r));
+    }
+#endif
+    CK(cudaDeviceSynchronize());
+    d->finalized = true;
+}
+
+// ------------------------------------------------------------------------------------------ step verbs
+struct TimerScope {
+    ax3d_domain *d;
+    int slot;
+    TimerScope(ax3d_domain *d_, int s) : d(d_), slot(s) {
+        if (d->timers) cudaEventRecord(d->ev0, d->stream);
+    }
+    ~TimerScope() {
+        if (d->timers) {
+            cudaEventRecord(d->ev1, d->stream);
+            cudaEventSynchronize(d->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+            d->timer_ms[slot] += ms;
+        }
+    }
+};
+
+static inline int nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
+
+static void update_newmark(ax3d_domain *d, double dt) {
+    TimerScope ts(d, 0);
+    const double half_dt = 0.5 * dt, half_dt_dt = half_dt * dt;   // SolidPoint.cpp:31-32 (double, then cast to Real)
+    if (!d->h_m3d_s.empty()) {
+        k_mass3d<3><<<(int)d->h_m3d_s.size(), 128, d->m3d_smem_s, d->stream>>>(d->s_tab, d->m3d_s.p, d->plans.p, d->twpool.p, d->impool.p,
+                                                                              d->s_field[AX3D_STIFF].p);
+        d->launches++;
+    }
+    if (!d->h_m3d_f.empty()) {
+        k_mass3d<1><<<(int)d->h_m3d_f.size(), 128, d->m3d_smem_f, d->stream>>>(d->f_tab, d->m3d_f.p, d->plans.p, d->twpool.p, d->impool.p,
+                                                                              d->f_field[AX3D_STIFF].p);
+        d->launches++;
+    }
+    if (d->s_tab.nrows) {
+        k_newmark_solid<<<nblk(d->s_tab.nrows, 256), 256, 0, d->stream>>>(d->s_tab, d->s_field[0].p, d->s_field[1].p, d->s_field[2].p,
+                                                                         d->s_field[3].p, (float)half_dt, (float)dt, (float)half_dt_dt);
+        d->launches++;
+    }
+    if (d->f_tab.nrows) {
+        k_newmark_fluid<<<nblk(d->f_tab.nrows, 256), 256, 0, d->stream>>>(d->f_tab, d->f_field[0].p, d->f_field[1].p, d->f_field[2].p,
+                                                                         d->f_field[3].p, (float)half_dt, (float)dt, (float)half_dt_dt);
+        d->launches++;
+    }
+    CK(cudaGetLastError());
+}
+
+static void apply_source(ax3d_domain *d, float stf) {
+    TimerScope ts(d, 2);
+    if (d->n_src) {
+        k_source<<<nblk(d->n_src, 128), 128, 0, d->stream>>>(d->n_src, d->src_off.p, d->src_val.p, stf, d->s_field[AX3D_STIFF].p);
+        d->launches++;
+        CK(cudaGetLastError());
+    }
+}
+
+static void compute_stiff(ax3d_domain *d) {
+    TimerScope ts(d, 1);
+    const int TB = AX_TILE * AX_NPE;
+    if (d->n_work[CLS_S1D]) {
+        k_elem1d<false><<<d->n_work[CLS_S1D], TB, 0, d->stream>>>(d->desc[CLS_S1D].p, d->w_elem[CLS_S1D].p, d->w_a0[CLS_S1D].p, d->geom.p,
+                                                                  d->coef.p, d->attpar.p, d->attstate1d.p, d->s_field[AX3D_DISPL].p,
+                                                                  d->s_field[AX3D_STIFF].p);
+        d->launches++;
+    }
+    if (d->n_work[CLS_F1D]) {
+        k_elem1d<true><<<d->n_work[CLS_F1D], TB, 0, d->stream>>>(d->desc[CLS_F1D].p, d->w_elem[CLS_F1D].p, d->w_a0[CLS_F1D].p, d->geom.p,
+                                                                 d->coef.p, d->attpar.p, d->attstate1d.p, d->f_field[AX3D_DISPL].p,
+                                                                 d->f_field[AX3D_STIFF].p);
+        d->launches++;
+    }
+    for (const Chunk &ch : d->chunks) {
+        const int c = ch.cls;
+        if (c == CLS_S3D) {
+            k_grad3d<false><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
+                                                              d->s_field[AX3D_DISPL].p, d->scratch.p);
+            k_fft3d<false><<<ch.f_count, 256, ch.fft_smem, d->stream>>>(d->desc[c].p, d->fft_items[c].p + ch.f_begin, d->plans.p, d->twpool.p,
+                                                                        d->coef.p, d->attpar.p, d->attstate3d.p, d->scratch.p);
+            k_quad3d<false><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
+                                                              d->scratch.p, d->s_field[AX3D_STIFF].p);
+        } else {
+            k_grad3d<true><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
+                                                             d->f_field[AX3D_DISPL].p, d->scratch.p);
+            k_fft3d<true><<<ch.f_count, 256, ch.fft_smem, d->stream>>>(d->desc[c].p, d->fft_items[c].p + ch.f_begin, d->plans.p, d->twpool.p,
+                                                                       d->coef.p, d->attpar.p, d->attstate3d.p, d->scratch.p);
+            k_quad3d<true><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
+                                                             d->scratch.p, d->f_field[AX3D_STIFF].p);
+        }
+        d->launches += 3;
+    }
+    CK(cudaGetLastError());
+}
+
+static void couple_solid_fluid(ax3d_domain *d) {
+    TimerScope ts(d, 2);
+    if (d->sf_tab.nrows) {
+        k_sf_couple<<<nblk(d->sf_tab.nrows, 128), 128, 0, d->stream>>>(d->sf_tab, d->s_field[AX3D_DISPL].p, d->s_field[AX3D_STIFF].p,
+                                                                      d->f_field[AX3D_STIFF].p);
+        d->launches++;
+    }
+    if (!d->h_sf3d.empty()) {
+        k_sf_couple3d<<<(int)d->h_sf3d.size(), 128, d->sf3d_smem, d->stream>>>(d->sf3d.p, d->plans.p, d->twpool.p, d->sf3d_pool.p,
+                                                                              d->s_field[AX3D_DISPL].p, d->s_field[AX3D_STIFF].p,
+                                                                              d->f_field[AX3D_STIFF].p);
+        d->launches++;
+    }
+    CK(cudaGetLastError());
+}
+
+static void assemble_stiff(ax3d_domain *d, int phase) {
+    if (d->nproc <= 1 || d->neigh_rank.empty()) return;
+    TimerScope ts(d, 3);
+#ifdef AX3D_WITH_NCCL
+    if (!d->comm) fail("Domain::assembleStiff || no NCCL communicator (ax3d_set_messaging needs the unique id)");
+    const size_t total = d->neigh_begin.back();
+    if (phase <= 0) {
+        k_pack<<<nblk(total, 256), 256, 0, d->stream>>>((int)total, d->halo_idx.p, d->s_field[AX3D_STIFF].p, d->f_field[AX3D_STIFF].p,
+                                                        d->halo_send.p);
+        d->launches++;
+        ncclGroupStart();
+        for (size_t n = 0; n < d->neigh_rank.size(); ++n) {
+            const size_t b = d->neigh_begin[n], cnt = d->neigh_begin[n + 1] - b;
+            ncclSend(d->halo_send.p + b, cnt * 2, ncclFloat, d->neigh_rank[n], d->comm, d->stream);
+            ncclRecv(d->halo_recv.p + b, cnt * 2, ncclFloat, d->neigh_rank[n], d->comm, d->stream);
+        }
+        ncclGroupEnd();
+    }
+    if (phase >= 0) {
+        // neighbour order = reference order (Domain.cpp:143-149); one launch per neighbour keeps the sum order fixed
+        for (size_t n = 0; n < d->neigh_rank.size(); ++n) {
+            const size_t b = d->neigh_begin[n], cnt = d->neigh_begin[n + 1] - b;
+            if (!cnt) continue;
+            k_unpack_add<<<nblk(cnt, 256), 256, 0, d->stream>>>((int)cnt, d->halo_idx.p + b, d->halo_recv.p + b, d->s_field[AX3D_STIFF].p,
+                                                                d->f_field[AX3D_STIFF].p);
+            d->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+#else
+    (void)phase;
+    fail("Domain::assembleStiff || library built without NCCL");
+#endif
+}
+
+// ------------------------------------------------------------------------------------------ extern "C"
+#define API_BEGIN try {
+#define API_END                          \
+    return 0;                            \
+    }                                    \
+    catch (const std::exception &e) {    \
+        g_last_error = e.what();         \
+        return 1;                        \
+    }                                    \
+    catch (...) {                        \
+        g_last_error = "ax3d || unknown exception"; \
+        return 1;                        \
+    }
+
+extern "C" {
+
+const char *ax3d_last_error(void) { return g_last_error.c_str(); }
+int ax3d_version(void) { return 100; }
+
+int ax3d_create(int device, ax3d_domain **out) {
+    API_BEGIN
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) fail("Domain::Domain || no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= n) fail("Domain::Domain || invalid device ordinal");
+    CK(cudaSetDevice(device));
+    ax3d_domain *d = new ax3d_domain();
+    d->device = device;
+    *out = d;
+    API_END
+}
+
+int ax3d_destroy(ax3d_domain *d) {
+    API_BEGIN
+    if (!d) return 0;
+    cudaSetDevice(d->device);
+    cudaDeviceSynchronize();
+#ifdef AX3D_WITH_NCCL
+    if (d->comm) ncclCommDestroy(d->comm);
+#endif
+    if (d->stream) cudaStreamDestroy(d->stream);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->rec_host) cudaFreeHost(d->rec_host);
+    delete d;
+    API_END
+}
+
+int ax3d_set_gmat(ax3d_domain *d, const double G_GLL[25], const double G_GLJ[25]) {
+    API_BEGIN
+    check_open(d);
+    memcpy(d->G_GLL, G_GLL, sizeof(d->G_GLL));
+    memcpy(d->G_GLJ, G_GLJ, sizeof(d->G_GLJ));
+    d->have_g = true;
+    API_END
+}
+
+int ax3d_add_solid_point(ax3d_domain *d, int nr, int axial, const double crds[2], int n_invmass, const float *invmass, int *tag) {
+    API_BEGIN
+    (void)crds;
+    *tag = add_point(d, 0, nr, axial, n_invmass, invmass, 0, nullptr, 0, 0, nullptr, nullptr);
+    API_END
+}
+int ax3d_add_fluid_point(ax3d_domain *d, int nr, int axial, const double crds[2], int n_invmass, const float *invmass, int fluid_surf,
+                         int *tag) {
+    API_BEGIN
+    (void)crds;
+    *tag = add_point(d, 1, nr, axial, 0, nullptr, n_invmass, invmass, fluid_surf, 0, nullptr, nullptr);
+    API_END
+}
+int ax3d_add_solid_fluid_point(ax3d_domain *d, int nr, int axial, const double crds[2], int n_s, const float *im_s, int n_f,
+                               const float *im_f, int fluid_surf, int n_sf, const float *n_un, const float *n_as, int *tag) {
+    API_BEGIN
+    (void)crds;
+    *tag = add_point(d, 2, nr, axial, n_s, im_s, n_f, im_f, fluid_surf, n_sf, n_un, n_as);
+    API_END
+}
+
+int ax3d_add_solid_element(ax3d_domain *d, const int tags[25], const double *geom, int axial, const double *theta, int law, int rows,
+                           const float *coef, const ax3d_attenuation *att, int *tag) {
+    API_BEGIN
+    HElem e;
+    common_elem(d, e, tags, geom, axial, false);
+    if (law < 0 || law > 2) fail("SolidElement::SolidElement || unknown elastic law");
+    if (rows != 1 && rows != e.nr) fail("Elastic3D::checkCompatibility || Incompatible size.");
+    e.law = law;
+    e.rows = rows;
+    e.ncoef = law == AX3D_ISO ? 2 : law == AX3D_TI ? 5 : 21;
+    e.coef.assign(coef, coef + (size_t)e.ncoef * rows * AX_NPE);
+    if (law != AX3D_ISO) {
+        if (!theta) fail("SolidElement::SolidElement || theta is required for TI / anisotropic elements");
+        memcpy(e.theta, theta, sizeof(e.theta));
+    }
+    if (att && att->kind != AX3D_ATT_NONE) {
+        if (att->kind != AX3D_ATT_FULL && att->kind != AX3D_ATT_CG4) fail("Attenuation || unknown kind");
+        const int P = att->kind == AX3D_ATT_CG4 ? 4 : AX_NPE;
+        e.att.kind = att->kind;
+        e.att.nsls = att->nsls;
+        e.att.do_kappa = att->do_kappa;
+        e.att.alpha.assign(att->alpha, att->alpha + att->nsls);
+        e.att.beta.assign(att->beta, att->beta + att->nsls);
+        e.att.gamma.assign(att->gamma, att->gamma + att->nsls);
+        e.att.dkappa.assign(att->dkappa, att->dkappa + (size_t)rows * P);
+        e.att.dmu.assign(att->dmu, att->dmu + (size_t)rows * P);
+    }
+    d->elems.push_back(std::move(e));
+    *tag = (int)d->elems.size() - 1;
+    API_END
+}
+
+int ax3d_add_fluid_element(ax3d_domain *d, const int tags[25], const double *geom, int axial, int rows, const float *K, int *tag) {
+    API_BEGIN
+    HElem e;
+    common_elem(d, e, tags, geom, axial, true);
+    if (rows != 1 && rows != e.nr) fail("Acoustic3D::checkCompatibility || Incompatible size.");
+    e.law = AX3D_ISO;
+    e.rows = rows;
+    e.ncoef = 1;
+    e.coef.assign(K, K + (size_t)rows * AX_NPE);
+    d->elems.push_back(std::move(e));
+    *tag = (int)d->elems.size() - 1;
+    API_END
+}
+
+int ax3d_add_source_term(ax3d_domain *d, int elem_tag, const int nrow[25], const float *force) {
+    API_BEGIN
+    check_open(d);
+    if (elem_tag < 0 || elem_tag >= (int)d->elems.size()) fail("SourceTerm::SourceTerm || invalid element tag");
+    HSource s;
+    s.elem = elem_tag;
+    size_t tot = 0;
+    for (int i = 0; i < AX_NPE; ++i) {
+        s.nrow[i] = nrow[i];
+        tot += (size_t)3 * nrow[i];
+    }
+    s.force.assign(force, force + 2 * tot);
+    d->sources.push_back(std::move(s));
+    API_END
+}
+
+int ax3d_set_messaging(ax3d_domain *d, int rank, int nproc, const void *uid, int nneigh, const int *neigh_rank, const int *npoints,
+                       const int *point_tags) {
+    API_BEGIN
+    check_open(d);
+    d->rank = rank;
+    d->nproc = nproc;
+    d->neigh_rank.assign(neigh_rank, neigh_rank + nneigh);
+    d->neigh_pts.clear();
+    size_t pos = 0;
+    for (int n = 0; n < nneigh; ++n) {
+        d->neigh_pts.emplace_back(point_tags + pos, point_tags + pos + npoints[n]);
+        pos += npoints[n];
+    }
+    if (uid) {
+        memcpy(d->uid, uid, 128);
+        d->have_uid = true;
+    }
+    API_END
+}
+
+int ax3d_finalize_setup(ax3d_domain *d) {
+    API_BEGIN
+    finalize(d);
+    API_END
+}
+
+int ax3d_update_newmark(ax3d_domain *d, double dt) {
+    API_BEGIN
+    check_final(d);
+    update_newmark(d, dt);
+    API_END
+}
+int ax3d_apply_source(ax3d_domain *d, float stf) {
+    API_BEGIN
+    check_final(d);
+    apply_source(d, stf);
+    API_END
+}
+int ax3d_compute_stiff(ax3d_domain *d) {
+    API_BEGIN
+    check_final(d);
+    compute_stiff(d);
+    API_END
+}
+int ax3d_couple_solid_fluid(ax3d_domain *d) {
+    API_BEGIN
+    check_final(d);
+    couple_solid_fluid(d);
+    API_END
+}
+int ax3d_assemble_stiff(ax3d_domain *d, int phase) {
+    API_BEGIN
+    check_final(d);
+    assemble_stiff(d, phase);
+    API_END
+}
+
+int ax3d_check_stability(ax3d_domain *d, int *stable) {
+    API_BEGIN
+    check_final(d);
+    d->bad_flag.zero();
+    if (d->s_len) k_check_finite<<<296, 256, 0, d->stream>>>(d->s_len * 2, (const float *)d->s_field[0].p, d->bad_flag.p);
+    if (d->f_len) k_check_finite<<<296, 256, 0, d->stream>>>(d->f_len * 2, (const float *)d->f_field[0].p, d->bad_flag.p);
+    d->launches += 2;
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, d->bad_flag.p, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    *stable = bad ? 0 : 1;
+    API_END
+}
+
+int ax3d_reset_zero(ax3d_domain *d) {
+    API_BEGIN
+    check_final(d);
+    CK(cudaStreamSynchronize(d->stream));
+    for (int k = 0; k < 4; ++k) {
+        d->s_field[k].zero();
+        d->f_field[k].zero();
+    }
+    d->attstate1d.zero();
+    d->attstate3d.zero();
+    API_END
+}
+
+int ax3d_run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
+    API_BEGIN
+    check_final(d);
+    for (int i = 0; i < nsteps; ++i) {
+        update_newmark(d, dt);
+        apply_source(d, stf ? stf[i] : 0.f);
+        compute_stiff(d);
+        couple_solid_fluid(d);
+        assemble_stiff(d, -1);
+        assemble_stiff(d, 1);
+    }
+    API_END
+}
+
+int ax3d_synchronize(ax3d_domain *d) {
+    API_BEGIN
+    check_final(d);
+    CK(cudaStreamSynchronize(d->stream));
+    API_END
+}
+
+static void locate(ax3d_domain *d, int tag, int fluid_part, float2 **base, int field, size_t *n) {
+    if (tag < 0 || tag >= (int)d->points.size()) fail("Domain::getPoint || invalid point tag");
+    if (field < 0 || field > 3) fail("ax3d || invalid field id");
+    const HPoint &p = d->points[tag];
+    if (!fluid_part) {
+        if (p.s_idx < 0) fail("Point::getDispFourier || Incompatible point type.");
+        *base = d->s_field[field].p + p.s_off;
+        *n = (size_t)3 * (p.nu + 1);
+    } else {
+        if (p.f_idx < 0) fail("Point::getDispFourier || Incompatible point type.");
+        *base = d->f_field[field].p + p.f_off;
+        *n = (size_t)(p.nu + 1);
+    }
+}
+
+int ax3d_get_point_field(ax3d_domain *d, int tag, int field, int fluid_part, float *out, int cap) {
+    API_BEGIN
+    check_final(d);
+    float2 *b;
+    size_t n;
+    locate(d, tag, fluid_part, &b, field, &n);
+    if ((size_t)cap < n) fail("ax3d_get_point_field || output buffer too small");
+    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaMemcpy(out, b, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    API_END
+}
+int ax3d_set_point_field(ax3d_domain *d, int tag, int field, int fluid_part, const float *in, int n_in) {
+    API_BEGIN
+    check_final(d);
+    float2 *b;
+    size_t n;
+    locate(d, tag, fluid_part, &b, field, &n);
+    if ((size_t)n_in != n) fail("ax3d_set_point_field || size mismatch");
+    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaMemcpy(b, in, n * sizeof(float2), cudaMemcpyHostToDevice));
+    API_END
+}
+int ax3d_field_size(ax3d_domain *d, int fluid_part, size_t *n) {
+    API_BEGIN
+    check_final(d);
+    *n = fluid_part ? d->f_len : d->s_len;
+    API_END
+}
+int ax3d_get_field_bulk(ax3d_domain *d, int field, int fluid_part, float *out, size_t cap) {
+    API_BEGIN
+    check_final(d);
+    if (field < 0 || field > 3) fail("ax3d || invalid field id");
+    const size_t n = fluid_part ? d->f_len : d->s_len;
+    if (cap < n) fail("ax3d_get_field_bulk || output buffer too small");
+    CK(cudaStreamSynchronize(d->stream));
+    if (n) CK(cudaMemcpy(out, fluid_part ? d->f_field[field].p : d->s_field[field].p, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    API_END
+}
+int ax3d_set_field_bulk(ax3d_domain *d, int field, int fluid_part, const float *in, size_t n_in) {
+    API_BEGIN
+    check_final(d);
+    if (field < 0 || field > 3) fail("ax3d || invalid field id");
+    const size_t n = fluid_part ? d->f_len : d->s_len;
+    if (n_in != n) fail("ax3d_set_field_bulk || size mismatch");
+    CK(cudaStreamSynchronize(d->stream));
+    if (n) CK(cudaMemcpy(fluid_part ? d->f_field[field].p : d->s_field[field].p, in, n * sizeof(float2), cudaMemcpyHostToDevice));
+    API_END
+}
+
+int ax3d_record_ground_motion(ax3d_domain *d, int nrec, const int *elem_tags, const float *phi, const float *weights, float *out) {
+    API_BEGIN
+    check_final(d);
+    if (nrec <= 0) return 0;
+    std::vector<RecvItem> items(nrec);
+    for (int i = 0; i < nrec; ++i) {
+        if (elem_tags[i] < 0 || elem_tags[i] >= (int)d->elems.size()) fail("PointwiseRecorder::record || invalid element tag");
+        const HElem &E = d->elems[elem_tags[i]];
+        if (E.fluid) fail("FluidElement::computeGroundMotion || receivers in fluid are not supported yet");
+        if (E.cls != CLS_S1D && E.cls != CLS_S3D) fail("PointwiseRecorder::record || bad element class");
+        items[i].elem = E.idx | (E.cls == CLS_S3D ? 0x40000000 : 0);
+        items[i].phi = phi[i];
+    }
+    if ((size_t)nrec > d->rec_cap) {
+        if (d->rec_host) cudaFreeHost(d->rec_host);
+        CK(cudaMallocHost(&d->rec_host, (size_t)nrec * 3 * sizeof(float)));
+        d->rec_items.alloc(nrec);
+        d->rec_w.alloc((size_t)nrec * AX_NPE);
+        d->rec_out.alloc((size_t)nrec * 3);
+        d->rec_cap = nrec;
+    }
+    // receivers may sit in 1D or 3D elements: two launches over the respective descriptor arrays
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<RecvItem> sub;
+        std::vector<int> where;
+        for (int i = 0; i < nrec; ++i) {
+            const bool is3 = (items[i].elem & 0x40000000) != 0;
+            if ((pass == 1) == is3) {
+                RecvItem r = items[i];
+                r.elem &= 0x3fffffff;
+                sub.push_back(r);
+                where.push_back(i);
+            }
+        }
+        if (sub.empty()) continue;
+        // contiguous sub-launch: copy items + matching weights
+        std::vector<float> w(sub.size() * AX_NPE);
+        for (size_t k = 0; k < sub.size(); ++k) memcpy(&w[k * AX_NPE], weights + (size_t)where[k] * AX_NPE, AX_NPE * sizeof(float));
+        CK(cudaMemcpyAsync(d->rec_items.p, sub.data(), sub.size() * sizeof(RecvItem), cudaMemcpyHostToDevice, d->stream));
+        CK(cudaMemcpyAsync(d->rec_w.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, d->stream));
+        const int c = pass == 1 ? CLS_S3D : CLS_S1D;
+        k_ground_motion<<<(int)sub.size(), 128, 0, d->stream>>>(d->desc[c].p, d->rec_items.p, d->rec_w.p, d->s_field[AX3D_DISPL].p, d->rec_out.p);
+        d->launches++;
+        CK(cudaMemcpyAsync(d->rec_host, d->rec_out.p, sub.size() * 3 * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+        CK(cudaStreamSynchronize(d->stream));
+        for (size_t k = 0; k < sub.size(); ++k)
+            for (int cc = 0; cc < 3; ++cc) out[where[k] * 3 + cc] = d->rec_host[k * 3 + cc];
+    }
+    API_END
+}
+
+int ax3d_launch_count(ax3d_domain *d, long long *n) {
+    API_BEGIN
+    *n = d->launches;
+    API_END
+}
+int ax3d_work_per_step(ax3d_domain *d, long long *w) {
+    API_BEGIN
+    check_final(d);
+    *w = d->work;
+    API_END
+}
+int ax3d_algorithmic_bytes(ax3d_domain *d, double out[3]) {
+    API_BEGIN
+    check_final(d);
+    for (int i = 0; i < 3; ++i) out[i] = d->alg_bytes[i];
+    API_END
+}
+int ax3d_enable_timers(ax3d_domain *d, int on) {
+    API_BEGIN
+    d->timers = on != 0;
+    API_END
+}
+int ax3d_get_timers(ax3d_domain *d, double out_ms[4], int reset) {
+    API_BEGIN
+    for (int i = 0; i < 4; ++i) {
+        out_ms[i] = d->timer_ms[i];
+        if (reset) d->timer_ms[i] = 0;
+    }
+    API_END
+}
+
+}   // extern "C"

@@ -1,0 +1,242 @@
+// fft.cuh -- in-shared-memory mixed-radix complex FFT passes for the azimuthal transforms.
+//
+// Replaces SolverFFTW_{1,3,N3,N6,N9}::computeC2R/computeR2C (S/core/fftw/SolverFFTW_N6.cpp:45-53),
+// i.e. FFTW's fftwf_plan_many_dft_c2r / r2c on lucky-number lengths N = 2^a 3^b 5^c 7^d (11|13)^{<=1}
+// (S/preloop/utilities/PreloopFFTW.cpp:59-99).
+//
+// Design (DESIGN.md "FFT"):
+//  * two real columns are transformed as ONE complex column z = x + i y ("two-for-one"), which works
+//    for odd and even N alike; the Hermitian fill-in / split is fused into the producers/consumers;
+//  * c2r runs as an in-place decimation-in-frequency transform (natural -> digit-reversed order),
+//    r2c as the in-place decimation-in-time transpose (digit-reversed -> natural).  The pointwise
+//    physics in between does not care about the sample order, so no reordering pass exists: all
+//    phi-dependent material arrays are stored digit-reversed at upload time;
+//  * one thread owns one radix-R butterfly in registers; passes are separated by __syncthreads().
+#pragma once
+#include <cuda_runtime.h>
+
+#define AX_MAX_STAGES 10
+
+struct FftPlan {
+    int N;
+    int nstages;
+    int radix[AX_MAX_STAGES];
+    int tw_off;    // offset (float2) of W_N[k] = exp(+2 pi i k / N), k < N, in the twiddle pool
+    int perm_off;  // offset (int) of perm[pos] = sample index n stored at position pos after the DIF c2r
+};
+
+// cos/sin(2 pi k / R) for the in-register butterflies, R <= 16
+__constant__ float c_cos[17][16];
+__constant__ float c_sin[17][16];
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by SIGN * i
+template <int SIGN>
+__device__ __forceinline__ float2 cmul_i(float2 a) {
+    return SIGN > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+// ---------------------------------------------------------------- butterflies: y_p = sum_q a_q w^{pq},
+// w = exp(SIGN * 2 pi i / R)
+template <int R, int SIGN>
+struct Dft;
+
+template <int SIGN>
+struct Dft<2, SIGN> {
+    static __device__ __forceinline__ void run(float2 (&a)[2]) {
+        float2 t = a[0];
+        a[0] = cadd(t, a[1]);
+        a[1] = csub(t, a[1]);
+    }
+};
+
+template <int SIGN>
+struct Dft<4, SIGN> {
+    static __device__ __forceinline__ void run(float2 (&a)[4]) {
+        float2 s02 = cadd(a[0], a[2]), d02 = csub(a[0], a[2]);
+        float2 s13 = cadd(a[1], a[3]), d13 = cmul_i<SIGN>(csub(a[1], a[3]));
+        a[0] = cadd(s02, s13);
+        a[2] = csub(s02, s13);
+        a[1] = cadd(d02, d13);
+        a[3] = csub(d02, d13);
+    }
+};
+
+template <int SIGN>
+struct Dft<8, SIGN> {
+    static __device__ __forceinline__ void run(float2 (&a)[8]) {
+        float2 e[4] = {a[0], a[2], a[4], a[6]};
+        float2 o[4] = {a[1], a[3], a[5], a[7]};
+        Dft<4, SIGN>::run(e);
+        Dft<4, SIGN>::run(o);
+        const float h = 0.70710678118654752440f;
+        // w8^p = exp(SIGN i pi p / 4)
+        float2 w1 = make_float2(h, SIGN * h), w3 = make_float2(-h, SIGN * h);
+        o[1] = cmul(o[1], w1);
+        o[2] = cmul_i<SIGN>(o[2]);
+        o[3] = cmul(o[3], w3);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            a[p] = cadd(e[p], o[p]);
+            a[p + 4] = csub(e[p], o[p]);
+        }
+    }
+};
+
+template <int SIGN>
+struct Dft<16, SIGN> {
+    static __device__ __forceinline__ void run(float2 (&a)[16]) {
+        float2 e[8], o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            e[q] = a[2 * q];
+            o[q] = a[2 * q + 1];
+        }
+        Dft<8, SIGN>::run(e);
+        Dft<8, SIGN>::run(o);
+#pragma unroll
+        for (int p = 1; p < 8; ++p) {
+            if (p == 4) {
+                o[p] = cmul_i<SIGN>(o[p]);
+            } else {
+                o[p] = cmul(o[p], make_float2(c_cos[16][p], SIGN * c_sin[16][p]));
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            a[p] = cadd(e[p], o[p]);
+            a[p + 8] = csub(e[p], o[p]);
+        }
+    }
+};
+
+// odd prime radix via the symmetric/antisymmetric split (halves the multiplies)
+template <int R, int SIGN>
+struct DftOdd {
+    static __device__ __forceinline__ void run(float2 (&a)[R]) {
+        constexpr int H = (R - 1) / 2;
+        float2 s[H], d[H];
+#pragma unroll
+        for (int q = 1; q <= H; ++q) {
+            s[q - 1] = cadd(a[q], a[R - q]);
+            d[q - 1] = csub(a[q], a[R - q]);
+        }
+        float2 a0 = a[0];
+        float2 y0 = a0;
+#pragma unroll
+        for (int q = 0; q < H; ++q) y0 = cadd(y0, s[q]);
+        a[0] = y0;
+#pragma unroll
+        for (int p = 1; p <= H; ++p) {
+            float2 A = a0, B = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 1; q <= H; ++q) {
+                const int k = (p * q) % R;
+                const float c = c_cos[R][k], sn = c_sin[R][k];
+                A.x = fmaf(c, s[q - 1].x, A.x);
+                A.y = fmaf(c, s[q - 1].y, A.y);
+                B.x = fmaf(sn, d[q - 1].x, B.x);
+                B.y = fmaf(sn, d[q - 1].y, B.y);
+            }
+            // y_p = A + SIGN i B ; y_{R-p} = A - SIGN i B
+            float2 iB = cmul_i<SIGN>(B);
+            a[p] = cadd(A, iB);
+            a[R - p] = csub(A, iB);
+        }
+    }
+};
+template <int SIGN> struct Dft<3, SIGN> : DftOdd<3, SIGN> {};
+template <int SIGN> struct Dft<5, SIGN> : DftOdd<5, SIGN> {};
+template <int SIGN> struct Dft<7, SIGN> : DftOdd<7, SIGN> {};
+template <int SIGN> struct Dft<11, SIGN> : DftOdd<11, SIGN> {};
+template <int SIGN> struct Dft<13, SIGN> : DftOdd<13, SIGN> {};
+
+// ---------------------------------------------------------------- one pass over `ncols` columns
+// z: column c starts at z + c * ldz; tw = W_N table (shared or global); L = current block length.
+// DIF (c2r, SIGN=+1): butterfly then twiddle w_L^{j p}.  DIT (r2c, SIGN=-1): twiddle w_L^{j q} then butterfly.
+template <int R, int SIGN, bool DIF>
+__device__ __forceinline__ void fft_pass(float2 *z, int ldz, int ncols, int N, int L,
+                                         const float2 *__restrict__ tw, int tid, int nthreads) {
+    const int Ls = L / R;
+    const int nb = N / R;
+    const int tstride = N / L;
+    const int total = ncols * nb;
+    for (int idx = tid; idx < total; idx += nthreads) {
+        const int col = idx / nb;
+        const int b = idx - col * nb;
+        const int blk = b / Ls;
+        const int j = b - blk * Ls;
+        float2 *x = z + (size_t)col * ldz + blk * L + j;
+        float2 a[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) a[q] = x[q * Ls];
+        if (!DIF && j != 0) {
+            const int step = j * tstride;
+#pragma unroll
+            for (int q = 1; q < R; ++q) {
+                float2 w = tw[q * step];
+                w.y = SIGN * w.y;
+                a[q] = cmul(a[q], w);
+            }
+        }
+        Dft<R, SIGN>::run(a);
+        if (DIF && j != 0) {
+            const int step = j * tstride;
+#pragma unroll
+            for (int p = 1; p < R; ++p) {
+                float2 w = tw[p * step];
+                w.y = SIGN * w.y;
+                a[p] = cmul(a[p], w);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q * Ls] = a[q];
+    }
+}
+
+template <int SIGN, bool DIF>
+__device__ __forceinline__ void fft_pass_dispatch(int R, float2 *z, int ldz, int ncols, int N, int L,
+                                                  const float2 *__restrict__ tw, int tid, int nthreads) {
+    switch (R) {
+        case 2: fft_pass<2, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 3: fft_pass<3, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 4: fft_pass<4, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 5: fft_pass<5, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 7: fft_pass<7, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 8: fft_pass<8, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 11: fft_pass<11, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 13: fft_pass<13, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 16: fft_pass<16, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        default: break;
+    }
+}
+
+// c2r side: natural-order spectrum Z[k] -> samples z[n] stored at digit-reversed positions (unnormalised,
+// sign +, like FFTW's backward transform).  Ends with a __syncthreads().
+__device__ __forceinline__ void fft_inverse_dif(const FftPlan &pl, float2 *z, int ldz, int ncols,
+                                                const float2 *__restrict__ tw, int tid, int nthreads) {
+    int L = pl.N;
+    for (int s = 0; s < pl.nstages; ++s) {
+        const int R = pl.radix[s];
+        fft_pass_dispatch<+1, true>(R, z, ldz, ncols, pl.N, L, tw, tid, nthreads);
+        L /= R;
+        __syncthreads();
+    }
+}
+
+// r2c side: samples at digit-reversed positions -> natural-order spectrum (unnormalised, sign -).
+__device__ __forceinline__ void fft_forward_dit(const FftPlan &pl, float2 *z, int ldz, int ncols,
+                                                const float2 *__restrict__ tw, int tid, int nthreads) {
+    int L = 1;
+    for (int s = pl.nstages - 1; s >= 0; --s) {
+        const int R = pl.radix[s];
+        L *= R;
+        fft_pass_dispatch<-1, false>(R, z, ldz, ncols, pl.N, L, tw, tid, nthreads);
+        __syncthreads();
+    }
+}

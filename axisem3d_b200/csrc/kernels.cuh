@@ -1,0 +1,691 @@
+// kernels.cuh -- sm_100a kernels of the per-timestep hot path (Newmark.cpp:47-93).
+//
+//   k_newmark_{solid,fluid}   Domain::updateNewmark      (SolidPoint.cpp:23-38, FluidPoint.cpp:23-44)
+//   k_mass3d                  Mass3D::computeAccel        (Mass3D.cpp:13-57)
+//   k_source                  Domain::applySource         (SourceTerm.cpp:29-35)
+//   k_elem1d<FLUID>           Element::computeStiff, 1D material (no FFT): gather -> grad -> [rotate] ->
+//                             stress(+SLS) -> [rotate^-1] -> quad -> scatter, one CTA per (element, mode tile)
+//   k_grad3d / k_fft3d / k_quad3d  the same path for 3D material, split at the two points where the data
+//                             dependency changes axis (points <-> modes); the spectrum between them lives in an
+//                             L2-resident scratch ring ("Z-form": two real columns per complex column)
+//   k_sf_couple               Domain::coupleSolidFluid    (SFCoupling1D.cpp:9-19)
+//   k_pack / k_unpack_add     Domain::assembleStiff       (SolidPoint.cpp:163-173)
+//   k_check_finite            Domain::checkStability      (Domain.cpp:237-275)
+#pragma once
+#include "elem.cuh"
+
+struct ElemDesc {
+    int nr, nu, nyq, axial;
+    int tiso, law, att_kind, nsls;
+    int do_kappa, plan_id, ppb, is3d;
+    unsigned pt_off[AX_NPE];   // offset of the point's block in the solid / fluid field array (float2 units)
+    int pt_stride[AX_NPE];     // Nu_p + 1 (component stride inside the block)
+    int pt_nlive[AX_NPE];      // rows [0, nlive) are gathered / scattered (Nu_p - nyq_p + 1)
+    long long geom_off;        // float  [5][25]: dsdxii, dsdeta, dzdxii, dzdeta, inv_s
+    long long trig_off;        // float  [4][25]: sin t, cos t, sin 2t, cos 2t
+    long long coef_off;        // float  1D: [ncoef][25]      3D: [ncoef][25][Nr] (digit-reversed phi)
+    long long att_par_off;     // float  abg[3][nsls] then {3 dkappa, dmu, 2 dmu}: 1D [3][P], 3D [3][P][Nr]
+    long long att_state_off;   // 1D: float2 [nsls+1][6][P][M]   3D: float [nsls+1][6][P][Nr]; slot nsls = stressR
+    long long scratch_off;     // float2 [NPAIR][25][Nr] inside the scratch ring
+};
+
+struct PointTab {              // one per field family (solid: ncomp = 3, fluid: ncomp = 1)
+    const unsigned *off;       // [npoint] block offset (float2 units)
+    const int *nu;             // [npoint]
+    const int *nr;             // [npoint]
+    const unsigned char *flags;// bit0 axial, bit1 fluidSurf, bit2 mass3D
+    const float *invmass;      // [npoint] (1.0 for Mass3D points: k_mass3d already applied it)
+    const int *row_point;      // [nrows] point index of every (point, mode) row
+    const int *row_start;      // [npoint] first row of the point
+    int nrows;
+};
+
+// ------------------------------------------------------------------------------------ masks
+// SolidPoint::maskField (SolidPoint.cpp:216-238) on the 3 components of one mode
+__device__ __forceinline__ void mask_solid(float2 (&f)[3], int alpha, int nu, bool axial, bool nyq) {
+    if (alpha == 0) { f[0].y = 0.f; f[1].y = 0.f; f[2].y = 0.f; }
+    if (axial) {
+        if (alpha == 0) { f[0] = czero(); f[1] = czero(); }
+        else if (alpha == 1) {
+            float2 s0 = f[0], s1 = f[1];
+            f[0] = make_float2(0.5f * (s0.x + s1.y), 0.5f * (s0.y - s1.x));   // half (s0 - i s1)
+            f[1] = make_float2(0.5f * (s1.x - s0.y), 0.5f * (s1.y + s0.x));   // half (s1 + i s0)
+            f[2] = czero();
+        } else { f[0] = czero(); f[1] = czero(); f[2] = czero(); }
+    }
+    if (nyq && alpha == nu) { f[0] = czero(); f[1] = czero(); f[2] = czero(); }
+}
+// FluidPoint::maskField (FluidPoint.cpp:197-207)
+__device__ __forceinline__ void mask_fluid(float2 &f, int alpha, int nu, bool axial, bool nyq) {
+    if (alpha == 0) f.y = 0.f;
+    if (axial && alpha > 0) f = czero();
+    if (nyq && alpha == nu) f = czero();
+}
+
+// ------------------------------------------------------------------------------------ Newmark
+__global__ void __launch_bounds__(256) k_newmark_solid(PointTab pt, float2 *__restrict__ displ, float2 *__restrict__ veloc,
+                                                       float2 *__restrict__ accel, float2 *__restrict__ stiff,
+                                                       float half_dt, float dt, float half_dt_dt) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= pt.nrows) return;
+    const int p = pt.row_point[r];
+    const int alpha = r - pt.row_start[p];
+    const int nu = pt.nu[p];
+    const int st = nu + 1;
+    const unsigned char fl = pt.flags[p];
+    const bool axial = fl & 1, nyq = (pt.nr[p] & 1) == 0;
+    const size_t base = (size_t)pt.off[p] + alpha;
+    float2 f[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f[c] = stiff[base + (size_t)c * st];
+    mask_solid(f, alpha, nu, axial, nyq);
+    const float im = pt.invmass[p];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f[c] = cscale(f[c], im);
+    mask_solid(f, alpha, nu, axial, nyq);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t i = base + (size_t)c * st;
+        float2 a_old = accel[i], v = veloc[i], u = displ[i];
+        v.x += half_dt * (a_old.x + f[c].x);
+        v.y += half_dt * (a_old.y + f[c].y);
+        u.x += dt * v.x + half_dt_dt * f[c].x;
+        u.y += dt * v.y + half_dt_dt * f[c].y;
+        veloc[i] = v;
+        accel[i] = f[c];
+        displ[i] = u;
+        stiff[i] = czero();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_newmark_fluid(PointTab pt, float2 *__restrict__ displ, float2 *__restrict__ veloc,
+                                                       float2 *__restrict__ accel, float2 *__restrict__ stiff,
+                                                       float half_dt, float dt, float half_dt_dt) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= pt.nrows) return;
+    const int p = pt.row_point[r];
+    const int alpha = r - pt.row_start[p];
+    const int nu = pt.nu[p];
+    const unsigned char fl = pt.flags[p];
+    const size_t i = (size_t)pt.off[p] + alpha;
+    if (fl & 2) {   // surface fluid point: pinned to zero (FluidPoint.cpp:25-28)
+        displ[i] = veloc[i] = accel[i] = stiff[i] = czero();
+        return;
+    }
+    const bool axial = fl & 1, nyq = (pt.nr[p] & 1) == 0;
+    float2 f = stiff[i];
+    mask_fluid(f, alpha, nu, axial, nyq);
+    f = cscale(f, pt.invmass[p]);
+    mask_fluid(f, alpha, nu, axial, nyq);
+    float2 a_old = accel[i], v = veloc[i], u = displ[i];
+    v.x += half_dt * (a_old.x + f.x);
+    v.y += half_dt * (a_old.y + f.y);
+    u.x += dt * v.x + half_dt_dt * f.x;
+    u.y += dt * v.y + half_dt_dt * f.y;
+    veloc[i] = v;
+    accel[i] = f;
+    displ[i] = u;
+    stiff[i] = czero();
+}
+
+// ------------------------------------------------------------------------------------ point FFT helpers
+// spectrum X[k], k <= Nu (Hermitian) for up to two real columns -> complex column z[n], n < N:
+// Z[k] = A[k] + i B[k], Z[N-k] = conj(A[k]) + i conj(B[k])
+__device__ __forceinline__ void zform_store(float2 *z, int N, int k, float2 a, float2 b) {
+    z[k] = make_float2(a.x - b.y, a.y + b.x);
+    if (k >= 1 && 2 * k < N) z[N - k] = make_float2(a.x + b.y, b.x - a.y);
+}
+__device__ __forceinline__ void zform_load(const float2 *z, int N, int k, float scale, float2 &a, float2 &b) {
+    float2 zk = z[k];
+    if (k >= 1 && 2 * k < N) {
+        float2 w = z[N - k];
+        a = make_float2(0.5f * scale * (zk.x + w.x), 0.5f * scale * (zk.y - w.y));
+        b = make_float2(0.5f * scale * (zk.y + w.y), 0.5f * scale * (w.x - zk.x));
+    } else {
+        a = make_float2(scale * zk.x, 0.f);
+        b = make_float2(scale * zk.y, 0.f);
+    }
+}
+
+// Mass3D::computeAccel (Mass3D.cpp:13-57) for the points listed in `list`: mask -> c2r -> * invMass(phi) -> r2c/Nr.
+// One CTA per point; NCOMP = 3 (solid: columns s,phi | z,0) or 1 (fluid).  Result overwrites stiff.
+struct Mass3DItem {
+    int point;         // index into the point table
+    int plan_id;
+    long long im_off;  // float [Nr] inverse mass, digit-reversed phi
+};
+template <int NCOMP>
+__global__ void __launch_bounds__(128) k_mass3d(PointTab pt, const Mass3DItem *__restrict__ items,
+                                                const FftPlan *__restrict__ plans, const float2 *__restrict__ twpool,
+                                                const float *__restrict__ impool, float2 *__restrict__ stiff) {
+    extern __shared__ float2 smem[];
+    const Mass3DItem it = items[blockIdx.x];
+    const FftPlan pl = plans[it.plan_id];
+    const int N = pl.N, nu = pt.nu[it.point], st = nu + 1;
+    const bool axial = pt.flags[it.point] & 1, nyq = (N & 1) == 0;
+    constexpr int NCOL = NCOMP == 3 ? 2 : 1;
+    float2 *z = smem;               // [NCOL][N]
+    float2 *tw = smem + NCOL * N;   // [N]
+    const size_t base = pt.off[it.point];
+    for (int k = threadIdx.x; k < N; k += blockDim.x) tw[k] = twpool[pl.tw_off + k];
+    for (int k = threadIdx.x; k <= nu; k += blockDim.x) {
+        if (NCOMP == 3) {
+            float2 f[3] = {stiff[base + k], stiff[base + st + k], stiff[base + 2 * st + k]};
+            mask_solid(f, k, nu, axial, nyq);
+            zform_store(z, N, k, f[0], f[1]);
+            zform_store(z + N, N, k, f[2], czero());
+        } else {
+            float2 f = stiff[base + k];
+            mask_fluid(f, k, nu, axial, nyq);
+            zform_store(z, N, k, f, czero());
+        }
+    }
+    __syncthreads();
+    fft_inverse_dif(pl, z, N, NCOL, tw, threadIdx.x, blockDim.x);
+    const float *im = impool + it.im_off;
+    for (int idx = threadIdx.x; idx < NCOL * N; idx += blockDim.x) {
+        const int pos = idx % N;
+        z[idx] = cscale(z[idx], im[pos]);
+    }
+    __syncthreads();
+    fft_forward_dit(pl, z, N, NCOL, tw, threadIdx.x, blockDim.x);
+    const float sc = 1.f / (float)N;
+    for (int k = threadIdx.x; k <= nu; k += blockDim.x) {
+        float2 a, b;
+        zform_load(z, N, k, sc, a, b);
+        stiff[base + k] = a;
+        if (NCOMP == 3) {
+            stiff[base + st + k] = b;
+            float2 c, d;
+            zform_load(z + N, N, k, sc, c, d);
+            stiff[base + 2 * st + k] = c;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ source
+__global__ void k_source(int n, const unsigned *__restrict__ off, const float2 *__restrict__ val, float stf,
+                         float2 *__restrict__ stiff) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 v = val[i];
+    atomicAdd(&stiff[off[i]].x, v.x * stf);
+    atomicAdd(&stiff[off[i]].y, v.y * stf);
+}
+
+// ------------------------------------------------------------------------------------ element helpers
+__device__ __forceinline__ PointGeom load_geom(const float *__restrict__ geom, long long off, int p) {
+    PointGeom g;
+    g.dsdxii = geom[off + 0 * AX_NPE + p];
+    g.dsdeta = geom[off + 1 * AX_NPE + p];
+    g.dzdxii = geom[off + 2 * AX_NPE + p];
+    g.dzdeta = geom[off + 3 * AX_NPE + p];
+    g.inv_s = geom[off + 4 * AX_NPE + p];
+    return g;
+}
+
+// gather of SolidPoint::scatterDisplToElement (SolidPoint.cpp:175-195) for one (alpha, point)
+template <int NC>
+__device__ __forceinline__ void gather_tile(const ElemDesc &E, const float2 *__restrict__ displ, float2 *sU, int t, int p,
+                                            int alpha) {
+    const bool live = alpha < E.pt_nlive[p];
+    const size_t base = (size_t)E.pt_off[p] + alpha;
+    const int st = E.pt_stride[p];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float2 u = live ? displ[base + (size_t)c * st] : czero();
+        if (alpha == 0) u.y = 0.f;
+        sU[(c * AX_NPE + p) * AX_TILE + t] = u;
+    }
+}
+
+// scatter of SolidPoint::gatherStiffFromElement (SolidPoint.cpp:197-209): stiff -= f on live rows
+__device__ __forceinline__ void scatter_sub(float2 *__restrict__ stiff, size_t i, float2 f) {
+    atomicAdd(&stiff[i], make_float2(-f.x, -f.y));   // sm_90+ vector atomic (RED.E.ADD.F32x2)
+}
+
+static __device__ __forceinline__ int cg4_index(int p) {   // (1,1),(1,3),(3,1),(3,3) -> 0..3, else -1
+    return p == 6 ? 0 : p == 8 ? 1 : p == 16 ? 2 : p == 18 ? 3 : -1;
+}
+
+// ------------------------------------------------------------------------------------ 1D-material element kernel
+// grid: one CTA per work item (element, first mode of the tile); block: AX_TILE x 25 threads, lane = mode.
+template <bool FLUID>
+__global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
+                                                            const int *__restrict__ w_a0, const float *__restrict__ geom,
+                                                            const float *__restrict__ coef, const float *__restrict__ attpar,
+                                                            float2 *__restrict__ attstate, const float2 *__restrict__ displ,
+                                                            float2 *__restrict__ stiff) {
+    constexpr int NC = FLUID ? 1 : 3;
+    __shared__ float2 sU[NC * AX_NPE * AX_TILE];
+    __shared__ float2 sX[NC * AX_NPE * AX_TILE];
+    __shared__ float2 sY[NC * AX_NPE * AX_TILE];
+    const ElemDesc &E = elems[w_elem[blockIdx.x]];
+    const int t = threadIdx.x % AX_TILE, p = threadIdx.x / AX_TILE;
+    const int i = p / 5, j = p % 5;
+    const int alpha = w_a0[blockIdx.x] + t;
+    const int M = E.nu + 1;
+    const bool active = alpha < M;
+    gather_tile<NC>(E, displ, sU, t, p, active ? alpha : (1 << 30));
+    GCoef gc;
+    load_gcoef(gc, E.axial, i, j);
+    const PointGeom g = load_geom(geom, E.geom_off, p);
+    const bool ax0 = E.axial && i == 0;
+    const bool dead = !active || (E.nyq && alpha == E.nu);
+    __syncthreads();
+    float2 r[NC];
+    if constexpr (!FLUID) {
+        float2 e[6], s[6], X[3], Y[3];
+        grad6_point<AX_TILE>(sU, t, i, j, gc, g, (float)alpha, ax0, e);
+        if (dead) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) e[c] = czero();
+        }
+        float tr[4];
+        if (E.tiso) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+            rot_spz_to_rtz(e, tr[0], tr[1], tr[2], tr[3]);
+        }
+        const float *cf = coef + E.coef_off + p;
+        stress_law<float2>(E.law, e, s, [&](int k) { return cf[k * AX_NPE]; });
+        if (E.att_kind != ATT_NONE && active) {
+            const int P = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
+            const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
+            if (q >= 0) {
+                const float *ap = attpar + E.att_par_off;
+                const float *mod = ap + 3 * E.nsls;
+                float2 *stt = attstate + E.att_state_off;
+                const size_t cell = (size_t)q * M + alpha;
+                const size_t sl = (size_t)6 * P * M;
+                attenuation_cell<float2>(
+                    E.nsls, ap, mod[q], mod[P + q], mod[2 * P + q], E.do_kappa != 0, e, s,
+                    [&](int k, int c) -> float2 & { return stt[k * sl + (size_t)c * P * M + cell]; },
+                    [&](int c) -> float2 & { return stt[E.nsls * sl + (size_t)c * P * M + cell]; });
+            }
+        }
+        if (E.tiso) rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
+        quad6_pre(s, g, (float)alpha, ax0, X, Y, r);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            sX[(c * AX_NPE + p) * AX_TILE + t] = X[c];
+            sY[(c * AX_NPE + p) * AX_TILE + t] = Y[c];
+        }
+    } else {
+        float2 e[3], s[3], X, Y;
+        grad_fluid_point<AX_TILE>(sU, t, i, j, gc, g, (float)alpha, ax0, e);
+        const float K = dead ? 0.f : coef[E.coef_off + p];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s[c] = cscale(e[c], K);   // Acoustic1D.cpp:8-16
+        quad_fluid_pre(s, g, (float)alpha, ax0, X, Y, r[0]);
+        sX[p * AX_TILE + t] = X;
+        sY[p * AX_TILE + t] = Y;
+    }
+    __syncthreads();
+    if (dead || alpha >= E.pt_nlive[p]) return;
+    const size_t base = (size_t)E.pt_off[p] + alpha;
+    const int st = E.pt_stride[p];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float2 f = quad_post<AX_TILE>(sX, sY, c, t, i, j, gc, r[c]);
+        if (alpha == 0) f.y = 0.f;
+        scatter_sub(stiff, base + (size_t)c * st, f);
+    }
+}
+
+// ------------------------------------------------------------------------------------ 3D material: stage A (grad)
+template <bool FLUID>
+__global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
+                                                            const int *__restrict__ w_a0, const float *__restrict__ geom,
+                                                            const float2 *__restrict__ displ, float2 *__restrict__ scratch) {
+    constexpr int NC = FLUID ? 1 : 3;
+    __shared__ float2 sU[NC * AX_NPE * AX_TILE];
+    const ElemDesc &E = elems[w_elem[blockIdx.x]];
+    const int t = threadIdx.x % AX_TILE, p = threadIdx.x / AX_TILE;
+    const int i = p / 5, j = p % 5;
+    const int alpha = w_a0[blockIdx.x] + t;
+    const int N = E.nr;
+    const bool active = alpha <= E.nu;
+    gather_tile<NC>(E, displ, sU, t, p, active ? alpha : (1 << 30));
+    GCoef gc;
+    load_gcoef(gc, E.axial, i, j);
+    const PointGeom g = load_geom(geom, E.geom_off, p);
+    const bool ax0 = E.axial && i == 0;
+    __syncthreads();
+    if (!active) return;
+    const bool dead = E.nyq && alpha == E.nu;
+    float2 *z = scratch + E.scratch_off + (size_t)p * N;
+    if constexpr (!FLUID) {
+        float2 e[6];
+        grad6_point<AX_TILE>(sU, t, i, j, gc, g, (float)alpha, ax0, e);
+        if (dead) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) e[c] = czero();
+        }
+        if (E.tiso) {
+            float tr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+            rot_spz_to_rtz(e, tr[0], tr[1], tr[2], tr[3]);
+        }
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) zform_store(z + (size_t)pr * AX_NPE * N, N, alpha, e[2 * pr], e[2 * pr + 1]);
+    } else {
+        float2 e[3];
+        grad_fluid_point<AX_TILE>(sU, t, i, j, gc, g, (float)alpha, ax0, e);
+        if (dead) e[0] = e[1] = e[2] = czero();
+        zform_store(z, N, alpha, e[0], e[1]);
+        zform_store(z + (size_t)AX_NPE * N, N, alpha, e[2], czero());
+    }
+}
+
+// ------------------------------------------------------------------------------------ 3D material: stage B (c2r, stress, r2c)
+// grid: one CTA per (element, group of `ppb` points); block 256.  smem: z[NPAIR*ppb][N] + tw[N].
+struct FftItem {
+    int elem;
+    int p0;
+};
+template <bool FLUID>
+__global__ void __launch_bounds__(256) k_fft3d(const ElemDesc *__restrict__ elems, const FftItem *__restrict__ items,
+                                               const FftPlan *__restrict__ plans, const float2 *__restrict__ twpool,
+                                               const float *__restrict__ coef, const float *__restrict__ attpar,
+                                               float *__restrict__ attstate, float2 *__restrict__ scratch) {
+    constexpr int NPAIR = FLUID ? 2 : 3;
+    extern __shared__ float2 smem[];
+    const FftItem it = items[blockIdx.x];
+    const ElemDesc &E = elems[it.elem];
+    const FftPlan pl = plans[E.plan_id];
+    const int N = pl.N, ppb = E.ppb;
+    const int np = min(ppb, AX_NPE - it.p0);
+    const int ncols = NPAIR * np;
+    float2 *z = smem;                          // column (pr, pl) at (pr * np + pl) * N
+    float2 *tw = smem + (size_t)NPAIR * ppb * N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = tid; k < N; k += nt) tw[k] = twpool[pl.tw_off + k];
+    float2 *gz = scratch + E.scratch_off;
+    for (int pr = 0; pr < NPAIR; ++pr) {
+        const float2 *src = gz + ((size_t)pr * AX_NPE + it.p0) * N;
+        float2 *dst = z + (size_t)pr * np * N;
+        for (int k = tid; k < np * N; k += nt) dst[k] = src[k];
+    }
+    __syncthreads();
+    fft_inverse_dif(pl, z, N, ncols, tw, tid, nt);
+    // pointwise physics at (point, phi position)
+    for (int idx = tid; idx < np * N; idx += nt) {
+        const int plc = idx / N, pos = idx - plc * N;
+        const int p = it.p0 + plc;
+        if constexpr (!FLUID) {
+            float2 z0 = z[(size_t)(0 * np + plc) * N + pos], z1 = z[(size_t)(1 * np + plc) * N + pos],
+                   z2 = z[(size_t)(2 * np + plc) * N + pos];
+            float e[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
+            const float *cf = coef + E.coef_off + (size_t)p * N + pos;
+            const size_t cst = (size_t)AX_NPE * N;
+            stress_law<float>(E.law, e, s, [&](int k) { return cf[k * cst]; });
+            if (E.att_kind != ATT_NONE) {
+                const int P = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
+                const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
+                if (q >= 0) {
+                    const float *ap = attpar + E.att_par_off;
+                    const float *mod = ap + 3 * E.nsls;
+                    float *stt = attstate + E.att_state_off;
+                    const size_t cell = (size_t)q * N + pos;
+                    const size_t PN = (size_t)P * N, sl = 6 * PN;
+                    attenuation_cell<float>(
+                        E.nsls, ap, mod[cell], mod[PN + cell], mod[2 * PN + cell], E.do_kappa != 0, e, s,
+                        [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
+                        [&](int c) -> float & { return stt[E.nsls * sl + c * PN + cell]; });
+                }
+            }
+            z[(size_t)(0 * np + plc) * N + pos] = make_float2(s[0], s[1]);
+            z[(size_t)(1 * np + plc) * N + pos] = make_float2(s[2], s[3]);
+            z[(size_t)(2 * np + plc) * N + pos] = make_float2(s[4], s[5]);
+        } else {
+            const float K = coef[E.coef_off + (size_t)p * N + pos];   // Acoustic3D.cpp:9-16
+            float2 &a = z[(size_t)plc * N + pos], &b = z[(size_t)(np + plc) * N + pos];
+            a = cscale(a, K);
+            b = make_float2(b.x * K, 0.f);
+        }
+    }
+    __syncthreads();
+    fft_forward_dit(pl, z, N, ncols, tw, tid, nt);
+    for (int pr = 0; pr < NPAIR; ++pr) {
+        float2 *dst = gz + ((size_t)pr * AX_NPE + it.p0) * N;
+        const float2 *src = z + (size_t)pr * np * N;
+        for (int k = tid; k < np * N; k += nt) dst[k] = src[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------ 3D material: stage C (quad)
+template <bool FLUID>
+__global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
+                                                            const int *__restrict__ w_a0, const float *__restrict__ geom,
+                                                            const float2 *__restrict__ scratch, float2 *__restrict__ stiff) {
+    constexpr int NC = FLUID ? 1 : 3;
+    __shared__ float2 sX[NC * AX_NPE * AX_TILE];
+    __shared__ float2 sY[NC * AX_NPE * AX_TILE];
+    const ElemDesc &E = elems[w_elem[blockIdx.x]];
+    const int t = threadIdx.x % AX_TILE, p = threadIdx.x / AX_TILE;
+    const int i = p / 5, j = p % 5;
+    const int beta = w_a0[blockIdx.x] + t;
+    const int N = E.nr;
+    const bool active = beta <= E.nu;
+    const bool dead = !active || (E.nyq && beta == E.nu);
+    GCoef gc;
+    load_gcoef(gc, E.axial, i, j);
+    const PointGeom g = load_geom(geom, E.geom_off, p);
+    const bool ax0 = E.axial && i == 0;
+    const float2 *z = scratch + E.scratch_off + (size_t)p * N;
+    const float sc = 1.f / (float)N;   // SolverFFTW_N6::computeR2C scaling (SolverFFTW_N6.cpp:47-48)
+    float2 r[NC];
+    if constexpr (!FLUID) {
+        float2 s[6], X[3], Y[3];
+        if (!dead) {
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) zform_load(z + (size_t)pr * AX_NPE * N, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
+            if (E.tiso) {
+                float tr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+                rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) s[c] = czero();
+        }
+        quad6_pre(s, g, (float)beta, ax0, X, Y, r);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            sX[(c * AX_NPE + p) * AX_TILE + t] = X[c];
+            sY[(c * AX_NPE + p) * AX_TILE + t] = Y[c];
+        }
+    } else {
+        float2 s[3], X, Y, dummy;
+        if (!dead) {
+            zform_load(z, N, beta, sc, s[0], s[1]);
+            zform_load(z + (size_t)AX_NPE * N, N, beta, sc, s[2], dummy);
+        } else {
+            s[0] = s[1] = s[2] = czero();
+        }
+        quad_fluid_pre(s, g, (float)beta, ax0, X, Y, r[0]);
+        sX[p * AX_TILE + t] = X;
+        sY[p * AX_TILE + t] = Y;
+    }
+    __syncthreads();
+    if (dead || beta >= E.pt_nlive[p]) return;
+    const size_t base = (size_t)E.pt_off[p] + beta;
+    const int st = E.pt_stride[p];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float2 f = quad_post<AX_TILE>(sX, sY, c, t, i, j, gc, r[c]);
+        if (beta == 0) f.y = 0.f;
+        scatter_sub(stiff, base + (size_t)c * st, f);
+    }
+}
+
+// ------------------------------------------------------------------------------------ solid-fluid coupling
+// SolidFluidPoint::coupleSolidFluid (SolidFluidPoint.cpp:106-110) with SFCoupling1D (SFCoupling1D.cpp:9-19);
+// thread = (sf point, mode).  cpl: [4] = ns, nz, ns_invmf, nz_invmf.
+struct SFTab {
+    const unsigned *s_off, *f_off;
+    const int *nu;
+    const float *cpl;
+    const int *row_point, *row_start;
+    int nrows;
+};
+__global__ void k_sf_couple(SFTab sf, const float2 *__restrict__ s_displ, float2 *__restrict__ s_stiff,
+                            float2 *__restrict__ f_stiff) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= sf.nrows) return;
+    const int q = sf.row_point[r];
+    const int alpha = r - sf.row_start[q];
+    const int st = sf.nu[q] + 1;
+    const float *c = sf.cpl + 4 * q;
+    const size_t so = (size_t)sf.s_off[q] + alpha, fo = (size_t)sf.f_off[q] + alpha;
+    float2 us = s_displ[so], uz = s_displ[so + 2 * (size_t)st];
+    float2 ff = f_stiff[fo];
+    ff.x += c[0] * us.x + c[1] * uz.x;
+    ff.y += c[0] * us.y + c[1] * uz.y;
+    f_stiff[fo] = ff;
+    float2 a = s_stiff[so], b = s_stiff[so + 2 * (size_t)st];
+    a.x -= c[2] * ff.x; a.y -= c[2] * ff.y;
+    b.x -= c[3] * ff.x; b.y -= c[3] * ff.y;
+    s_stiff[so] = a;
+    s_stiff[so + 2 * (size_t)st] = b;
+}
+
+// SFCoupling3D (SFCoupling3D.cpp:9-54): one CTA per 3D solid-fluid point.
+struct SF3DItem {
+    unsigned s_off, f_off;
+    int nu, plan_id;
+    long long n_off;   // float [6][Nr]: n_un(s,phi,z), n_as_invmf(s,phi,z), digit-reversed phi
+};
+__global__ void __launch_bounds__(128) k_sf_couple3d(const SF3DItem *__restrict__ items, const FftPlan *__restrict__ plans,
+                                                     const float2 *__restrict__ twpool, const float *__restrict__ npool,
+                                                     const float2 *__restrict__ s_displ, float2 *__restrict__ s_stiff,
+                                                     float2 *__restrict__ f_stiff) {
+    extern __shared__ float2 smem[];
+    const SF3DItem it = items[blockIdx.x];
+    const FftPlan pl = plans[it.plan_id];
+    const int N = pl.N, nu = it.nu, st = nu + 1;
+    float2 *z = smem, *tw = smem + 2 * N;
+    const float *nn = npool + it.n_off;
+    const float sc = 1.f / (float)N;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) tw[k] = twpool[pl.tw_off + k];
+    // solid displacement -> physical space (columns: s + i phi | z)
+    for (int k = threadIdx.x; k <= nu; k += blockDim.x) {
+        zform_store(z, N, k, s_displ[it.s_off + k], s_displ[it.s_off + st + k]);
+        zform_store(z + N, N, k, s_displ[it.s_off + 2 * st + k], czero());
+    }
+    __syncthreads();
+    fft_inverse_dif(pl, z, N, 2, tw, threadIdx.x, blockDim.x);
+    for (int pos = threadIdx.x; pos < N; pos += blockDim.x) {
+        float2 a = z[pos], b = z[N + pos];
+        z[pos] = make_float2(nn[pos] * a.x + nn[N + pos] * a.y + nn[2 * N + pos] * b.x, 0.f);
+    }
+    __syncthreads();
+    fft_forward_dit(pl, z, N, 1, tw, threadIdx.x, blockDim.x);
+    // fluid stiff += ...; then fluid stiff -> physical space
+    for (int k = threadIdx.x; k <= nu; k += blockDim.x) {
+        float2 a, b;
+        zform_load(z, N, k, sc, a, b);
+        float2 ff = f_stiff[it.f_off + k];
+        ff.x += a.x; ff.y += a.y;
+        f_stiff[it.f_off + k] = ff;
+        z[N + k] = ff;   // stash (second column is free)
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k <= nu; k += blockDim.x) {
+        float2 ff = z[N + k];
+        zform_store(z, N, k, ff, czero());
+    }
+    __syncthreads();
+    fft_inverse_dif(pl, z, N, 1, tw, threadIdx.x, blockDim.x);
+    for (int pos = threadIdx.x; pos < N; pos += blockDim.x) {
+        const float fr = z[pos].x;
+        z[pos] = make_float2(nn[3 * N + pos] * fr, nn[4 * N + pos] * fr);
+        z[N + pos] = make_float2(nn[5 * N + pos] * fr, 0.f);
+    }
+    __syncthreads();
+    fft_forward_dit(pl, z, N, 2, tw, threadIdx.x, blockDim.x);
+    for (int k = threadIdx.x; k <= nu; k += blockDim.x) {
+        float2 a, b, c, d;
+        zform_load(z, N, k, sc, a, b);
+        zform_load(z + N, N, k, sc, c, d);
+        float2 *s0 = &s_stiff[it.s_off + k], *s1 = &s_stiff[it.s_off + st + k], *s2 = &s_stiff[it.s_off + 2 * st + k];
+        s0->x -= a.x; s0->y -= a.y;
+        s1->x -= b.x; s1->y -= b.y;
+        s2->x -= c.x; s2->y -= c.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------ halo
+// idx[i] : bit31 = fluid array, low bits = offset in the stiff array
+__global__ void k_pack(int n, const unsigned *__restrict__ idx, const float2 *__restrict__ s_stiff,
+                       const float2 *__restrict__ f_stiff, float2 *__restrict__ buf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = idx[i];
+    buf[i] = (k >> 31) ? f_stiff[k & 0x7fffffffu] : s_stiff[k];
+}
+__global__ void k_unpack_add(int n, const unsigned *__restrict__ idx, const float2 *__restrict__ buf,
+                             float2 *__restrict__ s_stiff, float2 *__restrict__ f_stiff) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = idx[i];
+    float2 *d = (k >> 31) ? &f_stiff[k & 0x7fffffffu] : &s_stiff[k];
+    float2 v = buf[i];
+    d->x += v.x;
+    d->y += v.y;
+}
+
+// ------------------------------------------------------------------------------------ stability
+__global__ void k_check_finite(size_t n, const float *__restrict__ a, int *__restrict__ bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int b = 0;
+    for (; i < n; i += stride) b |= !isfinite(a[i]);
+    if (b) atomicOr(bad, 1);
+}
+
+// ------------------------------------------------------------------------------------ receivers
+// SolidElement::computeGroundMotion (SolidElement.cpp:189-216); one CTA per receiver, 128 threads.
+struct RecvItem {
+    int elem;
+    float phi;
+};
+__global__ void __launch_bounds__(128) k_ground_motion(const ElemDesc *__restrict__ elems, const RecvItem *__restrict__ rec,
+                                                       const float *__restrict__ weights, const float2 *__restrict__ displ,
+                                                       float *__restrict__ out) {
+    const RecvItem R = rec[blockIdx.x];
+    const ElemDesc &E = elems[R.elem];
+    const float *w = weights + (size_t)blockIdx.x * AX_NPE;
+    const int top = E.nu - E.nyq;   // last mode used
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int idx = threadIdx.x; idx < AX_NPE * (top + 1); idx += blockDim.x) {
+        const int p = idx / (top + 1), alpha = idx - p * (top + 1);
+        const float wp = w[p];
+        if (fabsf(wp) < 1e-10f || alpha >= E.pt_nlive[p]) continue;
+        float sn, cs;
+        sincosf((float)alpha * R.phi, &sn, &cs);
+        const float fac = alpha == 0 ? 1.f : 2.f;
+        const size_t base = (size_t)E.pt_off[p] + alpha;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float2 u = displ[base + (size_t)c * E.pt_stride[p]];
+            const float re = alpha == 0 ? u.x : (cs * u.x - sn * u.y);
+            acc[c] += wp * fac * re;
+        }
+    }
+    __shared__ float red[3][128];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) red[c][threadIdx.x] = acc[c];
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) red[c][threadIdx.x] += red[c][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) out[blockIdx.x * 3 + threadIdx.x] = red[threadIdx.x][0];
+}

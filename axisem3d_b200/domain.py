@@ -1,0 +1,263 @@
+"""`Domain` with the reference's verbs (S/core/domain/Domain.h:27-89) over the CUDA C-ABI.
+
+Mirrors the call sites of Newmark::solve (Newmark.cpp:47-93) and Mesh::release (Mesh.cpp:177-208):
+addPoint / addElement / addSourceTerm / setMessaging, then updateNewmark, applySource, computeStiff,
+coupleSolidFluid, assembleStiff, checkStability.  All arithmetic happens in libaxisem3d_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from . import model as M
+
+_FIELD = {"displ": 0, "veloc": 1, "accel": 2, "stiff": 3}
+_LAW = {"iso": 0, "ti": 1, "aniso": 2}
+
+
+def _pf(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _pi(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _mass(m):
+    if m.is3D:
+        return _f32(m.invMass)
+    return np.array([m.invMass], dtype=np.float32)
+
+
+def _colmajor(a):
+    """(rows, ncol) array -> Eigen column-major flat float32."""
+    return _f32(np.asarray(a).T).reshape(-1)
+
+
+class Domain:
+    def __init__(self, device=0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        capi.check(self.lib.ax3d_create(int(device), C.byref(h)))
+        self.h = h
+        self.points, self.elements = [], []
+        self._final = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.ax3d_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ setup
+    def setGMat(self, G_GLL, G_GLJ):
+        a = np.ascontiguousarray(np.asarray(G_GLL, dtype=np.float64).reshape(25))
+        b = np.ascontiguousarray(np.asarray(G_GLJ, dtype=np.float64).reshape(25))
+        capi.check(self.lib.ax3d_set_gmat(self.h, _pd(a), _pd(b)))
+
+    def addPoint(self, p):
+        tag = C.c_int(-1)
+        crds = np.ascontiguousarray(p.crds, dtype=np.float64)
+        if p.kind == "solid":
+            im = _mass(p.mass)
+            capi.check(self.lib.ax3d_add_solid_point(self.h, p.nr, int(p.axial), _pd(crds), im.size, _pf(im), C.byref(tag)))
+        elif p.kind == "fluid":
+            im = _mass(p.mass)
+            capi.check(self.lib.ax3d_add_fluid_point(self.h, p.nr, int(p.axial), _pd(crds), im.size, _pf(im),
+                                                     int(p.fluidSurf), C.byref(tag)))
+        else:
+            ims, imf = _mass(p.solid.mass), _mass(p.fluid.mass)
+            c = p.couple
+            if c.is3D:
+                nun, nas, nsf = _colmajor(c.n_un), _colmajor(c.n_as), p.nr
+            else:
+                nun = np.array([c.ns, 0.0, c.nz], dtype=np.float32)
+                nas = np.array([c.ns_invmf, 0.0, c.nz_invmf], dtype=np.float32)
+                nsf = 1
+            capi.check(self.lib.ax3d_add_solid_fluid_point(
+                self.h, p.nr, int(p.axial), _pd(crds), ims.size, _pf(ims), imf.size, _pf(imf),
+                int(p.fluid.fluidSurf), nsf, _pf(nun), _pf(nas), C.byref(tag)))
+        p.domain_tag = tag.value
+        self.points.append(p)
+        return tag.value
+
+    def addElement(self, e):
+        tag = C.c_int(-1)
+        tags = np.array([p.domain_tag for p in e.points], dtype=np.int32)
+        g = e.grad
+        geom = np.ascontiguousarray(np.stack([g.dsdxii, g.dsdeta, g.dzdxii, g.dzdeta, g.inv_s]).reshape(-1), dtype=np.float64)
+        if e.kind == "solid":
+            el = e.elastic
+            rows = el.coef.shape[1]
+            # (ncoef, rows, 25) -> per array column-major rows x 25
+            coef = _f32(np.transpose(el.coef, (0, 2, 1))).reshape(-1)
+            theta = np.ascontiguousarray(e.formThetaMat().reshape(-1), dtype=np.float64)
+            att_ref = None
+            keep = []
+            if el.att is not None:
+                a = el.att
+                P = 4 if a.cg4 else 25
+                al, be, ga = _f32(a.alpha), _f32(a.beta), _f32(a.gamma)
+                dk = _colmajor(np.asarray(a.dkappa).reshape(rows, P))
+                dm = _colmajor(np.asarray(a.dmu).reshape(rows, P))
+                keep = [al, be, ga, dk, dm]
+                att_ref = capi.Attenuation(2 if a.cg4 else 1, a.nsls, _pf(al), _pf(be), _pf(ga), _pf(dk), _pf(dm),
+                                           int(a.doKappa))
+            capi.check(self.lib.ax3d_add_solid_element(
+                self.h, _pi(tags), _pd(geom), int(g.axial), _pd(theta), _LAW[el.law], rows, _pf(coef),
+                C.byref(att_ref) if att_ref is not None else None, C.byref(tag)))
+            del keep
+        else:
+            K = e.acoustic.K
+            rows = K.shape[0]
+            Kf = _colmajor(K)
+            capi.check(self.lib.ax3d_add_fluid_element(self.h, _pi(tags), _pd(geom), int(g.axial), rows, _pf(Kf), C.byref(tag)))
+        e.domain_tag = tag.value
+        self.elements.append(e)
+        return tag.value
+
+    def addSourceTerm(self, st):
+        nrow = np.array([f.shape[0] for f in st.force], dtype=np.int32)
+        flat = []
+        for f in st.force:
+            c = np.asarray(f, dtype=np.complex64).T.reshape(-1)     # column-major (nrow x 3)
+            flat.append(np.stack([c.real, c.imag], 1).reshape(-1))
+        force = _f32(np.concatenate(flat))
+        capi.check(self.lib.ax3d_add_source_term(self.h, st.element.domain_tag, _pi(nrow), _pf(force)))
+
+    def setMessaging(self, info, rank=0, nproc=1, nccl_unique_id=None):
+        neigh = np.array(info.mIProcComm, dtype=np.int32)
+        npts = np.array(info.mNLocalPoints, dtype=np.int32)
+        tags = np.array([t for l in info.mILocalPoints for t in l], dtype=np.int32)
+        uid = None
+        if nccl_unique_id is not None:
+            uid = (C.c_ubyte * 128).from_buffer_copy(bytes(nccl_unique_id)[:128].ljust(128, b"\0"))
+        capi.check(self.lib.ax3d_set_messaging(self.h, rank, nproc, C.cast(uid, C.c_void_p) if uid is not None else None,
+                                               len(neigh), _pi(neigh), _pi(npts), _pi(tags)))
+
+    def finalize(self):
+        capi.check(self.lib.ax3d_finalize_setup(self.h))
+        self._final = True
+
+    # ------------------------------------------------------------------ step verbs
+    def updateNewmark(self, dt):
+        capi.check(self.lib.ax3d_update_newmark(self.h, float(dt)))
+
+    def applySource(self, stf):
+        capi.check(self.lib.ax3d_apply_source(self.h, float(stf)))
+
+    def computeStiff(self):
+        capi.check(self.lib.ax3d_compute_stiff(self.h))
+
+    def coupleSolidFluid(self):
+        capi.check(self.lib.ax3d_couple_solid_fluid(self.h))
+
+    def assembleStiff(self, phase=0):
+        capi.check(self.lib.ax3d_assemble_stiff(self.h, int(phase)))
+
+    def checkStability(self):
+        ok = C.c_int(0)
+        capi.check(self.lib.ax3d_check_stability(self.h, C.byref(ok)))
+        return bool(ok.value)
+
+    def resetZero(self):
+        capi.check(self.lib.ax3d_reset_zero(self.h))
+
+    def step(self, dt, stf):
+        """One iteration of Newmark::solve's loop body (Newmark.cpp:49-91)."""
+        self.updateNewmark(dt)
+        self.applySource(stf)
+        self.computeStiff()
+        self.coupleSolidFluid()
+        self.assembleStiff(-1)
+        self.assembleStiff(1)
+
+    def runSteps(self, dt, stf):
+        stf = _f32(stf)
+        capi.check(self.lib.ax3d_run_steps(self.h, stf.size, float(dt), _pf(stf)))
+
+    def synchronize(self):
+        capi.check(self.lib.ax3d_synchronize(self.h))
+
+    # ------------------------------------------------------------------ read-back / test hooks
+    def get_solid(self, tag, which):
+        n = self.points[tag].nu + 1
+        out = np.zeros(3 * n * 2, dtype=np.float32)
+        capi.check(self.lib.ax3d_get_point_field(self.h, tag, _FIELD[which], 0, _pf(out), 3 * n))
+        return out.view(np.complex64).reshape(3, n).T.copy()
+
+    def get_fluid(self, tag, which):
+        n = self.points[tag].nu + 1
+        out = np.zeros(n * 2, dtype=np.float32)
+        capi.check(self.lib.ax3d_get_point_field(self.h, tag, _FIELD[which], 1, _pf(out), n))
+        return out.view(np.complex64).copy()
+
+    def set_solid(self, tag, which, val):
+        n = self.points[tag].nu + 1
+        v = np.ascontiguousarray(np.asarray(val, dtype=np.complex64).reshape(n, 3).T).view(np.float32).reshape(-1)
+        capi.check(self.lib.ax3d_set_point_field(self.h, tag, _FIELD[which], 0, _pf(v), 3 * n))
+
+    def set_fluid(self, tag, which, val):
+        n = self.points[tag].nu + 1
+        v = np.ascontiguousarray(np.asarray(val, dtype=np.complex64).reshape(n)).view(np.float32).reshape(-1)
+        capi.check(self.lib.ax3d_set_point_field(self.h, tag, _FIELD[which], 1, _pf(v), n))
+
+    def field_size(self, fluid):
+        n = C.c_size_t(0)
+        capi.check(self.lib.ax3d_field_size(self.h, int(fluid), C.byref(n)))
+        return n.value
+
+    def get_bulk(self, which, fluid):
+        """All solid (fluid=False) or fluid blocks concatenated in point-tag order, complex64."""
+        n = self.field_size(fluid)
+        out = np.zeros(2 * n, dtype=np.float32)
+        capi.check(self.lib.ax3d_get_field_bulk(self.h, _FIELD[which], int(fluid), _pf(out), n))
+        return out.view(np.complex64)
+
+    def set_bulk(self, which, fluid, val):
+        v = np.ascontiguousarray(np.asarray(val, dtype=np.complex64)).view(np.float32)
+        capi.check(self.lib.ax3d_set_field_bulk(self.h, _FIELD[which], int(fluid), _pf(v), v.size // 2))
+
+    def ground_motion(self, elem_tags, phi, weights):
+        et = np.ascontiguousarray(elem_tags, dtype=np.int32)
+        ph = _f32(phi)
+        w = _f32(np.asarray(weights).reshape(len(et), 25))
+        out = np.zeros((len(et), 3), dtype=np.float32)
+        capi.check(self.lib.ax3d_record_ground_motion(self.h, len(et), _pi(et), _pf(ph), _pf(w), _pf(out)))
+        return out
+
+    # ------------------------------------------------------------------ measurement
+    def launch_count(self):
+        n = C.c_longlong(0)
+        capi.check(self.lib.ax3d_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def work_per_step(self):
+        n = C.c_longlong(0)
+        capi.check(self.lib.ax3d_work_per_step(self.h, C.byref(n)))
+        return n.value
+
+    def algorithmic_bytes(self):
+        out = np.zeros(3, dtype=np.float64)
+        capi.check(self.lib.ax3d_algorithmic_bytes(self.h, _pd(out)))
+        return out
+
+    def enable_timers(self, on=True):
+        capi.check(self.lib.ax3d_enable_timers(self.h, int(on)))
+
+    def get_timers(self, reset=True):
+        out = np.zeros(4, dtype=np.float64)
+        capi.check(self.lib.ax3d_get_timers(self.h, _pd(out), int(reset)))
+        return out

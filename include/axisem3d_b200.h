@@ -1,0 +1,163 @@
+/* axisem3d_b200.h -- C-ABI of the B200-native stiffness + Newmark hot path of AxiSEM3D.
+ *
+ * The reference has no FFI layer: its boundary is the C++ class API between Newmark/Mesh and
+ * Domain/Element/Point.  Every entry point below names the reference interface
+ * it replaces (S/ = SOLVER/src/ of kuangdai/AxiSEM3D).  INTEGRATION.md shows the binding a
+ * maintainer adds on the reference side (a thin `Domain` facade, axisem3d_b200/host/).
+ *
+ * Conventions
+ *  - plain pointers + sizes; all arrays are caller-owned HOST memory and are copied by the callee;
+ *  - Real = float; complex = interleaved (re, im) floats; "RMatPP" = 25 values row-major (ipol, jpol);
+ *  - per-element phi-dependent arrays ("RMatXN") are column-major Nr x 25 exactly as Eigen stores
+ *    them in the reference: value(j, ipnt) at [ipnt * Nr + j], phi_j = 2 pi j / Nr;
+ *  - every function returns 0 on success, non-zero on error; ax3d_last_error() returns the message
+ *    in the reference's "Class::method || message" form (XMPI.cpp:52-90);
+ *  - one host thread per domain (the reference is single-threaded per rank);
+ *  - there is NO CPU fallback: every call fails if no CUDA device is usable.
+ */
+#ifndef AXISEM3D_B200_H
+#define AXISEM3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ax3d_domain ax3d_domain;
+
+/* ------------------------------------------------------------------ lifetime / errors */
+/* Domain::Domain (S/core/domain/Domain.cpp:17-25) on CUDA device `device`. */
+int ax3d_create(int device, ax3d_domain **out);
+/* Domain::~Domain (Domain.cpp:27-44). */
+int ax3d_destroy(ax3d_domain *dom);
+/* XMPI::printException text of the last failure on this thread. */
+const char *ax3d_last_error(void);
+/* library/ABI version, device name; for load checks. */
+int ax3d_version(void);
+
+/* ------------------------------------------------------------------ setup (Mesh::release) */
+/* Gradient::setGMat(G_GLL, G_GLJ) (S/core/element/grad/Gradient.cpp:324-329); G(i,j) = l_i'(x_j). */
+int ax3d_set_gmat(ax3d_domain *dom, const double G_GLL[25], const double G_GLJ[25]);
+
+/* mass descriptor: n_invmass == 1 -> Mass1D(invMass) (Mass1D.cpp:8), n_invmass == nr -> Mass3D(invMass[nr])
+ * (Mass3D.cpp:9).  Domain::addPoint(new SolidPoint(nr, axial, crds, mass)) (SolidPoint.cpp:9; Domain.cpp:46).
+ * Returns the domain tag (= insertion index) in *tag. */
+int ax3d_add_solid_point(ax3d_domain *dom, int nr, int axial, const double crds[2],
+                         int n_invmass, const float *invmass, int *tag);
+/* Domain::addPoint(new FluidPoint(nr, axial, crds, mass, fluidSurf)) (FluidPoint.cpp:9). */
+int ax3d_add_fluid_point(ax3d_domain *dom, int nr, int axial, const double crds[2],
+                         int n_invmass, const float *invmass, int fluid_surf, int *tag);
+/* Domain::addPoint + addSFPoint(new SolidFluidPoint(solid, fluid, couple)) (SolidFluidPoint.cpp:12;
+ * GLLPoint.cpp:99-118).  n_sf == 1 -> SFCoupling1D(ns, nz, ns_invmf, nz_invmf) with
+ * normal_un = {ns, 0, nz}, normal_as_invmf = {ns_invmf, 0, nz_invmf}; n_sf == nr -> SFCoupling3D with
+ * two RMatX3 (column-major nr x 3). */
+int ax3d_add_solid_fluid_point(ax3d_domain *dom, int nr, int axial, const double crds[2],
+                               int n_invmass_solid, const float *invmass_solid,
+                               int n_invmass_fluid, const float *invmass_fluid, int fluid_surf,
+                               int n_sf, const float *normal_un, const float *normal_as_invmf, int *tag);
+
+/* elastic law ids */
+enum { AX3D_ISO = 0, AX3D_TI = 1, AX3D_ANISO = 2 };
+/* attenuation ids */
+enum { AX3D_ATT_NONE = 0, AX3D_ATT_FULL = 1, AX3D_ATT_CG4 = 2 };
+
+/* Attenuation{1D,3D}_{Full,CG4}(nsls, alpha, beta, gamma, [Nu], dkappa, dmu, doKappa)
+ * (S/core/element/material/attenuation).  rows = 1 (1D) or Nr (3D) must match the elastic rows;
+ * dkappa/dmu: rows x P column-major with P = 25 (Full) or 4 (CG4; points (1,1),(1,3),(3,1),(3,3)). */
+typedef struct ax3d_attenuation {
+    int kind;            /* AX3D_ATT_* */
+    int nsls;
+    const float *alpha;  /* [nsls] */
+    const float *beta;   /* [nsls] */
+    const float *gamma;  /* [nsls] */
+    const float *dkappa; /* [rows * P] */
+    const float *dmu;    /* [rows * P] */
+    int do_kappa;
+} ax3d_attenuation;
+
+/* Domain::addElement(new SolidElement(new Gradient(dsdxii, dsdeta, dzdxii, dzdeta, inv_s, axial), 0,
+ * points, elastic)) (SolidElement.cpp:15; Gradient.cpp:9; Quad.cpp:386-404).
+ *  geom: 5 x 25 doubles in the order dsdxii, dsdeta, dzdxii, dzdeta, inv_s;
+ *  theta: 25 doubles (Element::formThetaMat, Element.cpp:48-58), used when law != AX3D_ISO;
+ *  law/rows/coef: Isotropic{1D,3D}(lambda, mu) (2 arrays), TransverselyIsotropic{1D,3D}(A, C, F, L, N)
+ *  (5), Anisotropic{1D,3D}(C11, C12, ..., C66) (21, upper triangle row by row); each array rows x 25
+ *  column-major, rows = 1 (1D classes) or the element's Nr (3D classes);
+ *  att: NULL or attenuation living in the same space.  Particle relabelling (PRT) is not supported. */
+int ax3d_add_solid_element(ax3d_domain *dom, const int point_tags[25], const double *geom, int axial,
+                           const double *theta, int law, int rows, const float *coef,
+                           const ax3d_attenuation *att, int *tag);
+/* Domain::addElement(new FluidElement(gradient, 0, points, new Acoustic{1D,3D}(K))) (FluidElement.cpp:15). */
+int ax3d_add_fluid_element(ax3d_domain *dom, const int point_tags[25], const double *geom, int axial,
+                           int rows, const float *K, int *tag);
+
+/* Domain::addSourceTerm(new SourceTerm(element, force)) (SourceTerm.cpp:15-27): force of point i is
+ * nrow[i] x 3 complex column-major, concatenated over the 25 points; rows beyond the point's Nu+1 are dropped. */
+int ax3d_add_source_term(ax3d_domain *dom, int elem_tag, const int nrow[25], const float *force);
+
+/* Domain::setMessaging(MessagingInfo*, MessagingBuffer*) (Domain.h:36; XMPI.h:330-348; Mesh.cpp:189-204):
+ * neighbour ranks and, per neighbour, the local point tags in global-GLL-tag order.  The halo sum runs over
+ * NCCL: nccl_unique_id is the 128-byte ncclUniqueId every rank received from rank 0 (the C++ driver
+ * broadcasts it with MPI_Bcast, the Python host with torch.distributed).  nproc == 1 or nneigh == 0 -> no-op. */
+int ax3d_set_messaging(ax3d_domain *dom, int rank, int nproc, const void *nccl_unique_id,
+                       int nneigh, const int *neigh_rank, const int *npoints, const int *point_tags);
+
+/* End of Mesh::release: builds buckets, index maps, FFT plans, uploads everything. */
+int ax3d_finalize_setup(ax3d_domain *dom);
+
+/* ------------------------------------------------------------------ per step (Newmark::solve) */
+/* Domain::updateNewmark(dt) (Domain.cpp:165-177). */
+int ax3d_update_newmark(ax3d_domain *dom, double dt);
+/* Domain::applySource(tstep) with stf = STF factor of that step (Domain.cpp:96-109). */
+int ax3d_apply_source(ax3d_domain *dom, float stf);
+/* Domain::computeStiff() (Domain.cpp:82-94). */
+int ax3d_compute_stiff(ax3d_domain *dom);
+/* Domain::coupleSolidFluid() (Domain.cpp:179-191). */
+int ax3d_couple_solid_fluid(ax3d_domain *dom);
+/* Domain::assembleStiff(phase): phase <= 0 pack + send/recv, phase >= 0 wait + unpack-add (Domain.cpp:111-163). */
+int ax3d_assemble_stiff(ax3d_domain *dom, int phase);
+/* Domain::checkStability (Domain.cpp:237-275): *stable = 0 if any displacement is non-finite. */
+int ax3d_check_stability(ax3d_domain *dom, int *stable);
+/* Domain::resetZero (Domain.cpp:67-74): all point fields and memory variables to zero. */
+int ax3d_reset_zero(ax3d_domain *dom);
+/* nsteps iterations of the Newmark::solve loop body (Newmark.cpp:47-93: update, source, stiff, couple,
+ * assemble) with stf[i] as the source factor of step i; launched as one CUDA graph replay per step. */
+int ax3d_run_steps(ax3d_domain *dom, int nsteps, double dt, const float *stf);
+/* blocks until the device finished all queued work of this domain. */
+int ax3d_synchronize(ax3d_domain *dom);
+
+/* ------------------------------------------------------------------ read-back / test hooks */
+enum { AX3D_DISPL = 0, AX3D_VELOC = 1, AX3D_ACCEL = 2, AX3D_STIFF = 3 };
+/* Point::getDispFourierSolid/Fluid and friends (Point.h:88-89): (Nu+1) x 3 complex column-major (solid part)
+ * or (Nu+1) complex (fluid part) of point `tag`.  cap = capacity of out in complex numbers. */
+int ax3d_get_point_field(ax3d_domain *dom, int tag, int field, int fluid_part, float *out, int cap);
+int ax3d_set_point_field(ax3d_domain *dom, int tag, int field, int fluid_part, const float *in, int n);
+/* bulk variants: all solid (fluid_part = 0) or fluid (= 1) blocks concatenated in point-tag order. */
+int ax3d_get_field_bulk(ax3d_domain *dom, int field, int fluid_part, float *out, size_t cap_complex);
+int ax3d_set_field_bulk(ax3d_domain *dom, int field, int fluid_part, const float *in, size_t n_complex);
+/* number of complex entries of the solid / fluid field arrays. */
+int ax3d_field_size(ax3d_domain *dom, int fluid_part, size_t *n_complex);
+/* Element::computeGroundMotion(phi, weights, u_spz) (SolidElement.cpp:189-216) for nrec receivers:
+ * out[3 * i + c].  Evaluated on the device from the current displacement, copied to host. */
+int ax3d_record_ground_motion(ax3d_domain *dom, int nrec, const int *elem_tags, const float *phi,
+                              const float *weights /* nrec x 25 */, float *out /* nrec x 3 */);
+
+/* ------------------------------------------------------------------ measurement hooks */
+/* number of CUDA kernel launches issued by this domain since creation (bench.py "gpu_launches"). */
+int ax3d_launch_count(ax3d_domain *dom, long long *n);
+/* sum over local GLL points of (Nu_p + 1): the work unit of BASELINE.json's metric. */
+int ax3d_work_per_step(ax3d_domain *dom, long long *w);
+/* algorithmic HBM bytes of one step (SURVEY.md §8d accounting) split per kernel family:
+ * out[0] points, out[1] solid+fluid elements, out[2] halo. */
+int ax3d_algorithmic_bytes(ax3d_domain *dom, double out[3]);
+/* device time [ms] spent in each kernel family since the last call with reset != 0, measured with CUDA
+ * events on the launching stream when profiling is enabled: out[0] newmark, [1] elements(stiff),
+ * [2] solid-fluid + source, [3] halo. */
+int ax3d_enable_timers(ax3d_domain *dom, int on);
+int ax3d_get_timers(ax3d_domain *dom, double out_ms[4], int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AXISEM3D_B200_H */

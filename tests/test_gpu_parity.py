@@ -1,0 +1,114 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle.  BASELINE.json north_star:
+per-step stiffness forces rel. L2 <= 1e-5; seismograms rel. L2 <= 1e-4 after 2000 steps."""
+import numpy as np
+import pytest
+
+from helpers import build_oracle, build_gpu, randomize_displ, push_fields, compare_field, rel_l2
+from axisem3d_b200.mesh_synth import SynthMesh
+
+pytestmark = pytest.mark.gpu
+
+TOL_FORCE = 1e-5     # north_star tolerance on per-step stiffness forces
+
+
+CASES = {
+    # cfg1-like: 1D TI PREM + CG4 attenuation, Nu = 2 (Nr = 5), fluid core, SF coupling
+    "cfg1_ti1d_cg4": dict(n_theta=8, n_r=8, nu=2, law="ti", model3d=False, attenuation="cg4"),
+    "iso1d_full": dict(n_theta=6, n_r=6, nu=5, law="iso", model3d=False, attenuation="full"),
+    "aniso1d": dict(n_theta=6, n_r=6, nu=4, law="aniso", model3d=False, attenuation=None),
+    # cfg2-like: 3D isotropic, no attenuation
+    "cfg2_iso3d": dict(n_theta=8, n_r=8, nu=12, law="iso", model3d=True, attenuation=None),
+    "cfg2_iso3d_nu100": dict(n_theta=4, n_r=6, nu=100, law="iso", model3d=True, attenuation=None),
+    "ti3d_cg4": dict(n_theta=6, n_r=8, nu=9, law="ti", model3d=True, attenuation="cg4"),
+    # cfg3-like: 3D anisotropic + SLS (CG4 and Full), 3D fluid, 3D mass
+    "cfg3_aniso3d_cg4": dict(n_theta=6, n_r=8, nu=20, law="aniso", model3d=True, attenuation="cg4", fluid3d=True),
+    "aniso3d_full_mass3d": dict(n_theta=5, n_r=8, nu=7, law="aniso", model3d=True, attenuation="full",
+                                fluid3d=True, perturb_rho=True),
+}
+
+
+def ragged_nu(s, z):
+    """cfg4-like: per-point Nu growing with distance from the axis."""
+    return int(3 + 40 * s / 6371e3)
+
+
+CASES["cfg4_ragged"] = dict(n_theta=10, n_r=6, nu_fn=ragged_nu, law="iso", model3d=True, attenuation=None)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_stiffness_forces_match_oracle(name):
+    m = SynthMesh(**CASES[name])
+    dt = m.estimate_dt()
+    d, _ = build_oracle(m, dt, np.float64)
+    g, _ = build_gpu(m, dt)
+    randomize_displ(d, seed=7)
+    push_fields(d, g, ("displ",))
+    for it in range(2):                       # second pass exercises the memory variables
+        d.computeStiff()
+        d.coupleSolidFluid()
+        g.computeStiff()
+        g.coupleSolidFluid()
+        err = compare_field(d, g, "stiff")
+        for k, v in err.items():
+            assert v <= TOL_FORCE, (name, it, k, v)
+        if it == 0:
+            d.S["stiff"][:] = 0
+            d.F["stiff"][:] = 0
+            s, f = g.get_bulk("stiff", False), g.get_bulk("stiff", True)
+            if s.size: g.set_bulk("stiff", False, np.zeros_like(s))
+            if f.size: g.set_bulk("stiff", True, np.zeros_like(f))
+
+
+@pytest.mark.parametrize("name", ["cfg1_ti1d_cg4", "cfg2_iso3d", "aniso3d_full_mass3d"])
+def test_time_loop_matches_oracle(name):
+    m = SynthMesh(**CASES[name])
+    dt = m.estimate_dt()
+    d, rel = build_oracle(m, dt, np.float64)
+    g, _ = build_gpu(m, dt)
+    nstep = 60
+    stf = np.exp(-((np.arange(nstep) - 15) / 5.0) ** 2)
+    for i in range(nstep):
+        d.step(dt, stf[i])
+    g.runSteps(dt, stf)
+    assert g.checkStability()
+    err = compare_field(d, g, "displ")
+    for k, v in err.items():
+        assert v <= 1e-4, (name, k, v)
+
+
+def test_seismograms_2000_steps():
+    """north_star: station seismograms within 1e-4 (rel. L2) of the reference after 2000 steps."""
+    m = SynthMesh(n_theta=6, n_r=6, nu=2, law="ti", model3d=False, attenuation="cg4")
+    dt = m.estimate_dt()
+    d, rel = build_oracle(m, dt, np.float64)
+    g, _ = build_gpu(m, dt)
+    nstep = 2000
+    stf = np.exp(-((np.arange(nstep) - 30) / 8.0) ** 2).astype(np.float32)
+    # 6 receivers in surface elements (top layer), arbitrary interpolation weights
+    rng = np.random.default_rng(3)
+    etags = [e.domain_tag for e in rel["elements"] if e.kind == "solid"][-6:]
+    phi = rng.uniform(0, 2 * np.pi, len(etags))
+    w = rng.uniform(0, 1, (len(etags), 25))
+    w /= w.sum(axis=1, keepdims=True)
+    so, sg = [], []
+    for i in range(nstep):
+        d.step(dt, float(stf[i]))
+        g.step(dt, float(stf[i]))
+        if i % 10 == 0:
+            so.append([d.ground_motion(t, p, ww) for t, p, ww in zip(etags, phi, w)])
+            sg.append(g.ground_motion(etags, phi, w))
+    so, sg = np.array(so), np.array(sg)
+    assert np.abs(so).max() > 0
+    assert rel_l2(so, sg) <= 1e-4
+
+
+def test_error_behaviour_matches_reference():
+    from axisem3d_b200 import model as M
+    from axisem3d_b200.domain import Domain
+    g = Domain(0)
+    with pytest.raises(RuntimeError, match="setGMat|finalize"):
+        g.updateNewmark(0.1)
+    sp = M.SolidPoint(5, False, [1.0, 2.0], M.Mass1D(1.0))
+    g.addPoint(sp)
+    with pytest.raises(RuntimeError, match="Incompatible size"):
+        M.SolidPoint(6, False, [1.0, 2.0], M.Mass3D(np.ones(5)))
