@@ -168,9 +168,22 @@ struct ax3d_domain {
     DevBuf<float> rec_w, rec_out;
     float *rec_host = nullptr;
     size_t rec_cap = 0;
-    // run_steps
+    // source factor: pinned host ring -> device scalar (4-byte H2D per step)
     DevBuf<float> stf_dev;
+    float *stf_pinned = nullptr;
+    int stf_slot = 0;
+    // CUDA graph of one step (single-GPU path)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    double graph_dt = 0;
+    bool use_graph = true;
+    // receivers registered with ax3d_set_receivers
+    int nrec1 = 0, nrec3 = 0;
+    std::vector<int> rec_where1, rec_where3;
+    DevBuf<RecvItem> rec1_items, rec3_items;
+    DevBuf<float> rec1_w, rec3_w;
 };
+#define STF_RING 4096
 
 static void fail(const std::string &m) { throw std::runtime_error(m); }
 
@@ -637,6 +650,13 @@ static void finalize(ax3d_domain *d) {
         d->alg_bytes[2] = hb;
     }
     d->bad_flag.alloc(1);
+    d->stf_dev.alloc(1);
+    d->stf_dev.zero();
+    CK(cudaMallocHost(&d->stf_pinned, STF_RING * sizeof(float)));
+    {
+        const char *g = getenv("AX3D_NO_GRAPH");
+        d->use_graph = !(g && atoi(g) != 0);
+    }
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&d->ev0));
     CK(cudaEventCreate(&d->ev1));
@@ -709,13 +729,29 @@ static void update_newmark(ax3d_domain *d, double dt) {
     CK(cudaGetLastError());
 }
 
-static void apply_source(ax3d_domain *d, float stf) {
-    TimerScope ts(d, 2);
+static void push_stf(ax3d_domain *d, float stf) {
+    // a slot is reused only after STF_RING further steps; synchronise before wrapping around
+    if (d->stf_slot == STF_RING) {
+        CK(cudaStreamSynchronize(d->stream));
+        d->stf_slot = 0;
+    }
+    d->stf_pinned[d->stf_slot] = stf;
+    CK(cudaMemcpyAsync(d->stf_dev.p, d->stf_pinned + d->stf_slot, sizeof(float), cudaMemcpyHostToDevice, d->stream));
+    d->stf_slot++;
+}
+
+static void launch_source(ax3d_domain *d) {
     if (d->n_src) {
-        k_source<<<nblk(d->n_src, 128), 128, 0, d->stream>>>(d->n_src, d->src_off.p, d->src_val.p, stf, d->s_field[AX3D_STIFF].p);
+        k_source<<<nblk(d->n_src, 128), 128, 0, d->stream>>>(d->n_src, d->src_off.p, d->src_val.p, d->stf_dev.p, d->s_field[AX3D_STIFF].p);
         d->launches++;
         CK(cudaGetLastError());
     }
+}
+
+static void apply_source(ax3d_domain *d, float stf) {
+    TimerScope ts(d, 2);
+    if (d->n_src) push_stf(d, stf);
+    launch_source(d);
 }
 
 static void compute_stiff(ax3d_domain *d) {
@@ -850,6 +886,9 @@ int ax3d_destroy(ax3d_domain *d) {
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->rec_host) cudaFreeHost(d->rec_host);
+    if (d->stf_pinned) cudaFreeHost(d->stf_pinned);
+    if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
+    if (d->graph) cudaGraphDestroy(d->graph);
     delete d;
     API_END
 }
@@ -966,6 +1005,22 @@ int ax3d_set_messaging(ax3d_domain *d, int rank, int nproc, const void *uid, int
     API_END
 }
 
+/* ncclGetUniqueId on the calling rank (rank 0 calls it and broadcasts the 128 bytes; XMPI::initialize analogue). */
+int ax3d_nccl_unique_id(void *out128) {
+    API_BEGIN
+#ifdef AX3D_WITH_NCCL
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) fail(std::string("XMPI::initialize || ncclGetUniqueId: ") + ncclGetErrorString(r));
+    memset(out128, 0, 128);
+    memcpy(out128, &id, sizeof(id) < 128 ? sizeof(id) : 128);
+#else
+    (void)out128;
+    fail("XMPI::initialize || library built without NCCL");
+#endif
+    API_END
+}
+
 int ax3d_finalize_setup(ax3d_domain *d) {
     API_BEGIN
     finalize(d);
@@ -1030,17 +1085,125 @@ int ax3d_reset_zero(ax3d_domain *d) {
     API_END
 }
 
+static void step_body(ax3d_domain *d, double dt) {
+    update_newmark(d, dt);
+    launch_source(d);
+    compute_stiff(d);
+    couple_solid_fluid(d);
+}
+
+static long long count_step_launches(ax3d_domain *d) {
+    long long n = 0;
+    n += !d->h_m3d_s.empty();
+    n += !d->h_m3d_f.empty();
+    n += d->s_tab.nrows > 0;
+    n += d->f_tab.nrows > 0;
+    n += d->n_src > 0;
+    n += d->n_work[CLS_S1D] > 0;
+    n += d->n_work[CLS_F1D] > 0;
+    n += 3 * (long long)d->chunks.size();
+    n += d->sf_tab.nrows > 0;
+    n += !d->h_sf3d.empty();
+    return n;
+}
+
+static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
+    const bool graph_ok = d->use_graph && !d->timers && (d->nproc <= 1 || d->neigh_rank.empty());
+    if (graph_ok && (!d->graph_exec || d->graph_dt != dt)) {
+        if (d->graph_exec) { cudaGraphExecDestroy(d->graph_exec); d->graph_exec = nullptr; }
+        if (d->graph) { cudaGraphDestroy(d->graph); d->graph = nullptr; }
+        const long long before = d->launches;
+        CK(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
+        step_body(d, dt);
+        CK(cudaStreamEndCapture(d->stream, &d->graph));
+        CK(cudaGraphInstantiate(&d->graph_exec, d->graph, 0));
+        d->launches = before;   // capture enqueues nothing
+        d->graph_dt = dt;
+    }
+    for (int i = 0; i < nsteps; ++i) {
+        if (d->n_src) push_stf(d, stf ? stf[i] : 0.f);
+        if (graph_ok) {
+            CK(cudaGraphLaunch(d->graph_exec, d->stream));
+            d->launches += count_step_launches(d);
+        } else {
+            step_body(d, dt);
+            assemble_stiff(d, -1);
+            assemble_stiff(d, 1);
+        }
+    }
+}
+
 int ax3d_run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
     API_BEGIN
     check_final(d);
-    for (int i = 0; i < nsteps; ++i) {
-        update_newmark(d, dt);
-        apply_source(d, stf ? stf[i] : 0.f);
-        compute_stiff(d);
-        couple_solid_fluid(d);
-        assemble_stiff(d, -1);
-        assemble_stiff(d, 1);
+    run_steps(d, nsteps, dt, stf);
+    API_END
+}
+
+/* nsteps of the loop timed with CUDA events on the launching stream; *ms = device time. */
+int ax3d_run_steps_timed(ax3d_domain *d, int nsteps, double dt, const float *stf, float *ms) {
+    API_BEGIN
+    check_final(d);
+    CK(cudaStreamSynchronize(d->stream));
+    CK(cudaEventRecord(d->ev0, d->stream));
+    run_steps(d, nsteps, dt, stf);
+    CK(cudaEventRecord(d->ev1, d->stream));
+    CK(cudaEventSynchronize(d->ev1));
+    CK(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+    API_END
+}
+
+/* PointwiseRecorder set-up (ReceiverCollection::release): registers nrec receivers once. */
+int ax3d_set_receivers(ax3d_domain *d, int nrec, const int *elem_tags, const float *phi, const float *weights) {
+    API_BEGIN
+    check_final(d);
+    std::vector<RecvItem> it1, it3;
+    std::vector<float> w1, w3;
+    d->rec_where1.clear();
+    d->rec_where3.clear();
+    for (int i = 0; i < nrec; ++i) {
+        if (elem_tags[i] < 0 || elem_tags[i] >= (int)d->elems.size()) fail("PointwiseRecorder::record || invalid element tag");
+        const HElem &E = d->elems[elem_tags[i]];
+        if (E.fluid) fail("FluidElement::computeGroundMotion || receivers in fluid are not supported yet");
+        RecvItem r{E.idx, phi[i]};
+        if (E.cls == CLS_S3D) { it3.push_back(r); w3.insert(w3.end(), weights + (size_t)i * AX_NPE, weights + (size_t)(i + 1) * AX_NPE); d->rec_where3.push_back(i); }
+        else { it1.push_back(r); w1.insert(w1.end(), weights + (size_t)i * AX_NPE, weights + (size_t)(i + 1) * AX_NPE); d->rec_where1.push_back(i); }
     }
+    d->nrec1 = (int)it1.size();
+    d->nrec3 = (int)it3.size();
+    d->rec1_items.upload(it1); d->rec1_w.upload(w1);
+    d->rec3_items.upload(it3); d->rec3_w.upload(w3);
+    if ((size_t)nrec > d->rec_cap) {
+        if (d->rec_host) cudaFreeHost(d->rec_host);
+        CK(cudaMallocHost(&d->rec_host, (size_t)nrec * 3 * sizeof(float)));
+        d->rec_out.alloc((size_t)nrec * 3);
+        d->rec_cap = nrec;
+    }
+    API_END
+}
+
+/* PointwiseRecorder::record (PointwiseRecorder.cpp:62-144) for the registered receivers: evaluates
+ * Element::computeGroundMotion on the device and copies nrec x 3 floats to the host (pinned staging). */
+int ax3d_record(ax3d_domain *d, float *out) {
+    API_BEGIN
+    check_final(d);
+    const int n = d->nrec1 + d->nrec3;
+    if (!n) return 0;
+    if (d->nrec1) {
+        k_ground_motion<<<d->nrec1, 128, 0, d->stream>>>(d->desc[CLS_S1D].p, d->rec1_items.p, d->rec1_w.p, d->s_field[AX3D_DISPL].p, d->rec_out.p);
+        d->launches++;
+    }
+    if (d->nrec3) {
+        k_ground_motion<<<d->nrec3, 128, 0, d->stream>>>(d->desc[CLS_S3D].p, d->rec3_items.p, d->rec3_w.p, d->s_field[AX3D_DISPL].p,
+                                                          d->rec_out.p + (size_t)3 * d->nrec1);
+        d->launches++;
+    }
+    CK(cudaMemcpyAsync(d->rec_host, d->rec_out.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    for (int k = 0; k < d->nrec1; ++k)
+        for (int c = 0; c < 3; ++c) out[d->rec_where1[k] * 3 + c] = d->rec_host[k * 3 + c];
+    for (int k = 0; k < d->nrec3; ++k)
+        for (int c = 0; c < 3; ++c) out[d->rec_where3[k] * 3 + c] = d->rec_host[(d->nrec1 + k) * 3 + c];
     API_END
 }
 

@@ -204,13 +204,15 @@ __global__ void __launch_bounds__(128) k_mass3d(PointTab pt, const Mass3DItem *_
 }
 
 // ------------------------------------------------------------------------------------ source
-__global__ void k_source(int n, const unsigned *__restrict__ off, const float2 *__restrict__ val, float stf,
-                         float2 *__restrict__ stiff) {
+// stf is read from device memory (written by a 4-byte H2D copy per step) so that the launch can be replayed
+// from a CUDA graph with a different source factor every step.
+__global__ void k_source(int n, const unsigned *__restrict__ off, const float2 *__restrict__ val,
+                         const float *__restrict__ stf_ptr, float2 *__restrict__ stiff) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float stf = *stf_ptr;
     float2 v = val[i];
-    atomicAdd(&stiff[off[i]].x, v.x * stf);
-    atomicAdd(&stiff[off[i]].y, v.y * stf);
+    atomicAdd(&stiff[off[i]], make_float2(v.x * stf, v.y * stf));
 }
 
 // ------------------------------------------------------------------------------------ element helpers

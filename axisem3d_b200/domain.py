@@ -44,6 +44,14 @@ def _colmajor(a):
     return _f32(np.asarray(a).T).reshape(-1)
 
 
+def nccl_unique_id():
+    """128-byte ncclUniqueId created on this rank (rank 0 creates it, the host broadcasts it)."""
+    lib = capi.load()
+    buf = (C.c_ubyte * 128)()
+    capi.check(lib.ax3d_nccl_unique_id(C.cast(buf, C.c_void_p)))
+    return bytes(buf)
+
+
 class Domain:
     def __init__(self, device=0):
         self.lib = capi.load()
@@ -187,6 +195,25 @@ class Domain:
     def runSteps(self, dt, stf):
         stf = _f32(stf)
         capi.check(self.lib.ax3d_run_steps(self.h, stf.size, float(dt), _pf(stf)))
+
+    def runStepsTimed(self, dt, stf):
+        """runSteps timed with CUDA events on the library's stream; returns milliseconds."""
+        stf = _f32(stf)
+        ms = C.c_float(0)
+        capi.check(self.lib.ax3d_run_steps_timed(self.h, stf.size, float(dt), _pf(stf), C.byref(ms)))
+        return ms.value
+
+    def setReceivers(self, elem_tags, phi, weights):
+        et = np.ascontiguousarray(elem_tags, dtype=np.int32)
+        ph = _f32(phi)
+        w = _f32(np.asarray(weights).reshape(len(et), 25))
+        self._nrec = len(et)
+        capi.check(self.lib.ax3d_set_receivers(self.h, len(et), _pi(et), _pf(ph), _pf(w)))
+
+    def record(self):
+        out = np.zeros((self._nrec, 3), dtype=np.float32)
+        capi.check(self.lib.ax3d_record(self.h, _pf(out)))
+        return out
 
     def synchronize(self):
         capi.check(self.lib.ax3d_synchronize(self.h))

@@ -103,6 +103,9 @@ int ax3d_add_source_term(ax3d_domain *dom, int elem_tag, const int nrow[25], con
 int ax3d_set_messaging(ax3d_domain *dom, int rank, int nproc, const void *nccl_unique_id,
                        int nneigh, const int *neigh_rank, const int *npoints, const int *point_tags);
 
+/* XMPI::initialize analogue for the halo communicator: rank 0 creates the 128-byte ncclUniqueId and broadcasts it. */
+int ax3d_nccl_unique_id(void *out128);
+
 /* End of Mesh::release: builds buckets, index maps, FFT plans, uploads everything. */
 int ax3d_finalize_setup(ax3d_domain *dom);
 
@@ -124,6 +127,8 @@ int ax3d_reset_zero(ax3d_domain *dom);
 /* nsteps iterations of the Newmark::solve loop body (Newmark.cpp:47-93: update, source, stiff, couple,
  * assemble) with stf[i] as the source factor of step i; launched as one CUDA graph replay per step. */
 int ax3d_run_steps(ax3d_domain *dom, int nsteps, double dt, const float *stf);
+/* the same loop, timed on the device with CUDA events on the launching stream; *ms = elapsed milliseconds. */
+int ax3d_run_steps_timed(ax3d_domain *dom, int nsteps, double dt, const float *stf, float *ms);
 /* blocks until the device finished all queued work of this domain. */
 int ax3d_synchronize(ax3d_domain *dom);
 
@@ -142,6 +147,13 @@ int ax3d_field_size(ax3d_domain *dom, int fluid_part, size_t *n_complex);
  * out[3 * i + c].  Evaluated on the device from the current displacement, copied to host. */
 int ax3d_record_ground_motion(ax3d_domain *dom, int nrec, const int *elem_tags, const float *phi,
                               const float *weights /* nrec x 25 */, float *out /* nrec x 3 */);
+
+/* Domain::setPointwiseRecorder (Domain.h:34; ReceiverCollection.cpp:135-223): registers nrec receivers
+ * (element, azimuth, 25 interpolation weights each) once ... */
+int ax3d_set_receivers(ax3d_domain *dom, int nrec, const int *elem_tags, const float *phi, const float *weights);
+/* ... and Domain::record -> PointwiseRecorder::record (Domain.cpp:207-220; PointwiseRecorder.cpp:62-144):
+ * one displacement sample (s, phi, z) per registered receiver, nrec x 3 floats, device -> host. */
+int ax3d_record(ax3d_domain *dom, float *out);
 
 /* ------------------------------------------------------------------ measurement hooks */
 /* number of CUDA kernel launches issued by this domain since creation (bench.py "gpu_launches"). */
