@@ -169,6 +169,7 @@ class SynthMesh:
         self.mass_s = [np.zeros(n) for n in self.p_nr]
         self.mass_f = [np.zeros(n) for n in self.p_nr]
         self.sf_n = [None] * ng
+        self.sf_contrib = {}          # GLL tag -> [(element, contribution)] for the rank-local (unassembled) normal
         for e in range(self.nelem):
             g = self.geo[e]
             tags = self.e2g[e]
@@ -189,6 +190,7 @@ class SynthMesh:
                     if self.sf_n[t] is None:
                         self.sf_n[t] = np.zeros((self.p_nr[t], 3))
                     self.sf_n[t] += 0.5 * n[None, :]
+                    self.sf_contrib.setdefault(int(t), []).append((e, 0.5 * n))
 
     def _sf_sides(self, e):
         a, b = self.ab[e]
@@ -287,7 +289,11 @@ class SynthMesh:
         return courant * hmin * 0.5
 
     # ---------------------------------------------------------------- descriptors
-    def _make_point(self, t):
+    def _make_point(self, t, local_mask=None):
+        """GLLPoint::release (GLLPoint.cpp:48-128).  Masses and the assembled SF normal are global sums (the
+        reference assembles them over MPI at setup, Mesh.cpp:339-389); the *unassembled* normal handed to
+        SFCoupling is the sum over this rank's elements only (GLLPoint.cpp:99-117), so that the halo sum of the
+        fluid stiffness adds up to the assembled coupling term."""
         nr = int(self.p_nr[t])
         crds = np.array([self.p_s[t], self.p_z[t]])
         axial = bool(self.p_axis[t])
@@ -302,12 +308,18 @@ class SynthMesh:
         fp = M.FluidPoint(nr, axial, crds, mk_mass(self.mass_f[t]), False) if is_f else None
         if sp is not None and fp is not None:
             n = self.sf_n[t]
+            n_un = n
+            if local_mask is not None:
+                n_un = np.zeros_like(n)
+                for e, c in self.sf_contrib[int(t)]:
+                    if local_mask[e]:
+                        n_un = n_un + c[None, :]
             mf = self.mass_f[t]
             if np.ptp(mf) <= 1e-12 * np.abs(mf).max() and np.abs(n - n[0]).max() <= 1e-12 * np.abs(n).max():
-                c = M.SFCoupling1D(np.float32(n[0, 0]), np.float32(n[0, 2]),
+                c = M.SFCoupling1D(np.float32(n_un[0, 0]), np.float32(n_un[0, 2]),
                                    np.float32(n[0, 0] / mf[0]), np.float32(n[0, 2] / mf[0]))
             else:
-                c = M.SFCoupling3D(n.astype(np.float32), (n / mf[:, None]).astype(np.float32))
+                c = M.SFCoupling3D(n_un.astype(np.float32), (n / mf[:, None]).astype(np.float32))
             return M.SolidFluidPoint(sp, fp, c)
         return sp if sp is not None else fp
 
@@ -398,7 +410,8 @@ class SynthMesh:
             elem_to_proc = np.zeros(self.nelem, dtype=np.int64)
         dec = CN.decompose(self.conn, elem_to_proc, rank, self.e2g, self.neighbours)
         l2g = dec.local_to_global_gll
-        pts = [self._make_point(int(t)) for t in l2g]
+        local_mask = np.asarray(elem_to_proc) == rank
+        pts = [self._make_point(int(t), None if local_mask.all() else local_mask) for t in l2g]
         for p in pts:
             domain.addPoint(p)
         elems = []
