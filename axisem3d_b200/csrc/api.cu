@@ -3,6 +3,7 @@
 // kernels of kernels.cuh for the Domain step verbs.  No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/axisem3d_b200.h"
 #include "kernels.cuh"
+#include "fused.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -92,6 +93,11 @@ struct Chunk {   // a run of 3D elements of one class whose spectra fit the scra
     size_t fft_smem;
 };
 
+struct FusedLaunch {   // a run of 3D elements of one class handled by k_elem3d_fused<FLUID, 512 >> bucket>
+    int cls, bucket, first, count;
+    size_t smem;
+};
+
 struct ax3d_domain {
     int device = 0;
     bool finalized = false;
@@ -124,6 +130,9 @@ struct ax3d_domain {
     std::map<int, int> plan_of_n;
     DevBuf<FftPlan> plans;
     DevBuf<float2> twpool;
+    std::vector<float2> h_stw;      // per-stage twiddle tables of all plans (fused kernel)
+    DevBuf<float2> stwpool;
+    std::vector<FusedLaunch> fused;
     // ---- elements
     std::vector<ElemDesc> h_desc[NCLS];
     DevBuf<ElemDesc> desc[NCLS];
@@ -235,6 +244,25 @@ static int get_plan(ax3d_domain *d, int N) {
         }
         perm[pos] = k;
     }
+    // per-stage twiddle tables T_s[j * R + p] = exp(+2 pi i j p / L_s) (fused.cuh)
+    pl.stw_base = (int)d->h_stw.size();
+    {
+        int L = N;
+        for (int s = 0; s < pl.nstages; ++s) {
+            const int R = pl.radix[s], Ls = L / R;
+            pl.stw_off[s] = -1;
+            if (Ls > 1) {
+                pl.stw_off[s] = (int)d->h_stw.size();
+                for (int j = 0; j < Ls; ++j)
+                    for (int p = 0; p < R; ++p) {
+                        const double a = 2.0 * M_PI * (double)j * (double)p / (double)L;
+                        d->h_stw.push_back(make_float2((float)cos(a), (float)sin(a)));
+                    }
+            }
+            L = Ls;
+        }
+    }
+    pl.stw_len = (int)d->h_stw.size() - pl.stw_base;
     int id = (int)d->h_plans.size();
     d->h_plans.push_back(pl);
     d->h_perm.push_back(perm);
@@ -299,6 +327,7 @@ static void common_elem(ax3d_domain *d, HElem &e, const int tags[25], const doub
 }
 
 // ------------------------------------------------------------------------------------------ finalize
+static void set_fused_smem(int device, const FusedLaunch &f);
 static int pick_ppb(int N, int npair) {
     const char *env = getenv("AX3D_FFT_SMEM_KB");
     const double budget = (env ? atof(env) : 48.0) * 1024.0;
@@ -431,6 +460,8 @@ static void finalize(ax3d_domain *d) {
     const char *env_sc = getenv("AX3D_SCRATCH_MB");
     const size_t scratch_cap = (size_t)((env_sc ? atof(env_sc) : 64.0) * 1024.0 * 1024.0 / sizeof(float2));
     size_t scratch_need = 0;
+    const char *env_nf = getenv("AX3D_NO_FUSED");
+    const bool use_fused = !(env_nf && atoi(env_nf) != 0);
 
     for (int c = 0; c < NCLS; ++c) {
         const bool fluid = (c == CLS_F1D || c == CLS_F3D), is3d = (c == CLS_S3D || c == CLS_F3D);
@@ -443,6 +474,11 @@ static void finalize(ax3d_domain *d) {
             if (ch.w_count > 0) d->chunks.push_back(ch);
             ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0};
             ch_scratch = 0;
+        };
+        FusedLaunch fl{c, -1, 0, 0, 0};
+        auto close_fused = [&]() {
+            if (fl.count > 0) d->fused.push_back(fl);
+            fl = FusedLaunch{c, -1, 0, 0, 0};
         };
         for (size_t k = 0; k < order[c].size(); ++k) {
             HElem &E = d->elems[order[c][k]];
@@ -517,23 +553,46 @@ static void finalize(ax3d_domain *d) {
                 }
                 bytes_el += b;
             }
+            D.bucket = -1;
+            D.mt = M;
             if (is3d) {
-                D.ppb = pick_ppb(N, npair);
-                const size_t need = (size_t)npair * AX_NPE * N;
-                if (need > scratch_cap && ch.w_count > 0) close_chunk();
-                if (ch_scratch + need > scratch_cap && ch.w_count > 0) close_chunk();
-                D.scratch_off = (long long)ch_scratch;
-                ch_scratch += need;
-                scratch_need = std::max(scratch_need, ch_scratch);
-                for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); ch.w_count++; }
-                for (int p0 = 0; p0 < AX_NPE; p0 += D.ppb) { fitems.push_back(FftItem{(int)k, p0}); ch.f_count++; }
-                ch.fft_smem = std::max(ch.fft_smem, (size_t)(npair * D.ppb + 1) * N * sizeof(float2));
+                // fused one-CTA-per-element kernel when the element's spectrum fits in shared memory (fused.cuh)
+                const int nc = fluid ? 1 : 3;
+                const size_t lim[3] = {231000, 115000, 56500};   // dynamic smem for 1 / 2 / 4 CTAs per SM
+                const size_t fixed = ((size_t)npair * AX_NPE * fused_ldz(N) + d->h_plans[D.plan_id = get_plan(d, N)].stw_len) * sizeof(float2);
+                size_t need = fixed + (size_t)nc * AX_NPE * M * sizeof(float2);
+                bool can_fuse = use_fused;
+                if (can_fuse && need > lim[0]) {
+                    const long long room = ((long long)lim[0] - (long long)fixed) / (long long)(nc * AX_NPE * sizeof(float2));
+                    D.mt = (int)(room / 16) * 16;
+                    if (D.mt < 16) can_fuse = false;
+                    need = fixed + (size_t)nc * AX_NPE * D.mt * sizeof(float2);
+                }
+                if (can_fuse) {
+                    D.bucket = need <= lim[2] ? 2 : need <= lim[1] ? 1 : 0;
+                    if (fl.count > 0 && fl.bucket != D.bucket) close_fused();
+                    if (fl.count == 0) { fl.first = (int)k; fl.bucket = D.bucket; }
+                    fl.count++;
+                    fl.smem = std::max(fl.smem, need);
+                } else {
+                    D.mt = M;
+                    D.ppb = pick_ppb(N, npair);
+                    const size_t need_sc = (size_t)npair * AX_NPE * N;
+                    if (need_sc > scratch_cap && ch.w_count > 0) close_chunk();
+                    if (ch_scratch + need_sc > scratch_cap && ch.w_count > 0) close_chunk();
+                    D.scratch_off = (long long)ch_scratch;
+                    ch_scratch += need_sc;
+                    scratch_need = std::max(scratch_need, ch_scratch);
+                    for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); ch.w_count++; }
+                    for (int p0 = 0; p0 < AX_NPE; p0 += D.ppb) { fitems.push_back(FftItem{(int)k, p0}); ch.f_count++; }
+                    ch.fft_smem = std::max(ch.fft_smem, (size_t)(npair * D.ppb + 1) * N * sizeof(float2));
+                }
             } else {
                 for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); }
             }
             d->h_desc[c].push_back(D);
         }
-        if (is3d) close_chunk();
+        if (is3d) { close_chunk(); close_fused(); }
         d->desc[c].upload(d->h_desc[c]);
         d->w_elem[c].upload(w_elem);
         d->w_a0[c].upload(w_a0);
@@ -623,6 +682,7 @@ static void finalize(ax3d_domain *d) {
             }
         }
         d->twpool.upload(tw);
+        d->stwpool.upload(d->h_stw);
         d->plans.upload(d->h_plans);
     }
     // ---------------- halo index lists
@@ -668,6 +728,7 @@ static void finalize(ax3d_domain *d) {
         CK(cudaFuncSetAttribute(k_fft3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
         CK(cudaFuncSetAttribute(k_fft3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
     }
+    for (const FusedLaunch &f : d->fused) set_fused_smem(d->device, f);
     if (d->m3d_smem_s > 48 * 1024) CK(cudaFuncSetAttribute(k_mass3d<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->m3d_smem_s));
     if (d->m3d_smem_f > 48 * 1024) CK(cudaFuncSetAttribute(k_mass3d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->m3d_smem_f));
     if (d->sf3d_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_sf_couple3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->sf3d_smem));
@@ -754,6 +815,39 @@ static void apply_source(ax3d_domain *d, float stf) {
     launch_source(d);
 }
 
+template <bool FLUID, int NT>
+static void launch_fused_t(ax3d_domain *d, const FusedLaunch &f) {
+    const int c = f.cls;
+    k_elem3d_fused<FLUID, NT><<<f.count, NT, f.smem, d->stream>>>(
+        d->desc[c].p + f.first, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
+        FLUID ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, FLUID ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p);
+}
+static void launch_fused(ax3d_domain *d, const FusedLaunch &f) {
+    const bool fluid = f.cls == CLS_F3D;
+    switch (f.bucket) {
+        case 0: fluid ? launch_fused_t<true, 512>(d, f) : launch_fused_t<false, 512>(d, f); break;
+        case 1: fluid ? launch_fused_t<true, 256>(d, f) : launch_fused_t<false, 256>(d, f); break;
+        default: fluid ? launch_fused_t<true, 128>(d, f) : launch_fused_t<false, 128>(d, f); break;
+    }
+}
+template <bool FLUID, int NT>
+static void set_fused_smem_t(int device, size_t smem) {
+    static size_t cur[64][2][3];   // per device: the attribute only ever grows (several domains may share a device)
+    size_t &c = cur[device & 63][FLUID ? 1 : 0][NT == 512 ? 0 : NT == 256 ? 1 : 2];
+    if (smem > 48 * 1024 && smem > c) {
+        CK(cudaFuncSetAttribute(k_elem3d_fused<FLUID, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c = smem;
+    }
+}
+static void set_fused_smem(int device, const FusedLaunch &f) {
+    const bool fluid = f.cls == CLS_F3D;
+    switch (f.bucket) {
+        case 0: fluid ? set_fused_smem_t<true, 512>(device, f.smem) : set_fused_smem_t<false, 512>(device, f.smem); break;
+        case 1: fluid ? set_fused_smem_t<true, 256>(device, f.smem) : set_fused_smem_t<false, 256>(device, f.smem); break;
+        default: fluid ? set_fused_smem_t<true, 128>(device, f.smem) : set_fused_smem_t<false, 128>(device, f.smem); break;
+    }
+}
+
 static void compute_stiff(ax3d_domain *d) {
     TimerScope ts(d, 1);
     const int TB = AX_TILE * AX_NPE;
@@ -787,6 +881,10 @@ static void compute_stiff(ax3d_domain *d) {
                                                              d->scratch.p, d->f_field[AX3D_STIFF].p);
         }
         d->launches += 3;
+    }
+    for (const FusedLaunch &f : d->fused) {
+        launch_fused(d, f);
+        d->launches++;
     }
     CK(cudaGetLastError());
 }
@@ -1102,6 +1200,7 @@ static long long count_step_launches(ax3d_domain *d) {
     n += d->n_work[CLS_S1D] > 0;
     n += d->n_work[CLS_F1D] > 0;
     n += 3 * (long long)d->chunks.size();
+    n += (long long)d->fused.size();
     n += d->sf_tab.nrows > 0;
     n += !d->h_sf3d.empty();
     return n;

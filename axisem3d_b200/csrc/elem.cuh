@@ -50,9 +50,9 @@ __device__ __forceinline__ void load_gcoef(GCoef &g, int axial, int i, int j) {
 
 // ------------------------------------------------------------------------------------------
 // Gradient::computeGrad6 (Gradient.cpp:206-265) at one (alpha, point).  sU: [3][25][T] tile.
+// sU layout: [component][point][T] (T = modes per tile, runtime).
 // Writes e[6] in Voigt order [ss, pp, zz, pz, sz, sp] (engineering shear).
-template <int T>
-__device__ __forceinline__ void grad6_point(const float2 *sU, int t, int i, int j, const GCoef &gc,
+__device__ __forceinline__ void grad6_point(const float2 *sU, int T, int t, int i, int j, const GCoef &gc,
                                             const PointGeom &g, float alpha, bool axial_row0,
                                             float2 (&e)[6]) {
     float2 GU[3], UG[3], u[3];
@@ -100,8 +100,7 @@ __device__ __forceinline__ void grad6_point(const float2 *sU, int t, int i, int 
 }
 
 // Gradient::computeGrad (fluid, Gradient.cpp:26-57).  sU: [1][25][T]; e[3].
-template <int T>
-__device__ __forceinline__ void grad_fluid_point(const float2 *sU, int t, int i, int j, const GCoef &gc,
+__device__ __forceinline__ void grad_fluid_point(const float2 *sU, int T, int t, int i, int j, const GCoef &gc,
                                                  const PointGeom &g, float alpha, bool axial_row0,
                                                  float2 (&e)[3]) {
     float2 GU = czero(), UG = czero();
@@ -146,8 +145,7 @@ __device__ __forceinline__ void quad6_pre(const float2 (&s)[6], const PointGeom 
 }
 
 // tensor-product half: f = Gxi X + Y Geta^T + r.  sX, sY: [NC][25][T].
-template <int T>
-__device__ __forceinline__ float2 quad_post(const float2 *sX, const float2 *sY, int c, int t, int i, int j,
+__device__ __forceinline__ float2 quad_post(const float2 *sX, const float2 *sY, int T, int c, int t, int i, int j,
                                             const GCoef &gc, float2 r) {
     float2 f = r;
 #pragma unroll

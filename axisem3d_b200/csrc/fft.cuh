@@ -23,6 +23,11 @@ struct FftPlan {
     int radix[AX_MAX_STAGES];
     int tw_off;    // offset (float2) of W_N[k] = exp(+2 pi i k / N), k < N, in the twiddle pool
     int perm_off;  // offset (int) of perm[pos] = sample index n stored at position pos after the DIF c2r
+    // per-stage twiddle tables for the fused element kernel (fused.cuh): stage s with block length L_s and radix R_s
+    // owns T_s[j * R_s + p] = exp(+2 pi i j p / L_s), j < L_s / R_s, p < R_s, at stwpool[stw_off[s]] (-1: no twiddles,
+    // i.e. L_s == R_s).  All tables of one plan are contiguous: [stw_base, stw_base + stw_len).
+    int stw_off[AX_MAX_STAGES];
+    int stw_base, stw_len;
 };
 
 // cos/sin(2 pi k / R) for the in-register butterflies, R <= 16

@@ -18,6 +18,7 @@ struct ElemDesc {
     int nr, nu, nyq, axial;
     int tiso, law, att_kind, nsls;
     int do_kappa, plan_id, ppb, is3d;
+    int mt, bucket;            // fused kernel (fused.cuh): modes per gather tile; launch bucket (-1: split pipeline)
     unsigned pt_off[AX_NPE];   // offset of the point's block in the solid / fluid field array (float2 units)
     int pt_stride[AX_NPE];     // Nu_p + 1 (component stride inside the block)
     int pt_nlive[AX_NPE];      // rows [0, nlive) are gathered / scattered (Nu_p - nyq_p + 1)
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
     float2 r[NC];
     if constexpr (!FLUID) {
         float2 e[6], s[6], X[3], Y[3];
-        grad6_point<AX_TILE>(sU, t, i, j, gc, g, (float)alpha, ax0, e);
+        grad6_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
         if (dead) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) e[c] = czero();
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
         }
     } else {
         float2 e[3], s[3], X, Y;
-        grad_fluid_point<AX_TILE>(sU, t, i, j, gc, g, (float)alpha, ax0, e);
+        grad_fluid_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
         const float K = dead ? 0.f : coef[E.coef_off + p];
 #pragma unroll
         for (int c = 0; c < 3; ++c) s[c] = cscale(e[c], K);   // Acoustic1D.cpp:8-16
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
     const int st = E.pt_stride[p];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        float2 f = quad_post<AX_TILE>(sX, sY, c, t, i, j, gc, r[c]);
+        float2 f = quad_post(sX, sY, AX_TILE, c, t, i, j, gc, r[c]);
         if (alpha == 0) f.y = 0.f;
         scatter_sub(stiff, base + (size_t)c * st, f);
     }
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__re
     float2 *z = scratch + E.scratch_off + (size_t)p * N;
     if constexpr (!FLUID) {
         float2 e[6];
-        grad6_point<AX_TILE>(sU, t, i, j, gc, g, (float)alpha, ax0, e);
+        grad6_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
         if (dead) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) e[c] = czero();
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__re
         for (int pr = 0; pr < 3; ++pr) zform_store(z + (size_t)pr * AX_NPE * N, N, alpha, e[2 * pr], e[2 * pr + 1]);
     } else {
         float2 e[3];
-        grad_fluid_point<AX_TILE>(sU, t, i, j, gc, g, (float)alpha, ax0, e);
+        grad_fluid_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
         if (dead) e[0] = e[1] = e[2] = czero();
         zform_store(z, N, alpha, e[0], e[1]);
         zform_store(z + (size_t)AX_NPE * N, N, alpha, e[2], czero());
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__re
     const int st = E.pt_stride[p];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        float2 f = quad_post<AX_TILE>(sX, sY, c, t, i, j, gc, r[c]);
+        float2 f = quad_post(sX, sY, AX_TILE, c, t, i, j, gc, r[c]);
         if (beta == 0) f.y = 0.f;
         scatter_sub(stiff, base + (size_t)c * st, f);
     }

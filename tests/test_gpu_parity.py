@@ -32,6 +32,9 @@ def ragged_nu(s, z):
     return int(3 + 40 * s / 6371e3)
 
 
+# fused-kernel corner cases: gather tile smaller than the spectrum (Nr = 288), and the split pipeline (Nr = 416)
+CASES["iso3d_nu140_tiled"] = dict(n_theta=3, n_r=4, nu=140, law="iso", model3d=True, attenuation=None, fluid3d=True)
+CASES["ti3d_nu200_split"] = dict(n_theta=3, n_r=4, nu=200, law="ti", model3d=True, attenuation="cg4", fluid3d=True)
 CASES["cfg4_ragged"] = dict(n_theta=10, n_r=6, nu_fn=ragged_nu, law="iso", model3d=True, attenuation=None)
 
 
