@@ -93,9 +93,12 @@ struct Chunk {   // a run of 3D elements of one class whose spectra fit the scra
     size_t fft_smem;
 };
 
-struct FusedLaunch {   // a run of 3D elements of one class handled by k_elem3d_fused<FLUID, 512 >> bucket>
+struct FusedLaunch {   // a run of 3D elements of one class handled by one persistent k_elem3d_fused<FLUID, 512 >> bucket, nct>
     int cls, bucket, first, count;
+    int nct;                     // > 0: every element has Nr == nct and a compile-time specialised kernel exists
+    int u_cap, tw_cap, ldz_max;  // shared-memory regions (float2 units)
     size_t smem;
+    int grid;
 };
 
 struct ax3d_domain {
@@ -109,6 +112,7 @@ struct ax3d_domain {
     std::vector<HSource> sources;
     long long launches = 0;
     long long work = 0;
+    int num_sm = 148;
     double alg_bytes[3] = {0, 0, 0};
 
     // ---- device: points
@@ -198,24 +202,9 @@ static void fail(const std::string &m) { throw std::runtime_error(m); }
 
 // ------------------------------------------------------------------------------------------ FFT plans
 static std::vector<int> choose_radices(int N) {
-    std::vector<int> r;
-    int n = N, e = 0;
-    while (n % 2 == 0) { n /= 2; ++e; }
-    // odd factors first for the DIF order: the LAST DIF stage (stride-1 butterflies, worst bank pattern) should be a
-    // power of two only when nothing else is available
-    std::vector<int> pow2;
-    while (e >= 4) { pow2.push_back(16); e -= 4; }
-    if (e == 3) pow2.push_back(8);
-    else if (e == 2) pow2.push_back(4);
-    else if (e == 1) pow2.push_back(2);
-    std::vector<int> odd;
-    const int ps[5] = {13, 11, 7, 5, 3};
-    for (int p : ps)
-        while (n % p == 0) { odd.push_back(p); n /= p; }
-    if (n != 1) fail("ax3d::plan || Nr = " + std::to_string(N) + " has a prime factor > 13 (not a lucky number, PreloopFFTW.cpp:59-99)");
-    r = pow2;
-    r.insert(r.end(), odd.begin(), odd.end());
-    if ((int)r.size() > AX_MAX_STAGES) fail("ax3d::plan || too many FFT stages");
+    const RadixList rl = choose_radices_ct(N);   // fft.cuh: the one definition host and kernels share
+    if (rl.n < 0) fail("ax3d::plan || Nr = " + std::to_string(N) + " is not a lucky number (prime factor > 13 or too many stages; PreloopFFTW.cpp:59-99)");
+    std::vector<int> r(rl.r, rl.r + rl.n);
     if (r.empty()) r.push_back(1);
     return r;
 }
@@ -328,6 +317,7 @@ static void common_elem(ax3d_domain *d, HElem &e, const int tags[25], const doub
 
 // ------------------------------------------------------------------------------------------ finalize
 static void set_fused_smem(int device, const FusedLaunch &f);
+static bool fused_specialised(bool fluid, int nt, int N);
 static int pick_ppb(int N, int npair) {
     const char *env = getenv("AX3D_FFT_SMEM_KB");
     const double budget = (env ? atof(env) : 48.0) * 1024.0;
@@ -342,6 +332,7 @@ static void finalize(ax3d_domain *d) {
     check_open(d);
     if (!d->have_g) fail("Gradient::setGMat || ax3d_set_gmat has not been called");
     CK(cudaSetDevice(d->device));
+    CK(cudaDeviceGetAttribute(&d->num_sm, cudaDevAttrMultiProcessorCount, d->device));
     // ---------------- constants
     {
         float G[2][25];
@@ -475,10 +466,14 @@ static void finalize(ax3d_domain *d) {
             ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0};
             ch_scratch = 0;
         };
-        FusedLaunch fl{c, -1, 0, 0, 0};
+        FusedLaunch fl{c, -1, 0, 0, 0, 0, 0, 0, 0, 0};
         auto close_fused = [&]() {
-            if (fl.count > 0) d->fused.push_back(fl);
-            fl = FusedLaunch{c, -1, 0, 0, 0};
+            if (fl.count > 0) {
+                fl.smem = ((size_t)fl.u_cap + fl.tw_cap + (size_t)npair * AX_NPE * fl.ldz_max) * sizeof(float2);
+                fl.grid = std::min(fl.count, d->num_sm * (1 << fl.bucket));
+                d->fused.push_back(fl);
+            }
+            fl = FusedLaunch{c, -1, 0, 0, 0, 0, 0, 0, 0, 0};
         };
         for (size_t k = 0; k < order[c].size(); ++k) {
             HElem &E = d->elems[order[c][k]];
@@ -558,8 +553,10 @@ static void finalize(ax3d_domain *d) {
             if (is3d) {
                 // fused one-CTA-per-element kernel when the element's spectrum fits in shared memory (fused.cuh)
                 const int nc = fluid ? 1 : 3;
-                const size_t lim[3] = {231000, 115000, 56500};   // dynamic smem for 1 / 2 / 4 CTAs per SM
-                const size_t fixed = ((size_t)npair * AX_NPE * fused_ldz(N) + d->h_plans[D.plan_id = get_plan(d, N)].stw_len) * sizeof(float2);
+                const size_t lim[3] = {231000, 114000, 56000};   // dynamic smem for 1 / 2 / 4 CTAs per SM
+                D.plan_id = get_plan(d, N);
+                const int stw_len = d->h_plans[D.plan_id].stw_len;
+                const size_t fixed = ((size_t)npair * AX_NPE * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2);   // twiddle tables <= 2 N
                 size_t need = fixed + (size_t)nc * AX_NPE * M * sizeof(float2);
                 bool can_fuse = use_fused;
                 if (can_fuse && need > lim[0]) {
@@ -570,10 +567,13 @@ static void finalize(ax3d_domain *d) {
                 }
                 if (can_fuse) {
                     D.bucket = need <= lim[2] ? 2 : need <= lim[1] ? 1 : 0;
-                    if (fl.count > 0 && fl.bucket != D.bucket) close_fused();
-                    if (fl.count == 0) { fl.first = (int)k; fl.bucket = D.bucket; }
+                    const int nct = fused_specialised(fluid, 512 >> D.bucket, N) ? N : 0;
+                    if (fl.count > 0 && (fl.bucket != D.bucket || fl.nct != nct)) close_fused();
+                    if (fl.count == 0) { fl.first = (int)k; fl.bucket = D.bucket; fl.nct = nct; }
                     fl.count++;
-                    fl.smem = std::max(fl.smem, need);
+                    fl.u_cap = std::max(fl.u_cap, nc * AX_NPE * D.mt);
+                    fl.tw_cap = std::max(fl.tw_cap, stw_len);
+                    fl.ldz_max = std::max(fl.ldz_max, fused_ldz(N));
                 } else {
                     D.mt = M;
                     D.ppb = pick_ppb(N, npair);
@@ -815,37 +815,51 @@ static void apply_source(ax3d_domain *d, float stf) {
     launch_source(d);
 }
 
-template <bool FLUID, int NT>
-static void launch_fused_t(ax3d_domain *d, const FusedLaunch &f) {
-    const int c = f.cls;
-    k_elem3d_fused<FLUID, NT><<<f.count, NT, f.smem, d->stream>>>(
-        d->desc[c].p + f.first, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
-        FLUID ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, FLUID ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p);
+// compile-time specialised instances of the fused kernel: (fluid, threads, Nr).  Add a line to specialise another size.
+#define AX_FUSED_SPECIALISATIONS(X) \
+    X(false, 512, 208)              \
+    X(true, 256, 208)
+
+static bool fused_specialised(bool fluid, int nt, int N) {
+    const char *env = getenv("AX3D_NO_SPECIALISED");
+    if (env && atoi(env) != 0) return false;
+#define X(F, NT, NCT) if (fluid == F && nt == NT && N == NCT) return true;
+    AX_FUSED_SPECIALISATIONS(X)
+#undef X
+    return false;
 }
+
+typedef void (*fused_kernel_t)(const ElemDesc *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
+                               float *, const float2 *, float2 *, int, int);
+
+static fused_kernel_t fused_kernel(const FusedLaunch &f) {
+    const bool fluid = f.cls == CLS_F3D;
+    const int nt = 512 >> f.bucket;
+#define X(F, NT, NCT) if (fluid == F && nt == NT && f.nct == NCT) return k_elem3d_fused<F, NT, NCT>;
+    AX_FUSED_SPECIALISATIONS(X)
+#undef X
+    if (f.nct != 0) fail("ax3d::fused || no specialised kernel for this launch");
+    switch (f.bucket) {
+        case 0: return fluid ? k_elem3d_fused<true, 512, 0> : k_elem3d_fused<false, 512, 0>;
+        case 1: return fluid ? k_elem3d_fused<true, 256, 0> : k_elem3d_fused<false, 256, 0>;
+        default: return fluid ? k_elem3d_fused<true, 128, 0> : k_elem3d_fused<false, 128, 0>;
+    }
+}
+
 static void launch_fused(ax3d_domain *d, const FusedLaunch &f) {
-    const bool fluid = f.cls == CLS_F3D;
-    switch (f.bucket) {
-        case 0: fluid ? launch_fused_t<true, 512>(d, f) : launch_fused_t<false, 512>(d, f); break;
-        case 1: fluid ? launch_fused_t<true, 256>(d, f) : launch_fused_t<false, 256>(d, f); break;
-        default: fluid ? launch_fused_t<true, 128>(d, f) : launch_fused_t<false, 128>(d, f); break;
-    }
+    const int c = f.cls;
+    const bool fluid = c == CLS_F3D;
+    fused_kernel(f)<<<f.grid, 512 >> f.bucket, f.smem, d->stream>>>(
+        d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
+        fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
+        f.u_cap, f.tw_cap);
 }
-template <bool FLUID, int NT>
-static void set_fused_smem_t(int device, size_t smem) {
-    static size_t cur[64][2][3];   // per device: the attribute only ever grows (several domains may share a device)
-    size_t &c = cur[device & 63][FLUID ? 1 : 0][NT == 512 ? 0 : NT == 256 ? 1 : 2];
-    if (smem > 48 * 1024 && smem > c) {
-        CK(cudaFuncSetAttribute(k_elem3d_fused<FLUID, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c = smem;
-    }
-}
+
 static void set_fused_smem(int device, const FusedLaunch &f) {
-    const bool fluid = f.cls == CLS_F3D;
-    switch (f.bucket) {
-        case 0: fluid ? set_fused_smem_t<true, 512>(device, f.smem) : set_fused_smem_t<false, 512>(device, f.smem); break;
-        case 1: fluid ? set_fused_smem_t<true, 256>(device, f.smem) : set_fused_smem_t<false, 256>(device, f.smem); break;
-        default: fluid ? set_fused_smem_t<true, 128>(device, f.smem) : set_fused_smem_t<false, 128>(device, f.smem); break;
-    }
+    (void)device;
+    if (f.smem > 232448) fail("ax3d::fused || shared-memory plan exceeds 227 KB");
+    // several launches (and domains) may share one kernel instance: opt in to the maximum once
+    CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048));
 }
 
 static void compute_stiff(ax3d_domain *d) {

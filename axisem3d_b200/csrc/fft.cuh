@@ -30,6 +30,29 @@ struct FftPlan {
     int stw_base, stw_len;
 };
 
+// Radix sequence of the DIF transform of length N (shared by the host planner and the compile-time specialised
+// kernels, which must agree because phi-dependent arrays are uploaded in the digit-reversed order of this plan):
+// powers of two first (16s, then the 8/4/2 remainder), then odd primes 13, 11, 7, 5, 3 -- so that the LAST DIF
+// stage (stride-1 butterflies) has an odd radix whenever N has an odd factor.  n == 0 marks an unsupported N.
+struct RadixList {
+    int n;
+    int r[AX_MAX_STAGES];
+};
+__host__ __device__ constexpr RadixList choose_radices_ct(int N) {
+    RadixList out{0, {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
+    int n = N, e = 0;
+    while (n % 2 == 0 && n > 0) { n /= 2; ++e; }
+    while (e >= 4) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 16; ++out.n; e -= 4; }
+    if (e == 3) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 8; ++out.n; }
+    else if (e == 2) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 4; ++out.n; }
+    else if (e == 1) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 2; ++out.n; }
+    const int ps[5] = {13, 11, 7, 5, 3};
+    for (int i = 0; i < 5; ++i)
+        while (n % ps[i] == 0) { if (out.n < AX_MAX_STAGES) out.r[out.n] = ps[i]; ++out.n; n /= ps[i]; }
+    if (n != 1 || out.n > AX_MAX_STAGES) out.n = -1;
+    return out;
+}
+
 // cos/sin(2 pi k / R) for the in-register butterflies, R <= 16
 __constant__ float c_cos[17][16];
 __constant__ float c_sin[17][16];

@@ -1,34 +1,52 @@
-// fused.cuh -- one-CTA-per-element kernel for elements with 3D (phi-dependent) material whose whole strain
-// spectrum fits in shared memory: SolidElement::computeStiff / FluidElement::computeStiff
+// fused.cuh -- persistent one-CTA-per-element kernel for elements with 3D (phi-dependent) material whose whole
+// strain spectrum fits in shared memory: SolidElement::computeStiff / FluidElement::computeStiff
 // (SolidElement.cpp:43-65, 404-443; FluidElement.cpp:43-65, 333-355) with no HBM/L2 round trip between
 // gather -> grad -> [rotate] -> c2r -> stress(+SLS) -> r2c -> [rotate^-1] -> quad -> scatter.
 //
-// Shared memory of one CTA (float2 units):
+// Shared memory of one CTA (float2 units), fixed offsets for every element of a launch:
+//   U  [u_cap]             gathered displacement, mode-major: U[a * NC*25 + c * 25 + point] (all contraction operands
+//                           of one thread sit at immediate offsets; the odd row stride keeps lanes = modes conflict free);
+//   TW [tw_cap]            per-stage twiddle tables of the plan;
 //   Z  [NPAIR * 25][ldz]   "Z-form" columns: two real strain/stress components of one GLL point as one complex
-//                           column of length N = Nr (ldz = (N + 1) | 1 is odd, so lanes that run over columns are
-//                           bank-conflict free, and slot N of every column is a spare);
-//   U  [NC * 25][Mt]       gathered displacement of Mt Fourier modes (Mt = Nu + 1 when it fits); reused by the
-//                           quad phase for the pointwise term r;
-//   TW [stw_len]           per-stage twiddle tables of the plan.
-// Phases (8 barriers for a two-stage plan with Mt = Nu + 1):
-//   gather | grad (thread = (mode, point), writes Z-form) | DIF stages (thread = (column, butterfly), column fastest)
-//   | stress (thread = (point, phi)) | DIT stages | quad-pre (in place: slot beta <- X, slot N - beta <- Y, U <- r)
+//                           column of length N = Nr.  ldz = (N + 1) | 1 is odd, so lanes that run over columns are
+//                           bank-conflict free, and slot N of every column is a spare.
+// One CTA loops over elements blockIdx.x, blockIdx.x + gridDim.x, ... (sorted by cost, so the static round robin is
+// LPT-like).  While element e is in its FFT/stress/quad phases the displacement of the NEXT element streams into U
+// with cp.async (U is dead after grad: the quad phase keeps its pointwise term in registers), its descriptor and plan
+// are prefetched, and the moduli of e are prefetched into L2 at the top of e.  Phases of one element:
+//   grad (thread = (mode, point), writes Z-form) | DIF stages (thread = (column, butterfly), column fastest)
+//   | stress (thread = (point, phi)) | DIT stages | quad-pre (in place: slot beta <- X, slot N - beta <- Y)
 //   | quad-post + scatter (RED.ADD.F32x2).
+// NCT > 0 instantiates the kernel for one compile-time Nr (strides, radices and twiddle offsets become immediates);
+// NCT = 0 is the generic version driven by the FftPlan.
 #pragma once
 #include "kernels.cuh"
 
+__host__ __device__ constexpr int fused_ldz(int N) { return (N + 1) | 1; }
+
+__device__ __forceinline__ void cp_async8(float2 *dst_smem, const float2 *src, bool pred) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int sz = pred ? 8 : 0;   // src-size 0: nothing is read, the 8 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
 // ---------------------------------------------------------------- one FFT stage over all columns
 // DIF (c2r, SIGN = +1): butterfly, then twiddle T[j][p].  DIT (r2c, SIGN = -1): conj twiddle, then butterfly.
-template <int R, int SIGN, bool DIF>
-__device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int ldz, int ncols, int N, int L,
-                                            const float2 *__restrict__ T, int tid, int nt) {
+// NCT > 0: N = NCT and L = LCT are compile-time.
+template <int R, int SIGN, bool DIF, int NT, int NCOLS, int NCT, int LCT>
+__device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int N_rt, int L_rt, const float2 *__restrict__ T, int tid) {
+    const int N = NCT ? NCT : N_rt;
+    const int L = NCT ? LCT : L_rt;
+    const int ldz = fused_ldz(N);
     const int Ls = L / R;
     const int nb = N / R;
-    const int total = ncols * nb;
+    const int total = NCOLS * nb;
     int idx = tid;
-    int b = idx / ncols, col = idx - b * ncols;
-    const int db = nt / ncols, dc = nt - db * ncols;
-    for (; idx < total; idx += nt) {
+    int b = idx / NCOLS, col = idx - b * NCOLS;
+    constexpr int db = NT / NCOLS, dc = NT - db * NCOLS;
+    for (; idx < total; idx += NT) {
         int blk, j;
         if (Ls == 1) { blk = b; j = 0; }
         else if (L == N) { blk = 0; j = b; }
@@ -37,7 +55,7 @@ __device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int ldz, int
         float2 a[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) a[q] = x[q * Ls];
-        if (!DIF && j != 0) {
+        if (!DIF && Ls > 1 && j != 0) {
             const float2 *t = T + j * R;
 #pragma unroll
             for (int q = 1; q < R; ++q) {
@@ -46,7 +64,7 @@ __device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int ldz, int
             }
         }
         Dft<R, SIGN>::run(a);
-        if (DIF && j != 0) {
+        if (DIF && Ls > 1 && j != 0) {
             const float2 *t = T + j * R;
 #pragma unroll
             for (int p = 1; p < R; ++p) a[p] = cmul(a[p], t[p]);
@@ -55,254 +73,399 @@ __device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int ldz, int
         for (int q = 0; q < R; ++q) x[q * Ls] = a[q];
         col += dc;
         b += db;
-        if (col >= ncols) { col -= ncols; ++b; }
+        if (col >= NCOLS) { col -= NCOLS; ++b; }
     }
 }
 
-template <int SIGN, bool DIF>
-__device__ __forceinline__ void fused_stage_dispatch(int R, float2 *z, int ldz, int ncols, int N, int L,
-                                                     const float2 *T, int tid, int nt) {
+template <int SIGN, bool DIF, int NT, int NCOLS>
+__device__ __forceinline__ void fused_stage_dispatch(int R, float2 *z, int N, int L, const float2 *T, int tid) {
     switch (R) {
-        case 2: fused_stage<2, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
-        case 3: fused_stage<3, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
-        case 4: fused_stage<4, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
-        case 5: fused_stage<5, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
-        case 7: fused_stage<7, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
-        case 8: fused_stage<8, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
-        case 11: fused_stage<11, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
-        case 13: fused_stage<13, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
-        case 16: fused_stage<16, SIGN, DIF>(z, ldz, ncols, N, L, T, tid, nt); break;
+        case 2: fused_stage<2, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 3: fused_stage<3, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 4: fused_stage<4, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 5: fused_stage<5, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 7: fused_stage<7, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 8: fused_stage<8, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 11: fused_stage<11, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 13: fused_stage<13, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 16: fused_stage<16, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
         default: break;
     }
 }
 
-__host__ __device__ __forceinline__ int fused_ldz(int N) { return (N + 1) | 1; }
+// compile-time plan: stage S of length-NCT transform has block length L; TWOFF = offset of its twiddle table
+template <int NT, int NCOLS, int NCT, int S, int L, int TWOFF>
+struct CtFft {
+    static __device__ __forceinline__ void inverse(float2 *Z, const float2 *TW, int tid) {
+        if constexpr (S < choose_radices_ct(NCT).n) {
+            constexpr int R = choose_radices_ct(NCT).r[S];
+            constexpr int Ls = L / R;
+            fused_stage<R, +1, true, NT, NCOLS, NCT, L>(Z, NCT, L, TW + TWOFF, tid);
+            __syncthreads();
+            CtFft<NT, NCOLS, NCT, S + 1, Ls, TWOFF + (Ls > 1 ? L : 0)>::inverse(Z, TW, tid);
+        }
+    }
+    static __device__ __forceinline__ void forward(float2 *Z, const float2 *TW, int tid) {
+        if constexpr (S < choose_radices_ct(NCT).n) {
+            constexpr int R = choose_radices_ct(NCT).r[S];
+            constexpr int Ls = L / R;
+            CtFft<NT, NCOLS, NCT, S + 1, Ls, TWOFF + (Ls > 1 ? L : 0)>::forward(Z, TW, tid);
+            fused_stage<R, -1, false, NT, NCOLS, NCT, L>(Z, NCT, L, TW + TWOFF, tid);
+            __syncthreads();
+        }
+    }
+};
+
+// ---------------------------------------------------------------- grad / quad on the mode-major tile
+// um = U + a * NC*25: the displacement of one mode, [c * 25 + point].
+__device__ __forceinline__ void grad6_mm(const float2 *__restrict__ um, int i, int j, const GCoef &gc, const PointGeom &g,
+                                         float alpha, bool axial_row0, float2 (&e)[6]) {
+    const float2 *col = um + j, *row = um + i * 5;
+    float2 GU[3], UG[3], u[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float2 a = czero(), b = czero();
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            a = cfma(gc.gxi_col[k], col[c * AX_NPE + k * 5], a);
+            b = cfma(gc.geta_col[k], row[c * AX_NPE + k], b);
+        }
+        GU[c] = a;
+        UG[c] = b;
+        u[c] = row[c * AX_NPE + j];
+    }
+    float2 ds[3], dz[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        ds[c] = make_float2(g.dzdeta * GU[c].x + g.dzdxii * UG[c].x, g.dzdeta * GU[c].y + g.dzdxii * UG[c].y);
+        dz[c] = make_float2(g.dsdeta * GU[c].x + g.dsdxii * UG[c].x, g.dsdeta * GU[c].y + g.dsdxii * UG[c].y);
+    }
+    const float2 v0 = cadd(u[0], mul_ialpha(u[1], alpha));
+    const float2 v1 = csub(mul_ialpha(u[0], alpha), u[1]);
+    const float2 v2 = mul_ialpha(u[2], alpha);
+    e[0] = ds[0];
+    e[1] = cscale(v0, g.inv_s);
+    e[2] = dz[2];
+    e[3] = cfma(g.inv_s, v2, dz[1]);
+    e[4] = cadd(dz[0], ds[2]);
+    e[5] = cfma(g.inv_s, v1, ds[1]);
+    if (axial_row0) {   // L'Hopital rows on the axis (Gradient.cpp:221-224, 245-254)
+        const float2 gv0 = cadd(GU[0], mul_ialpha(GU[1], alpha));
+        const float2 gv1 = csub(mul_ialpha(GU[0], alpha), GU[1]);
+        const float2 gv2 = mul_ialpha(GU[2], alpha);
+        e[1] = cfma(g.dzdeta, gv0, e[1]);
+        e[5] = cfma(g.dzdeta, gv1, e[5]);
+        e[3] = cfma(g.dzdeta, gv2, e[3]);
+        if (alpha == 1.f) {
+            const float2 uv0 = cadd(UG[0], mul_ialpha(UG[1], alpha));
+            const float2 uv1 = csub(mul_ialpha(UG[0], alpha), UG[1]);
+            e[1] = cfma(g.dzdxii, uv0, e[1]);
+            e[5] = cfma(g.dzdxii, uv1, e[5]);
+        }
+    }
+}
+__device__ __forceinline__ void grad_fluid_mm(const float2 *__restrict__ um, int i, int j, const GCoef &gc, const PointGeom &g,
+                                              float alpha, bool axial_row0, float2 (&e)[3]) {
+    const float2 *col = um + j, *row = um + i * 5;
+    float2 GU = czero(), UG = czero();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        GU = cfma(gc.gxi_col[k], col[k * 5], GU);
+        UG = cfma(gc.geta_col[k], row[k], UG);
+    }
+    const float2 v = mul_ialpha(row[j], alpha);
+    e[0] = make_float2(g.dzdeta * GU.x + g.dzdxii * UG.x, g.dzdeta * GU.y + g.dzdxii * UG.y);
+    e[1] = cscale(v, g.inv_s);
+    e[2] = make_float2(g.dsdeta * GU.x + g.dsdxii * UG.x, g.dsdeta * GU.y + g.dsdxii * UG.y);
+    if (axial_row0) e[1] = cfma(g.dzdeta, mul_ialpha(GU, alpha), e[1]);
+}
 
 // ---------------------------------------------------------------- the kernel
-// grid: one CTA per element elems[blockIdx.x]; block NT threads; 512 / NT CTAs per SM.
-template <bool FLUID, int NT>
+// grid: persistent, <= (512 / NT) CTAs per SM; block NT threads.
+template <bool FLUID, int NT, int NCT>
 __global__ void __launch_bounds__(NT, 512 / NT)
-    k_elem3d_fused(const ElemDesc *__restrict__ elems, const FftPlan *__restrict__ plans, const float2 *__restrict__ stwpool,
-                   const float *__restrict__ geom, const float *__restrict__ coef, const float *__restrict__ attpar,
-                   float *__restrict__ attstate, const float2 *__restrict__ displ, float2 *__restrict__ stiff) {
+    k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
+                   const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
+                   const float *__restrict__ attpar, float *__restrict__ attstate, const float2 *__restrict__ displ,
+                   float2 *__restrict__ stiff, int u_cap, int tw_cap) {
     constexpr int NC = FLUID ? 1 : 3, NPAIR = FLUID ? 2 : 3;
+    constexpr int US = NC * AX_NPE;                   // row stride of U (odd)
+    constexpr int NCOLS = NPAIR * AX_NPE;
     constexpr int NHW = NT / 16;
+    constexpr int PP = (AX_NPE + NHW - 1) / NHW;      // point passes per thread
+    constexpr int QIT = NT >= 512 ? 7 : NT >= 256 ? 4 : 2;   // 16-mode chunks per quad tile (r lives in registers)
+    constexpr int DESC_W = (int)(sizeof(ElemDesc) / sizeof(int)), PLAN_W = (int)(sizeof(FftPlan) / sizeof(int));
     extern __shared__ float2 smem[];
-    __shared__ ElemDesc sE;
-    __shared__ FftPlan sP;
+    __shared__ ElemDesc sE[2];
+    __shared__ FftPlan sP[2];
     const int tid = threadIdx.x;
-    {
-        const int *src = reinterpret_cast<const int *>(elems + blockIdx.x);
-        int *dst = reinterpret_cast<int *>(&sE);
-        for (int k = tid; k < (int)(sizeof(ElemDesc) / sizeof(int)); k += NT) dst[k] = src[k];
-    }
-    __syncthreads();
-    {
-        const int *src = reinterpret_cast<const int *>(plans + sE.plan_id);
-        int *dst = reinterpret_cast<int *>(&sP);
-        for (int k = tid; k < (int)(sizeof(FftPlan) / sizeof(int)); k += NT) dst[k] = src[k];
-    }
-    const ElemDesc &E = sE;
-    const int N = E.nr, nu = E.nu, M = nu + 1, Mt = E.mt;
-    const int ldz = fused_ldz(N);
-    const bool nyq = E.nyq != 0;
-    float2 *Z = smem;
-    float2 *U = Z + NPAIR * AX_NPE * ldz;
-    float2 *TW = U + NC * AX_NPE * Mt;
     const int hw = tid >> 4, t = tid & 15;
-    __syncthreads();
-    for (int k = tid; k < sP.stw_len; k += NT) TW[k] = stwpool[sP.stw_base + k];
+    float2 *U = smem;
+    float2 *TW = U + u_cap;
+    float2 *Z = TW + tw_cap;
 
-    // ------------------------------------------------------------ gather + grad, Mt modes at a time
-    for (int a0 = 0; a0 < M; a0 += Mt) {
-        const int mt = min(Mt, M - a0);
-        if (a0) __syncthreads();
-        // Point::scatterDisplToElement (SolidPoint.cpp:175-195): half-warp per (component, point) row
-        for (int row = hw; row < NC * AX_NPE; row += NHW) {
+    int e = blockIdx.x;
+    if (e >= nelem) return;
+    // descriptor + plan of element e -> slot s (plain loads; visible after the next barrier)
+    auto load_desc = [&](int s, int el) {
+        if (tid < DESC_W) reinterpret_cast<int *>(&sE[s])[tid] = reinterpret_cast<const int *>(elems + el)[tid];
+        if (tid >= 64 && tid < 64 + PLAN_W) {
+            const int pid = elems[el].plan_id;
+            reinterpret_cast<int *>(&sP[s])[tid - 64] = reinterpret_cast<const int *>(plans + pid)[tid - 64];
+        }
+    };
+    // Point::scatterDisplToElement (SolidPoint.cpp:175-195) for modes [a0, a0 + mt): half-warp per (component, point)
+    auto gather = [&](const ElemDesc &E, int a0, int mt) {
+        for (int row = hw; row < US; row += NHW) {
             const int c = row / AX_NPE, p = row - c * AX_NPE;
             const float2 *src = displ + (size_t)E.pt_off[p] + (size_t)c * E.pt_stride[p];
             const int nlive = E.pt_nlive[p];
-            float2 *dst = U + row * Mt;
             for (int a = t; a < mt; a += 16) {
                 const int al = a0 + a;
-                float2 u = al < nlive ? __ldg(src + al) : czero();
-                if (al == 0) u.y = 0.f;
-                dst[a] = u;
+                const bool live = al < nlive;
+                cp_async8(U + a * US + row, live ? src + al : src, live);
+            }
+        }
+    };
+    static_assert(DESC_W <= NT && 64 + PLAN_W <= NT, "descriptor loaders need NT >= descriptor words");
+    load_desc(0, e);
+    __syncthreads();
+    gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1));
+    int tw_plan = -1;
+    if (NCT) {
+        for (int k = tid; k < sP[0].stw_len; k += NT) TW[k] = stwpool[sP[0].stw_base + k];
+        tw_plan = sE[0].plan_id;
+    }
+
+    for (int it = 0; e < nelem; e += gridDim.x, it ^= 1) {
+        const ElemDesc &E = sE[it];
+        const FftPlan &P = sP[it];
+        const int en = e + gridDim.x;
+        const int N = NCT ? NCT : E.nr, nu = N / 2, M = nu + 1, Mt = E.mt;
+        const int ldz = fused_ldz(N);
+        const bool nyq = (N & 1) == 0;
+        if (!NCT && tw_plan != E.plan_id) {   // Z/TW are idle here (the previous element ended with a barrier-separated scatter)
+            for (int k = tid; k < P.stw_len; k += NT) TW[k] = stwpool[P.stw_base + k];
+            tw_plan = E.plan_id;
+        }
+        // moduli of this element -> L2 while gather/grad/c2r run
+        {
+            const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
+            const float *cb = coef + E.coef_off;
+            const int nline = (ncoef * AX_NPE * N + 31) / 32;
+            for (int k = tid; k < nline; k += NT) prefetch_l2(cb + (size_t)k * 32);
+        }
+
+        // ------------------------------------------------------------ gather (prefetched) + grad, Mt modes at a time
+        for (int a0 = 0; a0 < M; a0 += Mt) {
+            const int mt = min(Mt, M - a0);
+            if (a0) {
+                __syncthreads();
+                gather(E, a0, mt);
+            }
+            cp_async_wait_all();
+            if (a0 == 0 && t == 0)   // Im(u) of mode 0 is not used (Gradient.cpp:209-224): this thread copied these entries
+                for (int row = hw; row < US; row += NHW) U[row].y = 0.f;
+            __syncthreads();
+            // every thread is past the previous element's scatter now: its descriptor slot can take the next element
+            if (a0 == 0 && en < nelem) load_desc(it ^ 1, en);
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+                const int p = pp * NHW + hw;
+                if (p < AX_NPE) {
+                    const int i = p / 5, j = p - 5 * i;
+                    GCoef gc;
+                    load_gcoef(gc, E.axial, i, j);
+                    const PointGeom g = load_geom(geom, E.geom_off, p);
+                    const bool ax0 = E.axial && i == 0;
+                    float tr[4] = {0.f, 1.f, 0.f, 1.f};
+                    if (!FLUID && E.tiso) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+                    }
+                    float2 *zp = Z + p * ldz;
+                    for (int a = t; a < mt; a += 16) {
+                        const int alpha = a0 + a;
+                        const bool dead = nyq && alpha == nu;
+                        if constexpr (!FLUID) {
+                            float2 ee[6];
+                            grad6_mm(U + a * US, i, j, gc, g, (float)alpha, ax0, ee);
+                            if (dead) {
+#pragma unroll
+                                for (int c = 0; c < 6; ++c) ee[c] = czero();
+                            }
+                            if (E.tiso) rot_spz_to_rtz(ee, tr[0], tr[1], tr[2], tr[3]);
+#pragma unroll
+                            for (int pr = 0; pr < 3; ++pr) zform_store(zp + pr * AX_NPE * ldz, N, alpha, ee[2 * pr], ee[2 * pr + 1]);
+                        } else {
+                            float2 ee[3];
+                            grad_fluid_mm(U + a * US, i, j, gc, g, (float)alpha, ax0, ee);
+                            if (dead) ee[0] = ee[1] = ee[2] = czero();
+                            zform_store(zp, N, alpha, ee[0], ee[1]);
+                            zform_store(zp + AX_NPE * ldz, N, alpha, ee[2], czero());
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // Z complete, U dead
+        if (en < nelem) {  // displacement of the next element streams in behind the FFTs
+            const ElemDesc &En = sE[it ^ 1];
+            gather(En, 0, min(En.mt, En.nu + 1));
+        }
+
+        // ------------------------------------------------------------ c2r (SolverFFTW_N6::computeC2R, unnormalised, sign +)
+        if constexpr (NCT != 0) {
+            CtFft<NT, NCOLS, NCT, 0, NCT, 0>::inverse(Z, TW, tid);
+        } else {
+            int L = N;
+            for (int s = 0; s < P.nstages; ++s) {
+                const int R = P.radix[s];
+                fused_stage_dispatch<+1, true, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+                L /= R;
+                __syncthreads();
+            }
+        }
+
+        // ------------------------------------------------------------ physical space: stress (+ SLS attenuation)
+        {
+            const int total = AX_NPE * N;
+            int idx = tid;
+            int p = idx / N, pos = idx - p * N;
+            const int dp = NT / N, dpos = NT - dp * N;
+            const int cs = AX_NPE * ldz;
+            for (; idx < total; idx += NT) {
+                float2 *zc = Z + p * ldz + pos;
+                if constexpr (!FLUID) {
+                    const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
+                    float ee[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
+                    const float *cf = coef + E.coef_off + idx;   // [k][point][pos] with point * N + pos == idx
+                    stress_law<float>(E.law, ee, s, [&](int k) { return __ldcs(cf + (size_t)k * total); });
+                    if (E.att_kind != ATT_NONE) {
+                        const int Pn = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
+                        const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
+                        if (q >= 0) {
+                            const float *ap = attpar + E.att_par_off;
+                            const float *mod = ap + 3 * E.nsls;
+                            float *stt = attstate + E.att_state_off;
+                            const size_t cell = (size_t)q * N + pos;
+                            const size_t PN = (size_t)Pn * N, sl = 6 * PN;
+                            const int nsls = E.nsls;
+                            attenuation_cell<float>(
+                                nsls, ap, mod[cell], mod[PN + cell], mod[2 * PN + cell], E.do_kappa != 0, ee, s,
+                                [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
+                                [&](int c) -> float & { return stt[nsls * sl + c * PN + cell]; });
+                        }
+                    }
+                    zc[0] = make_float2(s[0], s[1]);
+                    zc[cs] = make_float2(s[2], s[3]);
+                    zc[2 * cs] = make_float2(s[4], s[5]);
+                } else {
+                    const float K = __ldcs(coef + E.coef_off + idx);   // Acoustic3D.cpp:9-16
+                    const float2 a = zc[0], b = zc[cs];
+                    zc[0] = cscale(a, K);
+                    zc[cs] = make_float2(b.x * K, 0.f);
+                }
+                p += dp;
+                pos += dpos;
+                if (pos >= N) { pos -= N; ++p; }
             }
         }
         __syncthreads();
-        for (int p = hw; p < AX_NPE; p += NHW) {
-            const int i = p / 5, j = p - 5 * i;
-            GCoef gc;
-            load_gcoef(gc, E.axial, i, j);
-            const PointGeom g = load_geom(geom, E.geom_off, p);
-            const bool ax0 = E.axial && i == 0;
-            float tr[4] = {0.f, 1.f, 0.f, 1.f};
-            if (!FLUID && E.tiso) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
-            }
-            float2 *zp = Z + p * ldz;
-            for (int a = t; a < mt; a += 16) {
-                const int alpha = a0 + a;
-                const bool dead = nyq && alpha == nu;
-                if constexpr (!FLUID) {
-                    float2 e[6];
-                    grad6_point(U, Mt, a, i, j, gc, g, (float)alpha, ax0, e);
-                    if (dead) {
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) e[c] = czero();
-                    }
-                    if (E.tiso) rot_spz_to_rtz(e, tr[0], tr[1], tr[2], tr[3]);
-#pragma unroll
-                    for (int pr = 0; pr < 3; ++pr) zform_store(zp + pr * AX_NPE * ldz, N, alpha, e[2 * pr], e[2 * pr + 1]);
-                } else {
-                    float2 e[3];
-                    grad_fluid_point(U, Mt, a, i, j, gc, g, (float)alpha, ax0, e);
-                    if (dead) e[0] = e[1] = e[2] = czero();
-                    zform_store(zp, N, alpha, e[0], e[1]);
-                    zform_store(zp + AX_NPE * ldz, N, alpha, e[2], czero());
-                }
+
+        // ------------------------------------------------------------ r2c (computeR2C; the 1/Nr is applied at load below)
+        if constexpr (NCT != 0) {
+            CtFft<NT, NCOLS, NCT, 0, NCT, 0>::forward(Z, TW, tid);
+        } else {
+            int L = 1;
+            for (int s = P.nstages - 1; s >= 0; --s) {
+                const int R = P.radix[s];
+                L *= R;
+                fused_stage_dispatch<-1, false, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+                __syncthreads();
             }
         }
-    }
-    __syncthreads();
 
-    // ------------------------------------------------------------ c2r (SolverFFTW_N6::computeC2R, unnormalised, sign +)
-    {
-        int L = N;
-        for (int s = 0; s < sP.nstages; ++s) {
-            const int R = sP.radix[s];
-            fused_stage_dispatch<+1, true>(R, Z, ldz, NPAIR * AX_NPE, N, L, TW + (sP.stw_off[s] - sP.stw_base), tid, NT);
-            L /= R;
+        // ------------------------------------------------------------ quad + scatter, 16 * QIT modes at a time
+        const float sc = 1.f / (float)N;   // SolverFFTW_N6::computeR2C scaling (SolverFFTW_N6.cpp:47-48)
+        for (int a0 = 0; a0 < M; a0 += 16 * QIT) {
+            float2 r[PP][QIT][NC];
+            // pointwise half, in place: slot beta <- X, slot N - beta <- Y (beta = 0: the spare slot N); r stays in registers
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+                const int p = pp * NHW + hw;
+                if (p < AX_NPE) {
+                    const int i = p / 5;
+                    const PointGeom g = load_geom(geom, E.geom_off, p);
+                    const bool ax0 = E.axial && i == 0;
+                    float tr[4] = {0.f, 1.f, 0.f, 1.f};
+                    if (!FLUID && E.tiso) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+                    }
+                    float2 *zp = Z + p * ldz;
+#pragma unroll
+                    for (int q = 0; q < QIT; ++q) {
+                        const int beta = a0 + 16 * q + t;
+                        if (beta < M && !(nyq && beta == nu)) {
+                            if constexpr (!FLUID) {
+                                float2 s[6], X[3], Y[3];
+#pragma unroll
+                                for (int pr = 0; pr < 3; ++pr)
+                                    zform_load(zp + pr * AX_NPE * ldz, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
+                                if (E.tiso) rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
+                                quad6_pre(s, g, (float)beta, ax0, X, Y, r[pp][q]);
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    zp[c * AX_NPE * ldz + beta] = X[c];
+                                    zp[c * AX_NPE * ldz + N - beta] = Y[c];
+                                }
+                            } else {
+                                float2 s[3], X, Y, dummy;
+                                zform_load(zp, N, beta, sc, s[0], s[1]);
+                                zform_load(zp + AX_NPE * ldz, N, beta, sc, s[2], dummy);
+                                quad_fluid_pre(s, g, (float)beta, ax0, X, Y, r[pp][q][0]);
+                                zp[beta] = X;
+                                zp[N - beta] = Y;
+                            }
+                        }
+                    }
+                }
+            }
             __syncthreads();
-        }
-    }
-
-    // ------------------------------------------------------------ physical space: stress (+ SLS attenuation)
-    {
-        const int total = AX_NPE * N;
-        int idx = tid;
-        int p = idx / N, pos = idx - p * N;
-        const int dp = NT / N, dpos = NT - dp * N;
-        const int cs = AX_NPE * ldz;
-        for (; idx < total; idx += NT) {
-            float2 *zc = Z + p * ldz + pos;
-            if constexpr (!FLUID) {
-                const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
-                float e[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
-                const float *cf = coef + E.coef_off + idx;   // [k][point][pos] with point * N + pos == idx
-                stress_law<float>(E.law, e, s, [&](int k) { return __ldcs(cf + (size_t)k * total); });
-                if (E.att_kind != ATT_NONE) {
-                    const int P = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
-                    const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
-                    if (q >= 0) {
-                        const float *ap = attpar + E.att_par_off;
-                        const float *mod = ap + 3 * E.nsls;
-                        float *stt = attstate + E.att_state_off;
-                        const size_t cell = (size_t)q * N + pos;
-                        const size_t PN = (size_t)P * N, sl = 6 * PN;
-                        attenuation_cell<float>(
-                            E.nsls, ap, mod[cell], mod[PN + cell], mod[2 * PN + cell], E.do_kappa != 0, e, s,
-                            [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
-                            [&](int c) -> float & { return stt[E.nsls * sl + c * PN + cell]; });
+            // tensor-product half + Point::gatherStiffFromElement (SolidPoint.cpp:197-209)
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+                const int p = pp * NHW + hw;
+                if (p < AX_NPE) {
+                    const int i = p / 5, j = p - 5 * i;
+                    GCoef gc;
+                    load_gcoef(gc, E.axial, i, j);
+                    const int nlive = E.pt_nlive[p];
+                    const size_t base = (size_t)E.pt_off[p];
+                    const int st = E.pt_stride[p];
+#pragma unroll
+                    for (int q = 0; q < QIT; ++q) {
+                        const int beta = a0 + 16 * q + t;
+                        if (beta < M && !(nyq && beta == nu) && beta < nlive) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                float2 f = r[pp][q][c];
+                                const float2 *zx = Z + (c * AX_NPE + j) * ldz + beta;           // X(k, j), k = 0..4
+                                const float2 *zy = Z + (c * AX_NPE + i * 5) * ldz + N - beta;   // Y(i, k)
+#pragma unroll
+                                for (int k = 0; k < 5; ++k) {
+                                    f = cfma(gc.gxi_row[k], zx[k * 5 * ldz], f);
+                                    f = cfma(gc.geta_row[k], zy[k * ldz], f);
+                                }
+                                if (beta == 0) f.y = 0.f;
+                                scatter_sub(stiff, base + (size_t)c * st + beta, f);
+                            }
+                        }
                     }
                 }
-                zc[0] = make_float2(s[0], s[1]);
-                zc[cs] = make_float2(s[2], s[3]);
-                zc[2 * cs] = make_float2(s[4], s[5]);
-            } else {
-                const float K = __ldcs(coef + E.coef_off + idx);   // Acoustic3D.cpp:9-16
-                const float2 a = zc[0], b = zc[cs];
-                zc[0] = cscale(a, K);
-                zc[cs] = make_float2(b.x * K, 0.f);
-            }
-            p += dp;
-            pos += dpos;
-            if (pos >= N) { pos -= N; ++p; }
-        }
-    }
-    __syncthreads();
-
-    // ------------------------------------------------------------ r2c (computeR2C; the 1/Nr is applied at load below)
-    {
-        int L = 1;
-        for (int s = sP.nstages - 1; s >= 0; --s) {
-            const int R = sP.radix[s];
-            L *= R;
-            fused_stage_dispatch<-1, false>(R, Z, ldz, NPAIR * AX_NPE, N, L, TW + (sP.stw_off[s] - sP.stw_base), tid, NT);
-            __syncthreads();
-        }
-    }
-
-    // ------------------------------------------------------------ quad + scatter
-    const float sc = 1.f / (float)N;   // SolverFFTW_N6::computeR2C scaling (SolverFFTW_N6.cpp:47-48)
-    for (int a0 = 0; a0 < M; a0 += Mt) {
-        const int mt = min(Mt, M - a0);
-        if (a0) __syncthreads();
-        // pointwise half, in place: slot beta <- X, slot N - beta <- Y (beta = 0: the spare slot N), U <- r
-        for (int p = hw; p < AX_NPE; p += NHW) {
-            const int i = p / 5;
-            const PointGeom g = load_geom(geom, E.geom_off, p);
-            const bool ax0 = E.axial && i == 0;
-            float tr[4] = {0.f, 1.f, 0.f, 1.f};
-            if (!FLUID && E.tiso) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
-            }
-            float2 *zp = Z + p * ldz;
-            for (int a = t; a < mt; a += 16) {
-                const int beta = a0 + a;
-                if (nyq && beta == nu) continue;
-                if constexpr (!FLUID) {
-                    float2 s[6], X[3], Y[3], r[3];
-#pragma unroll
-                    for (int pr = 0; pr < 3; ++pr) zform_load(zp + pr * AX_NPE * ldz, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
-                    if (E.tiso) rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
-                    quad6_pre(s, g, (float)beta, ax0, X, Y, r);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        zp[c * AX_NPE * ldz + beta] = X[c];
-                        zp[c * AX_NPE * ldz + N - beta] = Y[c];
-                        U[(c * AX_NPE + p) * Mt + a] = r[c];
-                    }
-                } else {
-                    float2 s[3], X, Y, r, dummy;
-                    zform_load(zp, N, beta, sc, s[0], s[1]);
-                    zform_load(zp + AX_NPE * ldz, N, beta, sc, s[2], dummy);
-                    quad_fluid_pre(s, g, (float)beta, ax0, X, Y, r);
-                    zp[beta] = X;
-                    zp[N - beta] = Y;
-                    U[p * Mt + a] = r;
-                }
             }
         }
-        __syncthreads();
-        // tensor-product half + Point::gatherStiffFromElement (SolidPoint.cpp:197-209)
-        for (int p = hw; p < AX_NPE; p += NHW) {
-            const int i = p / 5, j = p - 5 * i;
-            GCoef gc;
-            load_gcoef(gc, E.axial, i, j);
-            const int nlive = E.pt_nlive[p];
-            const size_t base = (size_t)E.pt_off[p];
-            const int st = E.pt_stride[p];
-            for (int a = t; a < mt; a += 16) {
-                const int beta = a0 + a;
-                if ((nyq && beta == nu) || beta >= nlive) continue;
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    float2 f = U[(c * AX_NPE + p) * Mt + a];
-                    const float2 *zx = Z + (c * AX_NPE + j) * ldz + beta;           // X(k, j), k = 0..4
-                    const float2 *zy = Z + (c * AX_NPE + i * 5) * ldz + N - beta;   // Y(i, k)
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        f = cfma(gc.gxi_row[k], zx[k * 5 * ldz], f);
-                        f = cfma(gc.geta_row[k], zy[k * ldz], f);
-                    }
-                    if (beta == 0) f.y = 0.f;
-                    scatter_sub(stiff, base + (size_t)c * st + beta, f);
-                }
-            }
-        }
+        // the barrier after cp_async_wait_all at the top of the next element separates these reads of Z from its grad
     }
 }
