@@ -93,12 +93,13 @@ struct Chunk {   // a run of 3D elements of one class whose spectra fit the scra
     size_t fft_smem;
 };
 
-struct FusedLaunch {   // a run of 3D elements of one class handled by one persistent k_elem3d_fused<FLUID, 512 >> bucket, nct>
-    int cls, bucket, first, count;
-    int nct;                     // > 0: every element has Nr == nct and a compile-time specialised kernel exists
+struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_elem3d_fused<FLUID, 512, nct> launch
+    int cls, first, count;
+    int nct;                     // > 0: kernel instance with a compile-time specialised body for Nr == nct
     int u_cap, tw_cap, ldz_max;  // shared-memory regions (float2 units)
     size_t smem;
     int grid;
+    std::map<int, int> nr_hist;  // Nr -> element count (to pick nct)
 };
 
 struct ax3d_domain {
@@ -137,6 +138,7 @@ struct ax3d_domain {
     std::vector<float2> h_stw;      // per-stage twiddle tables of all plans (fused kernel)
     DevBuf<float2> stwpool;
     std::vector<FusedLaunch> fused;
+    DevBuf<unsigned> fused_work;    // per launch: {next element index, finished CTAs}
     // ---- elements
     std::vector<ElemDesc> h_desc[NCLS];
     DevBuf<ElemDesc> desc[NCLS];
@@ -317,7 +319,7 @@ static void common_elem(ax3d_domain *d, HElem &e, const int tags[25], const doub
 
 // ------------------------------------------------------------------------------------------ finalize
 static void set_fused_smem(int device, const FusedLaunch &f);
-static bool fused_specialised(bool fluid, int nt, int N);
+static bool fused_specialised(bool fluid, int N);
 static int pick_ppb(int N, int npair) {
     const char *env = getenv("AX3D_FFT_SMEM_KB");
     const double budget = (env ? atof(env) : 48.0) * 1024.0;
@@ -466,14 +468,17 @@ static void finalize(ax3d_domain *d) {
             ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0};
             ch_scratch = 0;
         };
-        FusedLaunch fl{c, -1, 0, 0, 0, 0, 0, 0, 0, 0};
+        FusedLaunch fl{};
+        fl.cls = c;
         auto close_fused = [&]() {
             if (fl.count > 0) {
                 fl.smem = ((size_t)fl.u_cap + fl.tw_cap + (size_t)npair * AX_NPE * fl.ldz_max) * sizeof(float2);
-                fl.grid = std::min(fl.count, d->num_sm * (1 << fl.bucket));
+                fl.grid = std::min(fl.count, d->num_sm);
+                int best = 0;
+                for (const auto &kv : fl.nr_hist)
+                    if (kv.second > best && fused_specialised(fluid, kv.first)) { best = kv.second; fl.nct = kv.first; }
                 d->fused.push_back(fl);
             }
-            fl = FusedLaunch{c, -1, 0, 0, 0, 0, 0, 0, 0, 0};
         };
         for (size_t k = 0; k < order[c].size(); ++k) {
             HElem &E = d->elems[order[c][k]];
@@ -553,7 +558,7 @@ static void finalize(ax3d_domain *d) {
             if (is3d) {
                 // fused one-CTA-per-element kernel when the element's spectrum fits in shared memory (fused.cuh)
                 const int nc = fluid ? 1 : 3;
-                const size_t lim[3] = {231000, 114000, 56000};   // dynamic smem for 1 / 2 / 4 CTAs per SM
+                const size_t lim[1] = {231000};   // dynamic smem of the one resident CTA per SM
                 D.plan_id = get_plan(d, N);
                 const int stw_len = d->h_plans[D.plan_id].stw_len;
                 const size_t fixed = ((size_t)npair * AX_NPE * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2);   // twiddle tables <= 2 N
@@ -566,11 +571,10 @@ static void finalize(ax3d_domain *d) {
                     need = fixed + (size_t)nc * AX_NPE * D.mt * sizeof(float2);
                 }
                 if (can_fuse) {
-                    D.bucket = need <= lim[2] ? 2 : need <= lim[1] ? 1 : 0;
-                    const int nct = fused_specialised(fluid, 512 >> D.bucket, N) ? N : 0;
-                    if (fl.count > 0 && (fl.bucket != D.bucket || fl.nct != nct)) close_fused();
-                    if (fl.count == 0) { fl.first = (int)k; fl.bucket = D.bucket; fl.nct = nct; }
+                    D.bucket = 0;
+                    if (fl.count == 0) fl.first = (int)k;
                     fl.count++;
+                    fl.nr_hist[N]++;
                     fl.u_cap = std::max(fl.u_cap, nc * AX_NPE * D.mt);
                     fl.tw_cap = std::max(fl.tw_cap, stw_len);
                     fl.ldz_max = std::max(fl.ldz_max, fused_ldz(N));
@@ -728,7 +732,15 @@ static void finalize(ax3d_domain *d) {
         CK(cudaFuncSetAttribute(k_fft3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
         CK(cudaFuncSetAttribute(k_fft3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
     }
-    for (const FusedLaunch &f : d->fused) set_fused_smem(d->device, f);
+    {
+        std::vector<unsigned> w;
+        for (const FusedLaunch &f : d->fused) {
+            set_fused_smem(d->device, f);
+            w.push_back((unsigned)f.grid);
+            w.push_back(0u);
+        }
+        d->fused_work.upload(w);
+    }
     if (d->m3d_smem_s > 48 * 1024) CK(cudaFuncSetAttribute(k_mass3d<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->m3d_smem_s));
     if (d->m3d_smem_f > 48 * 1024) CK(cudaFuncSetAttribute(k_mass3d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->m3d_smem_f));
     if (d->sf3d_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_sf_couple3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->sf3d_smem));
@@ -815,51 +827,46 @@ static void apply_source(ax3d_domain *d, float stf) {
     launch_source(d);
 }
 
-// compile-time specialised instances of the fused kernel: (fluid, threads, Nr).  Add a line to specialise another size.
+// kernel instances with a compile-time specialised body: (fluid, Nr).  Add a line to specialise another size.
 #define AX_FUSED_SPECIALISATIONS(X) \
-    X(false, 512, 208)              \
-    X(true, 256, 208)
+    X(false, 208)                   \
+    X(true, 208)
 
-static bool fused_specialised(bool fluid, int nt, int N) {
+static bool fused_specialised(bool fluid, int N) {
     const char *env = getenv("AX3D_NO_SPECIALISED");
     if (env && atoi(env) != 0) return false;
-#define X(F, NT, NCT) if (fluid == F && nt == NT && N == NCT) return true;
+#define X(F, NCT) if (fluid == F && N == NCT) return true;
     AX_FUSED_SPECIALISATIONS(X)
 #undef X
     return false;
 }
 
 typedef void (*fused_kernel_t)(const ElemDesc *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
-                               float *, const float2 *, float2 *, int, int);
+                               float *, const float2 *, float2 *, int, int, unsigned *);
 
 static fused_kernel_t fused_kernel(const FusedLaunch &f) {
     const bool fluid = f.cls == CLS_F3D;
-    const int nt = 512 >> f.bucket;
-#define X(F, NT, NCT) if (fluid == F && nt == NT && f.nct == NCT) return k_elem3d_fused<F, NT, NCT>;
+#define X(F, NCT) if (fluid == F && f.nct == NCT) return k_elem3d_fused<F, 512, NCT>;
     AX_FUSED_SPECIALISATIONS(X)
 #undef X
     if (f.nct != 0) fail("ax3d::fused || no specialised kernel for this launch");
-    switch (f.bucket) {
-        case 0: return fluid ? k_elem3d_fused<true, 512, 0> : k_elem3d_fused<false, 512, 0>;
-        case 1: return fluid ? k_elem3d_fused<true, 256, 0> : k_elem3d_fused<false, 256, 0>;
-        default: return fluid ? k_elem3d_fused<true, 128, 0> : k_elem3d_fused<false, 128, 0>;
-    }
+    return fluid ? k_elem3d_fused<true, 512, 0> : k_elem3d_fused<false, 512, 0>;
 }
 
-static void launch_fused(ax3d_domain *d, const FusedLaunch &f) {
+static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which) {
     const int c = f.cls;
     const bool fluid = c == CLS_F3D;
-    fused_kernel(f)<<<f.grid, 512 >> f.bucket, f.smem, d->stream>>>(
+    fused_kernel(f)<<<f.grid, 512, f.smem, d->stream>>>(
         d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
         fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
-        f.u_cap, f.tw_cap);
+        f.u_cap, f.tw_cap, d->fused_work.p + 2 * which);
 }
 
 static void set_fused_smem(int device, const FusedLaunch &f) {
     (void)device;
-    if (f.smem > 232448) fail("ax3d::fused || shared-memory plan exceeds 227 KB");
+    if (f.smem > 232448 - 1536) fail("ax3d::fused || shared-memory plan exceeds 227 KB");
     // several launches (and domains) may share one kernel instance: opt in to the maximum once
-    CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048));
+    CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1536));
 }
 
 static void compute_stiff(ax3d_domain *d) {
@@ -896,8 +903,8 @@ static void compute_stiff(ax3d_domain *d) {
         }
         d->launches += 3;
     }
-    for (const FusedLaunch &f : d->fused) {
-        launch_fused(d, f);
+    for (size_t k = 0; k < d->fused.size(); ++k) {
+        launch_fused(d, d->fused[k], (int)k);
         d->launches++;
     }
     CK(cudaGetLastError());

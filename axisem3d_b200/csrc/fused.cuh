@@ -10,15 +10,16 @@
 //   Z  [NPAIR * 25][ldz]   "Z-form" columns: two real strain/stress components of one GLL point as one complex
 //                           column of length N = Nr.  ldz = (N + 1) | 1 is odd, so lanes that run over columns are
 //                           bank-conflict free, and slot N of every column is a spare.
-// One CTA loops over elements blockIdx.x, blockIdx.x + gridDim.x, ... (sorted by cost, so the static round robin is
+// One CTA takes elements off a device-side work counter (elements are sorted by cost, largest first, so the queue is
 // LPT-like).  While element e is in its FFT/stress/quad phases the displacement of the NEXT element streams into U
 // with cp.async (U is dead after grad: the quad phase keeps its pointwise term in registers), its descriptor and plan
 // are prefetched, and the moduli of e are prefetched into L2 at the top of e.  Phases of one element:
 //   grad (thread = (mode, point), writes Z-form) | DIF stages (thread = (column, butterfly), column fastest)
 //   | stress (thread = (point, phi)) | DIT stages | quad-pre (in place: slot beta <- X, slot N - beta <- Y)
 //   | quad-post + scatter (RED.ADD.F32x2).
-// NCT > 0 instantiates the kernel for one compile-time Nr (strides, radices and twiddle offsets become immediates);
-// NCT = 0 is the generic version driven by the FftPlan.
+// The element body exists twice in a kernel instance: generic (driven by the FftPlan at run time) and, when NCT1 > 0,
+// specialised for the one compile-time Nr = NCT1 (strides, radices and twiddle offsets become immediates) -- the host
+// picks the instance whose NCT1 is the most frequent Nr of the domain.
 #pragma once
 #include "kernels.cuh"
 
@@ -180,33 +181,317 @@ __device__ __forceinline__ void grad_fluid_mm(const float2 *__restrict__ um, int
     if (axial_row0) e[1] = cfma(g.dzdeta, mul_ialpha(GU, alpha), e[1]);
 }
 
-// ---------------------------------------------------------------- the kernel
-// grid: persistent, <= (512 / NT) CTAs per SM; block NT threads.
-template <bool FLUID, int NT, int NCT>
-__global__ void __launch_bounds__(NT, 512 / NT)
-    k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
-                   const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
-                   const float *__restrict__ attpar, float *__restrict__ attstate, const float2 *__restrict__ displ,
-                   float2 *__restrict__ stiff, int u_cap, int tw_cap) {
+// ---------------------------------------------------------------- one element   @phase prologue
+template <bool FLUID>
+struct FusedCtx {
+    const float *__restrict__ geom;
+    const float *__restrict__ coef;
+    const float *__restrict__ attpar;
+    float *__restrict__ attstate;
+    const float2 *__restrict__ displ;
+    float2 *__restrict__ stiff;
+    float2 *U, *TW, *Z;
+};
+
+// stress of NB (point, phi) cells at once: all moduli are requested before the first use (Isotropic3D.cpp:10-27,
+// TransverselyIsotropic3D.cpp:10-28, Anisotropic3D.cpp:10-54; no attenuation on this path)
+template <int NCOEF, int NB, int NT>
+__device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, const float *__restrict__ cf, int total, int ldz, int N,
+                                             int tid) {
+    const int cs = AX_NPE * ldz;
+    const int dp = NT / N, dpos = NT - dp * N;
+    int idx = tid;
+    int p = idx / N, pos = idx - p * N;
+    for (; idx < total; idx += NB * NT) {
+        float c[NB][NCOEF];
+#pragma unroll
+        for (int u = 0; u < NB; ++u)
+            if (idx + u * NT < total) {
+#pragma unroll
+                for (int k = 0; k < NCOEF; ++k) c[u][k] = __ldcs(cf + (size_t)k * total + idx + u * NT);
+            }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            if (idx + u * NT < total) {
+                float2 *zc = Z + p * ldz + pos;
+                const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
+                float ee[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
+                stress_law<float>(law, ee, s, [&](int k) { return c[u][k]; });
+                zc[0] = make_float2(s[0], s[1]);
+                zc[cs] = make_float2(s[2], s[3]);
+                zc[2 * cs] = make_float2(s[4], s[5]);
+            }
+            p += dp;
+            pos += dpos;
+            if (pos >= N) { pos -= N; ++p; }
+        }
+    }
+}
+
+// E, P: descriptor and plan of this element (shared memory).  On entry the first gather tile of this element is in
+// flight (cp.async); `after_first_sync` runs behind the first barrier (every thread has left the previous element: its
+// descriptor slot is free), `after_grad` once U is dead (it starts the next element's gather).
+template <bool FLUID, int NT, int NCT, typename GatherFn, typename AfterSyncFn, typename AfterGradFn>
+__device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const ElemDesc &E, const FftPlan &P, int tid,
+                                              GatherFn gather, AfterSyncFn after_first_sync, AfterGradFn after_grad) {
     constexpr int NC = FLUID ? 1 : 3, NPAIR = FLUID ? 2 : 3;
     constexpr int US = NC * AX_NPE;                   // row stride of U (odd)
     constexpr int NCOLS = NPAIR * AX_NPE;
     constexpr int NHW = NT / 16;
     constexpr int PP = (AX_NPE + NHW - 1) / NHW;      // point passes per thread
     constexpr int QIT = NT >= 512 ? 7 : NT >= 256 ? 4 : 2;   // 16-mode chunks per quad tile (r lives in registers)
+    float2 *const U = cx.U, *const TW = cx.TW, *const Z = cx.Z;
+    const int hw = tid >> 4, t = tid & 15;
+    const int N = NCT ? NCT : E.nr, nu = N / 2, M = nu + 1, Mt = E.mt;
+    const int ldz = fused_ldz(N);
+    const bool nyq = (N & 1) == 0;
+    const bool axial = E.axial != 0, tiso = !FLUID && E.tiso != 0;
+    const int law = E.law;
+    const long long geom_off = E.geom_off, trig_off = E.trig_off, coef_off = E.coef_off;
+
+    // ------------------------------------------------------------ gather (prefetched) + grad, Mt modes at a time   @phase gather wait + grad
+    for (int a0 = 0; a0 < M; a0 += Mt) {
+        const int mt = min(Mt, M - a0);
+        if (a0) {
+            __syncthreads();
+            gather(E, a0, mt);
+        }
+        cp_async_wait_all();
+        if (a0 == 0 && t == 0)   // Im(u) of mode 0 is not used (Gradient.cpp:209-224): this thread copied these entries
+            for (int row = hw; row < US; row += NHW) U[row].y = 0.f;
+        __syncthreads();
+        if (a0 == 0) after_first_sync();
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            const int p = pp * NHW + hw;
+            if (p < AX_NPE) {
+                const int i = p / 5, j = p - 5 * i;
+                GCoef gc;
+                load_gcoef(gc, axial, i, j);
+                const PointGeom g = load_geom(cx.geom, geom_off, p);
+                const bool ax0 = axial && i == 0;
+                float tr[4] = {0.f, 1.f, 0.f, 1.f};
+                if (tiso) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tr[k] = cx.geom[trig_off + k * AX_NPE + p];
+                }
+                float2 *zp = Z + p * ldz;
+                for (int a = t; a < mt; a += 16) {
+                    const int alpha = a0 + a;
+                    const bool dead = nyq && alpha == nu;
+                    if constexpr (!FLUID) {
+                        float2 ee[6];
+                        grad6_mm(U + a * US, i, j, gc, g, (float)alpha, ax0, ee);
+                        if (dead) {
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) ee[c] = czero();
+                        }
+                        if (tiso) rot_spz_to_rtz(ee, tr[0], tr[1], tr[2], tr[3]);
+#pragma unroll
+                        for (int pr = 0; pr < 3; ++pr) zform_store(zp + pr * AX_NPE * ldz, N, alpha, ee[2 * pr], ee[2 * pr + 1]);
+                    } else {
+                        float2 ee[3];
+                        grad_fluid_mm(U + a * US, i, j, gc, g, (float)alpha, ax0, ee);
+                        if (dead) ee[0] = ee[1] = ee[2] = czero();
+                        zform_store(zp, N, alpha, ee[0], ee[1]);
+                        zform_store(zp + AX_NPE * ldz, N, alpha, ee[2], czero());
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();   // Z complete, U dead
+    after_grad();      // @phase next-element gather issue
+
+    // ------------------------------------------------------------ c2r (SolverFFTW_N6::computeC2R, unnormalised, sign +)   @phase c2r
+    if constexpr (NCT != 0) {
+        CtFft<NT, NCOLS, NCT, 0, NCT, 0>::inverse(Z, TW, tid);
+    } else {
+        int L = N;
+        for (int s = 0; s < P.nstages; ++s) {
+            const int R = P.radix[s];
+            fused_stage_dispatch<+1, true, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+            L /= R;
+            __syncthreads();
+        }
+    }
+
+    // ------------------------------------------------------------ physical space: stress (+ SLS attenuation)   @phase stress
+    {
+        const int total = AX_NPE * N;
+        const float *cf0 = cx.coef + coef_off;
+        bool done = false;
+        if constexpr (!FLUID) {
+            if (E.att_kind == ATT_NONE) {
+                if (law == LAW_ISO) stress_batch<2, 4, NT>(law, Z, cf0, total, ldz, N, tid);
+                else if (law == LAW_TI) stress_batch<5, 2, NT>(law, Z, cf0, total, ldz, N, tid);
+                else stress_batch<21, 1, NT>(law, Z, cf0, total, ldz, N, tid);
+                done = true;
+            }
+        }
+        if (!done) {
+            int idx = tid;
+            int p = idx / N, pos = idx - p * N;
+            const int dp = NT / N, dpos = NT - dp * N;
+            const int cs = AX_NPE * ldz;
+            for (; idx < total; idx += NT) {
+                float2 *zc = Z + p * ldz + pos;
+                if constexpr (!FLUID) {
+                    const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
+                    float ee[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
+                    const float *cf = cf0 + idx;   // [k][point][pos] with point * N + pos == idx
+                    stress_law<float>(law, ee, s, [&](int k) { return __ldcs(cf + (size_t)k * total); });
+                    const int Pn = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
+                    const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
+                    if (q >= 0) {
+                        const float *ap = cx.attpar + E.att_par_off;
+                        const float *mod = ap + 3 * E.nsls;
+                        float *stt = cx.attstate + E.att_state_off;
+                        const size_t cell = (size_t)q * N + pos;
+                        const size_t PN = (size_t)Pn * N, sl = 6 * PN;
+                        const int nsls = E.nsls;
+                        attenuation_cell<float>(
+                            nsls, ap, mod[cell], mod[PN + cell], mod[2 * PN + cell], E.do_kappa != 0, ee, s,
+                            [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
+                            [&](int c) -> float & { return stt[nsls * sl + c * PN + cell]; });
+                    }
+                    zc[0] = make_float2(s[0], s[1]);
+                    zc[cs] = make_float2(s[2], s[3]);
+                    zc[2 * cs] = make_float2(s[4], s[5]);
+                } else {
+                    const float K = __ldcs(cf0 + idx);   // Acoustic3D.cpp:9-16
+                    const float2 a = zc[0], b = zc[cs];
+                    zc[0] = cscale(a, K);
+                    zc[cs] = make_float2(b.x * K, 0.f);
+                }
+                p += dp;
+                pos += dpos;
+                if (pos >= N) { pos -= N; ++p; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ r2c (computeR2C; the 1/Nr is applied at load below)   @phase r2c
+    if constexpr (NCT != 0) {
+        CtFft<NT, NCOLS, NCT, 0, NCT, 0>::forward(Z, TW, tid);
+    } else {
+        int L = 1;
+        for (int s = P.nstages - 1; s >= 0; --s) {
+            const int R = P.radix[s];
+            L *= R;
+            fused_stage_dispatch<-1, false, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+            __syncthreads();
+        }
+    }
+
+    // ------------------------------------------------------------ quad + scatter, 16 * QIT modes at a time   @phase quad-pre
+    const float sc = 1.f / (float)N;   // SolverFFTW_N6::computeR2C scaling (SolverFFTW_N6.cpp:47-48)
+    for (int a0 = 0; a0 < M; a0 += 16 * QIT) {
+        float2 r[PP][QIT][NC];
+        // pointwise half, in place: slot beta <- X, slot N - beta <- Y (beta = 0: the spare slot N); r stays in registers
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            const int p = pp * NHW + hw;
+            if (p < AX_NPE) {
+                const int i = p / 5;
+                const PointGeom g = load_geom(cx.geom, geom_off, p);
+                const bool ax0 = axial && i == 0;
+                float tr[4] = {0.f, 1.f, 0.f, 1.f};
+                if (tiso) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tr[k] = cx.geom[trig_off + k * AX_NPE + p];
+                }
+                float2 *zp = Z + p * ldz;
+#pragma unroll
+                for (int q = 0; q < QIT; ++q) {
+                    const int beta = a0 + 16 * q + t;
+                    if (beta < M && !(nyq && beta == nu)) {
+                        if constexpr (!FLUID) {
+                            float2 s[6], X[3], Y[3];
+#pragma unroll
+                            for (int pr = 0; pr < 3; ++pr)
+                                zform_load(zp + pr * AX_NPE * ldz, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
+                            if (tiso) rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
+                            quad6_pre(s, g, (float)beta, ax0, X, Y, r[pp][q]);
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                zp[c * AX_NPE * ldz + beta] = X[c];
+                                zp[c * AX_NPE * ldz + N - beta] = Y[c];
+                            }
+                        } else {
+                            float2 s[3], X, Y, dummy;
+                            zform_load(zp, N, beta, sc, s[0], s[1]);
+                            zform_load(zp + AX_NPE * ldz, N, beta, sc, s[2], dummy);
+                            quad_fluid_pre(s, g, (float)beta, ax0, X, Y, r[pp][q][0]);
+                            zp[beta] = X;
+                            zp[N - beta] = Y;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // tensor-product half + Point::gatherStiffFromElement (SolidPoint.cpp:197-209)   @phase quad-post + scatter
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            const int p = pp * NHW + hw;
+            if (p < AX_NPE) {
+                const int i = p / 5, j = p - 5 * i;
+                GCoef gc;
+                load_gcoef(gc, axial, i, j);
+                const int nlive = E.pt_nlive[p];
+                float2 *const dst = cx.stiff + (size_t)E.pt_off[p];
+                const int st = E.pt_stride[p];
+#pragma unroll
+                for (int q = 0; q < QIT; ++q) {
+                    const int beta = a0 + 16 * q + t;
+                    if (beta < M && !(nyq && beta == nu) && beta < nlive) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            float2 f = r[pp][q][c];
+                            const float2 *zx = Z + (c * AX_NPE + j) * ldz + beta;           // X(k, j), k = 0..4
+                            const float2 *zy = Z + (c * AX_NPE + i * 5) * ldz + N - beta;   // Y(i, k)
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                f = cfma(gc.gxi_row[k], zx[k * 5 * ldz], f);
+                                f = cfma(gc.geta_row[k], zy[k * ldz], f);
+                            }
+                            if (beta == 0) f.y = 0.f;
+                            atomicAdd(dst + (size_t)c * st + beta, make_float2(-f.x, -f.y));   // stiff -= f (RED.ADD.F32x2)
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // the barrier after cp_async_wait_all at the top of the next element separates these reads of Z from its grad
+}
+
+// ---------------------------------------------------------------- the kernel   @phase kernel loop
+// grid: persistent, one CTA per SM; block NT threads.  work[0] = next element index (starts at gridDim.x),
+// work[1] = number of CTAs that have finished; the last one re-arms both for the next launch (graph replay).
+template <bool FLUID, int NT, int NCT1>
+__global__ void __launch_bounds__(NT, 512 / NT)
+    k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
+                   const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
+                   const float *__restrict__ attpar, float *__restrict__ attstate, const float2 *__restrict__ displ,
+                   float2 *__restrict__ stiff, int u_cap, int tw_cap, unsigned *__restrict__ work) {
+    constexpr int NC = FLUID ? 1 : 3;
+    constexpr int US = NC * AX_NPE;
+    constexpr int NHW = NT / 16;
     constexpr int DESC_W = (int)(sizeof(ElemDesc) / sizeof(int)), PLAN_W = (int)(sizeof(FftPlan) / sizeof(int));
+    static_assert(DESC_W <= NT && 64 + PLAN_W <= NT, "descriptor loaders need NT >= descriptor words");
     extern __shared__ float2 smem[];
     __shared__ ElemDesc sE[2];
     __shared__ FftPlan sP[2];
+    __shared__ int sNext[2];
     const int tid = threadIdx.x;
     const int hw = tid >> 4, t = tid & 15;
-    float2 *U = smem;
-    float2 *TW = U + u_cap;
-    float2 *Z = TW + tw_cap;
+    FusedCtx<FLUID> cx{geom, coef, attpar, attstate, displ, stiff, smem, smem + u_cap, smem + u_cap + tw_cap};
+    float2 *const U = cx.U;
 
-    int e = blockIdx.x;
-    if (e >= nelem) return;
-    // descriptor + plan of element e -> slot s (plain loads; visible after the next barrier)
+    // descriptor + plan of element el -> slot s (plain loads; visible after the next barrier)
     auto load_desc = [&](int s, int el) {
         if (tid < DESC_W) reinterpret_cast<int *>(&sE[s])[tid] = reinterpret_cast<const int *>(elems + el)[tid];
         if (tid >= 64 && tid < 64 + PLAN_W) {
@@ -227,245 +512,52 @@ __global__ void __launch_bounds__(NT, 512 / NT)
             }
         }
     };
-    static_assert(DESC_W <= NT && 64 + PLAN_W <= NT, "descriptor loaders need NT >= descriptor words");
-    load_desc(0, e);
-    __syncthreads();
-    gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1));
-    int tw_plan = -1;
-    if (NCT) {
-        for (int k = tid; k < sP[0].stw_len; k += NT) TW[k] = stwpool[sP[0].stw_base + k];
-        tw_plan = sE[0].plan_id;
-    }
 
-    for (int it = 0; e < nelem; e += gridDim.x, it ^= 1) {
-        const ElemDesc &E = sE[it];
-        const FftPlan &P = sP[it];
-        const int en = e + gridDim.x;
-        const int N = NCT ? NCT : E.nr, nu = N / 2, M = nu + 1, Mt = E.mt;
-        const int ldz = fused_ldz(N);
-        const bool nyq = (N & 1) == 0;
-        if (!NCT && tw_plan != E.plan_id) {   // Z/TW are idle here (the previous element ended with a barrier-separated scatter)
-            for (int k = tid; k < P.stw_len; k += NT) TW[k] = stwpool[P.stw_base + k];
-            tw_plan = E.plan_id;
-        }
-        // moduli of this element -> L2 while gather/grad/c2r run
-        {
-            const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
-            const float *cb = coef + E.coef_off;
-            const int nline = (ncoef * AX_NPE * N + 31) / 32;
-            for (int k = tid; k < nline; k += NT) prefetch_l2(cb + (size_t)k * 32);
-        }
-
-        // ------------------------------------------------------------ gather (prefetched) + grad, Mt modes at a time
-        for (int a0 = 0; a0 < M; a0 += Mt) {
-            const int mt = min(Mt, M - a0);
-            if (a0) {
-                __syncthreads();
-                gather(E, a0, mt);
-            }
-            cp_async_wait_all();
-            if (a0 == 0 && t == 0)   // Im(u) of mode 0 is not used (Gradient.cpp:209-224): this thread copied these entries
-                for (int row = hw; row < US; row += NHW) U[row].y = 0.f;
-            __syncthreads();
-            // every thread is past the previous element's scatter now: its descriptor slot can take the next element
-            if (a0 == 0 && en < nelem) load_desc(it ^ 1, en);
-#pragma unroll
-            for (int pp = 0; pp < PP; ++pp) {
-                const int p = pp * NHW + hw;
-                if (p < AX_NPE) {
-                    const int i = p / 5, j = p - 5 * i;
-                    GCoef gc;
-                    load_gcoef(gc, E.axial, i, j);
-                    const PointGeom g = load_geom(geom, E.geom_off, p);
-                    const bool ax0 = E.axial && i == 0;
-                    float tr[4] = {0.f, 1.f, 0.f, 1.f};
-                    if (!FLUID && E.tiso) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
-                    }
-                    float2 *zp = Z + p * ldz;
-                    for (int a = t; a < mt; a += 16) {
-                        const int alpha = a0 + a;
-                        const bool dead = nyq && alpha == nu;
-                        if constexpr (!FLUID) {
-                            float2 ee[6];
-                            grad6_mm(U + a * US, i, j, gc, g, (float)alpha, ax0, ee);
-                            if (dead) {
-#pragma unroll
-                                for (int c = 0; c < 6; ++c) ee[c] = czero();
-                            }
-                            if (E.tiso) rot_spz_to_rtz(ee, tr[0], tr[1], tr[2], tr[3]);
-#pragma unroll
-                            for (int pr = 0; pr < 3; ++pr) zform_store(zp + pr * AX_NPE * ldz, N, alpha, ee[2 * pr], ee[2 * pr + 1]);
-                        } else {
-                            float2 ee[3];
-                            grad_fluid_mm(U + a * US, i, j, gc, g, (float)alpha, ax0, ee);
-                            if (dead) ee[0] = ee[1] = ee[2] = czero();
-                            zform_store(zp, N, alpha, ee[0], ee[1]);
-                            zform_store(zp + AX_NPE * ldz, N, alpha, ee[2], czero());
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();   // Z complete, U dead
-        if (en < nelem) {  // displacement of the next element streams in behind the FFTs
-            const ElemDesc &En = sE[it ^ 1];
-            gather(En, 0, min(En.mt, En.nu + 1));
-        }
-
-        // ------------------------------------------------------------ c2r (SolverFFTW_N6::computeC2R, unnormalised, sign +)
-        if constexpr (NCT != 0) {
-            CtFft<NT, NCOLS, NCT, 0, NCT, 0>::inverse(Z, TW, tid);
-        } else {
-            int L = N;
-            for (int s = 0; s < P.nstages; ++s) {
-                const int R = P.radix[s];
-                fused_stage_dispatch<+1, true, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
-                L /= R;
-                __syncthreads();
-            }
-        }
-
-        // ------------------------------------------------------------ physical space: stress (+ SLS attenuation)
-        {
-            const int total = AX_NPE * N;
-            int idx = tid;
-            int p = idx / N, pos = idx - p * N;
-            const int dp = NT / N, dpos = NT - dp * N;
-            const int cs = AX_NPE * ldz;
-            for (; idx < total; idx += NT) {
-                float2 *zc = Z + p * ldz + pos;
-                if constexpr (!FLUID) {
-                    const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
-                    float ee[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
-                    const float *cf = coef + E.coef_off + idx;   // [k][point][pos] with point * N + pos == idx
-                    stress_law<float>(E.law, ee, s, [&](int k) { return __ldcs(cf + (size_t)k * total); });
-                    if (E.att_kind != ATT_NONE) {
-                        const int Pn = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
-                        const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
-                        if (q >= 0) {
-                            const float *ap = attpar + E.att_par_off;
-                            const float *mod = ap + 3 * E.nsls;
-                            float *stt = attstate + E.att_state_off;
-                            const size_t cell = (size_t)q * N + pos;
-                            const size_t PN = (size_t)Pn * N, sl = 6 * PN;
-                            const int nsls = E.nsls;
-                            attenuation_cell<float>(
-                                nsls, ap, mod[cell], mod[PN + cell], mod[2 * PN + cell], E.do_kappa != 0, ee, s,
-                                [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
-                                [&](int c) -> float & { return stt[nsls * sl + c * PN + cell]; });
-                        }
-                    }
-                    zc[0] = make_float2(s[0], s[1]);
-                    zc[cs] = make_float2(s[2], s[3]);
-                    zc[2 * cs] = make_float2(s[4], s[5]);
-                } else {
-                    const float K = __ldcs(coef + E.coef_off + idx);   // Acoustic3D.cpp:9-16
-                    const float2 a = zc[0], b = zc[cs];
-                    zc[0] = cscale(a, K);
-                    zc[cs] = make_float2(b.x * K, 0.f);
-                }
-                p += dp;
-                pos += dpos;
-                if (pos >= N) { pos -= N; ++p; }
-            }
-        }
+    int e = blockIdx.x;
+    if (e < nelem) {
+        load_desc(0, e);
         __syncthreads();
-
-        // ------------------------------------------------------------ r2c (computeR2C; the 1/Nr is applied at load below)
-        if constexpr (NCT != 0) {
-            CtFft<NT, NCOLS, NCT, 0, NCT, 0>::forward(Z, TW, tid);
-        } else {
-            int L = 1;
-            for (int s = P.nstages - 1; s >= 0; --s) {
-                const int R = P.radix[s];
-                L *= R;
-                fused_stage_dispatch<-1, false, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
-                __syncthreads();
+        gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1));
+        int tw_plan = -1;
+        for (int it = 0; e < nelem; it ^= 1) {
+            const ElemDesc &E = sE[it];
+            const FftPlan &P = sP[it];
+            if (tid == 0) sNext[it] = (int)atomicAdd(&work[0], 1u);   // read by everybody after the first barrier below
+            if (tw_plan != E.plan_id) {   // TW is idle here: the FFT stages of the previous element are barrier-separated
+                for (int k = tid; k < P.stw_len; k += NT) cx.TW[k] = stwpool[P.stw_base + k];
+                tw_plan = E.plan_id;
             }
-        }
-
-        // ------------------------------------------------------------ quad + scatter, 16 * QIT modes at a time
-        const float sc = 1.f / (float)N;   // SolverFFTW_N6::computeR2C scaling (SolverFFTW_N6.cpp:47-48)
-        for (int a0 = 0; a0 < M; a0 += 16 * QIT) {
-            float2 r[PP][QIT][NC];
-            // pointwise half, in place: slot beta <- X, slot N - beta <- Y (beta = 0: the spare slot N); r stays in registers
-#pragma unroll
-            for (int pp = 0; pp < PP; ++pp) {
-                const int p = pp * NHW + hw;
-                if (p < AX_NPE) {
-                    const int i = p / 5;
-                    const PointGeom g = load_geom(geom, E.geom_off, p);
-                    const bool ax0 = E.axial && i == 0;
-                    float tr[4] = {0.f, 1.f, 0.f, 1.f};
-                    if (!FLUID && E.tiso) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
-                    }
-                    float2 *zp = Z + p * ldz;
-#pragma unroll
-                    for (int q = 0; q < QIT; ++q) {
-                        const int beta = a0 + 16 * q + t;
-                        if (beta < M && !(nyq && beta == nu)) {
-                            if constexpr (!FLUID) {
-                                float2 s[6], X[3], Y[3];
-#pragma unroll
-                                for (int pr = 0; pr < 3; ++pr)
-                                    zform_load(zp + pr * AX_NPE * ldz, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
-                                if (E.tiso) rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
-                                quad6_pre(s, g, (float)beta, ax0, X, Y, r[pp][q]);
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) {
-                                    zp[c * AX_NPE * ldz + beta] = X[c];
-                                    zp[c * AX_NPE * ldz + N - beta] = Y[c];
-                                }
-                            } else {
-                                float2 s[3], X, Y, dummy;
-                                zform_load(zp, N, beta, sc, s[0], s[1]);
-                                zform_load(zp + AX_NPE * ldz, N, beta, sc, s[2], dummy);
-                                quad_fluid_pre(s, g, (float)beta, ax0, X, Y, r[pp][q][0]);
-                                zp[beta] = X;
-                                zp[N - beta] = Y;
-                            }
-                        }
-                    }
+            // moduli of this element -> L2 while gather/grad/c2r run
+            {
+                const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
+                const float *cb = coef + E.coef_off;
+                const int nline = (ncoef * AX_NPE * E.nr + 31) / 32;
+                for (int k = tid; k < nline; k += NT) prefetch_l2(cb + (size_t)k * 32);
+            }
+            // next element: descriptor behind the first barrier, displacement (cp.async into the dead U) behind grad
+            auto after_first_sync = [&]() {
+                const int en = sNext[it];
+                if (en < nelem) load_desc(it ^ 1, en);
+            };
+            auto after_grad = [&]() {
+                if (sNext[it] < nelem) {
+                    const ElemDesc &En = sE[it ^ 1];
+                    gather(En, 0, min(En.mt, En.nu + 1));
                 }
-            }
-            __syncthreads();
-            // tensor-product half + Point::gatherStiffFromElement (SolidPoint.cpp:197-209)
-#pragma unroll
-            for (int pp = 0; pp < PP; ++pp) {
-                const int p = pp * NHW + hw;
-                if (p < AX_NPE) {
-                    const int i = p / 5, j = p - 5 * i;
-                    GCoef gc;
-                    load_gcoef(gc, E.axial, i, j);
-                    const int nlive = E.pt_nlive[p];
-                    const size_t base = (size_t)E.pt_off[p];
-                    const int st = E.pt_stride[p];
-#pragma unroll
-                    for (int q = 0; q < QIT; ++q) {
-                        const int beta = a0 + 16 * q + t;
-                        if (beta < M && !(nyq && beta == nu) && beta < nlive) {
-#pragma unroll
-                            for (int c = 0; c < NC; ++c) {
-                                float2 f = r[pp][q][c];
-                                const float2 *zx = Z + (c * AX_NPE + j) * ldz + beta;           // X(k, j), k = 0..4
-                                const float2 *zy = Z + (c * AX_NPE + i * 5) * ldz + N - beta;   // Y(i, k)
-#pragma unroll
-                                for (int k = 0; k < 5; ++k) {
-                                    f = cfma(gc.gxi_row[k], zx[k * 5 * ldz], f);
-                                    f = cfma(gc.geta_row[k], zy[k * ldz], f);
-                                }
-                                if (beta == 0) f.y = 0.f;
-                                scatter_sub(stiff, base + (size_t)c * st + beta, f);
-                            }
-                        }
-                    }
-                }
-            }
+            };
+            if (NCT1 != 0 && E.nr == NCT1) fused_element<FLUID, NT, NCT1>(cx, E, P, tid, gather, after_first_sync, after_grad);
+            else fused_element<FLUID, NT, 0>(cx, E, P, tid, gather, after_first_sync, after_grad);
+            e = sNext[it];
         }
-        // the barrier after cp_async_wait_all at the top of the next element separates these reads of Z from its grad
+    }
+    // re-arm the work counter once every CTA is done
+    if (tid == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&work[1], 1u);
+        if (done == gridDim.x - 1) {
+            work[0] = gridDim.x;
+            work[1] = 0u;
+            __threadfence();
+        }
     }
 }

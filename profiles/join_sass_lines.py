@@ -1,60 +1,84 @@
 #!/usr/bin/env python
-"""Join an `ncu --page source --csv` dump (SASS level) with `nvdisasm -g` line info and aggregate executed
-warp-instructions / stall samples / shared wavefronts per source line.  usage: join_sass_lines.py src.csv cubin kernel"""
-import csv, re, subprocess, sys, collections
+"""Join an `ncu --page source --csv` dump (SASS level) with `nvdisasm -gi` line info.
+
+usage: join_sass_lines.py src.csv cubin mangled_kernel [top_n] [sort: instr|samples|smem]
+
+Prints (1) totals, (2) the top source lines (innermost frame) and (3) a per-phase table, where a phase is the
+range between two `// @phase <name>` markers of the kernel's own source file (outermost inline frame)."""
+import collections, csv, re, subprocess, sys
+
 src_csv, cubin, kern = sys.argv[1:4]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+topn = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+sort = {"instr": 0, "samples": 1, "smem": 2}[sys.argv[5] if len(sys.argv) > 5 else "samples"]
+dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
 sec = dis[dis.index(".text." + kern + ":"):]
 nxt = sec.find("//--------------------- .text.", 10)
 sec = sec[:nxt] if nxt > 0 else sec
-line_of = {}
-cur = ("?", 0)
-stack = None
+loc_of, chain, fresh = {}, [("?", 0)], True
 for ln in sec.splitlines():
-    m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
+    m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
-        cur = (m.group(1).split("/")[-1], int(m.group(2)))
+        if fresh:
+            chain, fresh = [], False
+        chain.append((m.group(1), int(m.group(2))))
         continue
     m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*)", ln)
     if m:
-        line_of[int(m.group(1), 16)] = (cur, m.group(2))
+        loc_of[int(m.group(1), 16)] = (chain[0], chain[-1], m.group(2))
+        fresh = True
+# phase markers of the outermost file
+marks = {}
+def phases_of(path):
+    if path not in marks:
+        ms = []
+        try:
+            for n, l in enumerate(open(path), 1):
+                m = re.search(r"@phase\s+(.+?)\s*$", l)
+                if m:
+                    ms.append((n, m.group(1)))
+        except OSError:
+            pass
+        marks[path] = ms
+    return marks[path]
+def phase(outer):
+    name = "(unmarked) " + outer[0].split("/")[-1]
+    for n, nm in phases_of(outer[0]):
+        if outer[1] >= n:
+            name = nm
+    return name
 rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
 ia, ie, isamp, iwf = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("L1 Wavefronts Shared")
 base = int(rows[2][ia], 16)
 agg = collections.defaultdict(lambda: [0, 0, 0, 0])
+ph = collections.defaultdict(lambda: [0, 0, 0])
 tot = [0, 0, 0]
 for r in rows[2:]:
-    off = int(r[ia], 16) - base
-    (loc, ins) = line_of.get(off, (("?", 0), ""))
-    a = agg[loc]
-    a[0] += int(r[ie]); a[1] += int(r[isamp]); a[2] += int(r[iwf] or 0); a[3] += 1
-    tot[0] += int(r[ie]); tot[1] += int(r[isamp]); tot[2] += int(r[iwf] or 0)
+    inner, outer, ins = loc_of.get(int(r[ia], 16) - base, (("?", 0), ("?", 0), ""))
+    v = (int(r[ie]), int(r[isamp]), int(r[iwf] or 0))
+    a = agg[(inner[0].split("/")[-1], inner[1])]
+    p = ph[phase(outer)]
+    for k in range(3):
+        a[k] += v[k]; p[k] += v[k]; tot[k] += v[k]
+    a[3] += 1
 print("total warp-instr %d  samples %d  shared wavefronts %d" % tuple(tot))
-print("%-22s %6s %12s %7s %8s %7s %12s" % ("file:line", "sass", "warp-instr", "%instr", "samples", "%samp", "smem-wavefr"))
-for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][int(sys.argv[5]) if len(sys.argv) > 5 else 1])[:int(sys.argv[4]) if len(sys.argv) > 4 else 40]:
-    print("%-22s %6d %12d %6.1f%% %8d %6.1f%% %12d" % ("%s:%d" % loc, a[3], a[0], 100.0 * a[0] / tot[0], a[1], 100.0 * a[1] / tot[1], a[2]))
-
-# ---- phase totals for fused.cuh kernels (line ranges of the current source; informational)
-def phase(loc):
-    f, l = loc
-    if f == "fft.cuh": return "fft butterflies (fft.cuh)"
-    if f == "fused.cuh":
-        if 20 <= l <= 62: return "fft stage load/store/twiddle/index"
-        if 63 <= l <= 80: return "fft dispatch"
-        if 85 <= l <= 116: return "prologue"
-        if 117 <= l <= 134: return "gather"
-        if 135 <= l <= 168: return "grad"
-        if 169 <= l <= 181: return "c2r loop/barriers"
-        if 182 <= l <= 226: return "stress"
-        if 227 <= l <= 238: return "r2c loop/barriers"
-        if 239 <= l <= 282: return "quad-pre"
-        if l >= 283: return "quad-post+scatter"
-    return f
-ph = collections.defaultdict(lambda: [0, 0, 0])
-for loc, a in agg.items():
-    p = ph[phase(loc)]
-    p[0] += a[0]; p[1] += a[1]; p[2] += a[2]
+print("%-24s %6s %12s %7s %8s %7s %12s" % ("file:line (innermost)", "sass", "warp-instr", "%instr", "samples", "%samp", "smem-wavefr"))
+for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][sort])[:topn]:
+    print("%-24s %6d %12d %6.1f%% %8d %6.1f%% %12d" % ("%s:%d" % loc, a[3], a[0], 100.0 * a[0] / tot[0], a[1], 100.0 * a[1] / max(tot[1], 1), a[2]))
 print()
-for k, p in sorted(ph.items(), key=lambda kv: -kv[1][0]):
-    print("%-40s instr %5.1f%%  samples %5.1f%%  smem wavefronts %5.1f%%" % (k, 100.0 * p[0] / tot[0], 100.0 * p[1] / tot[1], 100.0 * p[2] / max(tot[2], 1)))
+print("%-44s %8s %9s %9s" % ("phase (outermost frame)", "%instr", "%samples", "%smem-wf"))
+for k, p in sorted(ph.items(), key=lambda kv: -kv[1][1]):
+    print("%-44s %7.1f%% %8.1f%% %8.1f%%" % (k, 100.0 * p[0] / tot[0], 100.0 * p[1] / max(tot[1], 1), 100.0 * p[2] / max(tot[2], 1)))
+
+if len(sys.argv) > 6:      # opcode mix of one phase
+    want = sys.argv[6]
+    ops = collections.Counter()
+    for r in rows[2:]:
+        inner, outer, ins = loc_of.get(int(r[ia], 16) - base, (("?", 0), ("?", 0), ""))
+        if phase(outer) == want:
+            op = ins.split()[0] if not ins.startswith("@") else ins.split()[1]
+            ops[op.split(".")[0] + ("." + op.split(".")[1] if op.startswith(("LDS", "STS", "LDG")) and "." in op else "")] += int(r[ie])
+    t = sum(ops.values())
+    print("\nopcode mix of phase '%s' (%d warp-instr)" % (want, t))
+    for op, n in ops.most_common(25):
+        print("  %-14s %10d %5.1f%%" % (op, n, 100.0 * n / t))
