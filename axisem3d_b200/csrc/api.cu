@@ -828,9 +828,9 @@ static void apply_source(ax3d_domain *d, float stf) {
 }
 
 // kernel instances with a compile-time specialised body: (fluid, Nr).  Add a line to specialise another size.
-#define AX_FUSED_SPECIALISATIONS(X) \
-    X(false, 208)                   \
-    X(true, 208)
+// (none is instantiated by default: on B200 the specialised body measured no faster than the generic one -- the kernel
+//  is latency-, not instruction-bound -- while doubling the code size; profiles/r1_fused_kernel_history.md)
+#define AX_FUSED_SPECIALISATIONS(X)
 
 static bool fused_specialised(bool fluid, int N) {
     const char *env = getenv("AX3D_NO_SPECIALISED");

@@ -239,7 +239,7 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
     constexpr int NCOLS = NPAIR * AX_NPE;
     constexpr int NHW = NT / 16;
     constexpr int PP = (AX_NPE + NHW - 1) / NHW;      // point passes per thread
-    constexpr int QIT = NT >= 512 ? 7 : NT >= 256 ? 4 : 2;   // 16-mode chunks per quad tile (r lives in registers)
+    constexpr int QIT = NT >= 256 ? 4 : 2;   // 16-mode chunks per quad tile (the pointwise term r lives in registers)
     float2 *const U = cx.U, *const TW = cx.TW, *const Z = cx.Z;
     const int hw = tid >> 4, t = tid & 15;
     const int N = NCT ? NCT : E.nr, nu = N / 2, M = nu + 1, Mt = E.mt;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(NT, 512 / NT)
     extern __shared__ float2 smem[];
     __shared__ ElemDesc sE[2];
     __shared__ FftPlan sP[2];
-    __shared__ int sNext[2];
+    __shared__ int sIdx[3];   // ring of element indices: current, next, next-next
     const int tid = threadIdx.x;
     const int hw = tid >> 4, t = tid & 15;
     FusedCtx<FLUID> cx{geom, coef, attpar, attstate, displ, stiff, smem, smem + u_cap, smem + u_cap + tw_cap};
@@ -501,14 +501,16 @@ __global__ void __launch_bounds__(NT, 512 / NT)
     };
     // Point::scatterDisplToElement (SolidPoint.cpp:175-195) for modes [a0, a0 + mt): half-warp per (component, point)
     auto gather = [&](const ElemDesc &E, int a0, int mt) {
+        const unsigned u0 = (unsigned)__cvta_generic_to_shared(U + t * US);
         for (int row = hw; row < US; row += NHW) {
             const int c = row / AX_NPE, p = row - c * AX_NPE;
-            const float2 *src = displ + (size_t)E.pt_off[p] + (size_t)c * E.pt_stride[p];
-            const int nlive = E.pt_nlive[p];
-            for (int a = t; a < mt; a += 16) {
-                const int al = a0 + a;
-                const bool live = al < nlive;
-                cp_async8(U + a * US + row, live ? src + al : src, live);
+            const float2 *src = displ + (size_t)E.pt_off[p] + (size_t)c * E.pt_stride[p] + a0 + t;
+            const int nlive = E.pt_nlive[p] - a0 - t;   // entries [0, nlive) of this lane's stride-16 sequence are live
+            unsigned dst = u0 + row * 8u;
+            for (int a = 0; a < mt - t; a += 16) {
+                const int sz = a < nlive ? 8 : 0;        // src-size 0: nothing is read, the 8 bytes are zero-filled
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(sz ? src + a : displ), "r"(sz) : "memory");
+                dst += 16u * US * 8u;
             }
         }
     };
@@ -516,13 +518,14 @@ __global__ void __launch_bounds__(NT, 512 / NT)
     int e = blockIdx.x;
     if (e < nelem) {
         load_desc(0, e);
+        if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
         __syncthreads();
         gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1));
         int tw_plan = -1;
-        for (int it = 0; e < nelem; it ^= 1) {
+        for (int it = 0, k = 0; e < nelem; it ^= 1, k = (k == 2 ? 0 : k + 1)) {
             const ElemDesc &E = sE[it];
             const FftPlan &P = sP[it];
-            if (tid == 0) sNext[it] = (int)atomicAdd(&work[0], 1u);   // read by everybody after the first barrier below
+            const int kn = k == 2 ? 0 : k + 1, knn = kn == 2 ? 0 : kn + 1;   // ring slots of the next two elements
             if (tw_plan != E.plan_id) {   // TW is idle here: the FFT stages of the previous element are barrier-separated
                 for (int k = tid; k < P.stw_len; k += NT) cx.TW[k] = stwpool[P.stw_base + k];
                 tw_plan = E.plan_id;
@@ -536,18 +539,19 @@ __global__ void __launch_bounds__(NT, 512 / NT)
             }
             // next element: descriptor behind the first barrier, displacement (cp.async into the dead U) behind grad
             auto after_first_sync = [&]() {
-                const int en = sNext[it];
+                const int en = sIdx[kn];   // fetched during the previous element
                 if (en < nelem) load_desc(it ^ 1, en);
             };
             auto after_grad = [&]() {
-                if (sNext[it] < nelem) {
+                if (tid == 0) sIdx[knn] = (int)atomicAdd(&work[0], 1u);   // needed one element from now: latency hidden
+                if (sIdx[kn] < nelem) {
                     const ElemDesc &En = sE[it ^ 1];
                     gather(En, 0, min(En.mt, En.nu + 1));
                 }
             };
             if (NCT1 != 0 && E.nr == NCT1) fused_element<FLUID, NT, NCT1>(cx, E, P, tid, gather, after_first_sync, after_grad);
             else fused_element<FLUID, NT, 0>(cx, E, P, tid, gather, after_first_sync, after_grad);
-            e = sNext[it];
+            e = sIdx[kn];
         }
     }
     // re-arm the work counter once every CTA is done

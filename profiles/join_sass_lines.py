@@ -14,6 +14,21 @@ dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text
 sec = dis[dis.index(".text." + kern + ":"):]
 nxt = sec.find("//--------------------- .text.", 10)
 sec = sec[:nxt] if nxt > 0 else sec
+_src = {}
+def src_line(path, n):
+    if path not in _src:
+        try:
+            _src[path] = open(path).read().split("\n")
+        except OSError:
+            _src[path] = []
+    L = _src[path]
+    return L[n - 1] if 0 < n <= len(L) else ""
+def pick_outer(chain):
+    """outermost frame that is not merely the call of an inlined element body (so phases inside it are seen)"""
+    for f in reversed(chain):
+        if "fused_element<" not in src_line(*f):
+            return f
+    return chain[-1]
 loc_of, chain, fresh = {}, [("?", 0)], True
 for ln in sec.splitlines():
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
@@ -24,7 +39,7 @@ for ln in sec.splitlines():
         continue
     m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*)", ln)
     if m:
-        loc_of[int(m.group(1), 16)] = (chain[0], chain[-1], m.group(2))
+        loc_of[int(m.group(1), 16)] = (chain[0], pick_outer(chain), m.group(2))
         fresh = True
 # phase markers of the outermost file
 marks = {}
@@ -82,3 +97,16 @@ if len(sys.argv) > 6:      # opcode mix of one phase
     print("\nopcode mix of phase '%s' (%d warp-instr)" % (want, t))
     for op, n in ops.most_common(25):
         print("  %-14s %10d %5.1f%%" % (op, n, 100.0 * n / t))
+
+# ---- stall reasons per phase (sampled)
+names = hdr[30:47]
+st = collections.defaultdict(lambda: [0] * len(names))
+for r in rows[2:]:
+    inner, outer, ins = loc_of.get(int(r[ia], 16) - base, (("?", 0), ("?", 0), ""))
+    a = st[phase(outer)]
+    for k in range(len(names)):
+        a[k] += int(r[30 + k] or 0)
+keep = [k for k in range(len(names)) if sum(a[k] for a in st.values()) > 0.01 * max(tot[1], 1)]
+print("\nstall samples per phase: " + " ".join("%9s" % names[k].replace("stall_", "")[:9] for k in keep))
+for ph_name, a in sorted(st.items(), key=lambda kv: -sum(kv[1])):
+    print("%-28s" % ph_name[:28] + " ".join("%9d" % a[k] for k in keep))
