@@ -472,7 +472,7 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
 // grid: persistent, one CTA per SM; block NT threads.  work[0] = next element index (starts at gridDim.x),
 // work[1] = number of CTAs that have finished; the last one re-arms both for the next launch (graph replay).
 template <bool FLUID, int NT, int NCT1>
-__global__ void __launch_bounds__(NT, 512 / NT)
+__global__ void __launch_bounds__(NT, (512 / NT) > 0 ? (512 / NT) : 1)
     k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
                    const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
                    const float *__restrict__ attpar, float *__restrict__ attstate, const float2 *__restrict__ displ,
