@@ -16,9 +16,6 @@ enum { ATT_NONE = 0, ATT_FULL = 1, ATT_CG4 = 2 };
 // i * alpha * a   and   -i * beta * a
 __device__ __forceinline__ float2 mul_ialpha(float2 a, float al) { return make_float2(-al * a.y, al * a.x); }
 __device__ __forceinline__ float2 mul_mibeta(float2 a, float be) { return make_float2(be * a.y, -be * a.x); }
-__device__ __forceinline__ float2 cfma(float r, float2 a, float2 acc) {
-    return make_float2(fmaf(r, a.x, acc.x), fmaf(r, a.y, acc.y));
-}
 __device__ __forceinline__ float2 czero() { return make_float2(0.f, 0.f); }
 
 struct PointGeom {
@@ -71,8 +68,8 @@ __device__ __forceinline__ void grad6_point(const float2 *sU, int T, int t, int 
     float2 ds[3], dz[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        ds[c] = make_float2(g.dzdeta * GU[c].x + g.dzdxii * UG[c].x, g.dzdeta * GU[c].y + g.dzdxii * UG[c].y);
-        dz[c] = make_float2(g.dsdeta * GU[c].x + g.dsdxii * UG[c].x, g.dsdeta * GU[c].y + g.dsdxii * UG[c].y);
+        ds[c] = cfma(g.dzdeta, GU[c], cscale(UG[c], g.dzdxii));
+        dz[c] = cfma(g.dsdeta, GU[c], cscale(UG[c], g.dsdxii));
     }
     float2 v0 = cadd(u[0], mul_ialpha(u[1], alpha));
     float2 v1 = csub(mul_ialpha(u[0], alpha), u[1]);
@@ -111,9 +108,9 @@ __device__ __forceinline__ void grad_fluid_point(const float2 *sU, int T, int t,
     }
     float2 u = sU[(i * 5 + j) * T + t];
     float2 v = mul_ialpha(u, alpha);
-    e[0] = make_float2(g.dzdeta * GU.x + g.dzdxii * UG.x, g.dzdeta * GU.y + g.dzdxii * UG.y);
+    e[0] = cfma(g.dzdeta, GU, cscale(UG, g.dzdxii));
     e[1] = cscale(v, g.inv_s);
-    e[2] = make_float2(g.dsdeta * GU.x + g.dsdxii * UG.x, g.dsdeta * GU.y + g.dsdxii * UG.y);
+    e[2] = cfma(g.dsdeta, GU, cscale(UG, g.dsdxii));
     if (axial_row0) e[1] = cfma(g.dzdeta, mul_ialpha(GU, alpha), e[1]);
 }
 
@@ -128,8 +125,8 @@ __device__ __forceinline__ void quad6_pre(const float2 (&s)[6], const PointGeom 
     const int pa[3] = {0, 5, 4}, pb[3] = {4, 3, 2};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        X[c] = make_float2(g.dzdeta * s[pa[c]].x + g.dsdeta * s[pb[c]].x, g.dzdeta * s[pa[c]].y + g.dsdeta * s[pb[c]].y);
-        Y[c] = make_float2(g.dzdxii * s[pa[c]].x + g.dsdxii * s[pb[c]].x, g.dzdxii * s[pa[c]].y + g.dsdxii * s[pb[c]].y);
+        X[c] = cfma(g.dzdeta, s[pa[c]], cscale(s[pb[c]], g.dsdeta));
+        Y[c] = cfma(g.dzdxii, s[pa[c]], cscale(s[pb[c]], g.dsdxii));
     }
     float2 gg[3] = {g0, g1, g2};
 #pragma unroll
@@ -160,8 +157,8 @@ __device__ __forceinline__ float2 quad_post(const float2 *sX, const float2 *sY, 
 __device__ __forceinline__ void quad_fluid_pre(const float2 (&s)[3], const PointGeom &g, float beta, bool axial_row0,
                                                float2 &X, float2 &Y, float2 &r) {
     float2 gg = mul_mibeta(s[1], beta);
-    X = make_float2(g.dzdeta * s[0].x + g.dsdeta * s[2].x, g.dzdeta * s[0].y + g.dsdeta * s[2].y);
-    Y = make_float2(g.dzdxii * s[0].x + g.dsdxii * s[2].x, g.dzdxii * s[0].y + g.dsdxii * s[2].y);
+    X = cfma(g.dzdeta, s[0], cscale(s[2], g.dsdeta));
+    Y = cfma(g.dzdxii, s[0], cscale(s[2], g.dsdxii));
     r = cscale(gg, g.inv_s);
     if (axial_row0) X = cfma(g.dzdeta, gg, X);
 }

@@ -57,12 +57,64 @@ __host__ __device__ constexpr RadixList choose_radices_ct(int N) {
 __constant__ float c_cos[17][16];
 __constant__ float c_sin[17][16];
 
+// Complex helpers.  sm_100a has packed fp32 arithmetic (PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2/FMUL2/FFMA2): one issue slot
+// per complex add or real x complex FMA instead of two.  The fused element kernel is issue-bound, not FP32-pipe-bound
+// (profiles/microbench/f32x2_rate.cu: FFMA2 = 2 cycles per warp-instruction per sub-partition, i.e. the same flops in half the
+// issue slots), so every complex helper goes through the packed forms.  Rounding is identical to the scalar forms (rn).
+#ifndef AX_F32X2
+#define AX_F32X2 1
+#endif
+typedef unsigned long long ax_u64;
+__device__ __forceinline__ ax_u64 f2_pack(float2 a) { ax_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ ax_u64 f2_splat(float s) { ax_u64 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(s)); return r; }
+__device__ __forceinline__ float2 f2_unpack(ax_u64 r) { float2 a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r)); return a; }
+#if AX_F32X2
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    ax_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    ax_u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(r);
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) {
+    ax_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_splat(s))); return f2_unpack(r);
+}
+// acc + r * a (r real)
+__device__ __forceinline__ float2 cfma(float r, float2 a, float2 acc) {
+    ax_u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_splat(r)), "l"(f2_pack(a)), "l"(f2_pack(acc))); return f2_unpack(d);
+}
+// acc + a .* b (component-wise)
+__device__ __forceinline__ float2 cfma2(float2 a, float2 b, float2 acc) {
+    ax_u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(acc))); return f2_unpack(d);
+}
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b) {
+    ax_u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(d);
+}
+// a * b = a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return cfma(a.x, b, cscale(make_float2(-b.y, b.x), a.y));
+}
+// a * conj(b) = a.x * (b.x, -b.y) + a.y * (b.y, b.x)
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
+    return cfma(a.x, make_float2(b.x, -b.y), cscale(make_float2(b.y, b.x), a.y));
+}
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 cfma(float r, float2 a, float2 acc) {
+    return make_float2(fmaf(r, a.x, acc.x), fmaf(r, a.y, acc.y));
+}
+__device__ __forceinline__ float2 cfma2(float2 a, float2 b, float2 acc) {
+    return make_float2(fmaf(a.x, b.x, acc.x), fmaf(a.y, b.y, acc.y));
+}
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#endif
 // multiply by SIGN * i
 template <int SIGN>
 __device__ __forceinline__ float2 cmul_i(float2 a) {
@@ -166,10 +218,8 @@ struct DftOdd {
             for (int q = 1; q <= H; ++q) {
                 const int k = (p * q) % R;
                 const float c = c_cos[R][k], sn = c_sin[R][k];
-                A.x = fmaf(c, s[q - 1].x, A.x);
-                A.y = fmaf(c, s[q - 1].y, A.y);
-                B.x = fmaf(sn, d[q - 1].x, B.x);
-                B.y = fmaf(sn, d[q - 1].y, B.y);
+                A = cfma(c, s[q - 1], A);
+                B = cfma(sn, d[q - 1], B);
             }
             // y_p = A + SIGN i B ; y_{R-p} = A - SIGN i B
             float2 iB = cmul_i<SIGN>(B);

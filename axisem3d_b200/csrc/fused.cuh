@@ -61,7 +61,7 @@ __device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int N_rt, in
 #pragma unroll
             for (int q = 1; q < R; ++q) {
                 const float2 w = t[q];
-                a[q] = make_float2(a[q].x * w.x + a[q].y * w.y, a[q].y * w.x - a[q].x * w.y);   // * conj(w)
+                a[q] = cmul_conj(a[q], w);
             }
         }
         Dft<R, SIGN>::run(a);
@@ -138,8 +138,8 @@ __device__ __forceinline__ void grad6_mm(const float2 *__restrict__ um, int i, i
     float2 ds[3], dz[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        ds[c] = make_float2(g.dzdeta * GU[c].x + g.dzdxii * UG[c].x, g.dzdeta * GU[c].y + g.dzdxii * UG[c].y);
-        dz[c] = make_float2(g.dsdeta * GU[c].x + g.dsdxii * UG[c].x, g.dsdeta * GU[c].y + g.dsdxii * UG[c].y);
+        ds[c] = cfma(g.dzdeta, GU[c], cscale(UG[c], g.dzdxii));
+        dz[c] = cfma(g.dsdeta, GU[c], cscale(UG[c], g.dsdxii));
     }
     const float2 v0 = cadd(u[0], mul_ialpha(u[1], alpha));
     const float2 v1 = csub(mul_ialpha(u[0], alpha), u[1]);
@@ -175,9 +175,9 @@ __device__ __forceinline__ void grad_fluid_mm(const float2 *__restrict__ um, int
         UG = cfma(gc.geta_col[k], row[k], UG);
     }
     const float2 v = mul_ialpha(row[j], alpha);
-    e[0] = make_float2(g.dzdeta * GU.x + g.dzdxii * UG.x, g.dzdeta * GU.y + g.dzdxii * UG.y);
+    e[0] = cfma(g.dzdeta, GU, cscale(UG, g.dzdxii));
     e[1] = cscale(v, g.inv_s);
-    e[2] = make_float2(g.dsdeta * GU.x + g.dsdxii * UG.x, g.dsdeta * GU.y + g.dsdxii * UG.y);
+    e[2] = cfma(g.dsdeta, GU, cscale(UG, g.dsdxii));
     if (axial_row0) e[1] = cfma(g.dzdeta, mul_ialpha(GU, alpha), e[1]);
 }
 
