@@ -97,6 +97,8 @@ struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_e
     int cls, first, count;
     int nct;                     // > 0: kernel instance with a compile-time specialised body for Nr == nct
     int u_cap, tw_cap, ldz_max;  // shared-memory regions (float2 units)
+    int nww;                     // Newmark warps per CTA (0: none; the solid launch uses 2 when the domain has plain points)
+    int z_cap;
     size_t smem;
     int grid;
     std::map<int, int> nr_hist;  // Nr -> element count (to pick nct)
@@ -138,7 +140,15 @@ struct ax3d_domain {
     std::vector<float2> h_stw;      // per-stage twiddle tables of all plans (fused kernel)
     DevBuf<float2> stwpool;
     std::vector<FusedLaunch> fused;
-    DevBuf<unsigned> fused_work;    // per launch: {next element index, finished CTAs}
+    DevBuf<unsigned> fused_work;    // per launch: {next element index, finished warps}
+    // ---- in-kernel Newmark (fused.cuh): "plain" solid points are advanced by the element kernel of the previous step
+    bool nw_allowed = true;         // AX3D_NO_NW=1 switches the mechanism off
+    int n_plain = 0;
+    DevBuf<int> nw_cnt, nw_queue;
+    DevBuf<unsigned> nw_ctl;        // tail, head, -, error flag
+    DevBuf<int> s_row_point_sp, s_row_start_sp;
+    PointTab s_tab_sp{};            // rows of the solid points the stand-alone Newmark kernel still owns
+    bool plain_advanced = false;    // the plain points already hold the state of the step about to start
     // ---- elements
     std::vector<ElemDesc> h_desc[NCLS];
     DevBuf<ElemDesc> desc[NCLS];
@@ -188,8 +198,8 @@ struct ax3d_domain {
     float *stf_pinned = nullptr;
     int stf_slot = 0;
     // CUDA graph of one step (single-GPU path)
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph[4] = {nullptr, nullptr, nullptr, nullptr};          // [special_only * 2 + nw_on]
+    cudaGraphExec_t graph_exec[4] = {nullptr, nullptr, nullptr, nullptr};
     double graph_dt = 0;
     bool use_graph = true;
     // receivers registered with ax3d_set_receivers
@@ -420,7 +430,7 @@ static void finalize(ax3d_domain *d) {
     d->s_len = s_len;
     d->f_len = f_len;
     for (int k = 0; k < 4; ++k) {
-        d->s_field[k].alloc(s_len);
+        d->s_field[k].alloc(s_len + 2);   // + 2: the in-kernel Newmark loads 16-byte aligned supersets of a point's block
         d->s_field[k].zero();
         d->f_field[k].alloc(f_len);
         d->f_field[k].zero();
@@ -455,6 +465,10 @@ static void finalize(ax3d_domain *d) {
     size_t scratch_need = 0;
     const char *env_nf = getenv("AX3D_NO_FUSED");
     const bool use_fused = !(env_nf && atoi(env_nf) != 0);
+    {
+        const char *env_nw = getenv("AX3D_NO_NW");
+        d->nw_allowed = !(env_nw && atoi(env_nw) != 0) && so.size() < (1u << 24);
+    }
 
     for (int c = 0; c < NCLS; ++c) {
         const bool fluid = (c == CLS_F1D || c == CLS_F3D), is3d = (c == CLS_S3D || c == CLS_F3D);
@@ -472,7 +486,8 @@ static void finalize(ax3d_domain *d) {
         fl.cls = c;
         auto close_fused = [&]() {
             if (fl.count > 0) {
-                fl.smem = ((size_t)fl.u_cap + fl.tw_cap + (size_t)npair * AX_NPE * fl.ldz_max) * sizeof(float2);
+                fl.z_cap = npair * AX_NPE * fl.ldz_max;
+                fl.smem = ((size_t)fl.u_cap + fl.tw_cap + (size_t)fl.z_cap) * sizeof(float2);
                 fl.grid = std::min(fl.count, d->num_sm);
                 int best = 0;
                 for (const auto &kv : fl.nr_hist)
@@ -558,7 +573,8 @@ static void finalize(ax3d_domain *d) {
             if (is3d) {
                 // fused one-CTA-per-element kernel when the element's spectrum fits in shared memory (fused.cuh)
                 const int nc = fluid ? 1 : 3;
-                const size_t lim[1] = {231000};   // dynamic smem of the one resident CTA per SM
+                // dynamic smem of the one resident CTA per SM (the solid launch keeps room for its Newmark warps' stages)
+                const size_t lim[1] = {(size_t)231000 - ((!fluid && d->nw_allowed) ? (size_t)AX_NWW * NW_WARP_SMEM : 0)};
                 D.plan_id = get_plan(d, N);
                 const int stw_len = d->h_plans[D.plan_id].stw_len;
                 const size_t fixed = ((size_t)npair * AX_NPE * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2);   // twiddle tables <= 2 N
@@ -602,6 +618,80 @@ static void finalize(ax3d_domain *d) {
         d->w_a0[c].upload(w_a0);
         d->n_work[c] = (int)w_elem.size();
         d->fft_items[c].upload(fitems);
+    }
+    // ---------------- in-kernel Newmark: plain points, arrival counts, special-row table
+    {
+        const size_t ns = d->ns;
+        std::vector<int> need(ns, 0);
+        std::vector<char> ok(ns, 0);
+        FusedLaunch *fs = nullptr;
+        for (FusedLaunch &f : d->fused)
+            if (f.cls == CLS_S3D) fs = &f;
+        if (d->nw_allowed && fs) {
+            for (const HPoint &p : d->points)
+                if (p.kind == 0 && !p.axial && p.im_s.size() == 1) ok[p.s_idx] = 1;
+            for (const auto &nb : d->neigh_pts)
+                for (int t : nb)
+                    if (t >= 0 && t < (int)d->points.size() && d->points[t].s_idx >= 0) ok[d->points[t].s_idx] = 0;
+            for (const HSource &sc : d->sources)
+                for (int i = 0; i < AX_NPE; ++i) {
+                    const HPoint &p = d->points[d->elems[sc.elem].pt[i]];
+                    if (p.s_idx >= 0) ok[p.s_idx] = 0;
+                }
+            for (const HElem &E : d->elems) {
+                if (E.fluid) continue;
+                const bool in_launch = E.cls == CLS_S3D && d->h_desc[CLS_S3D][E.idx].bucket == 0;
+                for (int i = 0; i < AX_NPE; ++i) {
+                    const int sp = d->points[E.pt[i]].s_idx;
+                    if (sp < 0) continue;
+                    if (in_launch) need[sp]++;
+                    else ok[sp] = 0;
+                }
+            }
+        }
+        std::vector<int> srp_sp, srs_sp(ns, 0);
+        int n_plain = 0;
+        for (size_t sp = 0; sp < ns; ++sp) {
+            if (ok[sp] && need[sp] > 0 && need[sp] < 128) { n_plain++; continue; }
+            ok[sp] = 0;
+            srs_sp[sp] = (int)srp_sp.size();
+            for (int a = 0; a <= snu[sp]; ++a) srp_sp.push_back((int)sp);
+        }
+        if (n_plain * 8 < (int)ns) {   // not worth a specialised launch: everything stays with k_newmark_solid
+            n_plain = 0;
+            std::fill(ok.begin(), ok.end(), 0);
+        }
+        d->n_plain = n_plain;
+        for (ElemDesc &D : d->h_desc[CLS_S3D]) {
+            for (int i = 0; i < AX_NPE; ++i) D.pt_nw[i] = -1;
+        }
+        if (n_plain > 0) {
+            for (const HElem &E : d->elems) {
+                if (E.fluid || E.cls != CLS_S3D) continue;
+                ElemDesc &D = d->h_desc[CLS_S3D][E.idx];
+                if (D.bucket != 0) continue;
+                for (int i = 0; i < AX_NPE; ++i) {
+                    const int sp = d->points[E.pt[i]].s_idx;
+                    // a point listed twice in one element would arrive twice: count per listing (need counted listings)
+                    if (sp >= 0 && ok[sp]) D.pt_nw[i] = sp | (need[sp] << 24);
+                }
+            }
+            d->desc[CLS_S3D].upload(d->h_desc[CLS_S3D]);
+            fs->nww = AX_NWW;
+            fs->smem += (size_t)AX_NWW * NW_WARP_SMEM + 8;   // + 8: the stages start on a 16-byte boundary behind the tile
+            d->nw_cnt.alloc(ns);
+            d->nw_cnt.zero();
+            std::vector<int> q((size_t)n_plain, -1);
+            d->nw_queue.upload(q);
+            d->nw_ctl.alloc(4);
+            d->nw_ctl.zero();
+            d->s_row_point_sp.upload(srp_sp);
+            d->s_row_start_sp.upload(srs_sp);
+            d->s_tab_sp = d->s_tab;
+            d->s_tab_sp.row_point = d->s_row_point_sp.p;
+            d->s_tab_sp.row_start = d->s_row_start_sp.p;
+            d->s_tab_sp.nrows = (int)srp_sp.size();
+        }
     }
     d->geom.upload(geom);
     d->coef.upload(coef);
@@ -776,7 +866,8 @@ struct TimerScope {
 
 static inline int nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
 
-static void update_newmark(ax3d_domain *d, double dt) {
+// special_only: the plain solid points were already advanced by the previous step's element kernel (fused.cuh)
+static void update_newmark(ax3d_domain *d, double dt, bool special_only = false) {
     TimerScope ts(d, 0);
     const double half_dt = 0.5 * dt, half_dt_dt = half_dt * dt;   // SolidPoint.cpp:31-32 (double, then cast to Real)
     if (!d->h_m3d_s.empty()) {
@@ -789,9 +880,10 @@ static void update_newmark(ax3d_domain *d, double dt) {
                                                                               d->f_field[AX3D_STIFF].p);
         d->launches++;
     }
-    if (d->s_tab.nrows) {
-        k_newmark_solid<<<nblk(d->s_tab.nrows, 256), 256, 0, d->stream>>>(d->s_tab, d->s_field[0].p, d->s_field[1].p, d->s_field[2].p,
-                                                                         d->s_field[3].p, (float)half_dt, (float)dt, (float)half_dt_dt);
+    const PointTab &stab = special_only ? d->s_tab_sp : d->s_tab;
+    if (stab.nrows) {
+        k_newmark_solid<<<nblk(stab.nrows, 256), 256, 0, d->stream>>>(stab, d->s_field[0].p, d->s_field[1].p, d->s_field[2].p,
+                                                                     d->s_field[3].p, (float)half_dt, (float)dt, (float)half_dt_dt);
         d->launches++;
     }
     if (d->f_tab.nrows) {
@@ -842,28 +934,52 @@ static bool fused_specialised(bool fluid, int N) {
 }
 
 // 512 threads = 128 registers/thread.  Measured on B200 (cfg2, elements family): 416 -> 0.270 ms, 448 -> 0.266, 512 -> 0.259,
-// 640 (96 regs) -> 0.289, 768 (80 regs) -> 0.310: the kernel is not occupancy-limited.
-static int fused_nt() { return 512; }
+// 640 (96 regs) -> 0.289, 768 (80 regs) -> 0.310: the kernel is not occupancy-limited.  With Newmark warps the CTA is
+// 448 compute + 64 Newmark threads.
+static int fused_nt(const FusedLaunch &f) { return 512; (void)f; }
 
 typedef void (*fused_kernel_t)(const ElemDesc *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
-                               float *, const float2 *, float2 *, int, int, unsigned *);
+                               float *, const float2 *, float2 *, int, int, int, unsigned *, const NwArgs);
 
 static fused_kernel_t fused_kernel(const FusedLaunch &f) {
     const bool fluid = f.cls == CLS_F3D;
-#define X(F, NCT) if (fluid == F && f.nct == NCT) return k_elem3d_fused<F, 512, NCT>;
+#define X(F, NCT) if (fluid == F && f.nct == NCT && f.nww == 0) return k_elem3d_fused<F, 512, 0, NCT>;
     AX_FUSED_SPECIALISATIONS(X)
 #undef X
     if (f.nct != 0) fail("ax3d::fused || no specialised kernel for this launch");
-    return fluid ? k_elem3d_fused<true, 512, 0> : k_elem3d_fused<false, 512, 0>;
+    if (fluid) return k_elem3d_fused<true, 512, 0, 0>;
+    return f.nww ? k_elem3d_fused<false, 512 - 32 * AX_NWW, AX_NWW, 0> : k_elem3d_fused<false, 512, 0, 0>;
 }
 
-static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which) {
+// nw_on: this launch also advances the plain solid points to the next step (its dt is the step being integrated)
+static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool nw_on, double dt) {
     const int c = f.cls;
     const bool fluid = c == CLS_F3D;
-    fused_kernel(f)<<<f.grid, fused_nt(), f.smem, d->stream>>>(
+    NwArgs nw;
+    memset(&nw, 0, sizeof(nw));
+    if (f.nww > 0 && nw_on) {
+        const double half_dt = 0.5 * dt, half_dt_dt = half_dt * dt;
+        nw.on = 1;
+        nw.n_plain = d->n_plain;
+        nw.cnt = d->nw_cnt.p;
+        nw.queue = d->nw_queue.p;
+        nw.ctl = d->nw_ctl.p;
+        nw.off = d->s_off.p;
+        nw.nu = d->s_nu.p;
+        nw.nr = d->s_nr.p;
+        nw.invmass = d->s_invmass.p;
+        nw.displ = d->s_field[AX3D_DISPL].p;
+        nw.veloc = d->s_field[AX3D_VELOC].p;
+        nw.accel = d->s_field[AX3D_ACCEL].p;
+        nw.stiff = d->s_field[AX3D_STIFF].p;
+        nw.half_dt = (float)half_dt;
+        nw.dt = (float)dt;
+        nw.half_dt_dt = (float)half_dt_dt;
+    }
+    fused_kernel(f)<<<f.grid, fused_nt(f), f.smem, d->stream>>>(
         d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
         fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
-        f.u_cap, f.tw_cap, d->fused_work.p + 2 * which);
+        f.u_cap, f.tw_cap, f.z_cap, d->fused_work.p + 2 * which, nw);
 }
 
 static void set_fused_smem(int device, const FusedLaunch &f) {
@@ -873,7 +989,7 @@ static void set_fused_smem(int device, const FusedLaunch &f) {
     CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1536));
 }
 
-static void compute_stiff(ax3d_domain *d) {
+static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0) {
     TimerScope ts(d, 1);
     const int TB = AX_TILE * AX_NPE;
     if (d->n_work[CLS_S1D]) {
@@ -908,7 +1024,7 @@ static void compute_stiff(ax3d_domain *d) {
         d->launches += 3;
     }
     for (size_t k = 0; k < d->fused.size(); ++k) {
-        launch_fused(d, d->fused[k], (int)k);
+        launch_fused(d, d->fused[k], (int)k, nw_on, dt);
         d->launches++;
     }
     CK(cudaGetLastError());
@@ -1010,8 +1126,10 @@ int ax3d_destroy(ax3d_domain *d) {
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->rec_host) cudaFreeHost(d->rec_host);
     if (d->stf_pinned) cudaFreeHost(d->stf_pinned);
-    if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
-    if (d->graph) cudaGraphDestroy(d->graph);
+    for (int v = 0; v < 4; ++v) {
+        if (d->graph_exec[v]) cudaGraphExecDestroy(d->graph_exec[v]);
+        if (d->graph[v]) cudaGraphDestroy(d->graph[v]);
+    }
     delete d;
     API_END
 }
@@ -1191,6 +1309,11 @@ int ax3d_check_stability(ax3d_domain *d, int *stable) {
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, d->bad_flag.p, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream));
+    if (d->n_plain > 0) {
+        unsigned ctl[4] = {0, 0, 0, 0};
+        CK(cudaMemcpy(ctl, d->nw_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost));
+        if (ctl[3]) fail("Domain::updateNewmark || in-kernel Newmark queue timed out (internal bookkeeping error)");
+    }
     *stable = bad ? 0 : 1;
     API_END
 }
@@ -1208,18 +1331,20 @@ int ax3d_reset_zero(ax3d_domain *d) {
     API_END
 }
 
-static void step_body(ax3d_domain *d, double dt) {
-    update_newmark(d, dt);
+// One iteration of Newmark::solve (Newmark.cpp:47-93).  special_only: the plain solid points already hold this step's
+// state (advanced under the previous step's element kernel); nw_on: this step's element kernel advances them to the next.
+static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool nw_on = false) {
+    update_newmark(d, dt, special_only);
     launch_source(d);
-    compute_stiff(d);
+    compute_stiff(d, nw_on, dt);
     couple_solid_fluid(d);
 }
 
-static long long count_step_launches(ax3d_domain *d) {
+static long long count_step_launches(ax3d_domain *d, bool special_only) {
     long long n = 0;
     n += !d->h_m3d_s.empty();
     n += !d->h_m3d_f.empty();
-    n += d->s_tab.nrows > 0;
+    n += (special_only ? d->s_tab_sp.nrows : d->s_tab.nrows) > 0;
     n += d->f_tab.nrows > 0;
     n += d->n_src > 0;
     n += d->n_work[CLS_S1D] > 0;
@@ -1233,27 +1358,38 @@ static long long count_step_launches(ax3d_domain *d) {
 
 static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
     const bool graph_ok = d->use_graph && !d->timers && (d->nproc <= 1 || d->neigh_rank.empty());
-    if (graph_ok && (!d->graph_exec || d->graph_dt != dt)) {
-        if (d->graph_exec) { cudaGraphExecDestroy(d->graph_exec); d->graph_exec = nullptr; }
-        if (d->graph) { cudaGraphDestroy(d->graph); d->graph = nullptr; }
-        const long long before = d->launches;
-        CK(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
-        step_body(d, dt);
-        CK(cudaStreamEndCapture(d->stream, &d->graph));
-        CK(cudaGraphInstantiate(&d->graph_exec, d->graph, 0));
-        d->launches = before;   // capture enqueues nothing
+    if (graph_ok && d->graph_dt != dt) {
+        for (int v = 0; v < 4; ++v) {
+            if (d->graph_exec[v]) { cudaGraphExecDestroy(d->graph_exec[v]); d->graph_exec[v] = nullptr; }
+            if (d->graph[v]) { cudaGraphDestroy(d->graph[v]); d->graph[v] = nullptr; }
+        }
         d->graph_dt = dt;
     }
+    const bool can_nw = d->n_plain > 0;
     for (int i = 0; i < nsteps; ++i) {
+        // every step but the last of this call advances the plain points to the next step under its element kernel,
+        // so that the state after the call is exactly the reference's (all points at step i, stiff = this step's force)
+        const bool special_only = d->plain_advanced;
+        const bool nw_on = can_nw && i + 1 < nsteps;
         if (d->n_src) push_stf(d, stf ? stf[i] : 0.f);
         if (graph_ok) {
-            CK(cudaGraphLaunch(d->graph_exec, d->stream));
-            d->launches += count_step_launches(d);
+            const int v = (special_only ? 2 : 0) + (nw_on ? 1 : 0);
+            if (!d->graph_exec[v]) {
+                const long long before = d->launches;
+                CK(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
+                step_body(d, dt, special_only, nw_on);
+                CK(cudaStreamEndCapture(d->stream, &d->graph[v]));
+                CK(cudaGraphInstantiate(&d->graph_exec[v], d->graph[v], 0));
+                d->launches = before;   // capture enqueues nothing
+            }
+            CK(cudaGraphLaunch(d->graph_exec[v], d->stream));
+            d->launches += count_step_launches(d, special_only);
         } else {
-            step_body(d, dt);
+            step_body(d, dt, special_only, nw_on);
             assemble_stiff(d, -1);
             assemble_stiff(d, 1);
         }
+        d->plain_advanced = nw_on;
     }
 }
 

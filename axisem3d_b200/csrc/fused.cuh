@@ -33,6 +33,16 @@ __device__ __forceinline__ void cp_async8(float2 *dst_smem, const float2 *src, b
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
+
+// ---------------------------------------------------------------- compute-warp barrier
+// With in-kernel Newmark warps (NWW > 0) the CTA has NT compute threads + 32 * NWW Newmark threads; the compute warps
+// synchronise among themselves on named barrier 1 and the Newmark warps never join a CTA-wide barrier.
+template <int NT, int NWW>
+__device__ __forceinline__ void cta_sync() {
+    if constexpr (NWW > 0) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    else __syncthreads();
+}
+
 // ---------------------------------------------------------------- one FFT stage over all columns
 // DIF (c2r, SIGN = +1): butterfly, then twiddle T[j][p].  DIT (r2c, SIGN = -1): conj twiddle, then butterfly.
 // NCT > 0: N = NCT and L = LCT are compile-time.
@@ -95,24 +105,24 @@ __device__ __forceinline__ void fused_stage_dispatch(int R, float2 *z, int N, in
 }
 
 // compile-time plan: stage S of length-NCT transform has block length L; TWOFF = offset of its twiddle table
-template <int NT, int NCOLS, int NCT, int S, int L, int TWOFF>
+template <int NT, int NWW, int NCOLS, int NCT, int S, int L, int TWOFF>
 struct CtFft {
     static __device__ __forceinline__ void inverse(float2 *Z, const float2 *TW, int tid) {
         if constexpr (S < choose_radices_ct(NCT).n) {
             constexpr int R = choose_radices_ct(NCT).r[S];
             constexpr int Ls = L / R;
             fused_stage<R, +1, true, NT, NCOLS, NCT, L>(Z, NCT, L, TW + TWOFF, tid);
-            __syncthreads();
-            CtFft<NT, NCOLS, NCT, S + 1, Ls, TWOFF + (Ls > 1 ? L : 0)>::inverse(Z, TW, tid);
+            cta_sync<NT, NWW>();
+            CtFft<NT, NWW, NCOLS, NCT, S + 1, Ls, TWOFF + (Ls > 1 ? L : 0)>::inverse(Z, TW, tid);
         }
     }
     static __device__ __forceinline__ void forward(float2 *Z, const float2 *TW, int tid) {
         if constexpr (S < choose_radices_ct(NCT).n) {
             constexpr int R = choose_radices_ct(NCT).r[S];
             constexpr int Ls = L / R;
-            CtFft<NT, NCOLS, NCT, S + 1, Ls, TWOFF + (Ls > 1 ? L : 0)>::forward(Z, TW, tid);
+            CtFft<NT, NWW, NCOLS, NCT, S + 1, Ls, TWOFF + (Ls > 1 ? L : 0)>::forward(Z, TW, tid);
             fused_stage<R, -1, false, NT, NCOLS, NCT, L>(Z, NCT, L, TW + TWOFF, tid);
-            __syncthreads();
+            cta_sync<NT, NWW>();
         }
     }
 };
@@ -231,7 +241,7 @@ __device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, co
 // E, P: descriptor and plan of this element (shared memory).  On entry the first gather tile of this element is in
 // flight (cp.async); `after_first_sync` runs behind the first barrier (every thread has left the previous element: its
 // descriptor slot is free), `after_grad` once U is dead (it starts the next element's gather).
-template <bool FLUID, int NT, int NCT, typename GatherFn, typename AfterSyncFn, typename AfterGradFn>
+template <bool FLUID, int NT, int NWW, int NCT, typename GatherFn, typename AfterSyncFn, typename AfterGradFn>
 __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const ElemDesc &E, const FftPlan &P, int tid,
                                               GatherFn gather, AfterSyncFn after_first_sync, AfterGradFn after_grad) {
     constexpr int NC = FLUID ? 1 : 3, NPAIR = FLUID ? 2 : 3;
@@ -253,13 +263,13 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
     for (int a0 = 0; a0 < M; a0 += Mt) {
         const int mt = min(Mt, M - a0);
         if (a0) {
-            __syncthreads();
+            cta_sync<NT, NWW>();
             gather(E, a0, mt);
         }
         cp_async_wait_all();
         if (a0 == 0 && t == 0)   // Im(u) of mode 0 is not used (Gradient.cpp:209-224): this thread copied these entries
             for (int row = hw; row < US; row += NHW) U[row].y = 0.f;
-        __syncthreads();
+        cta_sync<NT, NWW>();
         if (a0 == 0) after_first_sync();
 #pragma unroll
         for (int pp = 0; pp < PP; ++pp) {
@@ -300,19 +310,19 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
             }
         }
     }
-    __syncthreads();   // Z complete, U dead
+    cta_sync<NT, NWW>();   // Z complete, U dead
     after_grad();      // @phase next-element gather issue
 
     // ------------------------------------------------------------ c2r (SolverFFTW_N6::computeC2R, unnormalised, sign +)   @phase c2r
     if constexpr (NCT != 0) {
-        CtFft<NT, NCOLS, NCT, 0, NCT, 0>::inverse(Z, TW, tid);
+        CtFft<NT, NWW, NCOLS, NCT, 0, NCT, 0>::inverse(Z, TW, tid);
     } else {
         int L = N;
         for (int s = 0; s < P.nstages; ++s) {
             const int R = P.radix[s];
             fused_stage_dispatch<+1, true, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
             L /= R;
-            __syncthreads();
+            cta_sync<NT, NWW>();
         }
     }
 
@@ -370,18 +380,18 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
             }
         }
     }
-    __syncthreads();
+    cta_sync<NT, NWW>();
 
     // ------------------------------------------------------------ r2c (computeR2C; the 1/Nr is applied at load below)   @phase r2c
     if constexpr (NCT != 0) {
-        CtFft<NT, NCOLS, NCT, 0, NCT, 0>::forward(Z, TW, tid);
+        CtFft<NT, NWW, NCOLS, NCT, 0, NCT, 0>::forward(Z, TW, tid);
     } else {
         int L = 1;
         for (int s = P.nstages - 1; s >= 0; --s) {
             const int R = P.radix[s];
             L *= R;
             fused_stage_dispatch<-1, false, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
-            __syncthreads();
+            cta_sync<NT, NWW>();
         }
     }
 
@@ -431,7 +441,7 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
                 }
             }
         }
-        __syncthreads();
+        cta_sync<NT, NWW>();
         // tensor-product half + Point::gatherStiffFromElement (SolidPoint.cpp:197-209)   @phase quad-post + scatter
 #pragma unroll
         for (int pp = 0; pp < PP; ++pp) {
@@ -468,99 +478,294 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
     // the barrier after cp_async_wait_all at the top of the next element separates these reads of Z from its grad
 }
 
+// ---------------------------------------------------------------- in-kernel Newmark   @phase newmark warps
+// The point update (SolidPoint::updateNewmark, SolidPoint.cpp:23-38) is HBM-bound, the element pipeline above is
+// latency-bound and leaves HBM ~93 % idle.  So the update of step n+1 runs *under* the element kernel of step n: a "plain"
+// solid point (pure solid, Mass1D, not axial, not on a halo, not in a source element, touched by fused elements only) can
+// be advanced as soon as the last element that touches it has scattered its force.  Compute warps count arrivals per point
+// (nw.cnt) and push completed points into a ready queue; NWW specialised warps per CTA (and, once the element queue is
+// empty, the compute warps too) pop points, fetch stiff/accel/veloc/displ with TMA bulk loads into a double-buffered
+// shared-memory stage (no registers held across the HBM latency), update, and store with plain coalesced stores.
+// All other points are advanced by k_newmark_* at the start of the next step, as before.
+struct NwArgs {
+    int on;                    // 0: this launch does no in-kernel Newmark (single step, last step of a run, verb-wise calls)
+    int n_plain;               // queue length = number of plain points
+    int *cnt;                  // [ns] arrivals per point (consumer resets to 0)
+    int *queue;                // [n_plain] ready queue, -1 = empty (consumer resets)
+    unsigned *ctl;             // [0] tail (producers), [1] head (consumers), [2] finished warps; last warp re-arms
+    const unsigned *off;       // per solid point: block offset (float2 units), Nu, Nr, inverse mass
+    const int *nu;
+    const int *nr;
+    const float *invmass;
+    float2 *displ, *veloc, *accel, *stiff;
+    float half_dt, dt, half_dt_dt;
+};
+
+#define AX_NWW 2               // Newmark warps per CTA of the solid launch (compute threads: 512 - 32 * AX_NWW)
+#define NW_CHR 160             // rows (complex entries) per chunk
+#define NW_CHS (NW_CHR + 2)    // stage row capacity: the 16-byte aligned superset of a chunk
+#define NW_NSTAGE 2
+#define NW_WARP_SMEM (NW_NSTAGE * 4 * NW_CHS * 8)   // bytes of stage buffers per consumer warp
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// 1D TMA bulk load global -> shared, completion on an mbarrier (bytes and both addresses are multiples of 16)
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// One consumer warp.  stage: NW_WARP_SMEM bytes of shared memory owned by this warp; bar: NW_NSTAGE mbarriers owned by it.
+__device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, unsigned long long *bar, int lane) {
+    int cur_p = -1, cur_r = 0, cur_total = 0;          // point being chunked (warp-uniform)
+    unsigned cur_off = 0;
+    int q_p[NW_NSTAGE], q_r0[NW_NSTAGE], q_n[NW_NSTAGE], q_skew[NW_NSTAGE];
+    unsigned q_g0[NW_NSTAGE], q_par[NW_NSTAGE];
+    bool q_ok[NW_NSTAGE];
+#pragma unroll
+    for (int s = 0; s < NW_NSTAGE; ++s) { q_ok[s] = false; q_par[s] = 0u; }
+
+    // next chunk -> slot s, loads issued by lane 0; false when the queue is exhausted
+    auto fetch = [&](int s) -> bool {
+        if (cur_p < 0 || cur_r >= cur_total) {
+            int p = -1;
+            if (lane == 0) {
+                const unsigned slot = atomicAdd(&nw.ctl[1], 1u);
+                if (slot < (unsigned)nw.n_plain) {
+                    volatile int *qs = nw.queue + slot;
+                    unsigned spins = 0;
+                    while ((p = *qs) < 0) {
+                        __nanosleep(256);
+                        if (++spins > (1u << 22)) { nw.ctl[3] = 1u; break; }   // ~1 s: never hang the GPU on a bookkeeping error
+                    }
+                    if (p < 0) { p = -1; }
+                    else {
+                    __threadfence();                       // acquire: the forces of every element touching p are visible
+                    asm volatile("fence.proxy.async;\n" ::: "memory");   // ... also to the TMA loads below
+                    *qs = -1;                              // re-arm the slot and the arrival counter for the next launch
+                    nw.cnt[p] = 0;
+                    }
+                }
+            }
+            p = __shfl_sync(0xffffffffu, p, 0);
+            if (p < 0) return false;
+            cur_p = p;
+            cur_r = 0;
+            cur_total = 3 * (nw.nu[p] + 1);
+            cur_off = nw.off[p];
+        }
+        const int n = min(NW_CHR, cur_total - cur_r);
+        const unsigned g0 = cur_off + (unsigned)cur_r;     // first entry of the chunk (float2 index)
+        const unsigned a0 = g0 & ~1u;                      // 16-byte aligned superset [a0, a1)
+        const unsigned a1 = (g0 + (unsigned)n + 1u) & ~1u;
+        q_p[s] = cur_p; q_r0[s] = cur_r; q_n[s] = n; q_g0[s] = g0; q_skew[s] = (int)(g0 - a0); q_ok[s] = true;
+        cur_r += n;
+        if (lane == 0) {
+            const unsigned bytes = (a1 - a0) * 8u;
+            float2 *st = stage + s * 4 * NW_CHS;
+            mbar_expect_tx(bar + s, 4u * bytes);
+            bulk_load(st + 0 * NW_CHS, nw.stiff + a0, bytes, bar + s);
+            bulk_load(st + 1 * NW_CHS, nw.accel + a0, bytes, bar + s);
+            bulk_load(st + 2 * NW_CHS, nw.veloc + a0, bytes, bar + s);
+            bulk_load(st + 3 * NW_CHS, nw.displ + a0, bytes, bar + s);
+        }
+        return true;
+    };
+
+    bool more = true;
+#pragma unroll
+    for (int s = 0; s < NW_NSTAGE; ++s)
+        if (more) more = fetch(s);
+    for (;;) {
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < NW_NSTAGE; ++s) {   // unrolled: the q_* arrays stay in registers
+            if (!q_ok[s]) continue;
+            any = true;
+            mbar_wait(bar + s, q_par[s]);
+            q_par[s] ^= 1u;
+            const int p = q_p[s];
+            const int nu = nw.nu[p], stp = nu + 1;
+            const bool nyq = (nw.nr[p] & 1) == 0;
+            const float im = nw.invmass[p];
+            const float2 *st = stage + s * 4 * NW_CHS + q_skew[s];
+            for (int i = lane; i < q_n[s]; i += 32) {
+                const int row = q_r0[s] + i;
+                const int c = row >= 2 * stp ? 2 : (row >= stp ? 1 : 0);
+                const int alpha = row - c * stp;
+                float2 f = st[i];
+                const float2 a_old = st[NW_CHS + i];
+                float2 v = st[2 * NW_CHS + i], u = st[3 * NW_CHS + i];
+                // SolidPoint::maskField for a non-axial point (SolidPoint.cpp:216-238), M^-1, mask again
+                if (alpha == 0) f.y = 0.f;
+                if (nyq && alpha == nu) f = czero();
+                f = make_float2(f.x * im, f.y * im);
+                if (alpha == 0) f.y = 0.f;
+                if (nyq && alpha == nu) f = czero();
+                newmark_entry(f, a_old, v, u, nw.half_dt, nw.dt, nw.half_dt_dt);
+                const size_t g = (size_t)q_g0[s] + i;
+                nw.veloc[g] = v;
+                nw.accel[g] = f;
+                nw.displ[g] = u;
+                nw.stiff[g] = czero();
+            }
+            __syncwarp();            // every lane has read the stage before the next bulk load overwrites it
+            q_ok[s] = false;
+            if (more) more = fetch(s);
+        }
+        if (!any) break;
+    }
+}
+
 // ---------------------------------------------------------------- the kernel   @phase kernel loop
-// grid: persistent, one CTA per SM; block NT threads.  work[0] = next element index (starts at gridDim.x),
-// work[1] = number of CTAs that have finished; the last one re-arms both for the next launch (graph replay).
-template <bool FLUID, int NT, int NCT1>
-__global__ void __launch_bounds__(NT, (512 / NT) > 0 ? (512 / NT) : 1)
+// grid: persistent, one CTA per SM; block NT compute threads (+ 32 * NWW Newmark threads).  work[0] = next element index
+// (starts at gridDim.x), work[1] = number of warps that have finished; the last one re-arms the counters for the next
+// launch (graph replay).
+template <bool FLUID, int NT, int NWW, int NCT1>
+__global__ void __launch_bounds__(NT + 32 * NWW, 1)
     k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
                    const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
                    const float *__restrict__ attpar, float *__restrict__ attstate, const float2 *__restrict__ displ,
-                   float2 *__restrict__ stiff, int u_cap, int tw_cap, unsigned *__restrict__ work) {
+                   float2 *__restrict__ stiff, int u_cap, int tw_cap, int z_cap, unsigned *__restrict__ work, const NwArgs nw) {
     constexpr int NC = FLUID ? 1 : 3;
     constexpr int US = NC * AX_NPE;
     constexpr int NHW = NT / 16;
+    constexpr int NWARP = NT / 32 + NWW;
     constexpr int DESC_W = (int)(sizeof(ElemDesc) / sizeof(int)), PLAN_W = (int)(sizeof(FftPlan) / sizeof(int));
-    static_assert(DESC_W <= NT && 64 + PLAN_W <= NT, "descriptor loaders need NT >= descriptor words");
-    extern __shared__ float2 smem[];
+    static_assert(DESC_W <= NT && DESC_W + PLAN_W <= NT, "descriptor loaders need NT >= descriptor words");
+    extern __shared__ __align__(16) float2 smem[];
     __shared__ ElemDesc sE[2];
     __shared__ FftPlan sP[2];
     __shared__ int sIdx[3];   // ring of element indices: current, next, next-next
+    __shared__ unsigned long long sBar[NWARP][NW_NSTAGE];
     const int tid = threadIdx.x;
-    const int hw = tid >> 4, t = tid & 15;
-    FusedCtx<FLUID> cx{geom, coef, attpar, attstate, displ, stiff, smem, smem + u_cap, smem + u_cap + tw_cap};
-    float2 *const U = cx.U;
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool nw_on = NWW > 0 && nw.on != 0;
 
-    // descriptor + plan of element el -> slot s (plain loads; visible after the next barrier)
-    auto load_desc = [&](int s, int el) {
-        if (tid < DESC_W) reinterpret_cast<int *>(&sE[s])[tid] = reinterpret_cast<const int *>(elems + el)[tid];
-        if (tid >= 64 && tid < 64 + PLAN_W) {
-            const int pid = elems[el].plan_id;
-            reinterpret_cast<int *>(&sP[s])[tid - 64] = reinterpret_cast<const int *>(plans + pid)[tid - 64];
-        }
-    };
-    // Point::scatterDisplToElement (SolidPoint.cpp:175-195) for modes [a0, a0 + mt): half-warp per (component, point)
-    auto gather = [&](const ElemDesc &E, int a0, int mt) {
-        const unsigned u0 = (unsigned)__cvta_generic_to_shared(U + t * US);
-        for (int row = hw; row < US; row += NHW) {
-            const int c = row / AX_NPE, p = row - c * AX_NPE;
-            const float2 *src = displ + (size_t)E.pt_off[p] + (size_t)c * E.pt_stride[p] + a0 + t;
-            const int nlive = E.pt_nlive[p] - a0 - t;   // entries [0, nlive) of this lane's stride-16 sequence are live
-            unsigned dst = u0 + row * 8u;
-            for (int a = 0; a < mt - t; a += 16) {
-                const int sz = a < nlive ? 8 : 0;        // src-size 0: nothing is read, the 8 bytes are zero-filled
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(sz ? src + a : displ), "r"(sz) : "memory");
-                dst += 16u * US * 8u;
-            }
-        }
-    };
-
-    int e = blockIdx.x;
-    if (e < nelem) {
-        load_desc(0, e);
-        if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
-        __syncthreads();
-        gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1));
-        int tw_plan = -1;
-        for (int it = 0, k = 0; e < nelem; it ^= 1, k = (k == 2 ? 0 : k + 1)) {
-            const ElemDesc &E = sE[it];
-            const FftPlan &P = sP[it];
-            const int kn = k == 2 ? 0 : k + 1, knn = kn == 2 ? 0 : kn + 1;   // ring slots of the next two elements
-            if (tw_plan != E.plan_id) {   // TW is idle here: the FFT stages of the previous element are barrier-separated
-                for (int k = tid; k < P.stw_len; k += NT) cx.TW[k] = stwpool[P.stw_base + k];
-                tw_plan = E.plan_id;
-            }
-            // moduli of this element -> L2 while gather/grad/c2r run
-            {
-                const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
-                const float *cb = coef + E.coef_off;
-                const int nline = (ncoef * AX_NPE * E.nr + 31) / 32;
-                for (int k = tid; k < nline; k += NT) prefetch_l2(cb + (size_t)k * 32);
-            }
-            // next element: descriptor behind the first barrier, displacement (cp.async into the dead U) behind grad
-            auto after_first_sync = [&]() {
-                const int en = sIdx[kn];   // fetched during the previous element
-                if (en < nelem) load_desc(it ^ 1, en);
-            };
-            auto after_grad = [&]() {
-                if (tid == 0) sIdx[knn] = (int)atomicAdd(&work[0], 1u);   // needed one element from now: latency hidden
-                if (sIdx[kn] < nelem) {
-                    const ElemDesc &En = sE[it ^ 1];
-                    gather(En, 0, min(En.mt, En.nu + 1));
-                }
-            };
-            if (NCT1 != 0 && E.nr == NCT1) fused_element<FLUID, NT, NCT1>(cx, E, P, tid, gather, after_first_sync, after_grad);
-            else fused_element<FLUID, NT, 0>(cx, E, P, tid, gather, after_first_sync, after_grad);
-            e = sIdx[kn];
-        }
+    if (NWW > 0 && nw_on && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NW_NSTAGE; ++s) mbar_init(&sBar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    // re-arm the work counter once every CTA is done
-    if (tid == 0) {
+    __syncwarp();
+
+    if (tid < NT) {
+        const int hw = tid >> 4, t = tid & 15;
+        FusedCtx<FLUID> cx{geom, coef, attpar, attstate, displ, stiff, smem, smem + u_cap, smem + u_cap + tw_cap};
+        float2 *const U = cx.U;
+
+        // descriptor + plan of element el -> slot s (plain loads; visible after the next barrier)
+        auto load_desc = [&](int s, int el) {
+            if (tid < DESC_W) reinterpret_cast<int *>(&sE[s])[tid] = reinterpret_cast<const int *>(elems + el)[tid];
+            if (tid >= DESC_W && tid < DESC_W + PLAN_W) {
+                const int pid = elems[el].plan_id;
+                reinterpret_cast<int *>(&sP[s])[tid - DESC_W] = reinterpret_cast<const int *>(plans + pid)[tid - DESC_W];
+            }
+        };
+        // Point::scatterDisplToElement (SolidPoint.cpp:175-195) for modes [a0, a0 + mt): half-warp per (component, point)
+        auto gather = [&](const ElemDesc &E, int a0, int mt) {
+            const unsigned u0 = (unsigned)__cvta_generic_to_shared(U + t * US);
+            for (int row = hw; row < US; row += NHW) {
+                const int c = row / AX_NPE, p = row - c * AX_NPE;
+                const float2 *src = displ + (size_t)E.pt_off[p] + (size_t)c * E.pt_stride[p] + a0 + t;
+                const int nlive = E.pt_nlive[p] - a0 - t;   // entries [0, nlive) of this lane's stride-16 sequence are live
+                unsigned dst = u0 + row * 8u;
+                for (int a = 0; a < mt - t; a += 16) {
+                    const int sz = a < nlive ? 8 : 0;        // src-size 0: nothing is read, the 8 bytes are zero-filled
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(sz ? src + a : displ), "r"(sz) : "memory");
+                    dst += 16u * US * 8u;
+                }
+            }
+        };
+        // a point whose last element has scattered goes to the ready queue (threads 0..24, one per point of the element)
+        auto nw_arrive = [&](int code) {
+            if (code >= 0) {
+                const int p = code & 0xffffff, need = code >> 24;
+                __threadfence();   // release: the CTA's forces (ordered before this thread by the barrier) before the count
+                if (atomicAdd(&nw.cnt[p], 1) + 1 == need) {
+                    const unsigned slot = atomicAdd(&nw.ctl[0], 1u);
+                    __threadfence();
+                    atomicExch(&nw.queue[slot], p);
+                }
+            }
+        };
+
+        int e = blockIdx.x;
+        int nw_prev = -1;   // threads 0..24: pt_nw of the element whose scatter precedes the next barrier
+        if (e < nelem) {
+            load_desc(0, e);
+            if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
+            cta_sync<NT, NWW>();
+            gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1));
+            int tw_plan = -1;
+            for (int it = 0, k = 0; e < nelem; it ^= 1, k = (k == 2 ? 0 : k + 1)) {
+                const ElemDesc &E = sE[it];
+                const FftPlan &P = sP[it];
+                const int kn = k == 2 ? 0 : k + 1, knn = kn == 2 ? 0 : kn + 1;   // ring slots of the next two elements
+                if (tw_plan != E.plan_id) {   // TW is idle here: the FFT stages of the previous element are barrier-separated
+                    for (int k = tid; k < P.stw_len; k += NT) cx.TW[k] = stwpool[P.stw_base + k];
+                    tw_plan = E.plan_id;
+                }
+                // moduli of this element -> L2 while gather/grad/c2r run
+                {
+                    const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
+                    const float *cb = coef + E.coef_off;
+                    const int nline = (ncoef * AX_NPE * E.nr + 31) / 32;
+                    for (int k = tid; k < nline; k += NT) prefetch_l2(cb + (size_t)k * 32);
+                }
+                // next element: descriptor behind the first barrier, displacement (cp.async into the dead U) behind grad
+                auto after_first_sync = [&]() {
+                    if (nw_on && tid < AX_NPE) nw_arrive(nw_prev);   // the previous element's scatter is complete (barrier)
+                    const int en = sIdx[kn];   // fetched during the previous element
+                    if (en < nelem) load_desc(it ^ 1, en);
+                };
+                auto after_grad = [&]() {
+                    if (tid == 0) sIdx[knn] = (int)atomicAdd(&work[0], 1u);   // needed one element from now: latency hidden
+                    if (sIdx[kn] < nelem) {
+                        const ElemDesc &En = sE[it ^ 1];
+                        gather(En, 0, min(En.mt, En.nu + 1));
+                    }
+                };
+                if (NCT1 != 0 && E.nr == NCT1) fused_element<FLUID, NT, NWW, NCT1>(cx, E, P, tid, gather, after_first_sync, after_grad);
+                else fused_element<FLUID, NT, NWW, 0>(cx, E, P, tid, gather, after_first_sync, after_grad);
+                if (nw_on && tid < AX_NPE) nw_prev = E.pt_nw[tid];
+                e = sIdx[kn];
+            }
+            if (nw_on) {
+                cta_sync<NT, NWW>();   // last element's scatter complete; shared memory is free from here on
+                if (tid < AX_NPE) nw_arrive(nw_prev);
+            }
+        }
+        // element queue empty: the compute warps join the Newmark consumers (their stages live in the now idle tile memory)
+        if (nw_on && (warp + 1) * NW_WARP_SMEM <= (u_cap + tw_cap + z_cap) * (int)sizeof(float2)) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy tile traffic before the TMA writes
+            nw_consumer(nw, smem + warp * (NW_WARP_SMEM / 8), sBar[warp], lane);
+        }
+    } else if (NWW > 0) {
+        if (nw_on) nw_consumer(nw, smem + ((u_cap + tw_cap + z_cap + 1) & ~1) + (warp - NT / 32) * (NW_WARP_SMEM / 8), sBar[warp], lane);
+    }
+    // re-arm the counters once every warp of every CTA is done
+    __syncwarp();
+    if (lane == 0) {
         __threadfence();
         const unsigned done = atomicAdd(&work[1], 1u);
-        if (done == gridDim.x - 1) {
+        if (done == gridDim.x * NWARP - 1) {
             work[0] = gridDim.x;
             work[1] = 0u;
+            if (NWW > 0 && nw_on) { nw.ctl[0] = 0u; nw.ctl[1] = 0u; }
             __threadfence();
         }
     }

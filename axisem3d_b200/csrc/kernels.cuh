@@ -22,6 +22,7 @@ struct ElemDesc {
     unsigned pt_off[AX_NPE];   // offset of the point's block in the solid / fluid field array (float2 units)
     int pt_stride[AX_NPE];     // Nu_p + 1 (component stride inside the block)
     int pt_nlive[AX_NPE];      // rows [0, nlive) are gathered / scattered (Nu_p - nyq_p + 1)
+    int pt_nw[AX_NPE];         // in-kernel Newmark (fused.cuh): -1, or solid point index | (number of fused elements touching it << 24)
     long long geom_off;        // float  [5][25]: dsdxii, dsdeta, dzdxii, dzdeta, inv_s
     long long trig_off;        // float  [4][25]: sin t, cos t, sin 2t, cos 2t
     long long coef_off;        // float  1D: [ncoef][25]      3D: [ncoef][25][Nr] (digit-reversed phi)
@@ -64,6 +65,17 @@ __device__ __forceinline__ void mask_fluid(float2 &f, int alpha, int nu, bool ax
 }
 
 // ------------------------------------------------------------------------------------ Newmark
+// SolidPoint::updateNewmark (SolidPoint.cpp:31-36) on one complex entry, f = masked acceleration.  One definition for
+// the stand-alone kernels and the in-kernel Newmark warps of fused.cuh, so that both round identically.
+__device__ __forceinline__ void newmark_entry(float2 f, float2 a_old, float2 &v, float2 &u, float half_dt, float dt, float half_dt_dt) {
+    v.x = fmaf(half_dt, a_old.x + f.x, v.x);
+    v.y = fmaf(half_dt, a_old.y + f.y, v.y);
+    u.x += fmaf(dt, v.x, half_dt_dt * f.x);
+    u.y += fmaf(dt, v.y, half_dt_dt * f.y);
+}
+
+// pt.row_point / row_start describe the rows this launch covers (all points, or the "special" ones the in-kernel Newmark
+// warps do not own); everything else is indexed by point.
 __global__ void __launch_bounds__(256) k_newmark_solid(PointTab pt, float2 *__restrict__ displ, float2 *__restrict__ veloc,
                                                        float2 *__restrict__ accel, float2 *__restrict__ stiff,
                                                        float half_dt, float dt, float half_dt_dt) {
@@ -82,16 +94,13 @@ __global__ void __launch_bounds__(256) k_newmark_solid(PointTab pt, float2 *__re
     mask_solid(f, alpha, nu, axial, nyq);
     const float im = pt.invmass[p];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) f[c] = cscale(f[c], im);
+    for (int c = 0; c < 3; ++c) f[c] = make_float2(f[c].x * im, f[c].y * im);
     mask_solid(f, alpha, nu, axial, nyq);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const size_t i = base + (size_t)c * st;
         float2 a_old = accel[i], v = veloc[i], u = displ[i];
-        v.x += half_dt * (a_old.x + f[c].x);
-        v.y += half_dt * (a_old.y + f[c].y);
-        u.x += dt * v.x + half_dt_dt * f[c].x;
-        u.y += dt * v.y + half_dt_dt * f[c].y;
+        newmark_entry(f[c], a_old, v, u, half_dt, dt, half_dt_dt);
         veloc[i] = v;
         accel[i] = f[c];
         displ[i] = u;
@@ -116,13 +125,11 @@ __global__ void __launch_bounds__(256) k_newmark_fluid(PointTab pt, float2 *__re
     const bool axial = fl & 1, nyq = (pt.nr[p] & 1) == 0;
     float2 f = stiff[i];
     mask_fluid(f, alpha, nu, axial, nyq);
-    f = cscale(f, pt.invmass[p]);
+    const float im = pt.invmass[p];
+    f = make_float2(f.x * im, f.y * im);
     mask_fluid(f, alpha, nu, axial, nyq);
     float2 a_old = accel[i], v = veloc[i], u = displ[i];
-    v.x += half_dt * (a_old.x + f.x);
-    v.y += half_dt * (a_old.y + f.y);
-    u.x += dt * v.x + half_dt_dt * f.x;
-    u.y += dt * v.y + half_dt_dt * f.y;
+    newmark_entry(f, a_old, v, u, half_dt, dt, half_dt_dt);
     veloc[i] = v;
     accel[i] = f;
     displ[i] = u;
