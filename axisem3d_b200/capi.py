@@ -28,7 +28,8 @@ class Attenuation(C.Structure):
 
 
 def lib_path():
-    return _build.LIB
+    # AX3D_LIB: developer override to A/B a differently compiled build of the same source (profiles/microbench/variants)
+    return os.environ.get("AX3D_LIB") or _build.LIB
 
 
 def load(build_if_missing=True):

@@ -84,6 +84,8 @@ struct HSource {
     std::vector<float> force;
 };
 
+// 227 KB per CTA minus the fused kernel's static shared memory (descriptors, plans, mbarriers, arrival ring: < 3 KB)
+#define AX_FUSED_DYN_MAX (232448 - 3072)
 enum { CLS_S1D = 0, CLS_F1D = 1, CLS_S3D = 2, CLS_F3D = 3, NCLS = 4 };
 
 struct Chunk {   // a run of 3D elements of one class whose spectra fit the scratch ring together
@@ -148,6 +150,7 @@ struct ax3d_domain {
     DevBuf<unsigned> nw_ctl;        // tail, head, -, error flag
     DevBuf<int> s_row_point_sp, s_row_start_sp;
     PointTab s_tab_sp{};            // rows of the solid points the stand-alone Newmark kernel still owns
+    DevBuf<unsigned long long> nw_dbg;
     bool plain_advanced = false;    // the plain points already hold the state of the step about to start
     // ---- elements
     std::vector<ElemDesc> h_desc[NCLS];
@@ -574,7 +577,7 @@ static void finalize(ax3d_domain *d) {
                 // fused one-CTA-per-element kernel when the element's spectrum fits in shared memory (fused.cuh)
                 const int nc = fluid ? 1 : 3;
                 // dynamic smem of the one resident CTA per SM (the solid launch keeps room for its Newmark warps' stages)
-                const size_t lim[1] = {(size_t)231000 - ((!fluid && d->nw_allowed) ? (size_t)AX_NWW * NW_WARP_SMEM : 0)};
+                const size_t lim[1] = {(size_t)AX_FUSED_DYN_MAX - ((!fluid && d->nw_allowed) ? (size_t)AX_NWW * NW_WARP_SMEM + 8 : 0)};
                 D.plan_id = get_plan(d, N);
                 const int stw_len = d->h_plans[D.plan_id].stw_len;
                 const size_t fixed = ((size_t)npair * AX_NPE * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2);   // twiddle tables <= 2 N
@@ -685,6 +688,7 @@ static void finalize(ax3d_domain *d) {
             d->nw_queue.upload(q);
             d->nw_ctl.alloc(4);
             d->nw_ctl.zero();
+            if (getenv("AX3D_NW_DEBUG")) { d->nw_dbg.alloc(4 * 256); d->nw_dbg.zero(); }
             d->s_row_point_sp.upload(srp_sp);
             d->s_row_start_sp.upload(srs_sp);
             d->s_tab_sp = d->s_tab;
@@ -936,7 +940,7 @@ static bool fused_specialised(bool fluid, int N) {
 // 512 threads = 128 registers/thread.  Measured on B200 (cfg2, elements family): 416 -> 0.270 ms, 448 -> 0.266, 512 -> 0.259,
 // 640 (96 regs) -> 0.289, 768 (80 regs) -> 0.310: the kernel is not occupancy-limited.  With Newmark warps the CTA is
 // 448 compute + 64 Newmark threads.
-static int fused_nt(const FusedLaunch &f) { return 512; (void)f; }
+static int fused_nt(const FusedLaunch &f) { return f.nww ? AX_NW_NT + 32 * AX_NWW : 512; }
 
 typedef void (*fused_kernel_t)(const ElemDesc *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
                                float *, const float2 *, float2 *, int, int, int, unsigned *, const NwArgs);
@@ -948,7 +952,7 @@ static fused_kernel_t fused_kernel(const FusedLaunch &f) {
 #undef X
     if (f.nct != 0) fail("ax3d::fused || no specialised kernel for this launch");
     if (fluid) return k_elem3d_fused<true, 512, 0, 0>;
-    return f.nww ? k_elem3d_fused<false, 512 - 32 * AX_NWW, AX_NWW, 0> : k_elem3d_fused<false, 512, 0, 0>;
+    return f.nww ? k_elem3d_fused<false, AX_NW_NT, AX_NWW, 0> : k_elem3d_fused<false, 512, 0, 0>;
 }
 
 // nw_on: this launch also advances the plain solid points to the next step (its dt is the step being integrated)
@@ -976,6 +980,7 @@ static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool n
         nw.dt = (float)dt;
         nw.half_dt_dt = (float)half_dt_dt;
     }
+    if (!fluid && d->nw_dbg.p && nw.on) nw.dbg = d->nw_dbg.p;
     fused_kernel(f)<<<f.grid, fused_nt(f), f.smem, d->stream>>>(
         d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
         fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
@@ -984,9 +989,9 @@ static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool n
 
 static void set_fused_smem(int device, const FusedLaunch &f) {
     (void)device;
-    if (f.smem > 232448 - 1536) fail("ax3d::fused || shared-memory plan exceeds 227 KB");
+    if (f.smem > AX_FUSED_DYN_MAX) fail("ax3d::fused || shared-memory plan exceeds 227 KB");
     // several launches (and domains) may share one kernel instance: opt in to the maximum once
-    CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1536));
+    CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, AX_FUSED_DYN_MAX));
 }
 
 static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0) {
@@ -1313,6 +1318,19 @@ int ax3d_check_stability(ax3d_domain *d, int *stable) {
         unsigned ctl[4] = {0, 0, 0, 0};
         CK(cudaMemcpy(ctl, d->nw_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost));
         if (ctl[3]) fail("Domain::updateNewmark || in-kernel Newmark queue timed out (internal bookkeeping error)");
+    }
+    if (d->nw_dbg.p) {
+        std::vector<unsigned long long> h(4 * 256);
+        CK(cudaMemcpy(h.data(), d->nw_dbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull, e_max = 0, e_min = ~0ull, n_max = 0, c_max = 0;
+        for (int b = 0; b < d->num_sm && b < 256; ++b) {
+            if (!h[4 * b]) continue;
+            t0 = std::min(t0, h[4 * b]);
+            e_max = std::max(e_max, h[4 * b + 1]); e_min = std::min(e_min, h[4 * b + 1]);
+            n_max = std::max(n_max, h[4 * b + 2]); c_max = std::max(c_max, h[4 * b + 3]);
+        }
+        fprintf(stderr, "[nw-debug] elements done: first CTA %.1f us, last CTA %.1f us; newmark warps done %.1f us; compute warps done %.1f us (n_plain %d of %zu)\n",
+                (e_min - t0) * 1e-3, (e_max - t0) * 1e-3, (n_max - t0) * 1e-3, (c_max - t0) * 1e-3, d->n_plain, d->ns);
     }
     *stable = bad ? 0 : 1;
     API_END

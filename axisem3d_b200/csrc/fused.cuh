@@ -499,12 +499,20 @@ struct NwArgs {
     const float *invmass;
     float2 *displ, *veloc, *accel, *stiff;
     float half_dt, dt, half_dt_dt;
+    unsigned long long *dbg;   // optional [grid][4] globaltimer stamps: start, elements done, consumers done (AX3D_NW_DEBUG)
 };
 
-#define AX_NWW 2               // Newmark warps per CTA of the solid launch (compute threads: 512 - 32 * AX_NWW)
+#ifndef AX_NWW
+#define AX_NWW 2               // Newmark warps per CTA of the solid launch
+#endif
+#ifndef AX_NW_NT
+#define AX_NW_NT (512 - 32 * AX_NWW)   // compute threads of that launch
+#endif
 #define NW_CHR 160             // rows (complex entries) per chunk
 #define NW_CHS (NW_CHR + 2)    // stage row capacity: the 16-byte aligned superset of a chunk
-#define NW_NSTAGE 2
+#ifndef NW_NSTAGE
+#define NW_NSTAGE 3
+#endif
 #define NW_WARP_SMEM (NW_NSTAGE * 4 * NW_CHS * 8)   // bytes of stage buffers per consumer warp
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -529,7 +537,10 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, unsig
 }
 
 // One consumer warp.  stage: NW_WARP_SMEM bytes of shared memory owned by this warp; bar: NW_NSTAGE mbarriers owned by it.
-__device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, unsigned long long *bar, int lane) {
+// service(): called by the whole warp whenever it would otherwise wait (Newmark warp 0 uses it to post the arrivals of
+// the elements its CTA has finished; a no-op elsewhere).
+template <typename ServiceFn>
+__device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, unsigned long long *bar, int lane, ServiceFn service) {
     int cur_p = -1, cur_r = 0, cur_total = 0;          // point being chunked (warp-uniform)
     unsigned cur_off = 0;
     int q_p[NW_NSTAGE], q_r0[NW_NSTAGE], q_n[NW_NSTAGE], q_skew[NW_NSTAGE];
@@ -542,26 +553,29 @@ __device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, uns
     auto fetch = [&](int s) -> bool {
         if (cur_p < 0 || cur_r >= cur_total) {
             int p = -1;
-            if (lane == 0) {
-                const unsigned slot = atomicAdd(&nw.ctl[1], 1u);
-                if (slot < (unsigned)nw.n_plain) {
-                    volatile int *qs = nw.queue + slot;
-                    unsigned spins = 0;
-                    while ((p = *qs) < 0) {
-                        __nanosleep(256);
-                        if (++spins > (1u << 22)) { nw.ctl[3] = 1u; break; }   // ~1 s: never hang the GPU on a bookkeeping error
-                    }
-                    if (p < 0) { p = -1; }
-                    else {
-                    __threadfence();                       // acquire: the forces of every element touching p are visible
-                    asm volatile("fence.proxy.async;\n" ::: "memory");   // ... also to the TMA loads below
-                    *qs = -1;                              // re-arm the slot and the arrival counter for the next launch
-                    nw.cnt[p] = 0;
-                    }
+            unsigned slot = 0;
+            if (lane == 0) slot = atomicAdd(&nw.ctl[1], 1u);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot >= (unsigned)nw.n_plain) return false;
+            volatile int *qs = nw.queue + slot;
+            for (unsigned spins = 0;; ++spins) {          // warp-wide wait for the producer of this slot
+                if (lane == 0) p = *qs;
+                p = __shfl_sync(0xffffffffu, p, 0);
+                if (p >= 0) break;
+                service();
+                __nanosleep(200);
+                if (spins > (1u << 22)) {                 // ~1 s: never hang the GPU on a bookkeeping error
+                    if (lane == 0) nw.ctl[3] = 1u;
+                    return false;
                 }
             }
-            p = __shfl_sync(0xffffffffu, p, 0);
-            if (p < 0) return false;
+            if (lane == 0) {
+                __threadfence();                           // acquire: the forces of every element touching p are visible
+                asm volatile("fence.proxy.async;\n" ::: "memory");   // ... also to the TMA loads below
+                *qs = -1;                                  // re-arm the slot and the arrival counter for the next launch
+                nw.cnt[p] = 0;
+            }
+            __syncwarp();
             cur_p = p;
             cur_r = 0;
             cur_total = 3 * (nw.nu[p] + 1);
@@ -595,6 +609,7 @@ __device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, uns
         for (int s = 0; s < NW_NSTAGE; ++s) {   // unrolled: the q_* arrays stay in registers
             if (!q_ok[s]) continue;
             any = true;
+            service();
             mbar_wait(bar + s, q_par[s]);
             q_par[s] ^= 1u;
             const int p = q_p[s];
@@ -651,6 +666,9 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     __shared__ FftPlan sP[2];
     __shared__ int sIdx[3];   // ring of element indices: current, next, next-next
     __shared__ unsigned long long sBar[NWARP][NW_NSTAGE];
+    __shared__ int sArrCode[4][AX_NPE];   // ring: pt_nw codes of the elements whose scatter is complete ...
+    __shared__ volatile int sArrHead;     // ... up to this count (written by compute thread 0 behind a barrier)
+    __shared__ volatile int sCtaDone;     // the compute warps have handed over their last element
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const bool nw_on = NWW > 0 && nw.on != 0;
@@ -660,7 +678,16 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
         for (int s = 0; s < NW_NSTAGE; ++s) mbar_init(&sBar[warp][s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    __syncwarp();
+    if (tid == 0) { sArrHead = 0; sCtaDone = 0; }
+    auto stamp = [&](int k) {
+        if (nw.dbg) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            nw.dbg[blockIdx.x * 4 + k] = t;
+        }
+    };
+    if (tid == 0) stamp(0);
+    __syncthreads();   // the only CTA-wide barrier: roles split below
 
     if (tid < NT) {
         const int hw = tid >> 4, t = tid & 15;
@@ -690,21 +717,8 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                 }
             }
         };
-        // a point whose last element has scattered goes to the ready queue (threads 0..24, one per point of the element)
-        auto nw_arrive = [&](int code) {
-            if (code >= 0) {
-                const int p = code & 0xffffff, need = code >> 24;
-                __threadfence();   // release: the CTA's forces (ordered before this thread by the barrier) before the count
-                if (atomicAdd(&nw.cnt[p], 1) + 1 == need) {
-                    const unsigned slot = atomicAdd(&nw.ctl[0], 1u);
-                    __threadfence();
-                    atomicExch(&nw.queue[slot], p);
-                }
-            }
-        };
-
         int e = blockIdx.x;
-        int nw_prev = -1;   // threads 0..24: pt_nw of the element whose scatter precedes the next barrier
+        int n_done = 0;     // elements of this CTA whose scatter has been issued (their codes are in the ring)
         if (e < nelem) {
             load_desc(0, e);
             if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
@@ -728,7 +742,10 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                 }
                 // next element: descriptor behind the first barrier, displacement (cp.async into the dead U) behind grad
                 auto after_first_sync = [&]() {
-                    if (nw_on && tid < AX_NPE) nw_arrive(nw_prev);   // the previous element's scatter is complete (barrier)
+                    if (nw_on && tid == 0) {   // the previous element's scatter is complete (barrier): hand it to Newmark warp 0
+                        __threadfence_block();
+                        sArrHead = n_done;
+                    }
                     const int en = sIdx[kn];   // fetched during the previous element
                     if (en < nelem) load_desc(it ^ 1, en);
                 };
@@ -741,24 +758,72 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                 };
                 if (NCT1 != 0 && E.nr == NCT1) fused_element<FLUID, NT, NWW, NCT1>(cx, E, P, tid, gather, after_first_sync, after_grad);
                 else fused_element<FLUID, NT, NWW, 0>(cx, E, P, tid, gather, after_first_sync, after_grad);
-                if (nw_on && tid < AX_NPE) nw_prev = E.pt_nw[tid];
+                if (nw_on) {
+                    if (tid < AX_NPE) sArrCode[n_done & 3][tid] = E.pt_nw[tid];
+                    ++n_done;
+                }
                 e = sIdx[kn];
             }
             if (nw_on) {
                 cta_sync<NT, NWW>();   // last element's scatter complete; shared memory is free from here on
-                if (tid < AX_NPE) nw_arrive(nw_prev);
+                if (tid == 0) {
+                    __threadfence_block();
+                    sArrHead = n_done;
+                }
             }
         }
+        if (nw_on && tid == 0) {
+            __threadfence_block();
+            sCtaDone = 1;
+        }
+        if (tid == 0) stamp(1);
         // element queue empty: the compute warps join the Newmark consumers (their stages live in the now idle tile memory)
         if (nw_on && (warp + 1) * NW_WARP_SMEM <= (u_cap + tw_cap + z_cap) * (int)sizeof(float2)) {
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy tile traffic before the TMA writes
-            nw_consumer(nw, smem + warp * (NW_WARP_SMEM / 8), sBar[warp], lane);
+            nw_consumer(nw, smem + warp * (NW_WARP_SMEM / 8), sBar[warp], lane, [] {});
         }
     } else if (NWW > 0) {
-        if (nw_on) nw_consumer(nw, smem + ((u_cap + tw_cap + z_cap + 1) & ~1) + (warp - NT / 32) * (NW_WARP_SMEM / 8), sBar[warp], lane);
+        if (nw_on) {
+            float2 *stage = smem + ((u_cap + tw_cap + z_cap + 1) & ~1) + (warp - NT / 32) * (NW_WARP_SMEM / 8);
+            if (warp == NT / 32) {
+                // Newmark warp 0 posts the arrivals: a point whose last element has scattered goes to the ready queue.
+                // (Kept off the compute warps: the release fence would sit on their critical path once per element.)
+                int seen = 0;
+                auto service = [&]() {
+                    const int h = sArrHead;
+                    if (seen < h) {
+                        __threadfence_block();
+                        __threadfence();   // release: the CTA's forces (ordered before sArrHead by its barrier) before the counts
+                        for (; seen < h; ++seen) {
+                            const int code = lane < AX_NPE ? sArrCode[seen & 3][lane] : -1;
+                            if (code >= 0) {
+                                const int p = code & 0xffffff, need = code >> 24;
+                                if (atomicAdd(&nw.cnt[p], 1) + 1 == need) {
+                                    const unsigned slot = atomicAdd(&nw.ctl[0], 1u);
+                                    __threadfence();
+                                    atomicExch(&nw.queue[slot], p);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                };
+                nw_consumer(nw, stage, sBar[warp], lane, service);
+                // the ready queue may be fully claimed long before this CTA's last element has scattered
+                while (!sCtaDone) {
+                    service();
+                    __nanosleep(500);
+                }
+                service();
+            } else {
+                nw_consumer(nw, stage, sBar[warp], lane, [] {});
+            }
+        }
     }
     // re-arm the counters once every warp of every CTA is done
     __syncwarp();
+    if (tid == NT) stamp(2);
+    if (tid == 0) stamp(3);
     if (lane == 0) {
         __threadfence();
         const unsigned done = atomicAdd(&work[1], 1u);
