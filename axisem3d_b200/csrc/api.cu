@@ -99,6 +99,7 @@ struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_e
     int cls, first, count;
     int nct;                     // > 0: kernel instance with a compile-time specialised body for Nr == nct
     int u_cap, tw_cap, ldz_max;  // shared-memory regions (float2 units)
+    int nr_max;                  // largest Nr of the launch (fixes the Z and twiddle regions)
     int nww;                     // Newmark warps per CTA (0: none; the solid launch uses 2 when the domain has plain points)
     int z_cap;
     size_t smem;
@@ -489,7 +490,7 @@ static void finalize(ax3d_domain *d) {
         fl.cls = c;
         auto close_fused = [&]() {
             if (fl.count > 0) {
-                fl.z_cap = npair * AX_NPE * fl.ldz_max;
+                fl.tw_cap = 2 * fl.nr_max;
                 fl.smem = ((size_t)fl.u_cap + fl.tw_cap + (size_t)fl.z_cap) * sizeof(float2);
                 fl.grid = std::min(fl.count, d->num_sm);
                 int best = 0;
@@ -580,14 +581,19 @@ static void finalize(ax3d_domain *d) {
                 const size_t lim[1] = {(size_t)AX_FUSED_DYN_MAX - ((!fluid && d->nw_allowed) ? (size_t)AX_NWW * NW_WARP_SMEM + 8 : 0)};
                 D.plan_id = get_plan(d, N);
                 const int stw_len = d->h_plans[D.plan_id].stw_len;
-                const size_t fixed = ((size_t)npair * AX_NPE * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2);   // twiddle tables <= 2 N
-                size_t need = fixed + (size_t)nc * AX_NPE * M * sizeof(float2);
+                // One shared-memory layout per launch: elements are sorted by Nr (descending), so the first element that
+                // fits fixes the Z and twiddle regions; what is left is the gather tile of every element of the launch.
+                const size_t fixed = fl.count ? ((size_t)fl.z_cap + 2 * (size_t)fl.nr_max) * sizeof(float2)
+                                              : ((size_t)npair * AX_NPE * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2);   // twiddle tables <= 2 N
                 bool can_fuse = use_fused;
-                if (can_fuse && need > lim[0]) {
+                if (can_fuse && fixed + (size_t)nc * AX_NPE * M * sizeof(float2) > lim[0]) {
                     const long long room = ((long long)lim[0] - (long long)fixed) / (long long)(nc * AX_NPE * sizeof(float2));
                     D.mt = (int)(room / 16) * 16;
                     if (D.mt < 16) can_fuse = false;
-                    need = fixed + (size_t)nc * AX_NPE * D.mt * sizeof(float2);
+                }
+                if (can_fuse && fl.count == 0) {
+                    fl.nr_max = N;
+                    fl.z_cap = npair * AX_NPE * fused_ldz(N);
                 }
                 if (can_fuse) {
                     D.bucket = 0;
@@ -597,6 +603,7 @@ static void finalize(ax3d_domain *d) {
                     fl.u_cap = std::max(fl.u_cap, nc * AX_NPE * D.mt);
                     fl.tw_cap = std::max(fl.tw_cap, stw_len);
                     fl.ldz_max = std::max(fl.ldz_max, fused_ldz(N));
+                    if (stw_len > 2 * fl.nr_max) fail("ax3d::fused || twiddle table larger than its bound");
                 } else {
                     D.mt = M;
                     D.ppb = pick_ppb(N, npair);

@@ -32,9 +32,29 @@ UNIT = "point-modes/s"
 N_THETA, N_R, NU = 72, 28, 100
 
 
+def cfg4_nu(s, z):
+    """configs[3]: per-point Nu 20 ... 500, growing with the distance from the axis (wisdom-style ragged expansion)."""
+    return int(20 + 480 * min(1.0, s / 6371e3))
+
+
+CONFIGS = {
+    # name: (mesh keyword arguments, description)
+    "cfg1": (dict(nu=2, law="ti", model3d=False, attenuation="cg4"),
+             "cfg1: 1D TI PREM-like + CG4 attenuation, Nu=2 (Nr=5), no FFT"),
+    "cfg2": (dict(nu=NU, law="iso", model3d=True, attenuation=None),
+             "cfg2: 3D isotropic, Nu=%d (Nr=208), no attenuation, fluid core + SF coupling" % NU),
+    "cfg3": (dict(nu=200, law="aniso", model3d=True, attenuation="cg4", fluid3d=False),
+             "cfg3: 3D anisotropic (21 C_ij) + CG4 SLS attenuation, Nu=200 (Nr=416), SF coupling through the outer core"),
+    "cfg4": (dict(nu_fn=cfg4_nu, law="iso", model3d=True, attenuation=None),
+             "cfg4: 3D isotropic, per-point Nu 20..500 (Nr 42..1008), ragged FFT sizes"),
+}
+CFG = "cfg2"
+
+
 def make_mesh(n_theta, **kw):
     from axisem3d_b200.mesh_synth import SynthMesh
-    args = dict(n_theta=n_theta, n_r=N_R, nu=NU, law="iso", model3d=True, attenuation=None, dtype_coef=np.float32)
+    args = dict(n_theta=n_theta, n_r=N_R, dtype_coef=np.float32)
+    args.update(CONFIGS[CFG][0])
     args.update(kw)
     return SynthMesh(**args)
 
@@ -45,8 +65,7 @@ def stf_series(n):
 
 
 def workload_name(n_theta):
-    return ("cfg2: 50 s-mesh-size synthetic meridional mesh (%d x %d = %d quads), 3D isotropic, Nu=%d (Nr=208), "
-            "no attenuation, fluid core + SF coupling" % (n_theta, N_R, n_theta * N_R, NU))
+    return "%s; 50 s-mesh-size synthetic meridional mesh (%d x %d = %d quads)" % (CONFIGS[CFG][1], n_theta, N_R, n_theta * N_R)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -316,7 +335,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS),
+                    help="BASELINE.json config (cfg2 = configs[1] is the headline; the others are extra measurements)")
     args = ap.parse_args()
+    global CFG
+    CFG = args.config
     if args.impl == "reference":
         run_reference(args)
     else:
