@@ -93,6 +93,7 @@ struct Chunk {   // a run of 3D elements of one class whose spectra fit the scra
     int w_begin, w_count;       // grad/quad work items
     int f_begin, f_count;       // fft work items
     size_t fft_smem;
+    int fft_np, fft_nt;         // k_fft3d_v2 instance: points per CTA (5 or 1), threads (256: two CTAs per SM, or 512)
 };
 
 struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_elem3d_fused<FLUID, 512, nct> launch
@@ -334,14 +335,13 @@ static void common_elem(ax3d_domain *d, HElem &e, const int tags[25], const doub
 // ------------------------------------------------------------------------------------------ finalize
 static void set_fused_smem(int device, const FusedLaunch &f);
 static bool fused_specialised(bool fluid, int N);
-static int pick_ppb(int N, int npair) {
-    const char *env = getenv("AX3D_FFT_SMEM_KB");
-    const double budget = (env ? atof(env) : 48.0) * 1024.0;
-    int ppb = (int)((budget / (8.0 * N) - 1.0) / npair);
-    const int choices[9] = {25, 13, 9, 7, 5, 4, 3, 2, 1};
-    for (int c : choices)
-        if (ppb >= c) return c;
-    return 1;
+typedef void (*fft_kernel_t)(const ElemDesc *, const FftItem *, const FftPlan *, const float2 *, const float *, const float *, float *,
+                             float2 *);
+static fft_kernel_t fft_kernel(const Chunk &ch) {
+    const bool fluid = ch.cls == CLS_F3D;
+    if (ch.fft_np == 1) return fluid ? k_fft3d_v2<true, 1, 256> : k_fft3d_v2<false, 1, 256>;
+    if (ch.fft_nt == 256) return fluid ? k_fft3d_v2<true, 5, 256> : k_fft3d_v2<false, 5, 256>;
+    return fluid ? k_fft3d_v2<true, 5, 512> : k_fft3d_v2<false, 5, 512>;
 }
 
 static void finalize(ax3d_domain *d) {
@@ -479,11 +479,12 @@ static void finalize(ax3d_domain *d) {
         const int npair = fluid ? 2 : 3;
         std::vector<int> w_elem, w_a0;
         std::vector<FftItem> fitems;
-        Chunk ch{c, 0, 0, 0, 0, 0};
+        Chunk ch{c, 0, 0, 0, 0, 0, 5, 256};
+        int cls_np = 0;   // points per k_fft3d_v2 CTA for this class: fixed by its largest split element
         size_t ch_scratch = 0;
         auto close_chunk = [&]() {
             if (ch.w_count > 0) d->chunks.push_back(ch);
-            ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0};
+            ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0, 5, 256};
             ch_scratch = 0;
         };
         FusedLaunch fl{};
@@ -606,7 +607,8 @@ static void finalize(ax3d_domain *d) {
                     if (stw_len > 2 * fl.nr_max) fail("ax3d::fused || twiddle table larger than its bound");
                 } else {
                     D.mt = M;
-                    D.ppb = pick_ppb(N, npair);
+                    if (!cls_np) cls_np = ((size_t)npair * 5 * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2) <= (size_t)220 * 1024 ? 5 : 1;
+                    D.ppb = cls_np;
                     const size_t need_sc = (size_t)npair * AX_NPE * N;
                     if (need_sc > scratch_cap && ch.w_count > 0) close_chunk();
                     if (ch_scratch + need_sc > scratch_cap && ch.w_count > 0) close_chunk();
@@ -615,7 +617,9 @@ static void finalize(ax3d_domain *d) {
                     scratch_need = std::max(scratch_need, ch_scratch);
                     for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); ch.w_count++; }
                     for (int p0 = 0; p0 < AX_NPE; p0 += D.ppb) { fitems.push_back(FftItem{(int)k, p0}); ch.f_count++; }
-                    ch.fft_smem = std::max(ch.fft_smem, (size_t)(npair * D.ppb + 1) * N * sizeof(float2));
+                    ch.fft_smem = std::max(ch.fft_smem, ((size_t)npair * D.ppb * fused_ldz(N) + (size_t)((stw_len + 1) & ~1)) * sizeof(float2));
+                    ch.fft_np = D.ppb;
+                    ch.fft_nt = ch.fft_smem <= (size_t)110 * 1024 ? 256 : 512;
                 }
             } else {
                 for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); }
@@ -826,12 +830,9 @@ static void finalize(ax3d_domain *d) {
     CK(cudaEventCreate(&d->ev0));
     CK(cudaEventCreate(&d->ev1));
     // opt in to large dynamic shared memory
-    size_t fmax = 0;
-    for (const Chunk &ch : d->chunks) fmax = std::max(fmax, ch.fft_smem);
-    if (fmax > 220 * 1024) fail("ax3d::finalize || Nr too large for the single-CTA FFT stage (needs > 220 KB shared memory)");
-    if (fmax > 48 * 1024) {
-        CK(cudaFuncSetAttribute(k_fft3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
-        CK(cudaFuncSetAttribute(k_fft3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
+    for (const Chunk &ch : d->chunks) {
+        if (ch.fft_smem > (size_t)224 * 1024) fail("ax3d::finalize || Nr too large for the FFT stage (needs > 224 KB shared memory per point)");
+        CK(cudaFuncSetAttribute((const void *)fft_kernel(ch), cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     }
     {
         std::vector<unsigned> w;
@@ -1021,15 +1022,15 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0) {
         if (c == CLS_S3D) {
             k_grad3d<false><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                               d->s_field[AX3D_DISPL].p, d->scratch.p);
-            k_fft3d<false><<<ch.f_count, 256, ch.fft_smem, d->stream>>>(d->desc[c].p, d->fft_items[c].p + ch.f_begin, d->plans.p, d->twpool.p,
-                                                                        d->coef.p, d->attpar.p, d->attstate3d.p, d->scratch.p);
+            fft_kernel(ch)<<<ch.f_count, ch.fft_np == 1 ? 256 : ch.fft_nt, ch.fft_smem, d->stream>>>(
+                d->desc[c].p, d->fft_items[c].p + ch.f_begin, d->plans.p, d->stwpool.p, d->coef.p, d->attpar.p, d->attstate3d.p, d->scratch.p);
             k_quad3d<false><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                               d->scratch.p, d->s_field[AX3D_STIFF].p);
         } else {
             k_grad3d<true><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                              d->f_field[AX3D_DISPL].p, d->scratch.p);
-            k_fft3d<true><<<ch.f_count, 256, ch.fft_smem, d->stream>>>(d->desc[c].p, d->fft_items[c].p + ch.f_begin, d->plans.p, d->twpool.p,
-                                                                       d->coef.p, d->attpar.p, d->attstate3d.p, d->scratch.p);
+            fft_kernel(ch)<<<ch.f_count, ch.fft_np == 1 ? 256 : ch.fft_nt, ch.fft_smem, d->stream>>>(
+                d->desc[c].p, d->fft_items[c].p + ch.f_begin, d->plans.p, d->stwpool.p, d->coef.p, d->attpar.p, d->attstate3d.p, d->scratch.p);
             k_quad3d<true><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                              d->scratch.p, d->f_field[AX3D_STIFF].p);
         }

@@ -205,10 +205,11 @@ struct FusedCtx {
 
 // stress of NB (point, phi) cells at once: all moduli are requested before the first use (Isotropic3D.cpp:10-27,
 // TransverselyIsotropic3D.cpp:10-28, Anisotropic3D.cpp:10-54; no attenuation on this path)
+// Z holds the columns of `np` consecutive points of one element: pair k of local point pl at Z + (k * np + pl) * ldz.
+// cf points at the first of those points in the element's moduli ([k][25][N]: cf_stride = 25 * N between moduli).
 template <int NCOEF, int NB, int NT>
-__device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, const float *__restrict__ cf, int total, int ldz, int N,
-                                             int tid) {
-    const int cs = AX_NPE * ldz;
+__device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, const float *__restrict__ cf, int total, int cf_stride, int cs,
+                                             int ldz, int N, int tid) {
     const int dp = NT / N, dpos = NT - dp * N;
     int idx = tid;
     int p = idx / N, pos = idx - p * N;
@@ -218,7 +219,7 @@ __device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, co
         for (int u = 0; u < NB; ++u)
             if (idx + u * NT < total) {
 #pragma unroll
-                for (int k = 0; k < NCOEF; ++k) c[u][k] = __ldcs(cf + (size_t)k * total + idx + u * NT);
+                for (int k = 0; k < NCOEF; ++k) c[u][k] = __ldcs(cf + (size_t)k * cf_stride + idx + u * NT);
             }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
@@ -235,6 +236,64 @@ __device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, co
             pos += dpos;
             if (pos >= N) { pos -= N; ++p; }
         }
+    }
+}
+
+// Physical space of `np` points [p0, p0 + np) of element E: stress (+ SLS attenuation) on the c2r output, in place
+// (Isotropic3D.cpp:10-27, TransverselyIsotropic3D.cpp:10-28, Anisotropic3D.cpp:10-54, Attenuation3D_{Full,CG4}.cpp,
+// Acoustic3D.cpp:9-16).  Phi positions are in the digit-reversed order of the plan, like the uploaded moduli.
+template <bool FLUID, int NT>
+__device__ __forceinline__ void physical_space(const ElemDesc &E, const float *__restrict__ coef, const float *__restrict__ attpar,
+                                               float *__restrict__ attstate, float2 *__restrict__ Z, int N, int ldz, int p0, int np,
+                                               int tid) {
+    const int total = np * N, cf_stride = AX_NPE * N, cs = np * ldz;
+    const float *cf0 = coef + E.coef_off + (size_t)p0 * N;
+    const int law = E.law;
+    if constexpr (!FLUID) {
+        if (E.att_kind == ATT_NONE) {
+            if (law == LAW_ISO) stress_batch<2, 4, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
+            else if (law == LAW_TI) stress_batch<5, 2, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
+            else stress_batch<21, 1, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
+            return;
+        }
+    }
+    int idx = tid;
+    int pl = idx / N, pos = idx - pl * N;
+    const int dp = NT / N, dpos = NT - dp * N;
+    for (; idx < total; idx += NT) {
+        float2 *zc = Z + pl * ldz + pos;
+        if constexpr (!FLUID) {
+            const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
+            float ee[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
+            const float *cf = cf0 + idx;   // [k][point][pos] with local point * N + pos == idx
+            stress_law<float>(law, ee, s, [&](int k) { return __ldcs(cf + (size_t)k * cf_stride); });
+            const int p = p0 + pl;
+            const int Pn = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
+            const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
+            if (q >= 0) {
+                const float *ap = attpar + E.att_par_off;
+                const float *mod = ap + 3 * E.nsls;
+                float *stt = attstate + E.att_state_off;
+                const size_t cell = (size_t)q * N + pos;
+                const size_t PN = (size_t)Pn * N, sl = 6 * PN;
+                const int nsls = E.nsls;
+                attenuation_cell<float>(
+                    nsls, ap, mod[cell], mod[PN + cell], mod[2 * PN + cell], E.do_kappa != 0, ee, s,
+                    [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
+                    [&](int c) -> float & { return stt[nsls * sl + c * PN + cell]; });
+            }
+            zc[0] = make_float2(s[0], s[1]);
+            zc[cs] = make_float2(s[2], s[3]);
+            zc[2 * cs] = make_float2(s[4], s[5]);
+        } else {
+            const float K = __ldcs(cf0 + idx);
+            const float2 a = zc[0], b = zc[cs];
+            zc[0] = cscale(a, K);
+            zc[cs] = make_float2(b.x * K, 0.f);
+        }
+        pl += dp;
+        pos += dpos;
+        if (pos >= N) { pos -= N; ++pl; }
     }
 }
 
@@ -327,59 +386,7 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
     }
 
     // ------------------------------------------------------------ physical space: stress (+ SLS attenuation)   @phase stress
-    {
-        const int total = AX_NPE * N;
-        const float *cf0 = cx.coef + coef_off;
-        bool done = false;
-        if constexpr (!FLUID) {
-            if (E.att_kind == ATT_NONE) {
-                if (law == LAW_ISO) stress_batch<2, 4, NT>(law, Z, cf0, total, ldz, N, tid);
-                else if (law == LAW_TI) stress_batch<5, 2, NT>(law, Z, cf0, total, ldz, N, tid);
-                else stress_batch<21, 1, NT>(law, Z, cf0, total, ldz, N, tid);
-                done = true;
-            }
-        }
-        if (!done) {
-            int idx = tid;
-            int p = idx / N, pos = idx - p * N;
-            const int dp = NT / N, dpos = NT - dp * N;
-            const int cs = AX_NPE * ldz;
-            for (; idx < total; idx += NT) {
-                float2 *zc = Z + p * ldz + pos;
-                if constexpr (!FLUID) {
-                    const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
-                    float ee[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
-                    const float *cf = cf0 + idx;   // [k][point][pos] with point * N + pos == idx
-                    stress_law<float>(law, ee, s, [&](int k) { return __ldcs(cf + (size_t)k * total); });
-                    const int Pn = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
-                    const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
-                    if (q >= 0) {
-                        const float *ap = cx.attpar + E.att_par_off;
-                        const float *mod = ap + 3 * E.nsls;
-                        float *stt = cx.attstate + E.att_state_off;
-                        const size_t cell = (size_t)q * N + pos;
-                        const size_t PN = (size_t)Pn * N, sl = 6 * PN;
-                        const int nsls = E.nsls;
-                        attenuation_cell<float>(
-                            nsls, ap, mod[cell], mod[PN + cell], mod[2 * PN + cell], E.do_kappa != 0, ee, s,
-                            [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
-                            [&](int c) -> float & { return stt[nsls * sl + c * PN + cell]; });
-                    }
-                    zc[0] = make_float2(s[0], s[1]);
-                    zc[cs] = make_float2(s[2], s[3]);
-                    zc[2 * cs] = make_float2(s[4], s[5]);
-                } else {
-                    const float K = __ldcs(cf0 + idx);   // Acoustic3D.cpp:9-16
-                    const float2 a = zc[0], b = zc[cs];
-                    zc[0] = cscale(a, K);
-                    zc[cs] = make_float2(b.x * K, 0.f);
-                }
-                p += dp;
-                pos += dpos;
-                if (pos >= N) { pos -= N; ++p; }
-            }
-        }
-    }
+    physical_space<FLUID, NT>(E, cx.coef, cx.attpar, cx.attstate, Z, N, ldz, 0, AX_NPE, tid);
     cta_sync<NT, NWW>();
 
     // ------------------------------------------------------------ r2c (computeR2C; the 1/Nr is applied at load below)   @phase r2c
@@ -476,6 +483,69 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
         }
     }
     // the barrier after cp_async_wait_all at the top of the next element separates these reads of Z from its grad
+}
+
+// ---------------------------------------------------------------- split pipeline, middle kernel
+// Elements whose spectrum does not fit one SM's shared memory go through k_grad3d -> k_fft3d_v2 -> k_quad3d with the
+// Z-form spectrum staged in an L2-resident scratch ring ([pair][25][Nr] per element).  This kernel is the FFT / physical
+// space part for NP consecutive GLL points of one element (the constitutive law couples the 6 components of one point,
+// never two points): load NPAIR * NP columns, c2r, stress (+SLS), r2c, store -- the same stage and stress code as the
+// fused kernel, on a tile that is 1/5 (NP = 5) or 1/25 (NP = 1) of an element, so that even Nr = 2016 fits.
+template <bool FLUID, int NP, int NT>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_fft3d_v2(const ElemDesc *__restrict__ elems, const FftItem *__restrict__ items,
+                                                 const FftPlan *__restrict__ plans, const float2 *__restrict__ stwpool,
+                                                 const float *__restrict__ coef, const float *__restrict__ attpar,
+                                                 float *__restrict__ attstate, float2 *__restrict__ scratch) {
+    constexpr int NPAIR = FLUID ? 2 : 3, NCOLS = NPAIR * NP;
+    constexpr int PLAN_W = (int)(sizeof(FftPlan) / sizeof(int));
+    static_assert(PLAN_W <= NT, "plan loader");
+    extern __shared__ __align__(16) float2 smem[];
+    __shared__ FftPlan sP;
+    const int tid = threadIdx.x;
+    const FftItem it = items[blockIdx.x];
+    const ElemDesc &E = elems[it.elem];
+    if (tid < PLAN_W) reinterpret_cast<int *>(&sP)[tid] = reinterpret_cast<const int *>(plans + E.plan_id)[tid];
+    const int N = E.nr, ldz = fused_ldz(N), p0 = it.p0;
+    __syncthreads();
+    const FftPlan &P = sP;
+    float2 *const TW = smem, *const Z = smem + ((P.stw_len + 1) & ~1);
+    for (int k = tid; k < P.stw_len; k += NT) TW[k] = stwpool[P.stw_base + k];
+    float2 *const gz = scratch + E.scratch_off;
+#pragma unroll
+    for (int c = 0; c < NCOLS; ++c) {
+        const int pr = c / NP, pl = c - pr * NP;
+        const float2 *src = gz + ((size_t)pr * AX_NPE + p0 + pl) * N;
+        float2 *dst = Z + c * ldz;
+        for (int k = tid; k < N; k += NT) dst[k] = __ldcs(src + k);
+    }
+    __syncthreads();
+    {
+        int L = N;
+        for (int s = 0; s < P.nstages; ++s) {
+            const int R = P.radix[s];
+            fused_stage_dispatch<+1, true, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+            L /= R;
+            __syncthreads();
+        }
+    }
+    physical_space<FLUID, NT>(E, coef, attpar, attstate, Z, N, ldz, p0, NP, tid);
+    __syncthreads();
+    {
+        int L = 1;
+        for (int s = P.nstages - 1; s >= 0; --s) {
+            const int R = P.radix[s];
+            L *= R;
+            fused_stage_dispatch<-1, false, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCOLS; ++c) {
+        const int pr = c / NP, pl = c - pr * NP;
+        float2 *dst = gz + ((size_t)pr * AX_NPE + p0 + pl) * N;
+        const float2 *src = Z + c * ldz;
+        for (int k = tid; k < N; k += NT) dst[k] = src[k];
+    }
 }
 
 // ---------------------------------------------------------------- in-kernel Newmark   @phase newmark warps

@@ -395,76 +395,6 @@ struct FftItem {
     int elem;
     int p0;
 };
-template <bool FLUID>
-__global__ void __launch_bounds__(256) k_fft3d(const ElemDesc *__restrict__ elems, const FftItem *__restrict__ items,
-                                               const FftPlan *__restrict__ plans, const float2 *__restrict__ twpool,
-                                               const float *__restrict__ coef, const float *__restrict__ attpar,
-                                               float *__restrict__ attstate, float2 *__restrict__ scratch) {
-    constexpr int NPAIR = FLUID ? 2 : 3;
-    extern __shared__ float2 smem[];
-    const FftItem it = items[blockIdx.x];
-    const ElemDesc &E = elems[it.elem];
-    const FftPlan pl = plans[E.plan_id];
-    const int N = pl.N, ppb = E.ppb;
-    const int np = min(ppb, AX_NPE - it.p0);
-    const int ncols = NPAIR * np;
-    float2 *z = smem;                          // column (pr, pl) at (pr * np + pl) * N
-    float2 *tw = smem + (size_t)NPAIR * ppb * N;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int k = tid; k < N; k += nt) tw[k] = twpool[pl.tw_off + k];
-    float2 *gz = scratch + E.scratch_off;
-    for (int pr = 0; pr < NPAIR; ++pr) {
-        const float2 *src = gz + ((size_t)pr * AX_NPE + it.p0) * N;
-        float2 *dst = z + (size_t)pr * np * N;
-        for (int k = tid; k < np * N; k += nt) dst[k] = src[k];
-    }
-    __syncthreads();
-    fft_inverse_dif(pl, z, N, ncols, tw, tid, nt);
-    // pointwise physics at (point, phi position)
-    for (int idx = tid; idx < np * N; idx += nt) {
-        const int plc = idx / N, pos = idx - plc * N;
-        const int p = it.p0 + plc;
-        if constexpr (!FLUID) {
-            float2 z0 = z[(size_t)(0 * np + plc) * N + pos], z1 = z[(size_t)(1 * np + plc) * N + pos],
-                   z2 = z[(size_t)(2 * np + plc) * N + pos];
-            float e[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
-            const float *cf = coef + E.coef_off + (size_t)p * N + pos;
-            const size_t cst = (size_t)AX_NPE * N;
-            stress_law<float>(E.law, e, s, [&](int k) { return cf[k * cst]; });
-            if (E.att_kind != ATT_NONE) {
-                const int P = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
-                const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
-                if (q >= 0) {
-                    const float *ap = attpar + E.att_par_off;
-                    const float *mod = ap + 3 * E.nsls;
-                    float *stt = attstate + E.att_state_off;
-                    const size_t cell = (size_t)q * N + pos;
-                    const size_t PN = (size_t)P * N, sl = 6 * PN;
-                    attenuation_cell<float>(
-                        E.nsls, ap, mod[cell], mod[PN + cell], mod[2 * PN + cell], E.do_kappa != 0, e, s,
-                        [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
-                        [&](int c) -> float & { return stt[E.nsls * sl + c * PN + cell]; });
-                }
-            }
-            z[(size_t)(0 * np + plc) * N + pos] = make_float2(s[0], s[1]);
-            z[(size_t)(1 * np + plc) * N + pos] = make_float2(s[2], s[3]);
-            z[(size_t)(2 * np + plc) * N + pos] = make_float2(s[4], s[5]);
-        } else {
-            const float K = coef[E.coef_off + (size_t)p * N + pos];   // Acoustic3D.cpp:9-16
-            float2 &a = z[(size_t)plc * N + pos], &b = z[(size_t)(np + plc) * N + pos];
-            a = cscale(a, K);
-            b = make_float2(b.x * K, 0.f);
-        }
-    }
-    __syncthreads();
-    fft_forward_dit(pl, z, N, ncols, tw, tid, nt);
-    for (int pr = 0; pr < NPAIR; ++pr) {
-        float2 *dst = gz + ((size_t)pr * AX_NPE + it.p0) * N;
-        const float2 *src = z + (size_t)pr * np * N;
-        for (int k = tid; k < np * N; k += nt) dst[k] = src[k];
-    }
-}
-
 // ------------------------------------------------------------------------------------ 3D material: stage C (quad)
 template <bool FLUID>
 __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,

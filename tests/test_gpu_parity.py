@@ -35,6 +35,14 @@ def ragged_nu(s, z):
 # fused-kernel corner cases: gather tile smaller than the spectrum (Nr = 288), and the split pipeline (Nr = 416)
 CASES["iso3d_nu140_tiled"] = dict(n_theta=3, n_r=4, nu=140, law="iso", model3d=True, attenuation=None, fluid3d=True)
 CASES["ti3d_nu200_split"] = dict(n_theta=3, n_r=4, nu=200, law="ti", model3d=True, attenuation="cg4", fluid3d=True)
+# split pipeline with one point per CTA (Nr = 2016 needs > 224 KB for five points)
+def equator_nu1000(s, z):
+    """two equatorial elements of a thin shell at Nu = 1000 (Nr = 2016: the circumference cap needs ~20 km GLL spacing)."""
+    return 1000 if s > 0.9895 * 6371e3 and abs(z) < 40e3 else 6
+
+
+CASES["iso3d_nu1000_split_np1"] = dict(n_theta=320, n_r=1, r_in=6371e3 - 80e3, nu_fn=equator_nu1000, law="ti", model3d=True,
+                                       attenuation="cg4", fluid_layers=())
 CASES["cfg4_ragged"] = dict(n_theta=10, n_r=6, nu_fn=ragged_nu, law="iso", model3d=True, attenuation=None)
 
 
