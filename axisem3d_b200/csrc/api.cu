@@ -465,7 +465,7 @@ static void finalize(ax3d_domain *d) {
     size_t att1d_len = 0, att3d_len = 0;
     double bytes_el = 0;
     const char *env_sc = getenv("AX3D_SCRATCH_MB");
-    const size_t scratch_cap = (size_t)((env_sc ? atof(env_sc) : 64.0) * 1024.0 * 1024.0 / sizeof(float2));
+    const size_t scratch_cap = (size_t)((env_sc ? atof(env_sc) : 256.0) * 1024.0 * 1024.0 / sizeof(float2));
     size_t scratch_need = 0;
     const char *env_nf = getenv("AX3D_NO_FUSED");
     const bool use_fused = !(env_nf && atoi(env_nf) != 0);
@@ -1364,6 +1364,8 @@ static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool
     launch_source(d);
     compute_stiff(d, nw_on, dt);
     couple_solid_fluid(d);
+    assemble_stiff(d, -1);   // no-ops on a single rank
+    assemble_stiff(d, 1);
 }
 
 static long long count_step_launches(ax3d_domain *d, bool special_only) {
@@ -1379,11 +1381,18 @@ static long long count_step_launches(ax3d_domain *d, bool special_only) {
     n += (long long)d->fused.size();
     n += d->sf_tab.nrows > 0;
     n += !d->h_sf3d.empty();
+    if (d->nproc > 1 && !d->neigh_rank.empty()) {
+        n += 1;   // k_pack
+        for (size_t k = 0; k < d->neigh_rank.size(); ++k) n += d->neigh_begin[k + 1] > d->neigh_begin[k];   // k_unpack_add
+    }
     return n;
 }
 
 static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
-    const bool graph_ok = d->use_graph && !d->timers && (d->nproc <= 1 || d->neigh_rank.empty());
+    // Multi-rank steps run eagerly: capturing the NCCL send/recv group into the step graph hung on 2 x B200 (NCCL 2.28.9,
+    // thread-local capture), so it stays an opt-in experiment (AX3D_HALO_GRAPH=1).
+    static const bool halo_graph = getenv("AX3D_HALO_GRAPH") && atoi(getenv("AX3D_HALO_GRAPH")) != 0;
+    const bool graph_ok = d->use_graph && !d->timers && (d->nproc <= 1 || d->neigh_rank.empty() || halo_graph);
     if (graph_ok && d->graph_dt != dt) {
         for (int v = 0; v < 4; ++v) {
             if (d->graph_exec[v]) { cudaGraphExecDestroy(d->graph_exec[v]); d->graph_exec[v] = nullptr; }
@@ -1412,8 +1421,6 @@ static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
             d->launches += count_step_launches(d, special_only);
         } else {
             step_body(d, dt, special_only, nw_on);
-            assemble_stiff(d, -1);
-            assemble_stiff(d, 1);
         }
         d->plain_advanced = nw_on;
     }
