@@ -17,7 +17,7 @@ SYMBOLS = [
     "ax3d_run_steps", "ax3d_synchronize", "ax3d_get_point_field", "ax3d_set_point_field",
     "ax3d_get_field_bulk", "ax3d_set_field_bulk", "ax3d_field_size", "ax3d_record_ground_motion",
     "ax3d_launch_count", "ax3d_work_per_step", "ax3d_algorithmic_bytes", "ax3d_enable_timers",
-    "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
+    "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_dominant_kernel", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
 ]
 
 
@@ -69,6 +69,8 @@ def load(build_if_missing=True):
     lib.ax3d_run_steps.argtypes = [vp, i, d, pf]
     lib.ax3d_synchronize.argtypes = [vp]
     lib.ax3d_run_steps_timed.argtypes = [vp, i, d, pf, pf]
+    lib.ax3d_run_steps_record.argtypes = [vp, i, d, pf, pf]
+    lib.ax3d_dominant_kernel.argtypes = [vp, pd, pd, i]
     lib.ax3d_set_receivers.argtypes = [vp, i, pi_, pf, pf]
     lib.ax3d_record.argtypes = [vp, pf]
     lib.ax3d_nccl_unique_id.argtypes = [vp]

@@ -77,6 +77,7 @@ struct HElem {
     std::vector<float> coef;
     HAtt att;
     int cls = -1, idx = -1;   // class and index inside the class after finalize
+    double alg_b = 0;         // algorithmic bytes of one stiffness evaluation of this element
 };
 struct HSource {
     int elem;
@@ -153,6 +154,10 @@ struct ax3d_domain {
     DevBuf<int> s_row_point_sp, s_row_start_sp;
     PointTab s_tab_sp{};            // rows of the solid points the stand-alone Newmark kernel still owns
     DevBuf<unsigned long long> nw_dbg;
+    // device-side record ring of ax3d_run_steps_record: [step][receiver][3]
+    DevBuf<float> rec_ring;
+    float *rec_ring_host = nullptr;
+    size_t rec_ring_steps = 0;
     bool plain_advanced = false;    // the plain points already hold the state of the step about to start
     // ---- elements
     std::vector<ElemDesc> h_desc[NCLS];
@@ -192,6 +197,10 @@ struct ax3d_domain {
     DevBuf<int> bad_flag;
     bool timers = false;
     double timer_ms[4] = {0, 0, 0, 0};
+    // dominant kernel (solid k_elem3d_fused launch): its own event pair, algorithmic bytes {elements, in-kernel Newmark points}
+    double dom_ms = 0, dom_bytes[2] = {0, 0};
+    long long dom_launches = 0;
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // receivers (scratch for ax3d_record_ground_motion)
     DevBuf<RecvItem> rec_items;
@@ -203,8 +212,8 @@ struct ax3d_domain {
     float *stf_pinned = nullptr;
     int stf_slot = 0;
     // CUDA graph of one step (single-GPU path)
-    cudaGraph_t graph[4] = {nullptr, nullptr, nullptr, nullptr};          // [special_only * 2 + nw_on]
-    cudaGraphExec_t graph_exec[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaGraph_t graph[8] = {};          // [record * 4 + special_only * 2 + nw_on]
+    cudaGraphExec_t graph_exec[8] = {};
     double graph_dt = 0;
     bool use_graph = true;
     // receivers registered with ax3d_set_receivers
@@ -572,6 +581,7 @@ static void finalize(ax3d_domain *d) {
                     b += 2.0 * (E.att.nsls + 1) * 6 * P * R + 2.0 * P * (is3d ? 4.0 * N : 4.0);
                 }
                 bytes_el += b;
+                E.alg_b = b;
             }
             D.bucket = -1;
             D.mt = M;
@@ -676,6 +686,10 @@ static void finalize(ax3d_domain *d) {
             std::fill(ok.begin(), ok.end(), 0);
         }
         d->n_plain = n_plain;
+        for (const HElem &E : d->elems)
+            if (!E.fluid && E.cls == CLS_S3D && d->h_desc[CLS_S3D][E.idx].bucket == 0) d->dom_bytes[0] += E.alg_b;
+        for (size_t sp = 0; sp < ns; ++sp)
+            if (ok[sp]) d->dom_bytes[1] += 192.0 * (snu[sp] + 1) + 4.0;
         for (ElemDesc &D : d->h_desc[CLS_S3D]) {
             for (int i = 0; i < AX_NPE; ++i) D.pt_nw[i] = -1;
         }
@@ -819,9 +833,9 @@ static void finalize(ax3d_domain *d) {
         d->alg_bytes[2] = hb;
     }
     d->bad_flag.alloc(1);
-    d->stf_dev.alloc(1);
+    d->stf_dev.alloc(2);   // {source factor (float), record-ring slot (int)} of the step being enqueued
     d->stf_dev.zero();
-    CK(cudaMallocHost(&d->stf_pinned, STF_RING * sizeof(float)));
+    CK(cudaMallocHost(&d->stf_pinned, 2 * STF_RING * sizeof(float)));
     {
         const char *g = getenv("AX3D_NO_GRAPH");
         d->use_graph = !(g && atoi(g) != 0);
@@ -829,6 +843,8 @@ static void finalize(ax3d_domain *d) {
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&d->ev0));
     CK(cudaEventCreate(&d->ev1));
+    CK(cudaEventCreate(&d->ev2));
+    CK(cudaEventCreate(&d->ev3));
     // opt in to large dynamic shared memory
     for (const Chunk &ch : d->chunks) {
         if (ch.fft_smem > (size_t)224 * 1024) fail("ax3d::finalize || Nr too large for the FFT stage (needs > 224 KB shared memory per point)");
@@ -906,15 +922,32 @@ static void update_newmark(ax3d_domain *d, double dt, bool special_only = false)
     CK(cudaGetLastError());
 }
 
-static void push_stf(ax3d_domain *d, float stf) {
+static void push_stf(ax3d_domain *d, float stf, int rec_slot = 0) {
     // a slot is reused only after STF_RING further steps; synchronise before wrapping around
     if (d->stf_slot == STF_RING) {
         CK(cudaStreamSynchronize(d->stream));
         d->stf_slot = 0;
     }
-    d->stf_pinned[d->stf_slot] = stf;
-    CK(cudaMemcpyAsync(d->stf_dev.p, d->stf_pinned + d->stf_slot, sizeof(float), cudaMemcpyHostToDevice, d->stream));
+    float *h = d->stf_pinned + 2 * d->stf_slot;
+    h[0] = stf;
+    memcpy(h + 1, &rec_slot, sizeof(int));
+    CK(cudaMemcpyAsync(d->stf_dev.p, h, 2 * sizeof(float), cudaMemcpyHostToDevice, d->stream));
     d->stf_slot++;
+}
+
+// Domain::record -> PointwiseRecorder::record (Domain.cpp:207-220): one sample per registered receiver into row
+// `*slot` of the device ring (slot == nullptr: row 0 of `out`).
+static void launch_record(ax3d_domain *d, float *out, const int *slot, int stride) {
+    if (d->nrec1) {
+        k_ground_motion<<<d->nrec1, AX_REC_NT, 0, d->stream>>>(d->desc[CLS_S1D].p, d->rec1_items.p, d->rec1_w.p, d->s_field[AX3D_DISPL].p, out, slot, stride);
+        d->launches++;
+    }
+    if (d->nrec3) {
+        k_ground_motion<<<d->nrec3, AX_REC_NT, 0, d->stream>>>(d->desc[CLS_S3D].p, d->rec3_items.p, d->rec3_w.p, d->s_field[AX3D_DISPL].p,
+                                                          out + (size_t)3 * d->nrec1, slot, stride);
+        d->launches++;
+    }
+    CK(cudaGetLastError());
 }
 
 static void launch_source(ax3d_domain *d) {
@@ -989,10 +1022,19 @@ static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool n
         nw.half_dt_dt = (float)half_dt_dt;
     }
     if (!fluid && d->nw_dbg.p && nw.on) nw.dbg = d->nw_dbg.p;
+    const bool time_it = d->timers && !fluid;
+    if (time_it) cudaEventRecord(d->ev2, d->stream);
     fused_kernel(f)<<<f.grid, fused_nt(f), f.smem, d->stream>>>(
         d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
         fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
         f.u_cap, f.tw_cap, f.z_cap, d->fused_work.p + 2 * which, nw);
+    if (time_it) {
+        cudaEventRecord(d->ev3, d->stream);
+        cudaEventSynchronize(d->ev3);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, d->ev2, d->ev3);
+        if (nw.on || d->n_plain == 0) { d->dom_ms += ms; d->dom_launches++; }   // launches that do the whole job of the kernel
+    }
 }
 
 static void set_fused_smem(int device, const FusedLaunch &f) {
@@ -1137,9 +1179,12 @@ int ax3d_destroy(ax3d_domain *d) {
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->ev2) cudaEventDestroy(d->ev2);
+    if (d->ev3) cudaEventDestroy(d->ev3);
     if (d->rec_host) cudaFreeHost(d->rec_host);
     if (d->stf_pinned) cudaFreeHost(d->stf_pinned);
-    for (int v = 0; v < 4; ++v) {
+    if (d->rec_ring_host) cudaFreeHost(d->rec_ring_host);
+    for (int v = 0; v < 8; ++v) {
         if (d->graph_exec[v]) cudaGraphExecDestroy(d->graph_exec[v]);
         if (d->graph[v]) cudaGraphDestroy(d->graph[v]);
     }
@@ -1359,8 +1404,11 @@ int ax3d_reset_zero(ax3d_domain *d) {
 
 // One iteration of Newmark::solve (Newmark.cpp:47-93).  special_only: the plain solid points already hold this step's
 // state (advanced under the previous step's element kernel); nw_on: this step's element kernel advances them to the next.
-static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool nw_on = false) {
+static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool nw_on = false, bool record = false) {
     update_newmark(d, dt, special_only);
+    // the reference records after the update of the step (Newmark.cpp:64-70); it must also precede this step's element
+    // kernel, which already advances the plain points to the next step
+    if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * (d->nrec1 + d->nrec3));
     launch_source(d);
     compute_stiff(d, nw_on, dt);
     couple_solid_fluid(d);
@@ -1368,8 +1416,9 @@ static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool
     assemble_stiff(d, 1);
 }
 
-static long long count_step_launches(ax3d_domain *d, bool special_only) {
+static long long count_step_launches(ax3d_domain *d, bool special_only, bool record) {
     long long n = 0;
+    if (record) n += (d->nrec1 > 0) + (d->nrec3 > 0);
     n += !d->h_m3d_s.empty();
     n += !d->h_m3d_f.empty();
     n += (special_only ? d->s_tab_sp.nrows : d->s_tab.nrows) > 0;
@@ -1388,13 +1437,13 @@ static long long count_step_launches(ax3d_domain *d, bool special_only) {
     return n;
 }
 
-static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
+static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf, bool record = false) {
     // Multi-rank steps run eagerly: capturing the NCCL send/recv group into the step graph hung on 2 x B200 (NCCL 2.28.9,
     // thread-local capture), so it stays an opt-in experiment (AX3D_HALO_GRAPH=1).
     static const bool halo_graph = getenv("AX3D_HALO_GRAPH") && atoi(getenv("AX3D_HALO_GRAPH")) != 0;
     const bool graph_ok = d->use_graph && !d->timers && (d->nproc <= 1 || d->neigh_rank.empty() || halo_graph);
     if (graph_ok && d->graph_dt != dt) {
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 8; ++v) {
             if (d->graph_exec[v]) { cudaGraphExecDestroy(d->graph_exec[v]); d->graph_exec[v] = nullptr; }
             if (d->graph[v]) { cudaGraphDestroy(d->graph[v]); d->graph[v] = nullptr; }
         }
@@ -1406,21 +1455,21 @@ static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
         // so that the state after the call is exactly the reference's (all points at step i, stiff = this step's force)
         const bool special_only = d->plain_advanced;
         const bool nw_on = can_nw && i + 1 < nsteps;
-        if (d->n_src) push_stf(d, stf ? stf[i] : 0.f);
+        if (d->n_src || record) push_stf(d, stf ? stf[i] : 0.f, i);
         if (graph_ok) {
-            const int v = (special_only ? 2 : 0) + (nw_on ? 1 : 0);
+            const int v = (record ? 4 : 0) + (special_only ? 2 : 0) + (nw_on ? 1 : 0);
             if (!d->graph_exec[v]) {
                 const long long before = d->launches;
                 CK(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
-                step_body(d, dt, special_only, nw_on);
+                step_body(d, dt, special_only, nw_on, record);
                 CK(cudaStreamEndCapture(d->stream, &d->graph[v]));
                 CK(cudaGraphInstantiate(&d->graph_exec[v], d->graph[v], 0));
                 d->launches = before;   // capture enqueues nothing
             }
             CK(cudaGraphLaunch(d->graph_exec[v], d->stream));
-            d->launches += count_step_launches(d, special_only);
+            d->launches += count_step_launches(d, special_only, record);
         } else {
-            step_body(d, dt, special_only, nw_on);
+            step_body(d, dt, special_only, nw_on, record);
         }
         d->plain_advanced = nw_on;
     }
@@ -1430,6 +1479,40 @@ int ax3d_run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
     API_BEGIN
     check_final(d);
     run_steps(d, nsteps, dt, stf);
+    API_END
+}
+
+/* Newmark::solve with the pointwise recorder buffering on the device (PointwiseRecorder's dump interval = nsteps):
+ * out[(i * nrec + r) * 3 + c] = sample of receiver r at step i, copied to the host once at the end. */
+int ax3d_run_steps_record(ax3d_domain *d, int nsteps, double dt, const float *stf, float *out) {
+    API_BEGIN
+    check_final(d);
+    const int n = d->nrec1 + d->nrec3;
+    if (!n) fail("PointwiseRecorder::record || no receivers registered (ax3d_set_receivers)");
+    if (nsteps <= 0) return 0;
+    if (nsteps > STF_RING) fail("Newmark::solve || ax3d_run_steps_record takes at most 4096 steps per call");
+    if ((size_t)nsteps > d->rec_ring_steps) {
+        CK(cudaStreamSynchronize(d->stream));
+        for (int v = 4; v < 8; ++v) {   // the ring address is baked into the recording graphs
+            if (d->graph_exec[v]) { cudaGraphExecDestroy(d->graph_exec[v]); d->graph_exec[v] = nullptr; }
+            if (d->graph[v]) { cudaGraphDestroy(d->graph[v]); d->graph[v] = nullptr; }
+        }
+        if (d->rec_ring_host) cudaFreeHost(d->rec_ring_host);
+        d->rec_ring.alloc((size_t)nsteps * n * 3);
+        CK(cudaMallocHost(&d->rec_ring_host, (size_t)nsteps * n * 3 * sizeof(float)));
+        d->rec_ring_steps = nsteps;
+    }
+    run_steps(d, nsteps, dt, stf, true);
+    CK(cudaMemcpyAsync(d->rec_ring_host, d->rec_ring.p, (size_t)nsteps * n * 3 * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    for (int i = 0; i < nsteps; ++i) {
+        const float *row = d->rec_ring_host + (size_t)i * n * 3;
+        float *o = out + (size_t)i * n * 3;
+        for (int k = 0; k < d->nrec1; ++k)
+            for (int c = 0; c < 3; ++c) o[d->rec_where1[k] * 3 + c] = row[k * 3 + c];
+        for (int k = 0; k < d->nrec3; ++k)
+            for (int c = 0; c < 3; ++c) o[d->rec_where3[k] * 3 + c] = row[(d->nrec1 + k) * 3 + c];
+    }
     API_END
 }
 
@@ -1482,15 +1565,7 @@ int ax3d_record(ax3d_domain *d, float *out) {
     check_final(d);
     const int n = d->nrec1 + d->nrec3;
     if (!n) return 0;
-    if (d->nrec1) {
-        k_ground_motion<<<d->nrec1, 128, 0, d->stream>>>(d->desc[CLS_S1D].p, d->rec1_items.p, d->rec1_w.p, d->s_field[AX3D_DISPL].p, d->rec_out.p);
-        d->launches++;
-    }
-    if (d->nrec3) {
-        k_ground_motion<<<d->nrec3, 128, 0, d->stream>>>(d->desc[CLS_S3D].p, d->rec3_items.p, d->rec3_w.p, d->s_field[AX3D_DISPL].p,
-                                                          d->rec_out.p + (size_t)3 * d->nrec1);
-        d->launches++;
-    }
+    launch_record(d, d->rec_out.p, nullptr, 0);
     CK(cudaMemcpyAsync(d->rec_host, d->rec_out.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream));
     for (int k = 0; k < d->nrec1; ++k)
@@ -1612,7 +1687,7 @@ int ax3d_record_ground_motion(ax3d_domain *d, int nrec, const int *elem_tags, co
         CK(cudaMemcpyAsync(d->rec_items.p, sub.data(), sub.size() * sizeof(RecvItem), cudaMemcpyHostToDevice, d->stream));
         CK(cudaMemcpyAsync(d->rec_w.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, d->stream));
         const int c = pass == 1 ? CLS_S3D : CLS_S1D;
-        k_ground_motion<<<(int)sub.size(), 128, 0, d->stream>>>(d->desc[c].p, d->rec_items.p, d->rec_w.p, d->s_field[AX3D_DISPL].p, d->rec_out.p);
+        k_ground_motion<<<(int)sub.size(), AX_REC_NT, 0, d->stream>>>(d->desc[c].p, d->rec_items.p, d->rec_w.p, d->s_field[AX3D_DISPL].p, d->rec_out.p, nullptr, 0);
         d->launches++;
         CK(cudaMemcpyAsync(d->rec_host, d->rec_out.p, sub.size() * 3 * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
         CK(cudaStreamSynchronize(d->stream));
@@ -1642,6 +1717,15 @@ int ax3d_algorithmic_bytes(ax3d_domain *d, double out[3]) {
 int ax3d_enable_timers(ax3d_domain *d, int on) {
     API_BEGIN
     d->timers = on != 0;
+    API_END
+}
+int ax3d_dominant_kernel(ax3d_domain *d, double *ms_per_launch, double bytes[2], int reset) {
+    API_BEGIN
+    check_final(d);
+    *ms_per_launch = d->dom_launches ? d->dom_ms / (double)d->dom_launches : 0.0;
+    bytes[0] = d->dom_bytes[0];
+    bytes[1] = d->n_plain > 0 ? d->dom_bytes[1] : 0.0;
+    if (reset) { d->dom_ms = 0; d->dom_launches = 0; }
     API_END
 }
 int ax3d_get_timers(ax3d_domain *d, double out_ms[4], int reset) {

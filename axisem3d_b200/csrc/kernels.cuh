@@ -593,39 +593,55 @@ struct RecvItem {
     int elem;
     float phi;
 };
-__global__ void __launch_bounds__(128) k_ground_motion(const ElemDesc *__restrict__ elems, const RecvItem *__restrict__ rec,
-                                                       const float *__restrict__ weights, const float2 *__restrict__ displ,
-                                                       float *__restrict__ out) {
+// Element::computeGroundMotion (SolidElement.cpp:189-216): u(phi) = sum_p w_p (u_0 + 2 Re sum_{alpha>=1} u_alpha e^{i alpha phi}).
+// One CTA of AX_REC_NT threads per receiver; thread = (point, mode) pairs, warp-shuffle + shared reduction.
+#define AX_REC_NT 512
+__global__ void __launch_bounds__(AX_REC_NT) k_ground_motion(const ElemDesc *__restrict__ elems, const RecvItem *__restrict__ rec,
+                                                             const float *__restrict__ weights, const float2 *__restrict__ displ,
+                                                             float *__restrict__ out, const int *__restrict__ slot, int slot_stride) {
+    if (slot) out += (size_t)(*slot) * slot_stride;   // device-side record ring (ax3d_run_steps_record): row of this step
+    __shared__ float s_w[AX_NPE];
+    __shared__ unsigned s_off[AX_NPE];
+    __shared__ int s_stride[AX_NPE], s_nlive[AX_NPE];
+    __shared__ float red[3][AX_REC_NT / 32];
     const RecvItem R = rec[blockIdx.x];
     const ElemDesc &E = elems[R.elem];
-    const float *w = weights + (size_t)blockIdx.x * AX_NPE;
+    if (threadIdx.x < AX_NPE) {
+        const int p = threadIdx.x;
+        s_w[p] = weights[(size_t)blockIdx.x * AX_NPE + p];
+        s_off[p] = E.pt_off[p];
+        s_stride[p] = E.pt_stride[p];
+        s_nlive[p] = E.pt_nlive[p];
+    }
     const int top = E.nu - E.nyq;   // last mode used
+    __syncthreads();
     float acc[3] = {0.f, 0.f, 0.f};
-    for (int idx = threadIdx.x; idx < AX_NPE * (top + 1); idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < AX_NPE * (top + 1); idx += AX_REC_NT) {
         const int p = idx / (top + 1), alpha = idx - p * (top + 1);
-        const float wp = w[p];
-        if (fabsf(wp) < 1e-10f || alpha >= E.pt_nlive[p]) continue;
+        const float wp = s_w[p];
+        if (fabsf(wp) < 1e-10f || alpha >= s_nlive[p]) continue;
         float sn, cs;
         sincosf((float)alpha * R.phi, &sn, &cs);
         const float fac = alpha == 0 ? 1.f : 2.f;
-        const size_t base = (size_t)E.pt_off[p] + alpha;
+        const size_t base = (size_t)s_off[p] + alpha;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float2 u = displ[base + (size_t)c * E.pt_stride[p]];
+            float2 u = displ[base + (size_t)c * s_stride[p]];
             const float re = alpha == 0 ? u.x : (cs * u.x - sn * u.y);
             acc[c] += wp * fac * re;
         }
     }
-    __shared__ float red[3][128];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) red[c][threadIdx.x] = acc[c];
-    __syncthreads();
-    for (int s = 64; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
+    for (int c = 0; c < 3; ++c) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) red[c][threadIdx.x] += red[c][threadIdx.x + s];
-        }
-        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        if ((threadIdx.x & 31) == 0) red[c][threadIdx.x >> 5] = acc[c];
     }
-    if (threadIdx.x < 3) out[blockIdx.x * 3 + threadIdx.x] = red[threadIdx.x][0];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < AX_REC_NT / 32; ++k) t += red[threadIdx.x][k];
+        out[blockIdx.x * 3 + threadIdx.x] = t;
+    }
 }

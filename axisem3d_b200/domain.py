@@ -203,6 +203,13 @@ class Domain:
         capi.check(self.lib.ax3d_run_steps_timed(self.h, stf.size, float(dt), _pf(stf), C.byref(ms)))
         return ms.value
 
+    def runStepsRecord(self, dt, stf):
+        """Newmark::solve with Domain::record after every update; returns the seismograms [nsteps][nrec][3] (s, phi, z)."""
+        stf = _f32(stf)
+        out = np.empty((stf.size, self._nrec, 3), dtype=np.float32)
+        capi.check(self.lib.ax3d_run_steps_record(self.h, stf.size, float(dt), _pf(stf), _pf(out)))
+        return out
+
     def setReceivers(self, elem_tags, phi, weights):
         et = np.ascontiguousarray(elem_tags, dtype=np.int32)
         ph = _f32(phi)
@@ -214,6 +221,13 @@ class Domain:
         out = np.zeros((self._nrec, 3), dtype=np.float32)
         capi.check(self.lib.ax3d_record(self.h, _pf(out)))
         return out
+
+    def dominant_kernel(self, reset=True):
+        """(ms per launch, algorithmic bytes [elements, in-kernel Newmark points]) of the solid fused element kernel."""
+        ms = C.c_double(0)
+        b = np.zeros(2, dtype=np.float64)
+        capi.check(self.lib.ax3d_dominant_kernel(self.h, C.byref(ms), b.ctypes.data_as(C.POINTER(C.c_double)), 1 if reset else 0))
+        return ms.value, b
 
     def synchronize(self):
         capi.check(self.lib.ax3d_synchronize(self.h))

@@ -559,6 +559,11 @@ public:
     }
     // whole time loop on the device, one CUDA-graph replay per step (what Newmark::solve uses when no recorder needs the host)
     void runSteps(int nsteps, double dt, const Real *stf) const { finalize(); check(ax3d_run_steps(mDom, nsteps, dt, stf)); }
+    // Newmark::solve with Domain::record after every update, recorder buffer on the device (dump interval = nsteps)
+    void runStepsRecord(int nsteps, double dt, const Real *stf, Real *out) const {
+        finalize();
+        check(ax3d_run_steps_record(mDom, nsteps, dt, stf, out));
+    }
     void synchronize() const { check(ax3d_synchronize(mDom)); }
     ax3d_domain *handle() const { return mDom; }
 

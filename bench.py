@@ -241,28 +241,33 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     stable = dom.checkStability()
 
-    # ---- end-to-end through the C-ABI verbs with host buffers: per step a pinned H2D copy of the source factor and a
-    #      D2H read of the 128 receiver samples (Newmark.cpp:49-70 order: update, source, stiff, couple, assemble, record)
+    # ---- end-to-end through the C-ABI with host buffers: ax3d_run_steps_record = Newmark::solve with the pointwise
+    #      recorder (Newmark.cpp:49-70 order: update, record, source, stiff, couple, assemble).  Per step the host source
+    #      factor goes H2D through a pinned slot (8 bytes) and the 128 receiver samples come back D2H (one copy per batch of
+    #      BATCH steps = the recorder's dump interval; the call returns only when the samples are in host memory).
+    BATCH = 25
+    dom.runStepsRecord(dt, stf[:3])          # graph variants of the recording path
     barrier()
     t0 = time.perf_counter()
-    for i in range(K):
-        dom.updateNewmark(dt)
-        dom.applySource(float(stf[W + K + i]))
-        dom.computeStiff()
-        dom.coupleSolidFluid()
-        dom.assembleStiff(-1)
-        seis = dom.record()
-        dom.assembleStiff(1)
+    done = 0
+    while done < K:
+        nb = min(BATCH, K - done)
+        seis = dom.runStepsRecord(dt, stf[W + K + done:W + K + done + nb])
+        done += nb
     barrier()
     e2e_s = time.perf_counter() - t0
+    seis_bytes_per_step = int(seis[0].nbytes)
 
-    # ---- per-family device times (CUDA events on the launching stream) for the roofline of the dominant kernel family
+    # ---- per-family device times and the dominant kernel's launch time: CUDA events on the launching stream around each
+    #      family / around the solid k_elem3d_fused launch, steps issued through ax3d_run_steps (eager, not the graph), so
+    #      the in-kernel Newmark is active exactly as in the timed region above
     dom.enable_timers(True)
     dom.get_timers(reset=True)
-    nt = min(K, 10)
-    for i in range(nt):
-        dom.step(dt, 0.0)
+    dom.dominant_kernel(reset=True)
+    nt = max(min(K, 12), 4)
+    dom.runSteps(dt, stf[:nt])
     fam = dom.get_timers(reset=True) / nt          # ms: newmark, elements, sf+source, halo
+    dk_ms, dk_bytes = dom.dominant_kernel(reset=True)
     dom.enable_timers(False)
 
     if dist is not None:
@@ -291,11 +296,21 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("elements_dram_bytes_per_step")
+        if CFG == "cfg2" and world == 1:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_elem3d_fused_dram_bytes_per_launch_cfg2")
     except Exception:
         pass
     el_ms = float(fam[1])
-    achieved = alg[1] / (el_ms * 1e-3) / 1e9 if el_ms > 0 else 0.0
+    if dk_ms > 0:
+        dk_name = "k_elem3d_fused<solid> (gather+grad+c2r+stress+r2c+quad+scatter of the 3D solid elements" + \
+                  (" + in-kernel Newmark of the plain solid points)" if dk_bytes[1] > 0 else ")")
+        dk_total = float(dk_bytes.sum())
+        achieved = dk_total / (dk_ms * 1e-3) / 1e9
+    else:   # no fused launch in this configuration (e.g. cfg1: all elements 1D): fall back to the element family
+        dk_name = "element stiffness family (k_elem1d)"
+        dk_total = float(alg[1])
+        achieved = alg[1] / (el_ms * 1e-3) / 1e9 if el_ms > 0 else 0.0
+        dk_ms = el_ms
     step_bytes = float(alg.sum())
     line = {
         "metric": METRIC, "value": work * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -307,12 +322,14 @@ def run_ours(args):
                          ((4 * 8 * (dom.field_size(False) + dom.field_size(True)) + alg[1] * 0.2) / 1e6),
                    "stable": bool(stable)},
         "clocks": clocks,
-        "e2e": {"value": work * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4, "d2h_bytes_per_step": int(seis.nbytes),
+        "e2e": {"value": work * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": seis_bytes_per_step, "batch_steps": BATCH,
                 "ms_per_step": 1e3 * e2e_s / K},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "element stiffness family (k_elem3d_fused dominant, + k_elem1d)",
+        "roofline": {"bound": "hbm", "kernel": dk_name,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src,
+                     "kernel_ms_per_launch": dk_ms, "kernel_algorithmic_bytes_per_launch": dk_total,
+                     "kernel_bytes_split": {"elements": float(dk_bytes[0]), "points_in_kernel": float(dk_bytes[1])},
                      "algorithmic_bytes_per_step": {"points": alg[0], "elements": alg[1], "halo": alg[2]},
                      "family_ms": {"newmark": float(fam[0]), "elements": el_ms, "sf_source": float(fam[2]), "halo": float(fam[3])},
                      "whole_step": {"achieved": step_bytes / (ms / K * 1e-3) / 1e9, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak}},

@@ -127,6 +127,10 @@ int ax3d_reset_zero(ax3d_domain *dom);
 /* nsteps iterations of the Newmark::solve loop body (Newmark.cpp:47-93: update, source, stiff, couple,
  * assemble) with stf[i] as the source factor of step i; launched as one CUDA graph replay per step. */
 int ax3d_run_steps(ax3d_domain *dom, int nsteps, double dt, const float *stf);
+/* the same loop with Domain::record (Domain.cpp:207-220) after the update of every step, for the receivers registered
+ * with ax3d_set_receivers: samples are buffered on the device (PointwiseRecorder's buffer, PointwiseRecorder.cpp:62-144,
+ * with dump interval = nsteps <= 4096) and copied once: out[(i * nrec + r) * 3 + c], i = step, r = receiver. */
+int ax3d_run_steps_record(ax3d_domain *dom, int nsteps, double dt, const float *stf, float *out);
 /* the same loop, timed on the device with CUDA events on the launching stream; *ms = elapsed milliseconds. */
 int ax3d_run_steps_timed(ax3d_domain *dom, int nsteps, double dt, const float *stf, float *ms);
 /* blocks until the device finished all queued work of this domain. */
@@ -167,6 +171,11 @@ int ax3d_algorithmic_bytes(ax3d_domain *dom, double out[3]);
  * events on the launching stream when profiling is enabled: out[0] newmark, [1] elements(stiff),
  * [2] solid-fluid + source, [3] halo. */
 int ax3d_enable_timers(ax3d_domain *dom, int on);
+/* the dominant kernel of the step (the solid k_elem3d_fused launch, which also advances the "plain" solid points to the
+ * next step): average device time per launch [ms] over the timed launches (CUDA events on the launching stream, timers
+ * enabled, steps issued through ax3d_run_steps) and its algorithmic bytes per launch: bytes[0] elements of the launch,
+ * bytes[1] points updated in-kernel (192 B per mode + mass). */
+int ax3d_dominant_kernel(ax3d_domain *dom, double *ms_per_launch, double bytes[2], int reset);
 int ax3d_get_timers(ax3d_domain *dom, double out_ms[4], int reset);
 
 #ifdef __cplusplus
