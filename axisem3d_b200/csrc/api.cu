@@ -227,8 +227,18 @@ struct ax3d_domain {
 static void fail(const std::string &m) { throw std::runtime_error(m); }
 
 // ------------------------------------------------------------------------------------------ FFT plans
+// Largest power-of-two radix of the plans of this process: 8 when the warp-per-point element kernel is in use (default),
+// 16 with AX3D_WP=0 (thread-per-(mode, point) kernel).  Every phi-dependent array is uploaded in the digit-reversed order
+// of these plans, so all kernels of a process share them.
+static bool use_wp() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("AX3D_WP"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v != 0;
+}
+static int plan_maxr2() { return use_wp() ? 8 : 16; }
+
 static std::vector<int> choose_radices(int N) {
-    const RadixList rl = choose_radices_ct(N);   // fft.cuh: the one definition host and kernels share
+    const RadixList rl = choose_radices_ct(N, plan_maxr2());   // fft.cuh: the one definition host and kernels share
     if (rl.n < 0) fail("ax3d::plan || Nr = " + std::to_string(N) + " is not a lucky number (prime factor > 13 or too many stages; PreloopFFTW.cpp:59-99)");
     std::vector<int> r(rl.r, rl.r + rl.n);
     if (r.empty()) r.push_back(1);
@@ -278,6 +288,20 @@ static int get_plan(ax3d_domain *d, int N) {
         }
     }
     pl.stw_len = (int)d->h_stw.size() - pl.stw_base;
+    // the same tables p-major (fused_wp.cuh): T2_s[p * Ls + j] at stw_off[s] + stw2_delta
+    pl.stw2_delta = pl.stw_len;
+    {
+        int L = N;
+        for (int s = 0; s < pl.nstages; ++s) {
+            const int R = pl.radix[s], Ls = L / R;
+            if (Ls > 1) {
+                const size_t src = (size_t)pl.stw_off[s];
+                for (int pp = 0; pp < R; ++pp)
+                    for (int j = 0; j < Ls; ++j) { const float2 w = d->h_stw[src + (size_t)j * R + pp]; d->h_stw.push_back(w); }
+            }
+            L = Ls;
+        }
+    }
     int id = (int)d->h_plans.size();
     d->h_plans.push_back(pl);
     d->h_perm.push_back(perm);
@@ -968,10 +992,19 @@ static void apply_source(ax3d_domain *d, float stf) {
 // (none is instantiated by default: on B200 the specialised body measured no faster than the generic one -- the kernel
 //  is latency-, not instruction-bound -- while doubling the code size; profiles/r1_fused_kernel_history.md)
 #define AX_FUSED_SPECIALISATIONS(X)
+// the same for the warp-per-point body (fused_wp.cuh), where compile-time strides and trip counts do pay: Nr = 208 is
+// Nu = 100 (configs[1]) after the lucky-number rounding of PreloopFFTW.cpp:59-99
+#define AX_WP_SPECIALISATIONS(X) X(false, 208)
 
 static bool fused_specialised(bool fluid, int N) {
     const char *env = getenv("AX3D_NO_SPECIALISED");
     if (env && atoi(env) != 0) return false;
+    if (use_wp()) {
+#define X(F, NCT) if (fluid == F && N == NCT) return true;
+        AX_WP_SPECIALISATIONS(X)
+#undef X
+        return false;
+    }
 #define X(F, NCT) if (fluid == F && N == NCT) return true;
     AX_FUSED_SPECIALISATIONS(X)
 #undef X
@@ -981,7 +1014,10 @@ static bool fused_specialised(bool fluid, int N) {
 // 512 threads = 128 registers/thread.  Measured on B200 (cfg2, elements family): 416 -> 0.270 ms, 448 -> 0.266, 512 -> 0.259,
 // 640 (96 regs) -> 0.289, 768 (80 regs) -> 0.310: the kernel is not occupancy-limited.  With Newmark warps the CTA is
 // 448 compute + 64 Newmark threads.
-static int fused_nt(const FusedLaunch &f) { return f.nww ? AX_NW_NT + 32 * AX_NWW : 512; }
+static int fused_nt(const FusedLaunch &f) {
+    if (use_wp()) return AX_WP_NT + 32 * f.nww;
+    return f.nww ? AX_NW_NT + 32 * AX_NWW : 512;
+}
 
 typedef void (*fused_kernel_t)(const ElemDesc *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
                                float *, const float2 *, float2 *, int, int, int, unsigned *, const NwArgs);
@@ -991,7 +1027,16 @@ static fused_kernel_t fused_kernel(const FusedLaunch &f) {
 #define X(F, NCT) if (fluid == F && f.nct == NCT && f.nww == 0) return k_elem3d_fused<F, 512, 0, NCT>;
     AX_FUSED_SPECIALISATIONS(X)
 #undef X
+    if (use_wp()) {
+#define X(F, NCT) if (fluid == F && f.nct == NCT) return f.nww ? k_elem3d_fused<F, AX_WP_NT, F ? 0 : AX_NWW, NCT, true> : k_elem3d_fused<F, AX_WP_NT, 0, NCT, true>;
+        AX_WP_SPECIALISATIONS(X)
+#undef X
+    }
     if (f.nct != 0) fail("ax3d::fused || no specialised kernel for this launch");
+    if (use_wp()) {
+        if (fluid) return k_elem3d_fused<true, AX_WP_NT, 0, 0, true>;
+        return f.nww ? k_elem3d_fused<false, AX_WP_NT, AX_NWW, 0, true> : k_elem3d_fused<false, AX_WP_NT, 0, 0, true>;
+    }
     if (fluid) return k_elem3d_fused<true, 512, 0, 0>;
     return f.nww ? k_elem3d_fused<false, AX_NW_NT, AX_NWW, 0> : k_elem3d_fused<false, 512, 0, 0>;
 }

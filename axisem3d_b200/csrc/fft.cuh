@@ -28,21 +28,32 @@ struct FftPlan {
     // i.e. L_s == R_s).  All tables of one plan are contiguous: [stw_base, stw_base + stw_len).
     int stw_off[AX_MAX_STAGES];
     int stw_base, stw_len;
+    // the same tables once more in p-major order, T2_s[p * (L_s / R_s) + j], for the warp-per-point kernel (fused_wp.cuh: lanes
+    // run over j, so the p-major rows are read conflict-free): table of stage s at stwpool[stw_off[s] + stw2_delta]
+    int stw2_delta;
 };
 
 // Radix sequence of the DIF transform of length N (shared by the host planner and the compile-time specialised
 // kernels, which must agree because phi-dependent arrays are uploaded in the digit-reversed order of this plan):
 // powers of two first (16s, then the 8/4/2 remainder), then odd primes 13, 11, 7, 5, 3 -- so that the LAST DIF
 // stage (stride-1 butterflies) has an odd radix whenever N has an odd factor.  n == 0 marks an unsupported N.
+// maxr2 = 16: powers of two as 16s + remainder (one thread per butterfly, many columns per CTA: fused.cuh, kernels.cuh);
+// maxr2 = 8: as 8s and 4s (2^4 -> 4 4, 2^5 -> 8 4, 2^6 -> 8 8, ...) for the warp-per-point kernel, whose 72-register
+// budget and 3 columns per warp favour small butterflies (fused_wp.cuh).
 struct RadixList {
     int n;
     int r[AX_MAX_STAGES];
 };
-__host__ __device__ constexpr RadixList choose_radices_ct(int N) {
+__host__ __device__ constexpr RadixList choose_radices_ct(int N, int maxr2 = 16) {
     RadixList out{0, {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
     int n = N, e = 0;
     while (n % 2 == 0 && n > 0) { n /= 2; ++e; }
-    while (e >= 4) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 16; ++out.n; e -= 4; }
+    if (maxr2 >= 16) {
+        while (e >= 4) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 16; ++out.n; e -= 4; }
+    } else {
+        while (e > 4 || e == 3) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 8; ++out.n; e -= 3; }
+        while (e >= 2) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 4; ++out.n; e -= 2; }
+    }
     if (e == 3) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 8; ++out.n; }
     else if (e == 2) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 4; ++out.n; }
     else if (e == 1) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 2; ++out.n; }

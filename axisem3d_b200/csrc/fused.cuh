@@ -245,8 +245,9 @@ __device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, co
 template <bool FLUID, int NT>
 __device__ __forceinline__ void physical_space(const ElemDesc &E, const float *__restrict__ coef, const float *__restrict__ attpar,
                                                float *__restrict__ attstate, float2 *__restrict__ Z, int N, int ldz, int p0, int np,
-                                               int tid) {
-    const int total = np * N, cf_stride = AX_NPE * N, cs = np * ldz;
+                                               int tid, int cs_in = 0) {
+    // cs: distance between the columns of two pairs of one point (cs_in != 0: Z is a window into a full 25-point tile)
+    const int total = np * N, cf_stride = AX_NPE * N, cs = cs_in ? cs_in : np * ldz;
     const float *cf0 = coef + E.coef_off + (size_t)p0 * N;
     const int law = E.law;
     if constexpr (!FLUID) {
@@ -715,11 +716,14 @@ __device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, uns
     }
 }
 
+#include "fused_wp.cuh"
+
 // ---------------------------------------------------------------- the kernel   @phase kernel loop
 // grid: persistent, one CTA per SM; block NT compute threads (+ 32 * NWW Newmark threads).  work[0] = next element index
 // (starts at gridDim.x), work[1] = number of warps that have finished; the last one re-arms the counters for the next
 // launch (graph replay).
-template <bool FLUID, int NT, int NWW, int NCT1>
+// WP: warp-per-point element body (fused_wp.cuh; NT = 800) instead of the thread-per-(mode, point) body above.
+template <bool FLUID, int NT, int NWW, int NCT1, bool WP = false>
 __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
                    const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
@@ -794,13 +798,16 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
             if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
             cta_sync<NT, NWW>();
             gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1));
+            float gv = 0.f, gv_next = 0.f;   // WP: geometry of the current / next element (wp_load_geom)
+            if constexpr (WP) gv = wp_load_geom(sE[0], geom, tid, FLUID);
             int tw_plan = -1;
             for (int it = 0, k = 0; e < nelem; it ^= 1, k = (k == 2 ? 0 : k + 1)) {
                 const ElemDesc &E = sE[it];
                 const FftPlan &P = sP[it];
                 const int kn = k == 2 ? 0 : k + 1, knn = kn == 2 ? 0 : kn + 1;   // ring slots of the next two elements
                 if (tw_plan != E.plan_id) {   // TW is idle here: the FFT stages of the previous element are barrier-separated
-                    for (int k = tid; k < P.stw_len; k += NT) cx.TW[k] = stwpool[P.stw_base + k];
+                    const int tb = P.stw_base + (WP ? P.stw2_delta : 0);   // WP: the p-major copies of the stage tables
+                    for (int k = tid; k < P.stw_len; k += NT) cx.TW[k] = stwpool[tb + k];
                     tw_plan = E.plan_id;
                 }
                 // moduli of this element -> L2 while gather/grad/c2r run
@@ -824,9 +831,14 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                     if (sIdx[kn] < nelem) {
                         const ElemDesc &En = sE[it ^ 1];
                         gather(En, 0, min(En.mt, En.nu + 1));
+                        if constexpr (WP) gv_next = wp_load_geom(En, geom, tid, FLUID);
                     }
                 };
-                if (NCT1 != 0 && E.nr == NCT1) fused_element<FLUID, NT, NWW, NCT1>(cx, E, P, tid, gather, after_first_sync, after_grad);
+                if constexpr (WP) {
+                    if (NCT1 != 0 && E.nr == NCT1) wp_element<FLUID, NT, NWW, NCT1>(cx, E, P, tid, gv, gather, after_first_sync, after_grad);
+                    else wp_element<FLUID, NT, NWW, 0>(cx, E, P, tid, gv, gather, after_first_sync, after_grad);
+                    gv = gv_next;
+                } else if (NCT1 != 0 && E.nr == NCT1) fused_element<FLUID, NT, NWW, NCT1>(cx, E, P, tid, gather, after_first_sync, after_grad);
                 else fused_element<FLUID, NT, NWW, 0>(cx, E, P, tid, gather, after_first_sync, after_grad);
                 if (nw_on) {
                     if (tid < AX_NPE) sArrCode[n_done & 3][tid] = E.pt_nw[tid];
