@@ -227,12 +227,12 @@ struct ax3d_domain {
 static void fail(const std::string &m) { throw std::runtime_error(m); }
 
 // ------------------------------------------------------------------------------------------ FFT plans
-// Largest power-of-two radix of the plans of this process: 8 when the warp-per-point element kernel is in use (default),
-// 16 with AX3D_WP=0 (thread-per-(mode, point) kernel).  Every phi-dependent array is uploaded in the digit-reversed order
+// Largest power-of-two radix of the plans of this process: 8 when the warp-per-point element kernel is in use (AX3D_WP=1),
+// 16 otherwise (thread-per-(mode, point) kernel, the default).  Every phi-dependent array is uploaded in the digit-reversed order
 // of these plans, so all kernels of a process share them.
 static bool use_wp() {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("AX3D_WP"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    if (v < 0) { const char *e = getenv("AX3D_WP"); v = (e && atoi(e) != 0) ? 1 : 0; }
     return v != 0;
 }
 static int plan_maxr2() { return use_wp() ? 8 : 16; }
