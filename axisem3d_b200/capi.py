@@ -18,6 +18,7 @@ SYMBOLS = [
     "ax3d_get_field_bulk", "ax3d_set_field_bulk", "ax3d_field_size", "ax3d_record_ground_motion",
     "ax3d_launch_count", "ax3d_work_per_step", "ax3d_algorithmic_bytes", "ax3d_enable_timers",
     "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_dominant_kernel", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
+    "ax3d_halo_export", "ax3d_halo_connect",
 ]
 
 
@@ -74,6 +75,8 @@ def load(build_if_missing=True):
     lib.ax3d_set_receivers.argtypes = [vp, i, pi_, pf, pf]
     lib.ax3d_record.argtypes = [vp, pf]
     lib.ax3d_nccl_unique_id.argtypes = [vp]
+    lib.ax3d_halo_export.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    lib.ax3d_halo_connect.argtypes = [vp, i, vp, C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), pi_]
     lib.ax3d_get_point_field.argtypes = [vp, i, i, i, pf, i]
     lib.ax3d_set_point_field.argtypes = [vp, i, i, i, pf, i]
     lib.ax3d_get_field_bulk.argtypes = [vp, i, i, pf, C.c_size_t]

@@ -188,6 +188,15 @@ struct ax3d_domain {
     std::vector<size_t> neigh_begin;   // offsets into the packed buffers (float2)
     DevBuf<unsigned> halo_idx;
     DevBuf<float2> halo_send, halo_recv;
+    // peer-memory halo (k_halo_put / k_halo_wait_add): own window = [2][total] float2 followed by one arrival counter
+    // per neighbour; the neighbours' windows are mapped with cudaIpcOpenMemHandle (or passed as raw pointers in-process)
+    DevBuf<float2> halo_win;
+    DevBuf<unsigned> halo_step;
+    std::vector<float2 *> peer_win;          // per neighbour: where my segment starts in its window (parity 0)
+    std::vector<size_t> peer_stride;         // per neighbour: its parity stride (= its total)
+    std::vector<unsigned *> peer_count;      // per neighbour: its arrival counter for me
+    std::vector<void *> peer_mapped;         // bases returned by cudaIpcOpenMemHandle (closed at destroy)
+    bool peer_halo = false;
     bool have_uid = false;
     unsigned char uid[128];
 #ifdef AX3D_WITH_NCCL
@@ -854,9 +863,14 @@ static void finalize(ax3d_domain *d) {
         d->halo_idx.upload(idx);
         d->halo_send.alloc(idx.size());
         d->halo_recv.alloc(idx.size());
+        d->halo_win.alloc(2 * idx.size() + (d->neigh_rank.size() + 1) / 2 + 1);   // window + counters: one IPC handle maps both
+        d->halo_win.zero();
+        d->halo_step.alloc(1);
+        d->halo_step.zero();
         d->alg_bytes[2] = hb;
     }
-    d->bad_flag.alloc(1);
+    d->bad_flag.alloc(2);   // [0] non-finite displacement (checkStability), [1] peer-halo wait timed out
+    d->bad_flag.zero();
     d->stf_dev.alloc(2);   // {source factor (float), record-ring slot (int)} of the step being enqueued
     d->stf_dev.zero();
     CK(cudaMallocHost(&d->stf_pinned, 2 * STF_RING * sizeof(float)));
@@ -1149,6 +1163,34 @@ static void couple_solid_fluid(ax3d_domain *d) {
 static void assemble_stiff(ax3d_domain *d, int phase) {
     if (d->nproc <= 1 || d->neigh_rank.empty()) return;
     TimerScope ts(d, 3);
+    if (d->peer_halo) {
+        const size_t total = d->neigh_begin.back();
+        if (phase <= 0) {
+            for (size_t n = 0; n < d->neigh_rank.size(); ++n) {
+                const size_t b = d->neigh_begin[n], cnt = d->neigh_begin[n + 1] - b;
+                if (!cnt) continue;
+                k_halo_put<<<nblk(cnt, 256), 256, 0, d->stream>>>((int)cnt, d->halo_idx.p + b, d->s_field[AX3D_STIFF].p, d->f_field[AX3D_STIFF].p,
+                                                                  d->peer_win[n], d->peer_stride[n], d->peer_count[n], d->halo_step.p);
+                d->launches++;
+            }
+        }
+        if (phase >= 0) {
+            // neighbour order = reference order (Domain.cpp:143-149); one launch per neighbour keeps the sum order fixed
+            for (size_t n = 0; n < d->neigh_rank.size(); ++n) {
+                const size_t b = d->neigh_begin[n], cnt = d->neigh_begin[n + 1] - b;
+                if (!cnt) continue;
+                k_halo_wait_add<<<nblk(cnt, 256), 256, 0, d->stream>>>((int)cnt, d->halo_idx.p + b, d->halo_win.p + b, total,
+                                                                       reinterpret_cast<unsigned *>(d->halo_win.p + 2 * total) + n,
+                                                                       d->halo_step.p, d->s_field[AX3D_STIFF].p, d->f_field[AX3D_STIFF].p,
+                                                                       d->bad_flag.p + 1);
+                d->launches++;
+            }
+            k_halo_advance<<<1, 1, 0, d->stream>>>(d->halo_step.p);
+            d->launches++;
+        }
+        CK(cudaGetLastError());
+        return;
+    }
 #ifdef AX3D_WITH_NCCL
     if (!d->comm) fail("Domain::assembleStiff || no NCCL communicator (ax3d_set_messaging needs the unique id)");
     const size_t total = d->neigh_begin.back();
@@ -1221,6 +1263,7 @@ int ax3d_destroy(ax3d_domain *d) {
 #ifdef AX3D_WITH_NCCL
     if (d->comm) ncclCommDestroy(d->comm);
 #endif
+    for (void *m : d->peer_mapped) cudaIpcCloseMemHandle(m);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
@@ -1349,6 +1392,60 @@ int ax3d_set_messaging(ax3d_domain *d, int rank, int nproc, const void *uid, int
     API_END
 }
 
+/* Peer-memory halo, step 1 (after ax3d_finalize_setup): describe this rank's receive window.  out_handle64 receives the
+ * cudaIpcMemHandle_t of the window, out_ptr its address in this process (for neighbours that live in the same process),
+ * neigh_begin[nneigh + 1] the start of every neighbour's segment (float2 units), counters follow the window:
+ * the counter for neighbour n is at ((unsigned *)(win + 2 * total)) -- i.e. byte offset 16 * total + 4 * n -- see below. */
+int ax3d_halo_export(ax3d_domain *d, void *out_handle64, void **out_ptr, long long *neigh_begin, long long *total) {
+    API_BEGIN
+    check_final(d);
+    if (d->nproc <= 1 || d->neigh_rank.empty()) fail("Domain::setMessaging || this rank has no neighbours");
+    // one allocation = window + counters, so that one handle maps both
+    const size_t tot = d->neigh_begin.back(), nn = d->neigh_rank.size();
+    if (out_handle64) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, d->halo_win.p));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t");
+        memcpy(out_handle64, &h, 64);
+    }
+    if (out_ptr) *out_ptr = d->halo_win.p;
+    for (size_t n = 0; n <= nn; ++n) neigh_begin[n] = (long long)d->neigh_begin[n];
+    *total = (long long)tot;
+    API_END
+}
+
+/* Peer-memory halo, step 2: for every neighbour (in ax3d_set_messaging order) the neighbour's window -- as a 64-byte IPC
+ * handle (handles != NULL: other process on the same node) or as a device pointer of this process (ptrs) --, the start
+ * of MY segment in it (peer_begin, float2 units), its total (= parity stride) and my index in its neighbour list
+ * (peer_slot: which of its counters is mine).  From here on Domain::assembleStiff uses k_halo_put / k_halo_wait_add
+ * and multi-rank steps replay from the CUDA graph. */
+int ax3d_halo_connect(ax3d_domain *d, int nneigh, const void *handles, void *const *ptrs, const long long *peer_begin,
+                      const long long *peer_total, const int *peer_slot) {
+    API_BEGIN
+    check_final(d);
+    if (nneigh != (int)d->neigh_rank.size()) fail("Domain::setMessaging || ax3d_halo_connect: neighbour count mismatch");
+    d->peer_win.assign(nneigh, nullptr);
+    d->peer_stride.assign(nneigh, 0);
+    d->peer_count.assign(nneigh, nullptr);
+    for (int n = 0; n < nneigh; ++n) {
+        void *base = nullptr;
+        if (handles) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char *)handles + 64 * n, 64);
+            CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            d->peer_mapped.push_back(base);
+        } else {
+            base = ptrs[n];
+        }
+        if (!base) fail("Domain::setMessaging || ax3d_halo_connect: null window");
+        d->peer_win[n] = (float2 *)base + peer_begin[n];
+        d->peer_stride[n] = (size_t)peer_total[n];
+        d->peer_count[n] = (unsigned *)((float2 *)base + 2 * peer_total[n]) + peer_slot[n];
+    }
+    d->peer_halo = true;
+    API_END
+}
+
 /* ncclGetUniqueId on the calling rank (rank 0 calls it and broadcasts the 128 bytes; XMPI::initialize analogue). */
 int ax3d_nccl_unique_id(void *out128) {
     API_BEGIN
@@ -1405,13 +1502,15 @@ int ax3d_assemble_stiff(ax3d_domain *d, int phase) {
 int ax3d_check_stability(ax3d_domain *d, int *stable) {
     API_BEGIN
     check_final(d);
-    d->bad_flag.zero();
+    CK(cudaMemsetAsync(d->bad_flag.p, 0, sizeof(int), d->stream));
     if (d->s_len) k_check_finite<<<296, 256, 0, d->stream>>>(d->s_len * 2, (const float *)d->s_field[0].p, d->bad_flag.p);
     if (d->f_len) k_check_finite<<<296, 256, 0, d->stream>>>(d->f_len * 2, (const float *)d->f_field[0].p, d->bad_flag.p);
     d->launches += 2;
-    int bad = 0;
-    CK(cudaMemcpyAsync(&bad, d->bad_flag.p, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    int bad2[2] = {0, 0};
+    CK(cudaMemcpyAsync(bad2, d->bad_flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream));
+    if (bad2[1]) fail("Domain::assembleStiff || peer-memory halo: a neighbour's boundary stiffness never arrived (timeout)");
+    const int bad = bad2[0];
     if (d->n_plain > 0) {
         unsigned ctl[4] = {0, 0, 0, 0};
         CK(cudaMemcpy(ctl, d->nw_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost));
@@ -1476,8 +1575,9 @@ static long long count_step_launches(ax3d_domain *d, bool special_only, bool rec
     n += d->sf_tab.nrows > 0;
     n += !d->h_sf3d.empty();
     if (d->nproc > 1 && !d->neigh_rank.empty()) {
-        n += 1;   // k_pack
-        for (size_t k = 0; k < d->neigh_rank.size(); ++k) n += d->neigh_begin[k + 1] > d->neigh_begin[k];   // k_unpack_add
+        n += 1;   // k_pack (NCCL path) / k_halo_advance (peer path)
+        for (size_t k = 0; k < d->neigh_rank.size(); ++k)
+            n += (d->peer_halo ? 2 : 1) * (d->neigh_begin[k + 1] > d->neigh_begin[k]);   // [k_halo_put +] k_unpack_add / k_halo_wait_add
     }
     return n;
 }
@@ -1486,7 +1586,7 @@ static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf, b
     // Multi-rank steps run eagerly: capturing the NCCL send/recv group into the step graph hung on 2 x B200 (NCCL 2.28.9,
     // thread-local capture), so it stays an opt-in experiment (AX3D_HALO_GRAPH=1).
     static const bool halo_graph = getenv("AX3D_HALO_GRAPH") && atoi(getenv("AX3D_HALO_GRAPH")) != 0;
-    const bool graph_ok = d->use_graph && !d->timers && (d->nproc <= 1 || d->neigh_rank.empty() || halo_graph);
+    const bool graph_ok = d->use_graph && !d->timers && (d->nproc <= 1 || d->neigh_rank.empty() || halo_graph || d->peer_halo);
     if (graph_ok && d->graph_dt != dt) {
         for (int v = 0; v < 8; ++v) {
             if (d->graph_exec[v]) { cudaGraphExecDestroy(d->graph_exec[v]); d->graph_exec[v] = nullptr; }

@@ -578,6 +578,60 @@ __global__ void k_unpack_add(int n, const unsigned *__restrict__ idx, const floa
     d->y += v.y;
 }
 
+// Peer-memory halo (Domain::assembleStiff over NVLink without a library call).  Every rank owns a receive window
+// win[2][total] (float2; parity = exchange number & 1) and one arrival counter per neighbour; the windows of the neighbours
+// are mapped into this process (cudaIpcOpenMemHandle).  k_halo_put packs the boundary stiffness of one neighbour straight
+// into that neighbour's window (SolidPoint::feedBuffer order, SolidPoint.cpp:163-167) and then bumps the neighbour's
+// counter once per block; k_halo_wait_add spins until all blocks of the matching put have arrived and does the
+// extractBuffer add (SolidPoint.cpp:169-173).  `step` (device memory) numbers the exchanges: it is read by both kernels
+// and advanced by k_halo_advance behind them, so the whole exchange is plain stream-ordered kernels and replays from a
+// CUDA graph.  The parity double buffer is enough: put(s + 2) into a window is ordered behind the owner's wait_add(s) by
+// the owner's own put(s + 1), which the writer waits for in its wait_add(s + 1).
+__global__ void k_halo_put(int n, const unsigned *__restrict__ idx, const float2 *__restrict__ s_stiff,
+                           const float2 *__restrict__ f_stiff, float2 *__restrict__ peer_win, size_t peer_parity_stride,
+                           unsigned *__restrict__ peer_count, const unsigned *__restrict__ step) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned s = *step;
+    if (i < n) {
+        const unsigned k = idx[i];
+        const float2 v = (k >> 31) ? f_stiff[k & 0x7fffffffu] : s_stiff[k];
+        __stcg(peer_win + (size_t)(s & 1u) * peer_parity_stride + i, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd_system(peer_count, 1u);
+}
+__global__ void k_halo_wait_add(int n, const unsigned *__restrict__ idx, const float2 *__restrict__ win, size_t parity_stride,
+                                const unsigned *__restrict__ count, const unsigned *__restrict__ step, float2 *__restrict__ s_stiff,
+                                float2 *__restrict__ f_stiff, int *__restrict__ timeout_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned s = *step;
+    if (threadIdx.x == 0) {
+        const unsigned want = (s + 1u) * gridDim.x;   // the matching put has the same grid
+        unsigned long long spins = 0;
+        for (;;) {
+            unsigned c;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(c) : "l"(count) : "memory");
+            if ((int)(c - want) >= 0) break;
+            __nanosleep(100);
+            if (++spins > (1ull << 26)) {   // ~10 s: never hang the GPU on a lost neighbour
+                *timeout_flag = 1;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (i < n) {
+        const unsigned k = idx[i];
+        float2 *d = (k >> 31) ? &f_stiff[k & 0x7fffffffu] : &s_stiff[k];
+        const float2 v = __ldcv(win + (size_t)(s & 1u) * parity_stride + i);   // written by the peer: never from L1
+        d->x += v.x;
+        d->y += v.y;
+    }
+}
+__global__ void k_halo_advance(unsigned *step) { *step += 1u; }
+
 // ------------------------------------------------------------------------------------ stability
 __global__ void k_check_finite(size_t n, const float *__restrict__ a, int *__restrict__ bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

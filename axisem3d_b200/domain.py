@@ -159,6 +159,45 @@ class Domain:
         capi.check(self.lib.ax3d_finalize_setup(self.h))
         self._final = True
 
+    # ------------------------------------------------------------------ peer-memory halo (include/axisem3d_b200.h)
+    def haloExport(self, neigh_ranks):
+        """This rank's receive window: {"rank", "handle" (64-byte cudaIpcMemHandle), "ptr" (device address in this process),
+        "begin" {neighbour rank: start of its segment}, "total", "slot" {neighbour rank: index in my neighbour list}}."""
+        nn = len(neigh_ranks)
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        begin = (C.c_longlong * (nn + 1))()
+        total = C.c_longlong()
+        capi.check(self.lib.ax3d_halo_export(self.h, C.cast(handle, C.c_void_p), C.byref(ptr), begin, C.byref(total)))
+        return {"handle": bytes(handle), "ptr": int(ptr.value or 0), "total": int(total.value),
+                "begin": {int(r): int(begin[k]) for k, r in enumerate(neigh_ranks)},
+                "slot": {int(r): k for k, r in enumerate(neigh_ranks)}}
+
+    def haloConnect(self, my_rank, neigh_ranks, windows, same_process=False):
+        """windows: {neighbour rank: that rank's haloExport()}.  same_process: the neighbours' domains live in this
+        process (raw device pointers instead of IPC handles)."""
+        nn = len(neigh_ranks)
+        pb = (C.c_longlong * nn)(*[windows[int(r)]["begin"][int(my_rank)] for r in neigh_ranks])
+        pt = (C.c_longlong * nn)(*[windows[int(r)]["total"] for r in neigh_ranks])
+        ps = np.array([windows[int(r)]["slot"][int(my_rank)] for r in neigh_ranks], dtype=np.int32)
+        if same_process:
+            ptrs = (C.c_void_p * nn)(*[windows[int(r)]["ptr"] for r in neigh_ranks])
+            capi.check(self.lib.ax3d_halo_connect(self.h, nn, None, ptrs, pb, pt, _pi(ps)))
+        else:
+            blob = b"".join(windows[int(r)]["handle"] for r in neigh_ranks)
+            buf = (C.c_ubyte * (64 * nn)).from_buffer_copy(blob)
+            capi.check(self.lib.ax3d_halo_connect(self.h, nn, C.cast(buf, C.c_void_p), None, pb, pt, _pi(ps)))
+
+    def connectHalo(self, info, rank, dist):
+        """Collective over the torch.distributed group: exchange the windows and switch Domain::assembleStiff to the
+        peer-memory kernels (ranks without neighbours only take part in the all_gather)."""
+        neigh = [int(r) for r in info.mIProcComm]
+        mine = self.haloExport(neigh) if neigh else None
+        everyone = [None] * dist.get_world_size()
+        dist.all_gather_object(everyone, mine)
+        if neigh:
+            self.haloConnect(rank, neigh, {r: everyone[r] for r in neigh})
+
     # ------------------------------------------------------------------ step verbs
     def updateNewmark(self, dt):
         capi.check(self.lib.ax3d_update_newmark(self.h, float(dt)))

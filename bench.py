@@ -210,6 +210,12 @@ def run_ours(args):
         dist.broadcast(uid, 0)
         dom.setMessaging(rel["msg"], rank, world, bytes(uid.cpu().numpy().tolist()))
     dom.finalize()
+    halo = "none"
+    if world > 1:
+        halo = "nccl send/recv (eager steps)"
+        if os.environ.get("AX3D_HALO", "peer") == "peer":
+            dom.connectHalo(rel["msg"], rank, dist)     # NVLink peer-memory windows; steps replay as CUDA graphs
+            halo = "peer-memory windows over NVLink (k_halo_put / k_halo_wait_add), steps replayed as CUDA graphs"
 
     # 128 receivers (the template STATIONS file has 128) in the outermost solid layer
     surf = [e.domain_tag for e in rel["elements"] if e.kind == "solid"]
@@ -322,7 +328,7 @@ def run_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(n_theta), "elements": int(mesh.nelem), "gll_points": int(mesh.ngll),
-                   "point_modes_per_step": int(work), "parallelism": "dd%d" % world,
+                   "point_modes_per_step": int(work), "parallelism": "dd%d" % world, "halo": halo,
                    "l2": "working set %.0f MB of point fields + moduli per GPU exceeds the 126 MB L2; no explicit flush" %
                          ((4 * 8 * (dom.field_size(False) + dom.field_size(True)) + alg[1] * 0.2) / 1e6),
                    "stable": bool(stable)},

@@ -106,6 +106,23 @@ int ax3d_set_messaging(ax3d_domain *dom, int rank, int nproc, const void *nccl_u
 /* XMPI::initialize analogue for the halo communicator: rank 0 creates the 128-byte ncclUniqueId and broadcasts it. */
 int ax3d_nccl_unique_id(void *out128);
 
+/* Peer-memory halo (replaces the MPI_Isend/Irecv pairs of Domain::assembleStiff, Domain.cpp:111-163, and
+ * MessagingBuffer, S/core/domain/Domain.h:88-96, by direct NVLink stores into the neighbour's receive window).
+ * Call after ax3d_finalize_setup on every rank that has neighbours:
+ *   1. ax3d_halo_export: out_handle64 <- cudaIpcMemHandle_t of this rank's window (may be NULL), *out_ptr <- its device
+ *      address (for neighbours living in the same process), neigh_begin[nneigh + 1] <- start of every neighbour's segment
+ *      in the window (float2 units), *total <- window length per parity.
+ *   2. the host exchanges (handle, neigh_begin, total, neighbour list) between neighbours (MPI_Allgather /
+ *      torch.distributed.all_gather_object);
+ *   3. ax3d_halo_connect: per neighbour n (ax3d_set_messaging order) its window as a 64-byte IPC handle (handles, other
+ *      process of the same node) or a device pointer of this process (ptrs), peer_begin[n] = start of THIS rank's segment in
+ *      it, peer_total[n] = its total, peer_slot[n] = index of this rank in ITS neighbour list.
+ * Afterwards ax3d_assemble_stiff / ax3d_run_steps use the peer-memory kernels and multi-rank steps replay as CUDA graphs;
+ * without these calls the NCCL send/recv path is used. */
+int ax3d_halo_export(ax3d_domain *dom, void *out_handle64, void **out_ptr, long long *neigh_begin, long long *total);
+int ax3d_halo_connect(ax3d_domain *dom, int nneigh, const void *handles, void *const *ptrs, const long long *peer_begin,
+                      const long long *peer_total, const int *peer_slot);
+
 /* End of Mesh::release: builds buckets, index maps, FFT plans, uploads everything. */
 int ax3d_finalize_setup(ax3d_domain *dom);
 
