@@ -85,8 +85,11 @@ struct HSource {
     std::vector<float> force;
 };
 
-// 227 KB per CTA minus the fused kernel's static shared memory (descriptors, plans, mbarriers, arrival ring: < 3 KB)
-#define AX_FUSED_DYN_MAX (232448 - 3072)
+// 227 KB per CTA minus the fused kernel's static shared memory (descriptors, plans, mbarriers, arrival ring, geometry: < 4.5 KB)
+#define AX_FUSED_DYN_MAX (232448 - 4608)
+#ifndef AX_DUAL_DEFAULT
+#define AX_DUAL_DEFAULT 2   // fluid chain of a step on a second stream (step_body): 0 off, 1 fork at the top of the step, 2 fork before the solid elements (B200, cfg2: 0.318 / 0.313 / 0.311 ms per step); AX3D_DUAL overrides
+#endif
 enum { CLS_S1D = 0, CLS_F1D = 1, CLS_S3D = 2, CLS_F3D = 3, NCLS = 4 };
 
 struct Chunk {   // a run of 3D elements of one class whose spectra fit the scratch ring together
@@ -211,6 +214,11 @@ struct ax3d_domain {
     long long dom_launches = 0;
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // fluid chain of a step on its own stream (step_body)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool dual_chain = false;
+    int dual_mode = 1;
     // receivers (scratch for ax3d_record_ground_motion)
     DevBuf<RecvItem> rec_items;
     DevBuf<float> rec_w, rec_out;
@@ -878,7 +886,17 @@ static void finalize(ax3d_domain *d) {
         const char *g = getenv("AX3D_NO_GRAPH");
         d->use_graph = !(g && atoi(g) != 0);
     }
-    CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority (numerically greatest)
+        CK(cudaStreamCreateWithPriority(&d->stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, lo));
+        CK(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+        const char *e = getenv("AX3D_DUAL");
+        d->dual_mode = e ? atoi(e) : AX_DUAL_DEFAULT;
+        d->dual_chain = d->dual_mode != 0 && d->nf > 0 && d->ns > 0;
+    }
     CK(cudaEventCreate(&d->ev0));
     CK(cudaEventCreate(&d->ev1));
     CK(cudaEventCreate(&d->ev2));
@@ -933,26 +951,27 @@ struct TimerScope {
 static inline int nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
 
 // special_only: the plain solid points were already advanced by the previous step's element kernel (fused.cuh)
-static void update_newmark(ax3d_domain *d, double dt, bool special_only = false) {
+// which: 1 = solid points, 2 = fluid points, 3 = both
+static void update_newmark(ax3d_domain *d, double dt, bool special_only = false, int which = 3) {
     TimerScope ts(d, 0);
     const double half_dt = 0.5 * dt, half_dt_dt = half_dt * dt;   // SolidPoint.cpp:31-32 (double, then cast to Real)
-    if (!d->h_m3d_s.empty()) {
+    if ((which & 1) && !d->h_m3d_s.empty()) {
         k_mass3d<3><<<(int)d->h_m3d_s.size(), 128, d->m3d_smem_s, d->stream>>>(d->s_tab, d->m3d_s.p, d->plans.p, d->twpool.p, d->impool.p,
                                                                               d->s_field[AX3D_STIFF].p);
         d->launches++;
     }
-    if (!d->h_m3d_f.empty()) {
+    if ((which & 2) && !d->h_m3d_f.empty()) {
         k_mass3d<1><<<(int)d->h_m3d_f.size(), 128, d->m3d_smem_f, d->stream>>>(d->f_tab, d->m3d_f.p, d->plans.p, d->twpool.p, d->impool.p,
                                                                               d->f_field[AX3D_STIFF].p);
         d->launches++;
     }
     const PointTab &stab = special_only ? d->s_tab_sp : d->s_tab;
-    if (stab.nrows) {
+    if ((which & 1) && stab.nrows) {
         k_newmark_solid<<<nblk(stab.nrows, 256), 256, 0, d->stream>>>(stab, d->s_field[0].p, d->s_field[1].p, d->s_field[2].p,
                                                                      d->s_field[3].p, (float)half_dt, (float)dt, (float)half_dt_dt);
         d->launches++;
     }
-    if (d->f_tab.nrows) {
+    if ((which & 2) && d->f_tab.nrows) {
         k_newmark_fluid<<<nblk(d->f_tab.nrows, 256), 256, 0, d->stream>>>(d->f_tab, d->f_field[0].p, d->f_field[1].p, d->f_field[2].p,
                                                                          d->f_field[3].p, (float)half_dt, (float)dt, (float)half_dt_dt);
         d->launches++;
@@ -1103,16 +1122,17 @@ static void set_fused_smem(int device, const FusedLaunch &f) {
     CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, AX_FUSED_DYN_MAX));
 }
 
-static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0) {
+// which: 1 = solid elements, 2 = fluid elements, 3 = both
+static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, int which = 3) {
     TimerScope ts(d, 1);
     const int TB = AX_TILE * AX_NPE;
-    if (d->n_work[CLS_S1D]) {
+    if ((which & 1) && d->n_work[CLS_S1D]) {
         k_elem1d<false><<<d->n_work[CLS_S1D], TB, 0, d->stream>>>(d->desc[CLS_S1D].p, d->w_elem[CLS_S1D].p, d->w_a0[CLS_S1D].p, d->geom.p,
                                                                   d->coef.p, d->attpar.p, d->attstate1d.p, d->s_field[AX3D_DISPL].p,
                                                                   d->s_field[AX3D_STIFF].p);
         d->launches++;
     }
-    if (d->n_work[CLS_F1D]) {
+    if ((which & 2) && d->n_work[CLS_F1D]) {
         k_elem1d<true><<<d->n_work[CLS_F1D], TB, 0, d->stream>>>(d->desc[CLS_F1D].p, d->w_elem[CLS_F1D].p, d->w_a0[CLS_F1D].p, d->geom.p,
                                                                  d->coef.p, d->attpar.p, d->attstate1d.p, d->f_field[AX3D_DISPL].p,
                                                                  d->f_field[AX3D_STIFF].p);
@@ -1120,6 +1140,7 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0) {
     }
     for (const Chunk &ch : d->chunks) {
         const int c = ch.cls;
+        if (!(which & (c == CLS_S3D ? 1 : 2))) continue;
         if (c == CLS_S3D) {
             k_grad3d<false><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                               d->s_field[AX3D_DISPL].p, d->scratch.p);
@@ -1138,6 +1159,7 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0) {
         d->launches += 3;
     }
     for (size_t k = 0; k < d->fused.size(); ++k) {
+        if (!(which & (d->fused[k].cls == CLS_S3D ? 1 : 2))) continue;
         launch_fused(d, d->fused[k], (int)k, nw_on, dt);
         d->launches++;
     }
@@ -1549,6 +1571,33 @@ int ax3d_reset_zero(ax3d_domain *d) {
 // One iteration of Newmark::solve (Newmark.cpp:47-93).  special_only: the plain solid points already hold this step's
 // state (advanced under the previous step's element kernel); nw_on: this step's element kernel advances them to the next.
 static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool nw_on = false, bool record = false) {
+    if (d->dual_chain && !d->timers && d->chunks.empty()) {
+        // Solid and fluid points / elements only meet in coupleSolidFluid: the fluid chain (point update, fluid elements)
+        // runs on a second, lower-priority stream next to the solid chain and fills the SMs the persistent solid element
+        // kernel leaves idle at its start and in its tail (fork / join by events: capturable into the step graph).
+        cudaStream_t s = d->stream;
+        auto fluid_chain = [&]() {
+            CK(cudaEventRecord(d->ev_fork, s));
+            CK(cudaStreamWaitEvent(d->stream2, d->ev_fork, 0));
+            d->stream = d->stream2;
+            update_newmark(d, dt, special_only, 2);
+            compute_stiff(d, nw_on, dt, 2);
+            CK(cudaEventRecord(d->ev_join, d->stream2));
+            d->stream = s;
+        };
+        if (d->dual_mode == 1) fluid_chain();          // fork at the top of the step
+        update_newmark(d, dt, special_only, 1);
+        if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * (d->nrec1 + d->nrec3));
+        launch_source(d);
+        if (d->dual_mode == 2) fluid_chain();          // fork just before the solid elements: the fluid chain fills their tail
+        compute_stiff(d, nw_on, dt, 1);
+        if (d->dual_mode == 3) fluid_chain();          // enqueued behind the solid element launch
+        CK(cudaStreamWaitEvent(s, d->ev_join, 0));
+        couple_solid_fluid(d);
+        assemble_stiff(d, -1);
+        assemble_stiff(d, 1);
+        return;
+    }
     update_newmark(d, dt, special_only);
     // the reference records after the update of the step (Newmark.cpp:64-70); it must also precede this step's element
     // kernel, which already advances the plain points to the next step

@@ -201,26 +201,47 @@ struct FusedCtx {
     const float2 *__restrict__ displ;
     float2 *__restrict__ stiff;
     float2 *U, *TW, *Z;
+    const float *sgeom;   // shared-memory copy of this element's geometry [5][25] + trig [4][25] (staged with the gather)
 };
 
 // stress of NB (point, phi) cells at once: all moduli are requested before the first use (Isotropic3D.cpp:10-27,
 // TransverselyIsotropic3D.cpp:10-28, Anisotropic3D.cpp:10-54; no attenuation on this path)
 // Z holds the columns of `np` consecutive points of one element: pair k of local point pl at Z + (k * np + pl) * ldz.
 // cf points at the first of those points in the element's moduli ([k][25][N]: cf_stride = 25 * N between moduli).
+#ifndef AX_STRESS_PIPE
+#define AX_STRESS_PIPE 0   // measured on B200 (profiles/microbench/ab.sh): no gain alone, +2 % step time together with AX_SGEOM (registers)
+#endif
+#ifndef AX_SGEOM
+#define AX_SGEOM 1     // element geometry staged in shared memory with the gather (0: read from global memory where used)
+#endif
 template <int NCOEF, int NB, int NT>
 __device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, const float *__restrict__ cf, int total, int cf_stride, int cs,
                                              int ldz, int N, int tid) {
+    constexpr bool PIPE = AX_STRESS_PIPE && NCOEF * NB <= 10;   // moduli of the next batch are requested before this batch is computed
     const int dp = NT / N, dpos = NT - dp * N;
     int idx = tid;
     int p = idx / N, pos = idx - p * N;
-    for (; idx < total; idx += NB * NT) {
-        float c[NB][NCOEF];
+    float c[NB][NCOEF], cn[PIPE ? NB : 1][PIPE ? NCOEF : 1];
+    auto load = [&](float (*dst)[PIPE ? NCOEF : 1], int at) {
 #pragma unroll
         for (int u = 0; u < NB; ++u)
-            if (idx + u * NT < total) {
+            if (at + u * NT < total) {
 #pragma unroll
-                for (int k = 0; k < NCOEF; ++k) c[u][k] = __ldcs(cf + (size_t)k * cf_stride + idx + u * NT);
+                for (int k = 0; k < NCOEF; ++k) dst[u][k] = __ldcs(cf + (size_t)k * cf_stride + at + u * NT);
             }
+    };
+    if constexpr (PIPE) load(c, idx);
+    for (; idx < total; idx += NB * NT) {
+        if constexpr (PIPE) {
+            load(cn, idx + NB * NT);
+        } else {
+#pragma unroll
+            for (int u = 0; u < NB; ++u)
+                if (idx + u * NT < total) {
+#pragma unroll
+                    for (int k = 0; k < NCOEF; ++k) c[u][k] = __ldcs(cf + (size_t)k * cf_stride + idx + u * NT);
+                }
+        }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
             if (idx + u * NT < total) {
@@ -235,6 +256,12 @@ __device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, co
             p += dp;
             pos += dpos;
             if (pos >= N) { pos -= N; ++p; }
+        }
+        if constexpr (PIPE) {
+#pragma unroll
+            for (int u = 0; u < NB; ++u)
+#pragma unroll
+                for (int k = 0; k < NCOEF; ++k) c[u][k] = cn[u][k];
         }
     }
 }
@@ -317,14 +344,13 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
     const bool nyq = (N & 1) == 0;
     const bool axial = E.axial != 0, tiso = !FLUID && E.tiso != 0;
     const int law = E.law;
-    const long long geom_off = E.geom_off, trig_off = E.trig_off, coef_off = E.coef_off;
 
     // ------------------------------------------------------------ gather (prefetched) + grad, Mt modes at a time   @phase gather wait + grad
     for (int a0 = 0; a0 < M; a0 += Mt) {
         const int mt = min(Mt, M - a0);
         if (a0) {
             cta_sync<NT, NWW>();
-            gather(E, a0, mt);
+            gather(E, a0, mt, -1);
         }
         cp_async_wait_all();
         if (a0 == 0 && t == 0)   // Im(u) of mode 0 is not used (Gradient.cpp:209-224): this thread copied these entries
@@ -338,12 +364,12 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
                 const int i = p / 5, j = p - 5 * i;
                 GCoef gc;
                 load_gcoef(gc, axial, i, j);
-                const PointGeom g = load_geom(cx.geom, geom_off, p);
+                const PointGeom g = load_geom(cx.sgeom, 0, p);
                 const bool ax0 = axial && i == 0;
                 float tr[4] = {0.f, 1.f, 0.f, 1.f};
                 if (tiso) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tr[k] = cx.geom[trig_off + k * AX_NPE + p];
+                    for (int k = 0; k < 4; ++k) tr[k] = cx.sgeom[(5 + k) * AX_NPE + p];
                 }
                 float2 *zp = Z + p * ldz;
                 for (int a = t; a < mt; a += 16) {
@@ -413,12 +439,12 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
             const int p = pp * NHW + hw;
             if (p < AX_NPE) {
                 const int i = p / 5;
-                const PointGeom g = load_geom(cx.geom, geom_off, p);
+                const PointGeom g = load_geom(cx.sgeom, 0, p);
                 const bool ax0 = axial && i == 0;
                 float tr[4] = {0.f, 1.f, 0.f, 1.f};
                 if (tiso) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tr[k] = cx.geom[trig_off + k * AX_NPE + p];
+                    for (int k = 0; k < 4; ++k) tr[k] = cx.sgeom[(5 + k) * AX_NPE + p];
                 }
                 float2 *zp = Z + p * ldz;
 #pragma unroll
@@ -738,6 +764,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     extern __shared__ __align__(16) float2 smem[];
     __shared__ ElemDesc sE[2];
     __shared__ FftPlan sP[2];
+    __shared__ float sGeom[2][9 * AX_NPE];   // geometry (+ trig) of the current / next element, staged with its gather
     __shared__ int sIdx[3];   // ring of element indices: current, next, next-next
     __shared__ unsigned long long sBar[NWARP][NW_NSTAGE];
     __shared__ int sArrCode[4][AX_NPE];   // ring: pt_nw codes of the elements whose scatter is complete ...
@@ -765,7 +792,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
 
     if (tid < NT) {
         const int hw = tid >> 4, t = tid & 15;
-        FusedCtx<FLUID> cx{geom, coef, attpar, attstate, displ, stiff, smem, smem + u_cap, smem + u_cap + tw_cap};
+        FusedCtx<FLUID> cx{geom, coef, attpar, attstate, displ, stiff, smem, smem + u_cap, smem + u_cap + tw_cap, sGeom[0]};
         float2 *const U = cx.U;
 
         // descriptor + plan of element el -> slot s (plain loads; visible after the next barrier)
@@ -777,7 +804,16 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
             }
         };
         // Point::scatterDisplToElement (SolidPoint.cpp:175-195) for modes [a0, a0 + mt): half-warp per (component, point)
-        auto gather = [&](const ElemDesc &E, int a0, int mt) {
+        // slot >= 0: first tile of an element -- its geometry goes to sGeom[slot] with the same cp.async group
+        auto gather = [&](const ElemDesc &E, int a0, int mt, int slot) {
+            if (AX_SGEOM && slot >= 0) {
+                const bool ti = !FLUID && E.tiso != 0;
+                if (tid < 5 * AX_NPE || (ti && tid >= 128 && tid < 128 + 4 * AX_NPE)) {
+                    const float *src = tid < 128 ? geom + E.geom_off + tid : geom + E.trig_off + (tid - 128);
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(&sGeom[slot][tid < 128 ? tid : 5 * AX_NPE + tid - 128]);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
+                }
+            }
             const unsigned u0 = (unsigned)__cvta_generic_to_shared(U + t * US);
             for (int row = hw; row < US; row += NHW) {
                 const int c = row / AX_NPE, p = row - c * AX_NPE;
@@ -797,13 +833,14 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
             load_desc(0, e);
             if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
             cta_sync<NT, NWW>();
-            gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1));
+            gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1), 0);
             float gv = 0.f, gv_next = 0.f;   // WP: geometry of the current / next element (wp_load_geom)
             if constexpr (WP) gv = wp_load_geom(sE[0], geom, tid, FLUID);
             int tw_plan = -1;
             for (int it = 0, k = 0; e < nelem; it ^= 1, k = (k == 2 ? 0 : k + 1)) {
                 const ElemDesc &E = sE[it];
                 const FftPlan &P = sP[it];
+                cx.sgeom = AX_SGEOM ? sGeom[it] : geom + E.geom_off;
                 const int kn = k == 2 ? 0 : k + 1, knn = kn == 2 ? 0 : kn + 1;   // ring slots of the next two elements
                 if (tw_plan != E.plan_id) {   // TW is idle here: the FFT stages of the previous element are barrier-separated
                     const int tb = P.stw_base + (WP ? P.stw2_delta : 0);   // WP: the p-major copies of the stage tables
@@ -830,7 +867,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                     if (tid == 0) sIdx[knn] = (int)atomicAdd(&work[0], 1u);   // needed one element from now: latency hidden
                     if (sIdx[kn] < nelem) {
                         const ElemDesc &En = sE[it ^ 1];
-                        gather(En, 0, min(En.mt, En.nu + 1));
+                        gather(En, 0, min(En.mt, En.nu + 1), it ^ 1);
                         if constexpr (WP) gv_next = wp_load_geom(En, geom, tid, FLUID);
                     }
                 };

@@ -179,7 +179,7 @@ __device__ __forceinline__ void wp_element(const FusedCtx<FLUID> &cx, const Elem
         const int mt = min(Mt, M - a0);
         if (a0) {
             cta_sync<NT, NWW>();
-            gather(E, a0, mt);
+            gather(E, a0, mt, -1);
         }
         cp_async_wait_all();
         if (a0 == 0 && (tid & 15) == 0)   // Im(u) of mode 0 is not used (Gradient.cpp:209-224): this thread copied these entries
