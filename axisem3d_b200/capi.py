@@ -43,6 +43,10 @@ def load(build_if_missing=True):
         if not build_if_missing:
             raise RuntimeError("axisem3d_b200: CUDA library %s is missing; run __graft_entry__.build()" % path)
         _build.build()
+    # The library links libnccl.so.2.  torch bundles a newer NCCL under the same SONAME than the system one; whichever is
+    # mapped first wins for the whole process, and libtorch_cuda does not load against the older system copy.  Import
+    # torch first so that one NCCL (torch's) serves both.
+    import torch  # noqa: F401
     lib = C.CDLL(path)
     lib.ax3d_last_error.restype = C.c_char_p
     for s in SYMBOLS:
