@@ -4,6 +4,7 @@
 #include "../../include/axisem3d_b200.h"
 #include "kernels.cuh"
 #include "fused.cuh"
+#include "cluster.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -90,6 +91,15 @@ struct HSource {
 #ifndef AX_DUAL_DEFAULT
 #define AX_DUAL_DEFAULT 2   // fluid chain of a step on a second stream (step_body): 0 off, 1 fork at the top of the step, 2 fork before the solid elements (B200, cfg2: 0.318 / 0.313 / 0.311 ms per step); AX3D_DUAL overrides
 #endif
+#define AX_CLUSTER_DYN_MAX (232448 - 1024)   // 227 KB per CTA minus the cluster kernel's static shared memory (plan, row geometry)
+#ifndef AX_CLUSTER_DEFAULT
+#define AX_CLUSTER_DEFAULT 0      // 0: off (split pipeline), 1: elements that do not fit the single-CTA kernel, 2: every 3D element; AX3D_CLUSTER overrides.
+                                  // Measured on B200 (profiles/r1_cluster_experiment.md): parity green, but DSMEM-latency- and cluster-barrier-bound --
+                                  // cfg2 elements 0.53 ms vs 0.31 ms single-CTA, cfg4 1.05 ms vs 0.84 ms split pipeline -- so it stays opt-in
+#endif
+#ifndef AX_CLUSTER_NT_DEFAULT
+#define AX_CLUSTER_NT_DEFAULT 128
+#endif
 enum { CLS_S1D = 0, CLS_F1D = 1, CLS_S3D = 2, CLS_F3D = 3, NCLS = 4 };
 
 struct Chunk {   // a run of 3D elements of one class whose spectra fit the scratch ring together
@@ -110,6 +120,12 @@ struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_e
     size_t smem;
     int grid;
     std::map<int, int> nr_hist;  // Nr -> element count (to pick nct)
+};
+
+struct ClusterLaunch {   // a run of 3D elements of one class that go through k_elem3d_cluster (cluster.cuh), one 5-CTA cluster each
+    int cls, begin, count;       // window into cl_list[cls]
+    int nt;                      // threads per CTA
+    size_t smem;                 // dynamic shared memory per CTA = that of the largest element of the run
 };
 
 struct ax3d_domain {
@@ -171,6 +187,8 @@ struct ax3d_domain {
     int n_work[NCLS] = {0, 0, 0, 0};
     DevBuf<FftItem> fft_items[NCLS];
     std::vector<Chunk> chunks;
+    std::vector<ClusterLaunch> clusters;
+    DevBuf<int> cl_list[NCLS];
     DevBuf<float2> scratch;
     // ---- source, solid-fluid
     DevBuf<unsigned> src_off;
@@ -384,6 +402,7 @@ static void common_elem(ax3d_domain *d, HElem &e, const int tags[25], const doub
 
 // ------------------------------------------------------------------------------------------ finalize
 static void set_fused_smem(int device, const FusedLaunch &f);
+static void set_cluster_smem(const ClusterLaunch &cl);
 static bool fused_specialised(bool fluid, int N);
 typedef void (*fft_kernel_t)(const ElemDesc *, const FftItem *, const FftPlan *, const float2 *, const float *, const float *, float *,
                              float2 *);
@@ -517,6 +536,10 @@ static void finalize(ax3d_domain *d) {
     const char *env_sc = getenv("AX3D_SCRATCH_MB");
     const size_t scratch_cap = (size_t)((env_sc ? atof(env_sc) : 256.0) * 1024.0 * 1024.0 / sizeof(float2));
     size_t scratch_need = 0;
+    const char *env_cl = getenv("AX3D_CLUSTER"), *env_clnt = getenv("AX3D_CL_NT");
+    const int cluster_mode = env_cl ? atoi(env_cl) : AX_CLUSTER_DEFAULT;
+    const int cluster_nt = env_clnt ? atoi(env_clnt) : AX_CLUSTER_NT_DEFAULT;
+    if (cluster_nt != 128 && cluster_nt != 192 && cluster_nt != 256) fail("ax3d::cluster || AX3D_CL_NT must be 128, 192 or 256");
     const char *env_nf = getenv("AX3D_NO_FUSED");
     const bool use_fused = !(env_nf && atoi(env_nf) != 0);
     {
@@ -537,6 +560,8 @@ static void finalize(ax3d_domain *d) {
             ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0, 5, 256};
             ch_scratch = 0;
         };
+        std::vector<int> cl_elems;
+        std::vector<size_t> cl_smem;
         FusedLaunch fl{};
         fl.cls = c;
         auto close_fused = [&]() {
@@ -643,6 +668,10 @@ static void finalize(ax3d_domain *d) {
                     D.mt = (int)(room / 16) * 16;
                     if (D.mt < 16) can_fuse = false;
                 }
+                // cluster kernel (cluster.cuh): mode 1 = elements too large for one SM's shared memory, 2 = every 3D element
+                const size_t cl_bytes = (size_t)cl_layout(fluid, N, stw_len).total * sizeof(float2);
+                const bool can_cluster = cluster_mode > 0 && cl_bytes <= (size_t)AX_CLUSTER_DYN_MAX && (cluster_mode == 2 || !can_fuse);
+                if (can_cluster) can_fuse = false;
                 if (can_fuse && fl.count == 0) {
                     fl.nr_max = N;
                     fl.z_cap = npair * AX_NPE * fused_ldz(N);
@@ -656,6 +685,11 @@ static void finalize(ax3d_domain *d) {
                     fl.tw_cap = std::max(fl.tw_cap, stw_len);
                     fl.ldz_max = std::max(fl.ldz_max, fused_ldz(N));
                     if (stw_len > 2 * fl.nr_max) fail("ax3d::fused || twiddle table larger than its bound");
+                } else if (can_cluster) {
+                    D.mt = M;
+                    D.bucket = 1;
+                    cl_elems.push_back((int)k);
+                    cl_smem.push_back(cl_bytes);
                 } else {
                     D.mt = M;
                     if (!cls_np) cls_np = ((size_t)npair * 5 * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2) <= (size_t)220 * 1024 ? 5 : 1;
@@ -678,6 +712,21 @@ static void finalize(ax3d_domain *d) {
             d->h_desc[c].push_back(D);
         }
         if (is3d) { close_chunk(); close_fused(); }
+        if (!cl_elems.empty()) {
+            // elements are sorted by Nr (descending); cut the list where one more resident CTA per SM becomes possible
+            auto per_sm = [](size_t bytes) { return (int)std::min<size_t>(8, (size_t)(228 * 1024) / (bytes + 1024)); };
+            ClusterLaunch cl{c, 0, 0, cluster_nt, cl_smem[0]};
+            for (size_t k = 0; k < cl_elems.size(); ++k) {
+                if (cl.count > 0 && per_sm(cl_smem[k]) > per_sm(cl.smem)) {
+                    d->clusters.push_back(cl);
+                    cl = ClusterLaunch{c, (int)k, 0, cluster_nt, cl_smem[k]};
+                }
+                cl.count++;
+                cl.smem = std::max(cl.smem, cl_smem[k]);   // not monotone in Nr: the twiddle tables depend on the factorisation
+            }
+            d->clusters.push_back(cl);
+            d->cl_list[c].upload(cl_elems);
+        }
         d->desc[c].upload(d->h_desc[c]);
         d->w_elem[c].upload(w_elem);
         d->w_a0[c].upload(w_a0);
@@ -906,6 +955,7 @@ static void finalize(ax3d_domain *d) {
         if (ch.fft_smem > (size_t)224 * 1024) fail("ax3d::finalize || Nr too large for the FFT stage (needs > 224 KB shared memory per point)");
         CK(cudaFuncSetAttribute((const void *)fft_kernel(ch), cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     }
+    for (const ClusterLaunch &cl : d->clusters) set_cluster_smem(cl);
     {
         std::vector<unsigned> w;
         for (const FusedLaunch &f : d->fused) {
@@ -1122,6 +1172,41 @@ static void set_fused_smem(int device, const FusedLaunch &f) {
     CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, AX_FUSED_DYN_MAX));
 }
 
+typedef void (*cluster_kernel_t)(const ElemDesc *, const int *, const FftPlan *, const float2 *, const float *, const float *, const float *,
+                                 float *, const float2 *, float2 *);
+static cluster_kernel_t cluster_kernel(bool fluid, int nt) {
+    if (nt == 128) return fluid ? k_elem3d_cluster<true, 128> : k_elem3d_cluster<false, 128>;
+    if (nt == 192) return fluid ? k_elem3d_cluster<true, 192> : k_elem3d_cluster<false, 192>;
+    return fluid ? k_elem3d_cluster<true, 256> : k_elem3d_cluster<false, 256>;
+}
+
+static void set_cluster_smem(const ClusterLaunch &cl) {
+    CK(cudaFuncSetAttribute((const void *)cluster_kernel(cl.cls == CLS_F3D, cl.nt), cudaFuncAttributeMaxDynamicSharedMemorySize, AX_CLUSTER_DYN_MAX));
+}
+
+static void launch_cluster(ax3d_domain *d, const ClusterLaunch &cl) {
+    const int c = cl.cls;
+    const bool fluid = c == CLS_F3D;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(AX_CL * cl.count), 1, 1);
+    cfg.blockDim = dim3((unsigned)cl.nt, 1, 1);
+    cfg.dynamicSmemBytes = cl.smem;
+    cfg.stream = d->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = AX_CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, cluster_kernel(fluid, cl.nt), (const ElemDesc *)d->desc[c].p, (const int *)(d->cl_list[c].p + cl.begin),
+                          (const FftPlan *)d->plans.p, (const float2 *)d->stwpool.p, (const float *)d->geom.p, (const float *)d->coef.p,
+                          (const float *)d->attpar.p, d->attstate3d.p,
+                          (const float2 *)(fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p),
+                          fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p));
+}
+
 // which: 1 = solid elements, 2 = fluid elements, 3 = both
 static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, int which = 3) {
     TimerScope ts(d, 1);
@@ -1157,6 +1242,11 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, i
                                                              d->scratch.p, d->f_field[AX3D_STIFF].p);
         }
         d->launches += 3;
+    }
+    for (const ClusterLaunch &cl : d->clusters) {
+        if (!(which & (cl.cls == CLS_S3D ? 1 : 2))) continue;
+        launch_cluster(d, cl);
+        d->launches++;
     }
     for (size_t k = 0; k < d->fused.size(); ++k) {
         if (!(which & (d->fused[k].cls == CLS_S3D ? 1 : 2))) continue;

@@ -43,6 +43,15 @@ def equator_nu1000(s, z):
 
 CASES["iso3d_nu1000_split_np1"] = dict(n_theta=320, n_r=1, r_in=6371e3 - 80e3, nu_fn=equator_nu1000, law="ti", model3d=True,
                                        attenuation="cg4", fluid_layers=())
+def equator_nu500(s, z):
+    """equatorial elements at Nu = 500 (Nr = 1008) and a neighbouring band at Nu = 290: the 5-CTA cluster kernel's range."""
+    if s > 0.9895 * 6371e3 and abs(z) < 40e3:
+        return 500
+    return 290 if s > 0.97 * 6371e3 and abs(z) < 120e3 else 6
+
+
+CASES["ti3d_nu500_cluster"] = dict(n_theta=320, n_r=1, r_in=6371e3 - 80e3, nu_fn=equator_nu500, law="ti", model3d=True,
+                                   attenuation="cg4", fluid_layers=())
 CASES["cfg4_ragged"] = dict(n_theta=10, n_r=6, nu_fn=ragged_nu, law="iso", model3d=True, attenuation=None)
 
 
@@ -183,3 +192,22 @@ def test_device_side_recorder_matches_per_step_record():
     b = np.array(b)
     assert a.shape == b.shape and np.abs(b).max() > 0
     assert rel_l2(b, a) <= 2e-5
+
+
+@pytest.mark.parametrize("name", ["cfg3_aniso3d_cg4", "cfg4_ragged", "ti3d_nu500_cluster"])
+def test_cluster_kernel_matches_oracle(name, monkeypatch):
+    """k_elem3d_cluster (csrc/cluster.cuh: one 5-CTA thread-block cluster per element, xi-derivative through distributed
+    shared memory) is opt-in (AX3D_CLUSTER, read at finalize); every 3D element of these cases goes through it."""
+    monkeypatch.setenv("AX3D_CLUSTER", "2")
+    m = SynthMesh(**CASES[name])
+    dt = m.estimate_dt()
+    d, _ = build_oracle(m, dt, np.float64)
+    g, _ = build_gpu(m, dt)
+    randomize_displ(d, seed=11)
+    push_fields(d, g, ("displ",))
+    d.computeStiff()
+    d.coupleSolidFluid()
+    g.computeStiff()
+    g.coupleSolidFluid()
+    for k, v in compare_field(d, g, "stiff").items():
+        assert v <= TOL_FORCE, (name, k, v)
