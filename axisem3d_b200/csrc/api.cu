@@ -252,10 +252,12 @@ struct ax3d_domain {
     double graph_dt = 0;
     bool use_graph = true;
     // receivers registered with ax3d_set_receivers
-    int nrec1 = 0, nrec3 = 0;
-    std::vector<int> rec_where1, rec_where3;
-    DevBuf<RecvItem> rec1_items, rec3_items;
-    DevBuf<float> rec1_w, rec3_w;
+    int nrec_c[NCLS] = {0, 0, 0, 0};            // per element class, rows of the device output in class order
+    std::vector<int> rec_where_c[NCLS];
+    DevBuf<RecvItem> rec_items_c[NCLS];
+    DevBuf<float> rec_w_c[NCLS];
+    size_t rec_fluid_smem = 0;                  // k_ground_motion_fluid: largest FFT tile of the registered fluid receivers
+    int nrec_total() const { return nrec_c[0] + nrec_c[1] + nrec_c[2] + nrec_c[3]; }
 };
 #define STF_RING 4096
 
@@ -1042,17 +1044,34 @@ static void push_stf(ax3d_domain *d, float stf, int rec_slot = 0) {
     d->stf_slot++;
 }
 
+static size_t recf_smem(int N) { return (size_t)2 * 5 * fused_ldz(N) * sizeof(float2); }   // one GLL row: 2 Z-form pairs x 5 points
+
+// device rows are grouped by element class; the caller's receiver order is restored on the host
+static void unscramble_record(const ax3d_domain *d, const float *row, float *out) {
+    int base = 0;
+    for (int c = 0; c < NCLS; ++c) {
+        for (int k = 0; k < d->nrec_c[c]; ++k)
+            for (int cc = 0; cc < 3; ++cc) out[d->rec_where_c[c][k] * 3 + cc] = row[(base + k) * 3 + cc];
+        base += d->nrec_c[c];
+    }
+}
+
 // Domain::record -> PointwiseRecorder::record (Domain.cpp:207-220): one sample per registered receiver into row
 // `*slot` of the device ring (slot == nullptr: row 0 of `out`).
 static void launch_record(ax3d_domain *d, float *out, const int *slot, int stride) {
-    if (d->nrec1) {
-        k_ground_motion<<<d->nrec1, AX_REC_NT, 0, d->stream>>>(d->desc[CLS_S1D].p, d->rec1_items.p, d->rec1_w.p, d->s_field[AX3D_DISPL].p, out, slot, stride);
+    int row = 0;
+    for (int c = 0; c < NCLS; ++c) {
+        const int n = d->nrec_c[c];
+        if (!n) continue;
+        if (c == CLS_S1D || c == CLS_S3D)
+            k_ground_motion<<<n, AX_REC_NT, 0, d->stream>>>(d->desc[c].p, d->rec_items_c[c].p, d->rec_w_c[c].p, d->s_field[AX3D_DISPL].p,
+                                                           out + (size_t)3 * row, slot, stride);
+        else
+            k_ground_motion_fluid<<<n, AX_RECF_NT, d->rec_fluid_smem, d->stream>>>(d->desc[c].p, d->rec_items_c[c].p, d->rec_w_c[c].p, d->plans.p,
+                                                                                   d->twpool.p, d->geom.p, d->coef.p, d->f_field[AX3D_DISPL].p,
+                                                                                   out + (size_t)3 * row, slot, stride);
         d->launches++;
-    }
-    if (d->nrec3) {
-        k_ground_motion<<<d->nrec3, AX_REC_NT, 0, d->stream>>>(d->desc[CLS_S3D].p, d->rec3_items.p, d->rec3_w.p, d->s_field[AX3D_DISPL].p,
-                                                          out + (size_t)3 * d->nrec1, slot, stride);
-        d->launches++;
+        row += n;
     }
     CK(cudaGetLastError());
 }
@@ -1677,7 +1696,7 @@ static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool
         };
         if (d->dual_mode == 1) fluid_chain();          // fork at the top of the step
         update_newmark(d, dt, special_only, 1);
-        if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * (d->nrec1 + d->nrec3));
+        if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * d->nrec_total());
         launch_source(d);
         if (d->dual_mode == 2) fluid_chain();          // fork just before the solid elements: the fluid chain fills their tail
         compute_stiff(d, nw_on, dt, 1);
@@ -1691,7 +1710,7 @@ static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool
     update_newmark(d, dt, special_only);
     // the reference records after the update of the step (Newmark.cpp:64-70); it must also precede this step's element
     // kernel, which already advances the plain points to the next step
-    if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * (d->nrec1 + d->nrec3));
+    if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * d->nrec_total());
     launch_source(d);
     compute_stiff(d, nw_on, dt);
     couple_solid_fluid(d);
@@ -1701,7 +1720,7 @@ static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool
 
 static long long count_step_launches(ax3d_domain *d, bool special_only, bool record) {
     long long n = 0;
-    if (record) n += (d->nrec1 > 0) + (d->nrec3 > 0);
+    if (record) for (int c = 0; c < NCLS; ++c) n += d->nrec_c[c] > 0;
     n += !d->h_m3d_s.empty();
     n += !d->h_m3d_f.empty();
     n += (special_only ? d->s_tab_sp.nrows : d->s_tab.nrows) > 0;
@@ -1771,7 +1790,7 @@ int ax3d_run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf) {
 int ax3d_run_steps_record(ax3d_domain *d, int nsteps, double dt, const float *stf, float *out) {
     API_BEGIN
     check_final(d);
-    const int n = d->nrec1 + d->nrec3;
+    const int n = d->nrec_total();
     if (!n) fail("PointwiseRecorder::record || no receivers registered (ax3d_set_receivers)");
     if (nsteps <= 0) return 0;
     if (nsteps > STF_RING) fail("Newmark::solve || ax3d_run_steps_record takes at most 4096 steps per call");
@@ -1792,10 +1811,7 @@ int ax3d_run_steps_record(ax3d_domain *d, int nsteps, double dt, const float *st
     for (int i = 0; i < nsteps; ++i) {
         const float *row = d->rec_ring_host + (size_t)i * n * 3;
         float *o = out + (size_t)i * n * 3;
-        for (int k = 0; k < d->nrec1; ++k)
-            for (int c = 0; c < 3; ++c) o[d->rec_where1[k] * 3 + c] = row[k * 3 + c];
-        for (int k = 0; k < d->nrec3; ++k)
-            for (int c = 0; c < 3; ++c) o[d->rec_where3[k] * 3 + c] = row[(d->nrec1 + k) * 3 + c];
+        unscramble_record(d, row, o);
     }
     API_END
 }
@@ -1817,22 +1833,27 @@ int ax3d_run_steps_timed(ax3d_domain *d, int nsteps, double dt, const float *stf
 int ax3d_set_receivers(ax3d_domain *d, int nrec, const int *elem_tags, const float *phi, const float *weights) {
     API_BEGIN
     check_final(d);
-    std::vector<RecvItem> it1, it3;
-    std::vector<float> w1, w3;
-    d->rec_where1.clear();
-    d->rec_where3.clear();
+    std::vector<RecvItem> it[NCLS];
+    std::vector<float> w[NCLS];
+    for (int c = 0; c < NCLS; ++c) d->rec_where_c[c].clear();
+    d->rec_fluid_smem = 0;
     for (int i = 0; i < nrec; ++i) {
         if (elem_tags[i] < 0 || elem_tags[i] >= (int)d->elems.size()) fail("PointwiseRecorder::record || invalid element tag");
         const HElem &E = d->elems[elem_tags[i]];
-        if (E.fluid) fail("FluidElement::computeGroundMotion || receivers in fluid are not supported yet");
         RecvItem r{E.idx, phi[i]};
-        if (E.cls == CLS_S3D) { it3.push_back(r); w3.insert(w3.end(), weights + (size_t)i * AX_NPE, weights + (size_t)(i + 1) * AX_NPE); d->rec_where3.push_back(i); }
-        else { it1.push_back(r); w1.insert(w1.end(), weights + (size_t)i * AX_NPE, weights + (size_t)(i + 1) * AX_NPE); d->rec_where1.push_back(i); }
+        it[E.cls].push_back(r);
+        w[E.cls].insert(w[E.cls].end(), weights + (size_t)i * AX_NPE, weights + (size_t)(i + 1) * AX_NPE);
+        d->rec_where_c[E.cls].push_back(i);
+        if (E.cls == CLS_F3D) d->rec_fluid_smem = std::max(d->rec_fluid_smem, recf_smem(E.nr));
     }
-    d->nrec1 = (int)it1.size();
-    d->nrec3 = (int)it3.size();
-    d->rec1_items.upload(it1); d->rec1_w.upload(w1);
-    d->rec3_items.upload(it3); d->rec3_w.upload(w3);
+    for (int c = 0; c < NCLS; ++c) {
+        d->nrec_c[c] = (int)it[c].size();
+        d->rec_items_c[c].upload(it[c]);
+        d->rec_w_c[c].upload(w[c]);
+    }
+    if (d->rec_fluid_smem > (size_t)224 * 1024) fail("FluidElement::computeGroundMotion || Nr too large for the receiver kernel");
+    if (d->rec_fluid_smem > (size_t)48 * 1024)
+        CK(cudaFuncSetAttribute(k_ground_motion_fluid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->rec_fluid_smem));
     if ((size_t)nrec > d->rec_cap) {
         if (d->rec_host) cudaFreeHost(d->rec_host);
         CK(cudaMallocHost(&d->rec_host, (size_t)nrec * 3 * sizeof(float)));
@@ -1847,15 +1868,12 @@ int ax3d_set_receivers(ax3d_domain *d, int nrec, const int *elem_tags, const flo
 int ax3d_record(ax3d_domain *d, float *out) {
     API_BEGIN
     check_final(d);
-    const int n = d->nrec1 + d->nrec3;
+    const int n = d->nrec_total();
     if (!n) return 0;
     launch_record(d, d->rec_out.p, nullptr, 0);
     CK(cudaMemcpyAsync(d->rec_host, d->rec_out.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream));
-    for (int k = 0; k < d->nrec1; ++k)
-        for (int c = 0; c < 3; ++c) out[d->rec_where1[k] * 3 + c] = d->rec_host[k * 3 + c];
-    for (int k = 0; k < d->nrec3; ++k)
-        for (int c = 0; c < 3; ++c) out[d->rec_where3[k] * 3 + c] = d->rec_host[(d->nrec1 + k) * 3 + c];
+    unscramble_record(d, d->rec_host, out);
     API_END
 }
 
@@ -1938,10 +1956,9 @@ int ax3d_record_ground_motion(ax3d_domain *d, int nrec, const int *elem_tags, co
     for (int i = 0; i < nrec; ++i) {
         if (elem_tags[i] < 0 || elem_tags[i] >= (int)d->elems.size()) fail("PointwiseRecorder::record || invalid element tag");
         const HElem &E = d->elems[elem_tags[i]];
-        if (E.fluid) fail("FluidElement::computeGroundMotion || receivers in fluid are not supported yet");
-        if (E.cls != CLS_S1D && E.cls != CLS_S3D) fail("PointwiseRecorder::record || bad element class");
-        items[i].elem = E.idx | (E.cls == CLS_S3D ? 0x40000000 : 0);
+        items[i].elem = E.idx | (E.cls << 28);
         items[i].phi = phi[i];
+        if (E.cls == CLS_F3D && recf_smem(E.nr) > (size_t)224 * 1024) fail("FluidElement::computeGroundMotion || Nr too large for the receiver kernel");
     }
     if ((size_t)nrec > d->rec_cap) {
         if (d->rec_host) cudaFreeHost(d->rec_host);
@@ -1952,16 +1969,17 @@ int ax3d_record_ground_motion(ax3d_domain *d, int nrec, const int *elem_tags, co
         d->rec_cap = nrec;
     }
     // receivers may sit in 1D or 3D elements: two launches over the respective descriptor arrays
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int c = 0; c < NCLS; ++c) {
         std::vector<RecvItem> sub;
         std::vector<int> where;
+        size_t fsmem = 0;
         for (int i = 0; i < nrec; ++i) {
-            const bool is3 = (items[i].elem & 0x40000000) != 0;
-            if ((pass == 1) == is3) {
+            if ((items[i].elem >> 28) == c) {
                 RecvItem r = items[i];
-                r.elem &= 0x3fffffff;
+                r.elem &= 0x0fffffff;
                 sub.push_back(r);
                 where.push_back(i);
+                if (c == CLS_F3D) fsmem = std::max(fsmem, recf_smem(d->h_desc[c][r.elem].nr));
             }
         }
         if (sub.empty()) continue;
@@ -1970,8 +1988,13 @@ int ax3d_record_ground_motion(ax3d_domain *d, int nrec, const int *elem_tags, co
         for (size_t k = 0; k < sub.size(); ++k) memcpy(&w[k * AX_NPE], weights + (size_t)where[k] * AX_NPE, AX_NPE * sizeof(float));
         CK(cudaMemcpyAsync(d->rec_items.p, sub.data(), sub.size() * sizeof(RecvItem), cudaMemcpyHostToDevice, d->stream));
         CK(cudaMemcpyAsync(d->rec_w.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, d->stream));
-        const int c = pass == 1 ? CLS_S3D : CLS_S1D;
-        k_ground_motion<<<(int)sub.size(), AX_REC_NT, 0, d->stream>>>(d->desc[c].p, d->rec_items.p, d->rec_w.p, d->s_field[AX3D_DISPL].p, d->rec_out.p, nullptr, 0);
+        if (c == CLS_S1D || c == CLS_S3D) {
+            k_ground_motion<<<(int)sub.size(), AX_REC_NT, 0, d->stream>>>(d->desc[c].p, d->rec_items.p, d->rec_w.p, d->s_field[AX3D_DISPL].p, d->rec_out.p, nullptr, 0);
+        } else {
+            if (fsmem > (size_t)48 * 1024) CK(cudaFuncSetAttribute(k_ground_motion_fluid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k_ground_motion_fluid<<<(int)sub.size(), AX_RECF_NT, fsmem, d->stream>>>(d->desc[c].p, d->rec_items.p, d->rec_w.p, d->plans.p, d->twpool.p,
+                                                                                     d->geom.p, d->coef.p, d->f_field[AX3D_DISPL].p, d->rec_out.p, nullptr, 0);
+        }
         d->launches++;
         CK(cudaMemcpyAsync(d->rec_host, d->rec_out.p, sub.size() * 3 * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
         CK(cudaStreamSynchronize(d->stream));

@@ -699,3 +699,114 @@ __global__ void __launch_bounds__(AX_REC_NT) k_ground_motion(const ElemDesc *__r
         out[blockIdx.x * 3 + threadIdx.x] = t;
     }
 }
+
+// FluidElement::computeGroundMotion (FluidElement.cpp:163-215): the fluid "displacement" is the acoustic stress of the
+// potential, u = K grad(chi) -- gather -> Gradient::computeGrad -> [c2r -> K(phi) -> r2c for 3D material] -- evaluated at
+// azimuth phi and interpolated with the receiver's 25 weights.  One CTA per receiver, one GLL row (5 points) at a time so
+// that the 3D case needs only 10 Z-form columns of shared memory whatever Nr; the potential is read straight from the
+// point arrays (a receiver kernel: <= a few hundred CTAs per recorded step, off the hot path).
+#define AX_RECF_NT 256
+__device__ __forceinline__ float2 recf_u(const ElemDesc &E, const float2 *__restrict__ displ, int p, int a) {
+    float2 v = a < E.pt_nlive[p] ? displ[(size_t)E.pt_off[p] + a] : czero();
+    if (a == 0) v.y = 0.f;
+    return v;
+}
+__device__ __forceinline__ void recf_grad(const ElemDesc &E, const float2 *__restrict__ displ, const float *__restrict__ geom, int i, int j,
+                                          int a, float2 (&e)[3]) {
+    GCoef gc;
+    load_gcoef(gc, E.axial, i, j);
+    const PointGeom g = load_geom(geom, E.geom_off, i * 5 + j);
+    float2 GU = czero(), UG = czero();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        GU = cfma(gc.gxi_col[k], recf_u(E, displ, k * 5 + j, a), GU);
+        UG = cfma(gc.geta_col[k], recf_u(E, displ, i * 5 + k, a), UG);
+    }
+    const float alpha = (float)a;
+    const float2 v = mul_ialpha(recf_u(E, displ, i * 5 + j, a), alpha);
+    e[0] = cfma(g.dzdeta, GU, cscale(UG, g.dzdxii));
+    e[1] = cscale(v, g.inv_s);
+    e[2] = cfma(g.dsdeta, GU, cscale(UG, g.dsdxii));
+    if (E.axial && i == 0) e[1] = cfma(g.dzdeta, mul_ialpha(GU, alpha), e[1]);
+    if (E.nyq && a == E.nu) e[0] = e[1] = e[2] = czero();
+}
+__global__ void __launch_bounds__(AX_RECF_NT) k_ground_motion_fluid(const ElemDesc *__restrict__ elems, const RecvItem *__restrict__ rec,
+                                                                    const float *__restrict__ weights, const FftPlan *__restrict__ plans,
+                                                                    const float2 *__restrict__ twpool, const float *__restrict__ geom,
+                                                                    const float *__restrict__ coef, const float2 *__restrict__ displ,
+                                                                    float *__restrict__ out, const int *__restrict__ slot, int slot_stride) {
+    if (slot) out += (size_t)(*slot) * slot_stride;
+    extern __shared__ float2 zsm[];            // 3D material only: [2 pairs][5 points][ldz]
+    __shared__ float red[3][AX_RECF_NT / 32];
+    __shared__ FftPlan sP;
+    const int tid = threadIdx.x;
+    const RecvItem R = rec[blockIdx.x];
+    const ElemDesc &E = elems[R.elem];
+    const int N = E.nr, top = E.nu - E.nyq, nm = top + 1;
+    const bool is3d = E.is3d != 0;
+    const int ldz = (N + 1) | 1;
+    if (is3d && tid < (int)(sizeof(FftPlan) / sizeof(int))) reinterpret_cast<int *>(&sP)[tid] = reinterpret_cast<const int *>(plans + E.plan_id)[tid];
+    __syncthreads();
+    const float *w = weights + (size_t)blockIdx.x * AX_NPE;
+    float acc[3] = {0.f, 0.f, 0.f};
+    auto add = [&](int p, int a, const float2 (&s)[3]) {
+        float sn, cs;
+        sincosf((float)a * R.phi, &sn, &cs);
+        const float f = (a == 0 ? 1.f : 2.f) * w[p];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += f * (a == 0 ? s[c].x : cs * s[c].x - sn * s[c].y);
+    };
+    for (int i = 0; i < 5; ++i) {
+        if (!is3d) {   // Acoustic1D::strainToStress (Acoustic1D.cpp:8-14): K per point, in Fourier space
+            for (int idx = tid; idx < 5 * nm; idx += AX_RECF_NT) {
+                const int j = idx / nm, a = idx - j * nm, p = i * 5 + j;
+                float2 e[3];
+                recf_grad(E, displ, geom, i, j, a, e);
+                const float K = coef[E.coef_off + p];
+                const float2 s[3] = {cscale(e[0], K), cscale(e[1], K), cscale(e[2], K)};
+                add(p, a, s);
+            }
+            continue;
+        }
+        const int M = E.nu + 1;
+        for (int idx = tid; idx < 5 * M; idx += AX_RECF_NT) {
+            const int j = idx / M, a = idx - j * M;
+            float2 e[3];
+            recf_grad(E, displ, geom, i, j, a, e);
+            zform_store(zsm + j * ldz, N, a, e[0], e[1]);
+            zform_store(zsm + (5 + j) * ldz, N, a, e[2], czero());
+        }
+        __syncthreads();
+        fft_inverse_dif(sP, zsm, ldz, 10, twpool + sP.tw_off, tid, AX_RECF_NT);
+        for (int idx = tid; idx < 5 * N; idx += AX_RECF_NT) {   // Acoustic3D::strainToStress (Acoustic3D.cpp:9-16), digit-reversed phi
+            const int j = idx / N, pos = idx - j * N;
+            const float K = coef[E.coef_off + (size_t)(i * 5 + j) * N + pos];
+            zsm[j * ldz + pos] = cscale(zsm[j * ldz + pos], K);
+            zsm[(5 + j) * ldz + pos] = cscale(zsm[(5 + j) * ldz + pos], K);
+        }
+        __syncthreads();
+        fft_forward_dit(sP, zsm, ldz, 10, twpool + sP.tw_off, tid, AX_RECF_NT);
+        const float sc = 1.f / (float)N;
+        for (int idx = tid; idx < 5 * nm; idx += AX_RECF_NT) {
+            const int j = idx / nm, a = idx - j * nm;
+            float2 s[3], dummy;
+            zform_load(zsm + j * ldz, N, a, sc, s[0], s[1]);
+            zform_load(zsm + (5 + j) * ldz, N, a, sc, s[2], dummy);
+            add(i * 5 + j, a, s);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        if ((tid & 31) == 0) red[c][tid >> 5] = acc[c];
+    }
+    __syncthreads();
+    if (tid < 3) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < AX_RECF_NT / 32; ++k) t += red[tid][k];
+        out[blockIdx.x * 3 + tid] = t;
+    }
+}

@@ -164,8 +164,10 @@ int ax3d_get_field_bulk(ax3d_domain *dom, int field, int fluid_part, float *out,
 int ax3d_set_field_bulk(ax3d_domain *dom, int field, int fluid_part, const float *in, size_t n_complex);
 /* number of complex entries of the solid / fluid field arrays. */
 int ax3d_field_size(ax3d_domain *dom, int fluid_part, size_t *n_complex);
-/* Element::computeGroundMotion(phi, weights, u_spz) (SolidElement.cpp:189-216) for nrec receivers:
- * out[3 * i + c].  Evaluated on the device from the current displacement, copied to host. */
+/* Element::computeGroundMotion(phi, weights, u_spz) for nrec receivers, out[3 * i + c]: SolidElement.cpp:189-216
+ * (interpolated displacement) or FluidElement.cpp:163-215 (acoustic stress of the potential: gather, Gradient::computeGrad,
+ * Acoustic1D/3D::strainToStress incl. the c2r/r2c pair for 3D material).  Evaluated on the device from the current
+ * displacement, copied to host. */
 int ax3d_record_ground_motion(ax3d_domain *dom, int nrec, const int *elem_tags, const float *phi,
                               const float *weights /* nrec x 25 */, float *out /* nrec x 3 */);
 

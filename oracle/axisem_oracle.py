@@ -739,6 +739,8 @@ class OracleDomain:
         """SolidElement::computeGroundMotion (SolidElement.cpp:189-216)."""
         e = self.elements[elem_tag]
         w = np.asarray(weights, float).reshape(nPE)
+        if e.kind == "fluid":
+            return self._ground_motion_fluid(e, phi, w)
         out = np.zeros(3)
         Nu, Nr = e.maxNu, e.maxNr
         top = Nu - int(Nr % 2 == 0)
@@ -752,3 +754,26 @@ class OracleDomain:
             up = d[:, 0].real + (ex[None, :] * d[:, 1:top + 1]).real.sum(axis=1)
             out += w[i] * up
         return out
+
+    def _ground_motion_fluid(self, e, phi, w):
+        """FluidElement::computeGroundMotion (FluidElement.cpp:163-215): gather, Gradient::computeGrad, [c2r, K, r2c | K],
+        then the same azimuthal evaluation on the acoustic stress (= the fluid displacement)."""
+        rd, cd = self.rd, self.cd
+        g, k = next((g, int(np.nonzero(g.tags == e.domain_tag)[0][0])) for g in self.groups
+                    if g.kind == "fluid" and (g.tags == e.domain_tag).any())
+        M = g.M
+        u = self._gather_fluid(g)                                   # [E,M,5,5]
+        E = u.shape[0]
+        ee = g.grad.grad_fluid(u, g.nyq)
+        K = g.K[:, :, None, :]
+        if g.elem3D:
+            eR = c2r(ee.reshape(E, M, 3, nPE), g.Nr, rd)
+            s = r2c((K * eR).astype(rd, copy=False), g.Nr, cd)      # [E,M,3,25]
+        else:
+            s = (K * ee.reshape(E, M, 3, nPE)).astype(cd, copy=False)
+        s = np.asarray(s).reshape(E, M, 3, nPE)[k]                  # [M,3,25]
+        top = g.Nu - g.nyq
+        al = np.arange(1, top + 1)
+        ex = 2.0 * np.exp(1j * al * phi)
+        up = s[0].real + (ex[:, None, None] * s[1:top + 1]).real.sum(axis=0)     # [3,25]
+        return (up * w[None, :]).sum(axis=1)

@@ -90,6 +90,30 @@ def dump_case(name, workdir):
     return m, dt, stf, d, path, kpath
 
 
+RECV_SEED = 20260103
+
+
+def make_receivers(elements, nper=4, seed=RECV_SEED):
+    """nper receivers in solid and nper in fluid elements: (element tags, phi, weights[25]) -- arbitrary interpolation weights."""
+    rng = np.random.default_rng(seed)
+    sol = [e.domain_tag for e in elements if e.kind == "solid"]
+    flu = [e.domain_tag for e in elements if e.kind == "fluid"]
+    tags = list(rng.choice(sol, min(nper, len(sol)), replace=False)) + list(rng.choice(flu, min(nper, len(flu)), replace=False))
+    phi = rng.uniform(0, 2 * np.pi, len(tags)).astype(np.float32)
+    w = rng.uniform(0, 1, (len(tags), 25))
+    w = (w / w.sum(axis=1, keepdims=True)).astype(np.float32)
+    return np.array(tags, dtype=np.int32), phi, w
+
+
+def write_receivers(path, tags, phi, w):
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", len(tags)))
+        for t, p, ww in zip(tags, phi, w):
+            f.write(struct.pack("<if", int(t), float(p)))
+            f.write(np.ascontiguousarray(ww, dtype=np.float32).tobytes())
+
+
 def split_output(raw, points):
     """ref_driver out.bin -> (displ, stiff), each a flat complex64 array in point order."""
     n = sum((p.nu + 1) * {"solid": 3, "fluid": 1}.get(p.kind, 4) for p in points)
@@ -105,13 +129,17 @@ def main():
         for name in CASES:
             m, dt, stf, d, path, kpath = dump_case(name, tmp)
             out = os.path.join(tmp, name + ".out")
-            r = subprocess.run([REF_DRIVER, path, out, kpath], capture_output=True, text=True, timeout=3600)
+            rin, rout = os.path.join(tmp, name + ".rin"), os.path.join(tmp, name + ".rout")
+            write_receivers(rin, *make_receivers(d.elements))
+            r = subprocess.run([REF_DRIVER, path, out, kpath, rin, rout], capture_output=True, text=True, timeout=3600)
             if r.returncode != 0:
                 raise SystemExit("%s: ref_driver failed: %s" % (name, r.stderr))
             displ, stiff = split_output(np.fromfile(out, dtype=np.complex64), d.points)
             meta = dict(case=name, params={k: (v.__name__ if callable(v) else v) for k, v in CASES[name].items()}, nstep=NSTEP,
                         kick_seed=KICK_SEED, dt=dt, source="oracle/_ref/ref_driver (reference sources + oracle/shim)")
-            np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_%s.npz" % name), displ=displ, stiff=stiff,
+            ground = np.fromfile(rout, dtype=np.float32).reshape(-1, 3)
+            meta["recv_seed"] = RECV_SEED
+            np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_%s.npz" % name), displ=displ, stiff=stiff, ground=ground,
                                 meta=np.array(json.dumps(meta)))
             print("%-24s %5d points %5d elements  |u| %.3e  |f| %.3e  %s" % (
                 name, len(d.points), len(d.elements), np.abs(displ).max(), np.abs(stiff).max(), r.stdout.strip()))

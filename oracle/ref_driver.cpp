@@ -9,7 +9,9 @@
 // Mesh.cpp:177-208), axisem.cpp:219-232 (static initialisation) and the serial Newmark::solve / Domain verbs
 // (Newmark.cpp:47-93, Domain.cpp:82-109,165-191) -- Domain.cpp itself drags in the recorders, NetCDF and Boost.
 //
-//   usage: ref_driver <dump.bin> <out.bin> [kick.bin]
+//   usage: ref_driver <dump.bin> <out.bin> [kick.bin|-] [recv.in recv.out]
+// recv.in (optional): int32 nrec, then per receiver int32 element tag, float phi, float weights[25] (ipol-major);
+// recv.out: float[nrec][3] = Element::computeGroundMotion(phi, weights) of the final state (PointwiseRecorder.cpp:62-144).
 // kick.bin (optional): one complex64 buffer per point in Point::feedBuffer order; it is added to the stiffness with
 // Point::extractBuffer before the first step, so the first updateNewmark turns it into a broadband displacement
 // (u = dt^2 M^-1 f) through the reference's own code -- the reference has no public displacement setter.
@@ -21,6 +23,7 @@
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "Acoustic1D.h"
@@ -237,7 +240,7 @@ int main(int argc, char **argv) {
         // ---- Newmark::solve (Newmark.cpp:19-93), serial: Domain::resetZero, then the step verbs in order
         for (Element *e : elements) e->resetZero();
         for (Point *p : points) p->resetZero();
-        if (argc > 3) {
+        if (argc > 3 && std::string(argv[3]) != "-") {
             std::ifstream kf(argv[3], std::ios::binary);
             if (!kf) throw std::runtime_error("ref_driver || cannot open kick file");
             for (Point *p : points) {
@@ -271,6 +274,21 @@ int main(int argc, char **argv) {
             int row = 0;
             p->feedBuffer(buf, row);
             out.write(reinterpret_cast<const char *>(buf.data()), (size_t)buf.size() * sizeof(Complex));
+        }
+        if (argc > 5) {
+            Reader rr(argv[4]);
+            std::ofstream ro(argv[5], std::ios::binary);
+            const int nrec = rr.get<int32_t>();
+            for (int ir = 0; ir < nrec; ++ir) {
+                const int etag = rr.get<int32_t>();
+                const float phi = rr.get<float>();
+                std::vector<float> wv = rr.vec<float>(25);
+                RMatPP w = take_pp(wv, 0);
+                RRow3 u;
+                elements[etag]->computeGroundMotion(phi, w, u);
+                const float o[3] = {u(0), u(1), u(2)};
+                ro.write(reinterpret_cast<const char *>(o), sizeof(o));
+            }
         }
         std::printf("ref_driver ok: %d points, %d elements, %d steps, maxNr %d\n", npoints, nelems, nsteps, maxNr);
         return 0;
