@@ -3,7 +3,8 @@
  *   (1) as the timed CPU baseline of bench.py ("cpu_baseline", "--impl reference", kind = "port": the
  *       reference itself cannot be built here -- no Eigen/FFTW/MPI/Boost/NetCDF), and
  *   (2) as an independent cross-check of oracle/axisem_oracle.py (tests/test_c_oracle.py).
- * PARITY UNPINNED: the reference holds no golden vectors for this path.
+ * Pinned by tests/test_golden_reference.py against vectors produced by the reference's own sources (oracle/_ref, built by
+ * oracle/Makefile.ref against the Eigen/FFTW stand-ins of oracle/shim); the reference holds no golden vectors itself.
  * Only tests/, __graft_entry__.smoke() and bench.py may load this library.
  *
  * It consumes the flattened per-group arrays of OracleDomain (axisem_oracle.py), so both oracles share

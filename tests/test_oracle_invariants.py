@@ -1,4 +1,4 @@
-"""The oracle is 'parity unpinned' (no golden vectors in the reference), so it is pinned by the
+"""Independent evidence next to tests/test_golden_reference.py (vectors from the reference's own sources): the
 reference's own self-checks restated here: SolidElement::test / FluidElement::test
 (self-adjoint, positive diagonal; SolidElement.cpp:96-187, FluidElement.cpp:94-161), 1D-vs-3D
 path equivalence, rotation round trip, rigid-motion null space, fp32-vs-fp64 agreement."""
