@@ -18,7 +18,7 @@ SYMBOLS = [
     "ax3d_get_field_bulk", "ax3d_set_field_bulk", "ax3d_field_size", "ax3d_record_ground_motion",
     "ax3d_launch_count", "ax3d_work_per_step", "ax3d_algorithmic_bytes", "ax3d_enable_timers",
     "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_dominant_kernel", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
-    "ax3d_halo_export", "ax3d_halo_connect",
+    "ax3d_halo_export", "ax3d_halo_connect", "ax3d_set_learn_parameters", "ax3d_learn_wisdom", "ax3d_get_nu_wisdom",
 ]
 
 
@@ -71,6 +71,9 @@ def load(build_if_missing=True):
     lib.ax3d_assemble_stiff.argtypes = [vp, i]
     lib.ax3d_check_stability.argtypes = [vp, pi_]
     lib.ax3d_reset_zero.argtypes = [vp]
+    lib.ax3d_set_learn_parameters.argtypes = [vp, i, f, i]
+    lib.ax3d_learn_wisdom.argtypes = [vp, i]
+    lib.ax3d_get_nu_wisdom.argtypes = [vp, pi_, i]
     lib.ax3d_run_steps.argtypes = [vp, i, d, pf]
     lib.ax3d_synchronize.argtypes = [vp]
     lib.ax3d_run_steps_timed.argtypes = [vp, i, d, pf, pf]

@@ -252,6 +252,13 @@ struct ax3d_domain {
     double graph_dt = 0;
     bool use_graph = true;
     // receivers registered with ax3d_set_receivers
+    // wisdom learning (Domain::setLearnParameters / learnWisdom / dumpWisdom)
+    bool learn_invoked = false;
+    float learn_cutoff = 0.f;
+    int learn_interval = 1;
+    long long tstep = 0;                        // steps taken by ax3d_run_steps* since set-up (Newmark.cpp:47: tstep - 1)
+    DevBuf<float> s_wis_max, f_wis_max;
+    DevBuf<int> s_wis_nu, f_wis_nu;
     int nrec_c[NCLS] = {0, 0, 0, 0};            // per element class, rows of the device output in class order
     std::vector<int> rec_where_c[NCLS];
     DevBuf<RecvItem> rec_items_c[NCLS];
@@ -1630,6 +1637,71 @@ int ax3d_assemble_stiff(ax3d_domain *d, int phase) {
     API_END
 }
 
+static void learn_wisdom(ax3d_domain *d) {
+    if (d->ns) {
+        k_learn_wisdom<3><<<nblk(d->ns * 3 * 32, 256), 256, 0, d->stream>>>(d->s_tab, (int)d->ns, d->s_field[AX3D_DISPL].p, d->learn_cutoff,
+                                                                           d->s_wis_max.p, d->s_wis_nu.p);
+        d->launches++;
+    }
+    if (d->nf) {
+        k_learn_wisdom<1><<<nblk(d->nf * 32, 256), 256, 0, d->stream>>>(d->f_tab, (int)d->nf, d->f_field[AX3D_DISPL].p, d->learn_cutoff,
+                                                                       d->f_wis_max.p, d->f_wis_nu.p);
+        d->launches++;
+    }
+    CK(cudaGetLastError());
+}
+
+/* Domain::setLearnParameters(LearnParameters{invoked, cutoff, interval}) (Domain.h:39; axisem.cpp:158-166) */
+int ax3d_set_learn_parameters(ax3d_domain *d, int invoked, float cutoff, int interval) {
+    API_BEGIN
+    check_final(d);
+    if (interval <= 0) fail("Domain::setLearnParameters || interval must be positive");
+    d->learn_invoked = invoked != 0;
+    d->learn_cutoff = cutoff;
+    d->learn_interval = interval;
+    if (d->learn_invoked && !d->s_wis_max.p && !d->f_wis_max.p) {
+        std::vector<float> m3(d->ns * 3, -1.f), m1(d->nf, -1.f);
+        std::vector<int> n3(d->ns * 3), n1(d->nf);
+        for (const HPoint &p : d->points) {
+            if (p.s_idx >= 0) for (int c = 0; c < 3; ++c) n3[(size_t)p.s_idx * 3 + c] = p.nu;
+            if (p.f_idx >= 0) n1[p.f_idx] = p.nu;
+        }
+        d->s_wis_max.upload(m3); d->s_wis_nu.upload(n3);
+        d->f_wis_max.upload(m1); d->f_wis_nu.upload(n1);
+    }
+    API_END
+}
+
+/* Domain::learnWisdom(tstep) (Domain.cpp:384-402): Point::learnWisdom(cutoff) on every point when tstep % interval == 0 */
+int ax3d_learn_wisdom(ax3d_domain *d, int tstep) {
+    API_BEGIN
+    check_final(d);
+    if (!d->learn_invoked) return 0;
+    if (tstep % d->learn_interval == 0) learn_wisdom(d);
+    API_END
+}
+
+/* what Domain::dumpWisdom (Domain.cpp:404-440) collects: Point::getNuWisdom() per point tag (solid: max over the three
+ * components, SolidPoint.cpp:268-272; solid-fluid: max of both parts, SolidFluidPoint.cpp:129-131) */
+int ax3d_get_nu_wisdom(ax3d_domain *d, int *nu_wisdom, int npoints) {
+    API_BEGIN
+    check_final(d);
+    if (npoints != (int)d->points.size()) fail("Domain::dumpWisdom || size mismatch");
+    if (!d->learn_invoked) fail("Domain::dumpWisdom || wisdom learning was not invoked (ax3d_set_learn_parameters)");
+    std::vector<int> n3(d->ns * 3), n1(d->nf);
+    CK(cudaStreamSynchronize(d->stream));
+    if (d->ns) CK(cudaMemcpy(n3.data(), d->s_wis_nu.p, n3.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    if (d->nf) CK(cudaMemcpy(n1.data(), d->f_wis_nu.p, n1.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < d->points.size(); ++t) {
+        const HPoint &p = d->points[t];
+        int v = 0;
+        if (p.s_idx >= 0) for (int c = 0; c < 3; ++c) v = std::max(v, n3[(size_t)p.s_idx * 3 + c]);
+        if (p.f_idx >= 0) v = std::max(v, n1[p.f_idx]);
+        nu_wisdom[t] = v;
+    }
+    API_END
+}
+
 int ax3d_check_stability(ax3d_domain *d, int *stable) {
     API_BEGIN
     check_final(d);
@@ -1757,7 +1829,10 @@ static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf, b
         // every step but the last of this call advances the plain points to the next step under its element kernel,
         // so that the state after the call is exactly the reference's (all points at step i, stiff = this step's force)
         const bool special_only = d->plain_advanced;
-        const bool nw_on = can_nw && i + 1 < nsteps;
+        // Domain::learnWisdom(tstep - 1) (Newmark.cpp:89): needs every point at this step, so a learning step does not
+        // advance the plain points under its element kernel
+        const bool learn_now = d->learn_invoked && d->tstep % d->learn_interval == 0;
+        const bool nw_on = can_nw && i + 1 < nsteps && !learn_now;
         if (d->n_src || record) push_stf(d, stf ? stf[i] : 0.f, i);
         if (graph_ok) {
             const int v = (record ? 4 : 0) + (special_only ? 2 : 0) + (nw_on ? 1 : 0);
@@ -1775,6 +1850,8 @@ static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf, b
             step_body(d, dt, special_only, nw_on, record);
         }
         d->plain_advanced = nw_on;
+        if (learn_now) learn_wisdom(d);
+        d->tstep++;
     }
 }
 

@@ -641,6 +641,47 @@ __global__ void k_check_finite(size_t n, const float *__restrict__ a, int *__res
     if (b) atomicOr(bad, 1);
 }
 
+// ------------------------------------------------------------------------------------ wisdom learning
+// Point::learnWisdom (SolidPoint.cpp:240-266, FluidPoint.cpp:209-229): one warp per (point, component).  When the Hilbert
+// norm h2 = |u|^2 - |u_0|^2 / 2 exceeds its running maximum, the smallest order newNu < Nu with
+// |u|^2 - |u_{0..newNu}|^2 <= cutoff^2 h2 is stored (Nu if none).  wis_max starts at -1, wis_nu at Nu (SolidPoint.cpp:16).
+template <int NCOMP>
+__global__ void k_learn_wisdom(PointTab pt, int npoint, const float2 *__restrict__ displ, float cutoff, float *__restrict__ wis_max,
+                               int *__restrict__ wis_nu) {
+    const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= npoint * NCOMP) return;
+    const int p = w / NCOMP, c = w - p * NCOMP;
+    const int nu = pt.nu[p];
+    const float2 *u = displ + (size_t)pt.off[p] + (size_t)c * (nu + 1);
+    float l2 = 0.f;
+    for (int a = lane; a <= nu; a += 32) l2 += u[a].x * u[a].x + u[a].y * u[a].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+    const float2 u0 = u[0];
+    const float h2 = l2 - 0.5f * (u0.x * u0.x + u0.y * u0.y);
+    if (h2 <= wis_max[w]) return;          // warp-uniform
+    const float tol = h2 * cutoff * cutoff;
+    int found = nu;
+    float carry = 0.f;
+    for (int base = 0; base < nu; base += 32) {
+        const int a = base + lane;
+        float v = a <= nu ? u[a].x * u[a].x + u[a].y * u[a].y : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {   // inclusive scan
+            const float t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        const float pre = carry + v;         // |u_{0..a}|^2
+        const unsigned m = __ballot_sync(0xffffffffu, a < nu && l2 - pre <= tol);
+        if (m) { found = base + __ffs(m) - 1; break; }
+        carry = __shfl_sync(0xffffffffu, pre, 31);
+    }
+    if (lane == 0) {
+        wis_max[w] = h2;
+        wis_nu[w] = found;
+    }
+}
+
 // ------------------------------------------------------------------------------------ receivers
 // SolidElement::computeGroundMotion (SolidElement.cpp:189-216); one CTA per receiver, 128 threads.
 struct RecvItem {

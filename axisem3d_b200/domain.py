@@ -219,6 +219,20 @@ class Domain:
         capi.check(self.lib.ax3d_check_stability(self.h, C.byref(ok)))
         return bool(ok.value)
 
+    def setLearnParameters(self, invoked, cutoff, interval=1):
+        """Domain::setLearnParameters (Domain.h:39)."""
+        capi.check(self.lib.ax3d_set_learn_parameters(self.h, int(bool(invoked)), float(cutoff), int(interval)))
+
+    def learnWisdom(self, tstep):
+        """Domain::learnWisdom(tstep) (Domain.cpp:384-402) for verb-wise stepping; runSteps does it itself."""
+        capi.check(self.lib.ax3d_learn_wisdom(self.h, int(tstep)))
+
+    def getNuWisdom(self):
+        """Point::getNuWisdom() per point tag (what Domain::dumpWisdom writes, Domain.cpp:404-440)."""
+        out = np.zeros(len(self.points), dtype=np.int32)
+        capi.check(self.lib.ax3d_get_nu_wisdom(self.h, _pi(out), len(out)))
+        return out
+
     def resetZero(self):
         capi.check(self.lib.ax3d_reset_zero(self.h))
 

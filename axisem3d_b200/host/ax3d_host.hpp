@@ -102,6 +102,13 @@ private:
 };
 
 // ------------------------------------------------------------------------------------------ points  (S/core/point)
+struct LearnParameters {                    // S/preloop/nrfield/wisdom/NuWisdom.h:37-43 (filled from inparam.nu there)
+    bool mInvoked = false;
+    double mCutoff = 0;
+    int mInterval = 1;
+    std::string mFileName;
+};
+
 class Domain;
 class Point {                               // Point.h:13
 public:
@@ -333,10 +340,30 @@ public:
 class Anisotropic1D : public Elastic {      // Anisotropic1D.cpp:9-54: C11 C12 ... C16 C22 ... C66 (upper triangle, row by row)
 public:
     Anisotropic1D(const std::array<RMatPP, 21> &Cij, Attenuation *att = 0) : Elastic(AX3D_ANISO, 1, att) { for (const RMatPP &c : Cij) push(c); }
+    // the reference's own 22-argument form (Anisotropic1D.h:13-27)
+    Anisotropic1D(const RMatPP &C11, const RMatPP &C12, const RMatPP &C13, const RMatPP &C14, const RMatPP &C15, const RMatPP &C16,
+                  const RMatPP &C22, const RMatPP &C23, const RMatPP &C24, const RMatPP &C25, const RMatPP &C26,
+                  const RMatPP &C33, const RMatPP &C34, const RMatPP &C35, const RMatPP &C36,
+                  const RMatPP &C44, const RMatPP &C45, const RMatPP &C46, const RMatPP &C55, const RMatPP &C56, const RMatPP &C66,
+                  Attenuation *att = 0)
+        : Elastic(AX3D_ANISO, 1, att) {
+        const RMatPP *all[21] = {&C11, &C12, &C13, &C14, &C15, &C16, &C22, &C23, &C24, &C25, &C26, &C33, &C34, &C35, &C36, &C44, &C45, &C46, &C55, &C56, &C66};
+        for (const RMatPP *c : all) push(*c);
+    }
 };
 class Anisotropic3D : public Elastic {      // Anisotropic3D.cpp:10-54
 public:
     Anisotropic3D(const std::array<RMatXN, 21> &Cij, Attenuation *att = 0) : Elastic(AX3D_ANISO, Cij[0].rows, att) { for (const RMatXN &c : Cij) push(c); }
+    // the reference's own 22-argument form (Anisotropic3D.h:13-27)
+    Anisotropic3D(const RMatXN &C11, const RMatXN &C12, const RMatXN &C13, const RMatXN &C14, const RMatXN &C15, const RMatXN &C16,
+                  const RMatXN &C22, const RMatXN &C23, const RMatXN &C24, const RMatXN &C25, const RMatXN &C26,
+                  const RMatXN &C33, const RMatXN &C34, const RMatXN &C35, const RMatXN &C36,
+                  const RMatXN &C44, const RMatXN &C45, const RMatXN &C46, const RMatXN &C55, const RMatXN &C56, const RMatXN &C66,
+                  Attenuation *att = 0)
+        : Elastic(AX3D_ANISO, C11.rows, att) {
+        const RMatXN *all[21] = {&C11, &C12, &C13, &C14, &C15, &C16, &C22, &C23, &C24, &C25, &C26, &C33, &C34, &C35, &C36, &C44, &C45, &C46, &C55, &C56, &C66};
+        for (const RMatXN *c : all) push(*c);
+    }
 };
 
 class Acoustic {                            // S/core/element/material/acoustic
@@ -548,6 +575,18 @@ public:
     void updateNewmark(double dt) const { finalize(); check(ax3d_update_newmark(mDom, dt)); }
     void coupleSolidFluid() const { finalize(); check(ax3d_couple_solid_fluid(mDom)); }
     void record(int /*tstep*/, double /*t*/) const {}   // PointwiseRecorder stays on the host side
+    // wisdom learning (Domain.h:39; Domain.cpp:384-402, 404-440)
+    void setLearnParameters(LearnParameters *lpar) {
+        finalize();
+        mLearnPar = lpar;
+        check(ax3d_set_learn_parameters(mDom, lpar->mInvoked ? 1 : 0, (float)lpar->mCutoff, lpar->mInterval));
+    }
+    void learnWisdom(int tstep) const { if (mLearnPar && mLearnPar->mInvoked) check(ax3d_learn_wisdom(mDom, tstep)); }
+    std::vector<int> getNuWisdom() const {   // Point::getNuWisdom() of every point, as Domain::dumpWisdom collects them
+        std::vector<int> nw(mPoints.size());
+        check(ax3d_get_nu_wisdom(mDom, nw.data(), (int)nw.size()));
+        return nw;
+    }
     void checkStability(double dt, int tstep, double t) const {            // Domain.cpp:237-275
         int ok = 1;
         check(ax3d_check_stability(mDom, &ok));
@@ -586,6 +625,7 @@ private:
     std::vector<Element *> mElements;
     std::vector<SourceTerm *> mSourceTerms;
     SourceTimeFunction *mSTF = nullptr;
+    LearnParameters *mLearnPar = nullptr;
     MessagingInfo *mMsgInfo = nullptr;
     MessagingBuffer *mMsgBuffer = nullptr;
     bool mSentG = false;
@@ -626,6 +666,7 @@ public:
             t += dt;
             if (tstep % mCheckStabInterval == 0) mDomain->checkStability(dt, tstep, t);
             if (verbose && tstep % mReportInterval == 0) std::printf("  step %d / %d   t = %g\n", tstep, maxStep, t);
+            mDomain->learnWisdom(tstep - 1);
             mDomain->assembleStiff(1);
         }
         mDomain->synchronize();

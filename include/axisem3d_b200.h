@@ -178,6 +178,14 @@ int ax3d_set_receivers(ax3d_domain *dom, int nrec, const int *elem_tags, const f
  * one displacement sample (s, phi, z) per registered receiver, nrec x 3 floats, device -> host. */
 int ax3d_record(ax3d_domain *dom, float *out);
 
+/* Wisdom learning (NU_WISDOM_LEARN in inparam.nu): Domain::setLearnParameters (Domain.h:39; LearnParameters = invoked, cutoff,
+ * interval), Domain::learnWisdom(tstep) (Domain.cpp:384-402) -> Point::learnWisdom(cutoff) (SolidPoint.cpp:240-266,
+ * FluidPoint.cpp:209-229), and the per-point Point::getNuWisdom() that Domain::dumpWisdom (Domain.cpp:404-440) writes.
+ * ax3d_run_steps* call the learning step themselves once it is invoked (Newmark.cpp:89). */
+int ax3d_set_learn_parameters(ax3d_domain *dom, int invoked, float cutoff, int interval);
+int ax3d_learn_wisdom(ax3d_domain *dom, int tstep);
+int ax3d_get_nu_wisdom(ax3d_domain *dom, int *nu_wisdom /* npoints, by point tag */, int npoints);
+
 /* ------------------------------------------------------------------ measurement hooks */
 /* number of CUDA kernel launches issued by this domain since creation (bench.py "gpu_launches"). */
 int ax3d_launch_count(ax3d_domain *dom, long long *n);

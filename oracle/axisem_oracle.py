@@ -760,6 +760,45 @@ class OracleDomain:
             out += w[i] * up
         return out
 
+    # ---- wisdom learning (Domain::learnWisdom, Domain.cpp:384-402) ----------------------
+    def learnWisdom(self, cutoff):
+        """Point::learnWisdom on every point (SolidPoint.cpp:240-266, FluidPoint.cpp:209-229): per component, when the
+        Hilbert norm of the displacement exceeds its running maximum, the smallest order whose truncation error stays
+        below cutoff^2 of it is remembered."""
+        if not hasattr(self, "_wis"):
+            self._wis = {}
+        rd = np.dtype(self.rd).type
+        for t, p in enumerate(self.points):
+            n = p.nu + 1
+            cols = []
+            if self.s_idx[t] >= 0:
+                cols += [("s", c, self.S["displ"][self.s_idx[t], c, :n]) for c in range(3)]
+            if self.f_idx[t] >= 0:
+                cols.append(("f", 0, self.F["displ"][self.f_idx[t], :n]))
+            for fam, c, u in cols:
+                e = (u.real.astype(rd) ** 2 + u.imag.astype(rd) ** 2).astype(rd)
+                l2 = rd(e.sum(dtype=rd))
+                h2 = rd(l2 - rd(0.5) * e[0])
+                st = self._wis.setdefault((t, fam, c), [rd(-1.0), p.nu])
+                if h2 <= st[0]:
+                    continue
+                st[0] = h2
+                tol = rd(h2 * rd(cutoff) * rd(cutoff))
+                diff = l2 - np.cumsum(e[:-1], dtype=rd)            # newNu = 0 .. nu-1
+                hit = np.nonzero(diff <= tol)[0]
+                st[1] = int(hit[0]) if hit.size else p.nu
+
+    def getNuWisdom(self):
+        """Point::getNuWisdom per point (SolidPoint.cpp:268-272: max over the 3 components; SolidFluidPoint.cpp:129-131)."""
+        out = np.array([p.nu for p in self.points], dtype=np.int32)
+        if hasattr(self, "_wis"):
+            best = {}
+            for (t, fam, c), st in self._wis.items():
+                best[t] = max(best.get(t, 0), st[1])
+            for t, v in best.items():
+                out[t] = v
+        return out
+
     def _ground_motion_fluid(self, e, phi, w):
         """FluidElement::computeGroundMotion (FluidElement.cpp:163-215): gather, Gradient::computeGrad, [c2r, K, r2c | K],
         then the same azimuthal evaluation on the acoustic stress (= the fluid displacement)."""

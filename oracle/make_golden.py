@@ -91,6 +91,7 @@ def dump_case(name, workdir):
 
 
 RECV_SEED = 20260103
+WISDOM_CUTOFF = 0.5       # Point::learnWisdom(cutoff): large, so that the white kick spectrum yields non-trivial orders
 
 
 def make_receivers(elements, nper=4, seed=RECV_SEED):
@@ -131,7 +132,9 @@ def main():
             out = os.path.join(tmp, name + ".out")
             rin, rout = os.path.join(tmp, name + ".rin"), os.path.join(tmp, name + ".rout")
             write_receivers(rin, *make_receivers(d.elements))
-            r = subprocess.run([REF_DRIVER, path, out, kpath, rin, rout], capture_output=True, text=True, timeout=3600)
+            wout = os.path.join(tmp, name + ".wout")
+            r = subprocess.run([REF_DRIVER, path, out, kpath, rin, rout, wout, repr(WISDOM_CUTOFF)], capture_output=True, text=True,
+                               timeout=3600)
             if r.returncode != 0:
                 raise SystemExit("%s: ref_driver failed: %s" % (name, r.stderr))
             displ, stiff = split_output(np.fromfile(out, dtype=np.complex64), d.points)
@@ -139,7 +142,10 @@ def main():
                         kick_seed=KICK_SEED, dt=dt, source="oracle/_ref/ref_driver (reference sources + oracle/shim)")
             ground = np.fromfile(rout, dtype=np.float32).reshape(-1, 3)
             meta["recv_seed"] = RECV_SEED
-            np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_%s.npz" % name), displ=displ, stiff=stiff, ground=ground,
+            meta["wisdom_cutoff"] = WISDOM_CUTOFF
+            nu_wisdom = np.fromfile(wout, dtype=np.int32)
+            assert nu_wisdom.size == len(d.points)
+            np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_%s.npz" % name), displ=displ, stiff=stiff, ground=ground, nu_wisdom=nu_wisdom,
                                 meta=np.array(json.dumps(meta)))
             print("%-24s %5d points %5d elements  |u| %.3e  |f| %.3e  %s" % (
                 name, len(d.points), len(d.elements), np.abs(displ).max(), np.abs(stiff).max(), r.stdout.strip()))

@@ -9,7 +9,9 @@
 // Mesh.cpp:177-208), axisem.cpp:219-232 (static initialisation) and the serial Newmark::solve / Domain verbs
 // (Newmark.cpp:47-93, Domain.cpp:82-109,165-191) -- Domain.cpp itself drags in the recorders, NetCDF and Boost.
 //
-//   usage: ref_driver <dump.bin> <out.bin> [kick.bin|-] [recv.in recv.out]
+//   usage: ref_driver <dump.bin> <out.bin> [kick.bin|-] [recv.in recv.out] [wisdom.out cutoff]
+// wisdom.out (optional): Point::learnWisdom(cutoff) is called on every point after every step (Domain::learnWisdom with
+// interval 1, Domain.cpp:384-402); the file receives int32 getNuWisdom() per point (Domain::dumpWisdom, Domain.cpp:404-440).
 // recv.in (optional): int32 nrec, then per receiver int32 element tag, float phi, float weights[25] (ipol-major);
 // recv.out: float[nrec][3] = Element::computeGroundMotion(phi, weights) of the final state (PointwiseRecorder.cpp:62-144).
 // kick.bin (optional): one complex64 buffer per point in Point::feedBuffer order; it is added to the stiffness with
@@ -20,6 +22,7 @@
 #include <array>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -255,6 +258,15 @@ int main(int argc, char **argv) {
             for (SourceTerm *s : sources) s->apply(stf[tstep - 1]);          // Domain.cpp:96-109
             for (Element *e : elements) e->computeStiff();                    // Domain.cpp:82-94
             for (SolidFluidPoint *sf : sfpoints) sf->coupleSolidFluid();      // Domain.cpp:178-191
+            if (argc > 7)
+                for (Point *p : points) p->learnWisdom((Real)std::atof(argv[7]));   // Domain.cpp:384-402
+        }
+        if (argc > 7) {
+            std::ofstream wo(argv[6], std::ios::binary);
+            for (Point *p : points) {
+                const int32_t nw = p->getNuWisdom();
+                wo.write(reinterpret_cast<const char *>(&nw), 4);
+            }
         }
 
         std::ofstream out(argv[2], std::ios::binary);

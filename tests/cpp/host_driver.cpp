@@ -136,9 +136,10 @@ int main(int argc, char **argv) {
                     else if (law == AX3D_TI)
                         el = new TransverselyIsotropic3D(take_xn(coef, 0, rows), take_xn(coef, 1, rows), take_xn(coef, 2, rows), take_xn(coef, 3, rows), take_xn(coef, 4, rows), att);
                     else {
-                        std::array<RMatXN, 21> C;
-                        for (int k = 0; k < 21; ++k) C[k] = take_xn(coef, k, rows);
-                        el = new Anisotropic3D(C, att);
+                        std::vector<RMatXN> C;
+                        for (int k = 0; k < 21; ++k) C.push_back(take_xn(coef, k, rows));
+                        el = new Anisotropic3D(C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8], C[9], C[10], C[11], C[12], C[13], C[14],
+                                               C[15], C[16], C[17], C[18], C[19], C[20], att);   // the reference's signature
                     }
                 }
                 domain->addElement(new SolidElement(grad, 0, pts, el));
