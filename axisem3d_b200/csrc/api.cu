@@ -98,7 +98,7 @@ struct HSource {
                                   // cfg2 elements 0.53 ms vs 0.31 ms single-CTA, cfg4 1.05 ms vs 0.84 ms split pipeline -- so it stays opt-in
 #endif
 #ifndef AX_CLUSTER_NT_DEFAULT
-#define AX_CLUSTER_NT_DEFAULT 128
+#define AX_CLUSTER_NT_DEFAULT 0
 #endif
 enum { CLS_S1D = 0, CLS_F1D = 1, CLS_S3D = 2, CLS_F3D = 3, NCLS = 4 };
 
@@ -548,7 +548,8 @@ static void finalize(ax3d_domain *d) {
     const char *env_cl = getenv("AX3D_CLUSTER"), *env_clnt = getenv("AX3D_CL_NT");
     const int cluster_mode = env_cl ? atoi(env_cl) : AX_CLUSTER_DEFAULT;
     const int cluster_nt = env_clnt ? atoi(env_clnt) : AX_CLUSTER_NT_DEFAULT;
-    if (cluster_nt != 128 && cluster_nt != 192 && cluster_nt != 256) fail("ax3d::cluster || AX3D_CL_NT must be 128, 192 or 256");
+    if (cluster_nt != 0 && cluster_nt != 128 && cluster_nt != 192 && cluster_nt != 256 && cluster_nt != 512)
+        fail("ax3d::cluster || AX3D_CL_NT must be 0 (by shared-memory class), 128, 192, 256 or 512");
     const char *env_nf = getenv("AX3D_NO_FUSED");
     const bool use_fused = !(env_nf && atoi(env_nf) != 0);
     {
@@ -724,11 +725,13 @@ static void finalize(ax3d_domain *d) {
         if (!cl_elems.empty()) {
             // elements are sorted by Nr (descending); cut the list where one more resident CTA per SM becomes possible
             auto per_sm = [](size_t bytes) { return (int)std::min<size_t>(8, (size_t)(228 * 1024) / (bytes + 1024)); };
-            ClusterLaunch cl{c, 0, 0, cluster_nt, cl_smem[0]};
+            // threads per CTA by residency: the warps of an SM come from 1, 2 or >= 3 CTAs (126 registers: <= 512 threads per SM)
+            auto nt_for = [&](size_t bytes) { return cluster_nt ? cluster_nt : per_sm(bytes) <= 1 ? 512 : per_sm(bytes) == 2 ? 256 : 128; };
+            ClusterLaunch cl{c, 0, 0, nt_for(cl_smem[0]), cl_smem[0]};
             for (size_t k = 0; k < cl_elems.size(); ++k) {
                 if (cl.count > 0 && per_sm(cl_smem[k]) > per_sm(cl.smem)) {
                     d->clusters.push_back(cl);
-                    cl = ClusterLaunch{c, (int)k, 0, cluster_nt, cl_smem[k]};
+                    cl = ClusterLaunch{c, (int)k, 0, nt_for(cl_smem[k]), cl_smem[k]};
                 }
                 cl.count++;
                 cl.smem = std::max(cl.smem, cl_smem[k]);   // not monotone in Nr: the twiddle tables depend on the factorisation
@@ -1203,6 +1206,7 @@ typedef void (*cluster_kernel_t)(const ElemDesc *, const int *, const FftPlan *,
 static cluster_kernel_t cluster_kernel(bool fluid, int nt) {
     if (nt == 128) return fluid ? k_elem3d_cluster<true, 128> : k_elem3d_cluster<false, 128>;
     if (nt == 192) return fluid ? k_elem3d_cluster<true, 192> : k_elem3d_cluster<false, 192>;
+    if (nt == 512) return fluid ? k_elem3d_cluster<true, 512> : k_elem3d_cluster<false, 512>;
     return fluid ? k_elem3d_cluster<true, 256> : k_elem3d_cluster<false, 256>;
 }
 

@@ -36,7 +36,7 @@ __host__ __device__ inline ClLayout cl_layout(bool fluid, int N, int stw_len) {
 }
 
 template <bool FLUID, int NT>
-__global__ void __launch_bounds__(NT) k_elem3d_cluster(const ElemDesc *__restrict__ elems, const int *__restrict__ list,
+__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : NT >= 256 ? 2 : 4) k_elem3d_cluster(const ElemDesc *__restrict__ elems, const int *__restrict__ list,
                                                       const FftPlan *__restrict__ plans, const float2 *__restrict__ stwpool,
                                                       const float *__restrict__ geom, const float *__restrict__ coef,
                                                       const float *__restrict__ attpar, float *__restrict__ attstate,
@@ -68,6 +68,14 @@ __global__ void __launch_bounds__(NT) k_elem3d_cluster(const ElemDesc *__restric
     const ClLayout lay = cl_layout(FLUID, N, P.stw_len);
     float2 *const TW = smem + lay.tw, *const U = smem + lay.u, *const Z = smem + lay.z;
     for (int k = tid; k < P.stw_len; k += NT) TW[k] = stwpool[P.stw_base + k];
+    {   // moduli (and SLS state) of this row are first touched two phases from now: pull their lines towards L2 meanwhile
+        const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
+        const int lines = (5 * N * 4 + 127) / 128;
+        for (int q = tid; q < ncoef * lines; q += NT) {
+            const int kc = q / lines, l = q - kc * lines;
+            prefetch_l2(coef + E.coef_off + ((size_t)kc * AX_NPE + row * 5) * N + (size_t)l * 32);
+        }
+    }
 
     // ------------------------------------------------------------ gather this row (Point::scatterDisplToElement, SolidPoint.cpp:175-195)
 #pragma unroll
