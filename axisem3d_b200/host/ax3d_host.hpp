@@ -34,6 +34,7 @@ typedef std::array<double, 2> RDCol2;
 typedef std::array<double, 25> RDMatPP;   // row-major (ipol, jpol)
 typedef std::array<Real, 25> RMatPP;      // row-major (ipol, jpol)
 typedef std::array<Real, 3> RRow3;
+typedef std::array<Real, 4> RRow4;        // eigen_cg4.h: the four CG4 points (1,1) (1,3) (3,1) (3,3)
 typedef std::vector<Real> RColX;
 struct RMatXN {                           // Nr x 25, column-major: (j, ipnt) at [ipnt * rows + j]
     int rows = 0;
@@ -277,8 +278,8 @@ public:
 };
 class Attenuation1D_CG4 : public Attenuation {
 public:
-    Attenuation1D_CG4(int nsls, const RColX &alpha, const RColX &beta, const RColX &gamma, int /*Nu*/, const std::array<Real, 4> &dkappa,
-                      const std::array<Real, 4> &dmu, bool doKappa)
+    Attenuation1D_CG4(int nsls, const RColX &alpha, const RColX &beta, const RColX &gamma, int /*Nu*/, const RRow4 &dkappa,
+                      const RRow4 &dmu, bool doKappa)
         : Attenuation(AX3D_ATT_CG4, nsls, alpha, beta, gamma, 1, 4, dkappa.data(), dmu.data(), doKappa) {}
 };
 // Attenuation3D_Full.h / _CG4.h: (nsls, alpha, beta, gamma, dkappa, dmu, doKappa) with RMatXN / RMatX4 moduli
@@ -478,9 +479,9 @@ private:
     arPP_CMatX3 mForce;
 };
 
-class SourceTimeFunction {                  // SourceTimeFunction.h: (dt, shift, samples)
+class SourceTimeFunction {                  // SourceTimeFunction.h:10-24
 public:
-    SourceTimeFunction(double dt, double shift, const std::vector<Real> &stf) : mDeltaT(dt), mShift(shift), mSTF(stf) {}
+    SourceTimeFunction(const std::vector<Real> &stf, double dt, double shift) : mDeltaT(dt), mShift(shift), mSTF(stf) {}   // the reference's order
     int getSize() const { return (int)mSTF.size(); }
     double getDeltaT() const { return mDeltaT; }
     double getShift() const { return mShift; }

@@ -167,7 +167,7 @@ int main(int argc, char **argv) {
         const int nsteps = r.get<int32_t>();
         const double dt = r.get<double>();
         std::vector<float> stf = r.vec<float>(nsteps);
-        domain->setSTF(new SourceTimeFunction(dt, 0., stf));
+        domain->setSTF(new SourceTimeFunction(stf, dt, 0.));
 
         Newmark *newmark = new Newmark(domain, 1000000, 20, false);   // axisem.cpp:169
         newmark->solve(0);                                            // axisem.cpp:181
