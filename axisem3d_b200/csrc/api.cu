@@ -77,6 +77,8 @@ struct HElem {
     int law, rows, nr, nu, ncoef;
     std::vector<float> coef;
     HAtt att;
+    int prt_rows = 0;         // particle relabelling: 0 none, 1 PRT_1D, Nr PRT_3D
+    std::vector<float> prtX;  // [4][25][prt_rows]
     int cls = -1, idx = -1;   // class and index inside the class after finalize
     double alg_b = 0;         // algorithmic bytes of one stiffness evaluation of this element
 };
@@ -108,6 +110,7 @@ struct Chunk {   // a run of 3D elements of one class whose spectra fit the scra
     int f_begin, f_count;       // fft work items
     size_t fft_smem;
     int fft_np, fft_nt;         // k_fft3d_v2 instance: points per CTA (5 or 1), threads (256: two CTAs per SM, or 512)
+    int prt;                    // 1: solid elements with particle relabelling (5 Z-form pairs per point instead of 3)
 };
 
 struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_elem3d_fused<FLUID, 512, nct> launch
@@ -417,6 +420,11 @@ typedef void (*fft_kernel_t)(const ElemDesc *, const FftItem *, const FftPlan *,
                              float2 *);
 static fft_kernel_t fft_kernel(const Chunk &ch) {
     const bool fluid = ch.cls == CLS_F3D;
+    if (ch.prt && !fluid) {
+        if (ch.fft_np == 1) return k_fft3d_v2<false, 1, 256, 5>;
+        if (ch.fft_nt == 256) return k_fft3d_v2<false, 5, 256, 5>;
+        return k_fft3d_v2<false, 5, 512, 5>;
+    }
     if (ch.fft_np == 1) return fluid ? k_fft3d_v2<true, 1, 256> : k_fft3d_v2<false, 1, 256>;
     if (ch.fft_nt == 256) return fluid ? k_fft3d_v2<true, 5, 256> : k_fft3d_v2<false, 5, 256>;
     return fluid ? k_fft3d_v2<true, 5, 512> : k_fft3d_v2<false, 5, 512>;
@@ -562,12 +570,12 @@ static void finalize(ax3d_domain *d) {
         const int npair = fluid ? 2 : 3;
         std::vector<int> w_elem, w_a0;
         std::vector<FftItem> fitems;
-        Chunk ch{c, 0, 0, 0, 0, 0, 5, 256};
+        Chunk ch{c, 0, 0, 0, 0, 0, 5, 256, 0};
         int cls_np = 0;   // points per k_fft3d_v2 CTA for this class: fixed by its largest split element
         size_t ch_scratch = 0;
         auto close_chunk = [&]() {
             if (ch.w_count > 0) d->chunks.push_back(ch);
-            ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0, 5, 256};
+            ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0, 5, 256, 0};
             ch_scratch = 0;
         };
         std::vector<int> cl_elems;
@@ -595,7 +603,8 @@ static void finalize(ax3d_domain *d) {
             D.nyq = (E.nr % 2 == 0) ? 1 : 0;
             D.axial = E.axial ? 1 : 0;
             D.law = E.law;
-            D.tiso = (!fluid && E.law != AX3D_ISO) ? 1 : 0;
+            D.prt = E.prt_rows > 0 ? 1 : 0;
+            D.tiso = (!fluid && (E.law != AX3D_ISO || D.prt)) ? 1 : 0;   // SolidElement.cpp:21: mInTIso = mHasPRT || needTIso
             D.is3d = is3d ? 1 : 0;
             D.att_kind = E.att.kind;
             D.nsls = E.att.nsls;
@@ -609,7 +618,7 @@ static void finalize(ax3d_domain *d) {
             }
             D.geom_off = (long long)geom.size();
             for (int i = 0; i < 5 * AX_NPE; ++i) geom.push_back((float)E.geom[i]);
-            if (D.tiso) {
+            if (D.tiso || D.prt) {   // fluid elements rotate only with PRT (FluidElement.cpp:21)
                 D.trig_off = (long long)geom.size();
                 for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)sin(E.theta[i]));
                 for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)cos(E.theta[i]));
@@ -626,6 +635,18 @@ static void finalize(ax3d_domain *d) {
                         for (int pos = 0; pos < N; ++pos) coef.push_back(E.coef[((size_t)kc * AX_NPE + p) * N + (*perm)[pos]]);
             } else {
                 coef.insert(coef.end(), E.coef.begin(), E.coef.end());
+            }
+            if (D.prt) {   // PRT_1D: [4][25]; PRT_3D: [4][25][Nr] in the plan's digit-reversed phi order, next to the moduli
+                if ((E.prt_rows == 1) == is3d) fail(std::string(fluid ? "FluidElement::FluidElement" : "SolidElement::SolidElement") +
+                                                    " || Particle Relabelling and Elasticity are generated in different spaces.");
+                D.prt_off = (long long)coef.size();
+                if (is3d) {
+                    for (int kc = 0; kc < 4; ++kc)
+                        for (int p = 0; p < AX_NPE; ++p)
+                            for (int pos = 0; pos < N; ++pos) coef.push_back(E.prtX[((size_t)kc * AX_NPE + p) * N + (*perm)[pos]]);
+                } else {
+                    coef.insert(coef.end(), E.prtX.begin(), E.prtX.end());
+                }
             }
             if (E.att.kind != ATT_NONE) {
                 const int P = E.att.kind == ATT_CG4 ? 4 : AX_NPE;
@@ -650,7 +671,7 @@ static void finalize(ax3d_domain *d) {
             {
                 const double nin = fluid ? 1 : 3;
                 double b = 2.0 * 200.0 * nin * M + 500.0 + (D.tiso ? 400.0 : 0.0);
-                b += (is3d ? 100.0 * N : 100.0) * E.ncoef;
+                b += (is3d ? 100.0 * N : 100.0) * (E.ncoef + (D.prt ? 4 : 0));
                 if (E.att.kind != ATT_NONE) {
                     const int P = E.att.kind == ATT_CG4 ? 4 : AX_NPE;
                     const double R = is3d ? 4.0 * N : 8.0 * M;
@@ -672,7 +693,7 @@ static void finalize(ax3d_domain *d) {
                 // fits fixes the Z and twiddle regions; what is left is the gather tile of every element of the launch.
                 const size_t fixed = fl.count ? ((size_t)fl.z_cap + 2 * (size_t)fl.nr_max) * sizeof(float2)
                                               : ((size_t)npair * AX_NPE * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2);   // twiddle tables <= 2 N
-                bool can_fuse = use_fused;
+                bool can_fuse = use_fused && !D.prt;   // the 9-component path runs through the split pipeline only
                 if (can_fuse && fixed + (size_t)nc * AX_NPE * M * sizeof(float2) > lim[0]) {
                     const long long room = ((long long)lim[0] - (long long)fixed) / (long long)(nc * AX_NPE * sizeof(float2));
                     D.mt = (int)(room / 16) * 16;
@@ -680,7 +701,7 @@ static void finalize(ax3d_domain *d) {
                 }
                 // cluster kernel (cluster.cuh): mode 1 = elements too large for one SM's shared memory, 2 = every 3D element
                 const size_t cl_bytes = (size_t)cl_layout(fluid, N, stw_len).total * sizeof(float2);
-                const bool can_cluster = cluster_mode > 0 && cl_bytes <= (size_t)AX_CLUSTER_DYN_MAX && (cluster_mode == 2 || !can_fuse);
+                const bool can_cluster = !D.prt && cluster_mode > 0 && cl_bytes <= (size_t)AX_CLUSTER_DYN_MAX && (cluster_mode == 2 || !can_fuse);
                 if (can_cluster) can_fuse = false;
                 if (can_fuse && fl.count == 0) {
                     fl.nr_max = N;
@@ -702,9 +723,15 @@ static void finalize(ax3d_domain *d) {
                     cl_smem.push_back(cl_bytes);
                 } else {
                     D.mt = M;
-                    if (!cls_np) cls_np = ((size_t)npair * 5 * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2) <= (size_t)220 * 1024 ? 5 : 1;
-                    D.ppb = cls_np;
-                    const size_t need_sc = (size_t)npair * AX_NPE * N;
+                    const int enp = (D.prt && !fluid) ? 5 : npair;   // Z-form pairs per point of this element
+                    // one k_fft3d_v2 instance per chunk: same pair count and same points per CTA (5, or 1 when five points of
+                    // this Nr do not fit in shared memory; elements come in descending Nr)
+                    const int my_np = ((size_t)enp * 5 * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2) <= (size_t)220 * 1024 ? 5 : 1;
+                    if (ch.w_count > 0 && ((D.prt && !fluid) != (ch.prt != 0) || my_np != ch.fft_np)) close_chunk();
+                    ch.prt = (D.prt && !fluid) ? 1 : 0;
+                    (void)cls_np;
+                    D.ppb = my_np;
+                    const size_t need_sc = (size_t)enp * AX_NPE * N;
                     if (need_sc > scratch_cap && ch.w_count > 0) close_chunk();
                     if (ch_scratch + need_sc > scratch_cap && ch.w_count > 0) close_chunk();
                     D.scratch_off = (long long)ch_scratch;
@@ -712,7 +739,7 @@ static void finalize(ax3d_domain *d) {
                     scratch_need = std::max(scratch_need, ch_scratch);
                     for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); ch.w_count++; }
                     for (int p0 = 0; p0 < AX_NPE; p0 += D.ppb) { fitems.push_back(FftItem{(int)k, p0}); ch.f_count++; }
-                    ch.fft_smem = std::max(ch.fft_smem, ((size_t)npair * D.ppb * fused_ldz(N) + (size_t)((stw_len + 1) & ~1)) * sizeof(float2));
+                    ch.fft_smem = std::max(ch.fft_smem, ((size_t)enp * D.ppb * fused_ldz(N) + (size_t)((stw_len + 1) & ~1)) * sizeof(float2));
                     ch.fft_np = D.ppb;
                     ch.fft_nt = ch.fft_smem <= (size_t)110 * 1024 ? 256 : 512;
                 }
@@ -1495,6 +1522,24 @@ int ax3d_add_fluid_element(ax3d_domain *d, const int tags[25], const double *geo
     e.coef.assign(K, K + (size_t)rows * AX_NPE);
     d->elems.push_back(std::move(e));
     *tag = (int)d->elems.size() - 1;
+    API_END
+}
+
+/* the PRT* argument of SolidElement / FluidElement (Quad.cpp:386-420, 527-547): PRT_1D(array<RMatPP, 4>) with rows = 1,
+ * PRT_3D(RMatXN4) with rows = Nr; X = [4][25][rows].  theta = Element::formThetaMat() (Element.cpp:48-58), needed by
+ * the fluid elements, which rotate only when they carry a PRT (FluidElement.cpp:21). */
+int ax3d_set_element_prt(ax3d_domain *d, int elem_tag, int rows, const float *X, const double theta[25]) {
+    API_BEGIN
+    check_open(d);
+    if (elem_tag < 0 || elem_tag >= (int)d->elems.size()) fail("Element::Element || invalid element tag");
+    HElem &e = d->elems[elem_tag];
+    if (rows != 1 && rows != e.nr) fail("PRT_3D::checkCompatibility || Incompatible size.");
+    if ((rows == 1) != (e.rows == 1))
+        fail(std::string(e.fluid ? "FluidElement::FluidElement" : "SolidElement::SolidElement") +
+             " || Particle Relabelling and Elasticity are generated in different spaces.");
+    e.prt_rows = rows;
+    e.prtX.assign(X, X + (size_t)4 * AX_NPE * rows);
+    memcpy(e.theta, theta, sizeof(e.theta));
     API_END
 }
 

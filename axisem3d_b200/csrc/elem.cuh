@@ -198,6 +198,136 @@ __device__ __forceinline__ void rot_rtz_to_spz(V (&u)[6], float s1, float c1, fl
 }
 
 // ------------------------------------------------------------------------------------------
+// Particle relabelling (undulated interfaces): the 9-component path of SolidElement::displToStiff (SolidElement.cpp:405-432)
+// and the PRT steps of FluidElement::displToStiff (FluidElement.cpp:333-355).
+//
+// Gradient::computeGrad9 (Gradient.cpp:84-141) at one (alpha, point): e[3 c + d] = d-th derivative of component c,
+// d = (s, phi incl. curvature terms, z).  sU as in grad6_point.
+__device__ __forceinline__ void grad9_point(const float2 *sU, int T, int t, int i, int j, const GCoef &gc, const PointGeom &g,
+                                            float alpha, bool axial_row0, float2 (&e)[9]) {
+    float2 GU[3], UG[3], u[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float2 a = czero(), b = czero();
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            a = cfma(gc.gxi_col[k], sU[(c * AX_NPE + k * 5 + j) * T + t], a);
+            b = cfma(gc.geta_col[k], sU[(c * AX_NPE + i * 5 + k) * T + t], b);
+        }
+        GU[c] = a;
+        UG[c] = b;
+        u[c] = sU[(c * AX_NPE + i * 5 + j) * T + t];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        e[3 * c + 0] = cfma(g.dzdeta, GU[c], cscale(UG[c], g.dzdxii));
+        e[3 * c + 2] = cfma(g.dsdeta, GU[c], cscale(UG[c], g.dsdxii));
+    }
+    const float2 v0 = cadd(u[0], mul_ialpha(u[1], alpha));
+    const float2 v1 = csub(mul_ialpha(u[0], alpha), u[1]);
+    const float2 v2 = mul_ialpha(u[2], alpha);
+    e[1] = cscale(v1, g.inv_s);
+    e[4] = cscale(v0, g.inv_s);
+    e[7] = cscale(v2, g.inv_s);
+    if (axial_row0) {   // Gradient.cpp:101-104, 127-136
+        const float2 gv0 = cadd(GU[0], mul_ialpha(GU[1], alpha));
+        const float2 gv1 = csub(mul_ialpha(GU[0], alpha), GU[1]);
+        const float2 gv2 = mul_ialpha(GU[2], alpha);
+        e[4] = cfma(g.dzdeta, gv0, e[4]);
+        e[1] = cfma(g.dzdeta, gv1, e[1]);
+        e[7] = cfma(g.dzdeta, gv2, e[7]);
+        if (alpha == 1.f) {
+            const float2 uv0 = cadd(UG[0], mul_ialpha(UG[1], alpha));
+            const float2 uv1 = csub(mul_ialpha(UG[0], alpha), UG[1]);
+            e[4] = cfma(g.dzdxii, uv0, e[4]);
+            e[1] = cfma(g.dzdxii, uv1, e[1]);
+        }
+    }
+}
+
+// Gradient::computeQuad9 (Gradient.cpp:143-204), pointwise half: same X, Y, r as quad6_pre, from 9 stresses.
+__device__ __forceinline__ void quad9_pre(const float2 (&s)[9], const PointGeom &g, float beta, bool axial_row0,
+                                          float2 (&X)[3], float2 (&Y)[3], float2 (&r)[3]) {
+    const float2 gg[3] = {cadd(s[4], mul_mibeta(s[1], beta)), csub(mul_mibeta(s[4], beta), s[1]), mul_mibeta(s[7], beta)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        X[c] = cfma(g.dzdeta, s[3 * c], cscale(s[3 * c + 2], g.dsdeta));
+        Y[c] = cfma(g.dzdxii, s[3 * c], cscale(s[3 * c + 2], g.dsdxii));
+        r[c] = cscale(gg[c], g.inv_s);
+    }
+    if (axial_row0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) X[c] = cfma(g.dzdeta, gg[c], X[c]);
+        if (beta == 1.f) {
+            Y[0] = cfma(g.dzdxii, gg[0], Y[0]);
+            Y[1] = cfma(g.dzdxii, gg[1], Y[1]);
+        }
+    }
+}
+
+// CrdTransTIsoSolid::transformSPZ_RTZ / RTZ_SPZ on 9 components (CrdTransTIsoSolid.cpp:44-83); back: s1, s2 -> -s1, -s2
+template <typename V>
+__device__ __forceinline__ void rot9(V (&u)[9], float s1, float c1, float s2, float c2, bool back) {
+    if (back) { s1 = -s1; s2 = -s2; }
+    const V sum08 = vadd(u[0], u[8]), dif08 = vsub(u[0], u[8]);
+    const V sum26 = vadd(u[2], u[6]), dif26 = vsub(u[2], u[6]);
+    const V u1 = u[1], u3 = u[3];
+    u[0] = vscale(vsub(vadd(sum08, vscale(dif08, c2)), vscale(sum26, s2)), 0.5f);
+    u[2] = vscale(vadd(vadd(dif26, vscale(sum26, c2)), vscale(dif08, s2)), 0.5f);
+    u[6] = vsub(u[2], dif26);
+    u[8] = vsub(sum08, u[0]);
+    u[1] = vsub(vscale(u1, c1), vscale(u[7], s1));
+    u[7] = vadd(vscale(u[7], c1), vscale(u1, s1));
+    u[3] = vsub(vscale(u3, c1), vscale(u[5], s1));
+    u[5] = vadd(vscale(u[5], c1), vscale(u3, s1));
+}
+// CrdTransTIsoFluid::transformSPZ_RTZ / RTZ_SPZ on 3 components (CrdTransTIsoFluid.cpp:16-34)
+template <typename V>
+__device__ __forceinline__ void rot3_fluid(V (&u)[3], float s1, float c1, bool back) {
+    if (back) s1 = -s1;
+    const V u0 = u[0];
+    u[0] = vsub(vscale(u0, c1), vscale(u[2], s1));
+    u[2] = vadd(vscale(u[2], c1), vscale(u0, s1));
+}
+
+// PRT_1D/3D::sphericalToUndulated(SolidResponse) (PRT_1D.cpp:32-52, PRT_3D.cpp:41-62): 9 -> 6; X[4] at this point (and phi)
+template <typename V>
+__device__ __forceinline__ void prt_s2u_solid(const V (&p)[9], const float (&X)[4], V (&u)[6]) {
+    u[0] = vadd(vscale(p[0], X[0]), vscale(p[2], X[1]));
+    u[1] = vadd(vscale(p[4], X[0]), vscale(p[5], X[2]));
+    u[2] = vscale(p[8], X[3]);
+    u[3] = vadd(vadd(vscale(p[7], X[0]), vscale(p[8], X[2])), vscale(p[5], X[3]));
+    u[4] = vadd(vadd(vscale(p[6], X[0]), vscale(p[8], X[1])), vscale(p[2], X[3]));
+    u[5] = vadd(vadd(vscale(vadd(p[3], p[1]), X[0]), vscale(p[5], X[1])), vscale(p[2], X[2]));
+}
+// PRT_1D/3D::undulatedToSpherical(SolidResponse) (PRT_1D.cpp:54-76, PRT_3D.cpp:64-86): 6 -> 9
+template <typename V>
+__device__ __forceinline__ void prt_u2s_solid(const V (&u)[6], const float (&X)[4], V (&p)[9]) {
+    p[0] = vscale(u[0], X[0]);
+    p[1] = vscale(u[5], X[0]);
+    p[2] = vadd(vadd(vscale(u[0], X[1]), vscale(u[4], X[3])), vscale(u[5], X[2]));
+    p[3] = p[1];
+    p[4] = vscale(u[1], X[0]);
+    p[5] = vadd(vadd(vscale(u[1], X[2]), vscale(u[3], X[3])), vscale(u[5], X[1]));
+    p[6] = vscale(u[4], X[0]);
+    p[7] = vscale(u[3], X[0]);
+    p[8] = vadd(vadd(vscale(u[2], X[3]), vscale(u[3], X[2])), vscale(u[4], X[1]));
+}
+// PRT_1D/3D::sphericalToUndulated / undulatedToSpherical(FluidResponse) (PRT_1D.cpp:9-30, PRT_3D.cpp:21-39), in place
+template <typename V>
+__device__ __forceinline__ void prt_s2u_fluid(V (&e)[3], const float (&X)[4]) {
+    e[0] = vadd(vscale(e[0], X[0]), vscale(e[2], X[1]));
+    e[1] = vadd(vscale(e[1], X[0]), vscale(e[2], X[2]));
+    e[2] = vscale(e[2], X[3]);
+}
+template <typename V>
+__device__ __forceinline__ void prt_u2s_fluid(V (&s)[3], const float (&X)[4]) {
+    s[2] = vadd(vadd(vscale(s[0], X[1]), vscale(s[1], X[2])), vscale(s[2], X[3]));
+    s[0] = vscale(s[0], X[0]);
+    s[1] = vscale(s[1], X[0]);
+}
+
+// ------------------------------------------------------------------------------------------
 // constitutive laws on V = float (physical space, 3D classes) or float2 (Fourier space, 1D classes).
 // coef(k) returns the k-th modulus at this (point[, phi]).
 template <typename V, typename CoefFn>

@@ -278,7 +278,7 @@ __device__ __forceinline__ void physical_space(const ElemDesc &E, const float *_
     const float *cf0 = coef + E.coef_off + (size_t)p0 * N;
     const int law = E.law;
     if constexpr (!FLUID) {
-        if (E.att_kind == ATT_NONE) {
+        if (E.att_kind == ATT_NONE && E.prt == 0) {
             if (law == LAW_ISO) stress_batch<2, 4, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
             else if (law == LAW_TI) stress_batch<5, 2, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
             else stress_batch<21, 1, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
@@ -288,16 +288,27 @@ __device__ __forceinline__ void physical_space(const ElemDesc &E, const float *_
     int idx = tid;
     int pl = idx / N, pos = idx - pl * N;
     const int dp = NT / N, dpos = NT - dp * N;
+    const bool prt = E.prt != 0;
+    const float *px0 = coef + E.prt_off + (size_t)p0 * N;   // X [4][25][N], digit-reversed phi like the moduli
     for (; idx < total; idx += NT) {
         float2 *zc = Z + pl * ldz + pos;
         if constexpr (!FLUID) {
-            const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
-            float ee[6] = {z0.x, z0.y, z1.x, z1.y, z2.x, z2.y}, s[6];
+            float ee[6], s[6], px[4] = {1.f, 0.f, 0.f, 1.f};
+            if (prt) {   // PRT_3D::sphericalToUndulated (PRT_3D.cpp:41-62): 5 Z-form pairs = 9 components -> 6 strains
+#pragma unroll
+                for (int k = 0; k < 4; ++k) px[k] = __ldcs(px0 + (size_t)k * cf_stride + idx);
+                const float2 q0 = zc[0], q1 = zc[cs], q2 = zc[2 * cs], q3 = zc[3 * cs], q4 = zc[4 * cs];
+                const float e9[9] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y, q4.x};
+                prt_s2u_solid(e9, px, ee);
+            } else {
+                const float2 z0 = zc[0], z1 = zc[cs], z2 = zc[2 * cs];
+                ee[0] = z0.x; ee[1] = z0.y; ee[2] = z1.x; ee[3] = z1.y; ee[4] = z2.x; ee[5] = z2.y;
+            }
             const float *cf = cf0 + idx;   // [k][point][pos] with local point * N + pos == idx
             stress_law<float>(law, ee, s, [&](int k) { return __ldcs(cf + (size_t)k * cf_stride); });
             const int p = p0 + pl;
             const int Pn = E.att_kind == ATT_CG4 ? 4 : AX_NPE;
-            const int q = E.att_kind == ATT_CG4 ? cg4_index(p) : p;
+            const int q = E.att_kind == ATT_NONE ? -1 : E.att_kind == ATT_CG4 ? cg4_index(p) : p;   // ATT_NONE reaches here only with PRT
             if (q >= 0) {
                 const float *ap = attpar + E.att_par_off;
                 const float *mod = ap + 3 * E.nsls;
@@ -310,14 +321,37 @@ __device__ __forceinline__ void physical_space(const ElemDesc &E, const float *_
                     [&](int k, int c) -> float & { return stt[k * sl + c * PN + cell]; },
                     [&](int c) -> float & { return stt[nsls * sl + c * PN + cell]; });
             }
-            zc[0] = make_float2(s[0], s[1]);
-            zc[cs] = make_float2(s[2], s[3]);
-            zc[2 * cs] = make_float2(s[4], s[5]);
+            if (prt) {   // PRT_3D::undulatedToSpherical (PRT_3D.cpp:64-86)
+                float s9[9];
+                prt_u2s_solid(s, px, s9);
+                zc[0] = make_float2(s9[0], s9[1]);
+                zc[cs] = make_float2(s9[2], s9[3]);
+                zc[2 * cs] = make_float2(s9[4], s9[5]);
+                zc[3 * cs] = make_float2(s9[6], s9[7]);
+                zc[4 * cs] = make_float2(s9[8], 0.f);
+            } else {
+                zc[0] = make_float2(s[0], s[1]);
+                zc[cs] = make_float2(s[2], s[3]);
+                zc[2 * cs] = make_float2(s[4], s[5]);
+            }
         } else {
             const float K = __ldcs(cf0 + idx);
             const float2 a = zc[0], b = zc[cs];
-            zc[0] = cscale(a, K);
-            zc[cs] = make_float2(b.x * K, 0.f);
+            if (prt) {   // PRT_3D on the fluid's 3 components (PRT_3D.cpp:21-39) around Acoustic3D::strainToStress
+                float px[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) px[k] = __ldcs(px0 + (size_t)k * cf_stride + idx);
+                float e3[3] = {a.x, a.y, b.x};
+                prt_s2u_fluid(e3, px);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) e3[c] *= K;
+                prt_u2s_fluid(e3, px);
+                zc[0] = make_float2(e3[0], e3[1]);
+                zc[cs] = make_float2(e3[2], 0.f);
+            } else {
+                zc[0] = cscale(a, K);
+                zc[cs] = make_float2(b.x * K, 0.f);
+            }
         }
         pl += dp;
         pos += dpos;
@@ -518,12 +552,12 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
 // space part for NP consecutive GLL points of one element (the constitutive law couples the 6 components of one point,
 // never two points): load NPAIR * NP columns, c2r, stress (+SLS), r2c, store -- the same stage and stress code as the
 // fused kernel, on a tile that is 1/5 (NP = 5) or 1/25 (NP = 1) of an element, so that even Nr = 2016 fits.
-template <bool FLUID, int NP, int NT>
+template <bool FLUID, int NP, int NT, int NPAIR_ = 0>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_fft3d_v2(const ElemDesc *__restrict__ elems, const FftItem *__restrict__ items,
                                                  const FftPlan *__restrict__ plans, const float2 *__restrict__ stwpool,
                                                  const float *__restrict__ coef, const float *__restrict__ attpar,
                                                  float *__restrict__ attstate, float2 *__restrict__ scratch) {
-    constexpr int NPAIR = FLUID ? 2 : 3, NCOLS = NPAIR * NP;
+    constexpr int NPAIR = NPAIR_ ? NPAIR_ : (FLUID ? 2 : 3), NCOLS = NPAIR * NP;   // NPAIR_ = 5: solid elements with PRT (9 components)
     constexpr int PLAN_W = (int)(sizeof(FftPlan) / sizeof(int));
     static_assert(PLAN_W <= NT, "plan loader");
     extern __shared__ __align__(16) float2 smem[];

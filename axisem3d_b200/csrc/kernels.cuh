@@ -29,6 +29,8 @@ struct ElemDesc {
     long long att_par_off;     // float  abg[3][nsls] then {3 dkappa, dmu, 2 dmu}: 1D [3][P], 3D [3][P][Nr]
     long long att_state_off;   // 1D: float2 [nsls+1][6][P][M]   3D: float [nsls+1][6][P][Nr]; slot nsls = stressR
     long long scratch_off;     // float2 [NPAIR][25][Nr] inside the scratch ring
+    long long prt_off;         // float  particle relabelling X: 1D [4][25], 3D [4][25][Nr] (digit-reversed phi), in the moduli pool
+    int prt, pad_;             // 1: the element carries a PRT (9-component path; trig_off is valid for fluid elements too)
 };
 
 struct PointTab {              // one per field family (solid: ncomp = 3, fluid: ncomp = 1)
@@ -286,16 +288,30 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
     float2 r[NC];
     if constexpr (!FLUID) {
         float2 e[6], s[6], X[3], Y[3];
-        grad6_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
-        if (dead) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) e[c] = czero();
-        }
-        float tr[4];
+        float tr[4] = {0.f, 1.f, 0.f, 1.f};
         if (E.tiso) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
-            rot_spz_to_rtz(e, tr[0], tr[1], tr[2], tr[3]);
+        }
+        float px[4] = {1.f, 0.f, 0.f, 1.f};
+        if (E.prt) {   // SolidElement.cpp:405-413: grad9 -> rotate -> sphericalToUndulated (PRT_1D, Fourier space)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) px[k] = coef[E.prt_off + k * AX_NPE + p];
+            float2 e9[9];
+            grad9_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e9);
+            if (dead) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) e9[c] = czero();
+            }
+            rot9(e9, tr[0], tr[1], tr[2], tr[3], false);
+            prt_s2u_solid(e9, px, e);
+        } else {
+            grad6_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
+            if (dead) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) e[c] = czero();
+            }
+            if (E.tiso) rot_spz_to_rtz(e, tr[0], tr[1], tr[2], tr[3]);
         }
         const float *cf = coef + E.coef_off + p;
         stress_law<float2>(E.law, e, s, [&](int k) { return cf[k * AX_NPE]; });
@@ -314,8 +330,15 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
                     [&](int c) -> float2 & { return stt[E.nsls * sl + (size_t)c * P * M + cell]; });
             }
         }
-        if (E.tiso) rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
-        quad6_pre(s, g, (float)alpha, ax0, X, Y, r);
+        if (E.prt) {   // SolidElement.cpp:424-432: undulatedToSpherical -> rotate back -> quad9
+            float2 s9[9];
+            prt_u2s_solid(s, px, s9);
+            rot9(s9, tr[0], tr[1], tr[2], tr[3], true);
+            quad9_pre(s9, g, (float)alpha, ax0, X, Y, r);
+        } else {
+            if (E.tiso) rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
+            quad6_pre(s, g, (float)alpha, ax0, X, Y, r);
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             sX[(c * AX_NPE + p) * AX_TILE + t] = X[c];
@@ -325,8 +348,21 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
         float2 e[3], s[3], X, Y;
         grad_fluid_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
         const float K = dead ? 0.f : coef[E.coef_off + p];
+        float px[4] = {1.f, 0.f, 0.f, 1.f}, s1 = 0.f, c1 = 1.f;
+        if (E.prt) {   // FluidElement.cpp:335-343: rotate -> sphericalToUndulated
+#pragma unroll
+            for (int k = 0; k < 4; ++k) px[k] = coef[E.prt_off + k * AX_NPE + p];
+            s1 = geom[E.trig_off + p];
+            c1 = geom[E.trig_off + AX_NPE + p];
+            rot3_fluid(e, s1, c1, false);
+            prt_s2u_fluid(e, px);
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) s[c] = cscale(e[c], K);   // Acoustic1D.cpp:8-16
+        if (E.prt) {   // FluidElement.cpp:345-352
+            prt_u2s_fluid(s, px);
+            rot3_fluid(s, s1, c1, true);
+        }
         quad_fluid_pre(s, g, (float)alpha, ax0, X, Y, r[0]);
         sX[p * AX_TILE + t] = X;
         sY[p * AX_TILE + t] = Y;
@@ -366,6 +402,22 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__re
     const bool dead = E.nyq && alpha == E.nu;
     float2 *z = scratch + E.scratch_off + (size_t)p * N;
     if constexpr (!FLUID) {
+        if (E.prt) {   // 9 components -> 5 Z-form pairs (the last one half empty)
+            float2 e9[9];
+            grad9_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e9);
+            if (dead) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) e9[c] = czero();
+            }
+            float tr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+            rot9(e9, tr[0], tr[1], tr[2], tr[3], false);
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) zform_store(z + (size_t)pr * AX_NPE * N, N, alpha, e9[2 * pr], e9[2 * pr + 1]);
+            zform_store(z + (size_t)4 * AX_NPE * N, N, alpha, e9[8], czero());
+            return;
+        }
         float2 e[6];
         grad6_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
         if (dead) {
@@ -383,6 +435,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__re
     } else {
         float2 e[3];
         grad_fluid_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
+        if (E.prt) rot3_fluid(e, geom[E.trig_off + p], geom[E.trig_off + AX_NPE + p], false);
         if (dead) e[0] = e[1] = e[2] = czero();
         zform_store(z, N, alpha, e[0], e[1]);
         zform_store(z + (size_t)AX_NPE * N, N, alpha, e[2], czero());
@@ -419,6 +472,22 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__re
     float2 r[NC];
     if constexpr (!FLUID) {
         float2 s[6], X[3], Y[3];
+        if (E.prt) {
+            float2 s9[9], dummy;
+            if (!dead) {
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) zform_load(z + (size_t)pr * AX_NPE * N, N, beta, sc, s9[2 * pr], s9[2 * pr + 1]);
+                zform_load(z + (size_t)4 * AX_NPE * N, N, beta, sc, s9[8], dummy);
+                float tr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+                rot9(s9, tr[0], tr[1], tr[2], tr[3], true);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) s9[c] = czero();
+            }
+            quad9_pre(s9, g, (float)beta, ax0, X, Y, r);
+        } else {
         if (!dead) {
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr) zform_load(z + (size_t)pr * AX_NPE * N, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
@@ -433,6 +502,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__re
             for (int c = 0; c < 6; ++c) s[c] = czero();
         }
         quad6_pre(s, g, (float)beta, ax0, X, Y, r);
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             sX[(c * AX_NPE + p) * AX_TILE + t] = X[c];
@@ -443,6 +513,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__re
         if (!dead) {
             zform_load(z, N, beta, sc, s[0], s[1]);
             zform_load(z + (size_t)AX_NPE * N, N, beta, sc, s[2], dummy);
+            if (E.prt) rot3_fluid(s, geom[E.trig_off + p], geom[E.trig_off + AX_NPE + p], true);
         } else {
             s[0] = s[1] = s[2] = czero();
         }
@@ -770,6 +841,7 @@ __device__ __forceinline__ void recf_grad(const ElemDesc &E, const float2 *__res
     e[2] = cfma(g.dsdeta, GU, cscale(UG, g.dsdxii));
     if (E.axial && i == 0) e[1] = cfma(g.dzdeta, mul_ialpha(GU, alpha), e[1]);
     if (E.nyq && a == E.nu) e[0] = e[1] = e[2] = czero();
+    if (E.prt) rot3_fluid(e, geom[E.trig_off + i * 5 + j], geom[E.trig_off + AX_NPE + i * 5 + j], false);   // FluidElement.cpp:176-178
 }
 __global__ void __launch_bounds__(AX_RECF_NT) k_ground_motion_fluid(const ElemDesc *__restrict__ elems, const RecvItem *__restrict__ rec,
                                                                     const float *__restrict__ weights, const FftPlan *__restrict__ plans,
@@ -804,7 +876,17 @@ __global__ void __launch_bounds__(AX_RECF_NT) k_ground_motion_fluid(const ElemDe
                 float2 e[3];
                 recf_grad(E, displ, geom, i, j, a, e);
                 const float K = coef[E.coef_off + p];
-                const float2 s[3] = {cscale(e[0], K), cscale(e[1], K), cscale(e[2], K)};
+                float px[4] = {1.f, 0.f, 0.f, 1.f};
+                if (E.prt) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) px[k] = coef[E.prt_off + k * AX_NPE + p];
+                    prt_s2u_fluid(e, px);
+                }
+                float2 s[3] = {cscale(e[0], K), cscale(e[1], K), cscale(e[2], K)};
+                if (E.prt) {
+                    prt_u2s_fluid(s, px);
+                    rot3_fluid(s, geom[E.trig_off + p], geom[E.trig_off + AX_NPE + p], true);
+                }
                 add(p, a, s);
             }
             continue;
@@ -822,8 +904,19 @@ __global__ void __launch_bounds__(AX_RECF_NT) k_ground_motion_fluid(const ElemDe
         for (int idx = tid; idx < 5 * N; idx += AX_RECF_NT) {   // Acoustic3D::strainToStress (Acoustic3D.cpp:9-16), digit-reversed phi
             const int j = idx / N, pos = idx - j * N;
             const float K = coef[E.coef_off + (size_t)(i * 5 + j) * N + pos];
-            zsm[j * ldz + pos] = cscale(zsm[j * ldz + pos], K);
-            zsm[(5 + j) * ldz + pos] = cscale(zsm[(5 + j) * ldz + pos], K);
+            const float2 z0 = zsm[j * ldz + pos], z1 = zsm[(5 + j) * ldz + pos];
+            float ee[3] = {z0.x, z0.y, z1.x};
+            float px[4] = {1.f, 0.f, 0.f, 1.f};
+            if (E.prt) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) px[k] = coef[E.prt_off + ((size_t)k * AX_NPE + i * 5 + j) * N + pos];
+                prt_s2u_fluid(ee, px);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ee[c] *= K;
+            if (E.prt) prt_u2s_fluid(ee, px);
+            zsm[j * ldz + pos] = make_float2(ee[0], ee[1]);
+            zsm[(5 + j) * ldz + pos] = make_float2(ee[2], 0.f);
         }
         __syncthreads();
         fft_forward_dit(sP, zsm, ldz, 10, twpool + sP.tw_off, tid, AX_RECF_NT);
@@ -833,6 +926,7 @@ __global__ void __launch_bounds__(AX_RECF_NT) k_ground_motion_fluid(const ElemDe
             float2 s[3], dummy;
             zform_load(zsm + j * ldz, N, a, sc, s[0], s[1]);
             zform_load(zsm + (5 + j) * ldz, N, a, sc, s[2], dummy);
+            if (E.prt) rot3_fluid(s, geom[E.trig_off + i * 5 + j], geom[E.trig_off + AX_NPE + i * 5 + j], true);
             add(i * 5 + j, a, s);
         }
         __syncthreads();

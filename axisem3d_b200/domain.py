@@ -132,6 +132,10 @@ class Domain:
             rows = K.shape[0]
             Kf = _colmajor(K)
             capi.check(self.lib.ax3d_add_fluid_element(self.h, _pi(tags), _pd(geom), int(g.axial), rows, _pf(Kf), C.byref(tag)))
+        if getattr(e, "prt", None) is not None:          # the PRT* constructor argument (Quad.cpp:386-420)
+            X = _f32(np.transpose(e.prt.X, (0, 2, 1))).reshape(-1)                 # [4][25][rows]
+            theta = np.ascontiguousarray(e.formThetaMat().reshape(-1), dtype=np.float64)
+            capi.check(self.lib.ax3d_set_element_prt(self.h, tag.value, int(e.prt.X.shape[1]), _pf(X), _pd(theta)))
         e.domain_tag = tag.value
         self.elements.append(e)
         return tag.value

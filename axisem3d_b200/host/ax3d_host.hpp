@@ -244,7 +244,45 @@ private:
     bool mAxial;
 };
 
-class PRT;   // particle relabelling is not part of this path: elements must be constructed with prt = 0
+// ------------------------------------------------------------------------------------------ particle relabelling  (S/core/element/prt)
+struct RMatXN4 {                          // Nr x 100 = [X0 | X1 | X2 | X3], column-major (eigenc.h: RMatXN4)
+    int rows = 0;
+    std::vector<Real> v;
+    RMatXN4() {}
+    RMatXN4(int r) : rows(r), v((size_t)r * 100, Real(0)) {}
+    Real &operator()(int j, int col) { return v[(size_t)col * rows + j]; }
+    const Real *data() const { return v.data(); }
+};
+class PRT {                                 // PRT.h:13-33
+public:
+    virtual ~PRT() {}
+    virtual bool is1D() const = 0;
+    virtual void checkCompatibility(int /*Nr*/) const {}
+    int rows() const { return mRows; }
+    const Real *X() const { return mX.data(); }     // [4][25][rows]
+protected:
+    int mRows = 1;
+    std::vector<Real> mX;
+};
+class PRT_1D : public PRT {                 // PRT_1D.h:12
+public:
+    PRT_1D(const std::array<RMatPP, 4> &X) {
+        mRows = 1;
+        for (const RMatPP &x : X) mX.insert(mX.end(), x.begin(), x.end());
+    }
+    bool is1D() const { return true; }
+};
+class PRT_3D : public PRT {                 // PRT_3D.cpp:13-19
+public:
+    PRT_3D(const RMatXN4 &X) {
+        mRows = X.rows;
+        mX = X.v;                             // column-major Nr x 100 is exactly [4][25][Nr]
+    }
+    bool is1D() const { return false; }
+    void checkCompatibility(int Nr) const {
+        if (mRows != Nr) throw std::runtime_error("PRT_3D::checkCompatibility || Incompatible size.");
+    }
+};
 
 class Attenuation {                         // S/core/element/material/attenuation
 public:
@@ -392,11 +430,11 @@ public:
 // ------------------------------------------------------------------------------------------ elements  (S/core/element)
 class Element {                             // Element.cpp:13-29: owns Gradient (and PRT); points are shared, not owned
 public:
-    Element(Gradient *grad, PRT *prt, const std::array<Point *, 25> &points) : mGradient(grad), mPoints(points) {
-        if (prt) throw std::runtime_error("Element::Element || particle relabelling (PRT) is not supported by the B200 path.");
+    Element(Gradient *grad, PRT *prt, const std::array<Point *, 25> &points) : mGradient(grad), mPRT(prt), mPoints(points) {
         mMaxNr = -1;
         for (Point *p : points) mMaxNr = p->getNr() > mMaxNr ? p->getNr() : mMaxNr;   // Element.cpp:13-18
         mMaxNu = mMaxNr / 2;
+        if (mPRT) mPRT->checkCompatibility(mMaxNr);                                   // Element.cpp:19-21
     }
     virtual ~Element() {}
     const Point *getPoint(int index) const { return mPoints[index]; }
@@ -427,7 +465,14 @@ protected:
             if (out[i] < 0) throw std::runtime_error("Domain::addElement || a point of this element has not been added to the domain.");
         }
     }
+    // hands the PRT* constructor argument to the library (after ax3d_add_*_element)
+    void releasePRT(ax3d_domain *dom, int tag) const {
+        if (!mPRT) return;
+        const RDMatPP theta = formThetaMat();
+        check(ax3d_set_element_prt(dom, tag, mPRT->rows(), mPRT->X(), theta.data()));
+    }
     std::unique_ptr<Gradient> mGradient;
+    std::unique_ptr<PRT> mPRT;
     std::array<Point *, 25> mPoints;
     int mMaxNr, mMaxNu, mDomainTag = -1;
     ax3d_domain *mDom = nullptr;
@@ -448,6 +493,7 @@ protected:
         if (mElastic->attenuation()) { att = mElastic->attenuation()->descriptor(); pa = &att; }
         check(ax3d_add_solid_element(dom, t, mGradient->geom(), mGradient->axial(), theta.data(), mElastic->law(), mElastic->rows(),
                                      mElastic->coef(), pa, &tag));
+        releasePRT(dom, tag);
         return tag;
     }
     std::unique_ptr<Elastic> mElastic;
@@ -463,6 +509,7 @@ protected:
         int t[25], tag = -1;
         tags(t);
         check(ax3d_add_fluid_element(dom, t, mGradient->geom(), mGradient->axial(), mAcoustic->rows(), mAcoustic->K(), &tag));
+        releasePRT(dom, tag);
         return tag;
     }
     std::unique_ptr<Acoustic> mAcoustic;

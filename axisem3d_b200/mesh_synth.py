@@ -41,11 +41,14 @@ def prem_like(r):
 class SynthMesh:
     def __init__(self, n_theta=12, n_r=8, r_in=600e3, r_out=R_EARTH, fluid_layers=None,
                  nu=2, lucky=True, law="iso", model3d=False, perturb=0.02, perturb_rho=False,
-                 fluid3d=False, attenuation=None, seed=20260101, nu_fn=None, dtype_coef=np.float64):
+                 fluid3d=False, attenuation=None, seed=20260101, nu_fn=None, dtype_coef=np.float64, prt=False):
         """law: 'iso' | 'ti' | 'aniso'.  model3d: phi-dependent material in solid elements.
         attenuation: None | 'cg4' | 'full'.  nu: constant Fourier order, or nu_fn(s, z) -> nu.
         fluid_layers: (b0, b1) radial element layers [b0, b1) that are fluid; default = the layers
-        whose centre lies in the outer-core range; pass () for an all-solid mesh."""
+        whose centre lies in the outer-core range; pass () for an all-solid mesh.
+        prt: every element carries a particle-relabelling transform (PRT_1D with 1D material, PRT_3D with 3D material) with
+        seeded X matrices close to the identity (X0, X3 ~ 1, X1, X2 ~ 0) -- arithmetic coverage, not a physical undulation."""
+        self.prt = bool(prt)
         self.nth, self.nr_ = int(n_theta), int(n_r)
         self.r_in, self.r_out = float(r_in), float(r_out)
         self.law, self.model3d, self.perturb = law, bool(model3d), float(perturb)
@@ -345,7 +348,7 @@ class SynthMesh:
         if self.is_fluid[e]:
             K = ff / rho
             ac = M.Acoustic3D(cast(K)) if is3d else M.Acoustic1D(K[0].reshape(5, 5))
-            return M.FluidElement(grad, None, points, ac)
+            return M.FluidElement(grad, self._make_prt(e, nr, is3d), points, ac)
         mu = rho * vs ** 2 * ff
         kp = rho * vp ** 2 * ff - 4.0 / 3.0 * mu
         att = None
@@ -400,7 +403,24 @@ class SynthMesh:
                 for j in range(6):
                     C6[i, j] = C6[i, j] + P[i, j] * mu
             el = (M.Anisotropic3D if is3d else M.Anisotropic1D)([cast(C6[i, j]) for (i, j) in M.ANISO_IJ], att)
-        return M.SolidElement(grad, None, points, el)
+        return M.SolidElement(grad, self._make_prt(e, nr, is3d), points, el)
+
+    def _make_prt(self, e, nr, is3d):
+        """PRT_1D(array<RMatPP, 4>) / PRT_3D(RMatXN4) in the space of the element's material (SolidElement.cpp:27-32)."""
+        if not self.prt:
+            return None
+        rs = np.random.default_rng(5000 + e)
+        base = rs.uniform(-0.05, 0.05, size=(4, 25))
+        base[0] += 1.0
+        base[3] += 1.0
+        if not is3d:
+            return M.PRT_1D(base.reshape(4, 5, 5))
+        phi = 2.0 * np.pi * np.arange(nr) / nr
+        X = np.zeros((nr, 100))
+        for k in range(4):
+            amp, ph = rs.uniform(0.0, 0.02, size=25), rs.uniform(0, 2 * np.pi, size=25)
+            X[:, 25 * k:25 * (k + 1)] = base[k][None, :] + amp[None, :] * np.cos((k + 1) * phi[:, None] + ph[None, :])
+        return M.PRT_3D(X)
 
     def release(self, domain, dt, rank=0, elem_to_proc=None):
         """Mesh::release (Mesh.cpp:177-208): points in local GLL order, then elements in global-id

@@ -320,17 +320,49 @@ class Acoustic3D:
             raise RuntimeError("Acoustic3D::checkCompatibility || Incompatible size.")
 
 
+# ------------------------------------------------------------------------- particle relabelling
+class PRT_1D:
+    """PRT_1D(const std::array<RMatPP, 4> &X) -- S/core/element/prt/PRT_1D.h:12.  X[k] is 5x5 (ipol, jpol)."""
+
+    def __init__(self, X):
+        self.X = _f(np.asarray(X, dtype=np.float64).reshape(4, 1, nPntElem))       # [4][rows = 1][25]
+
+    def is1D(self):
+        return True
+
+    def checkCompatibility(self, nr):
+        pass
+
+
+class PRT_3D:
+    """PRT_3D(const RMatXN4 &X) -- PRT_3D.cpp:13-19: X is Nr x 100 = [X0 | X1 | X2 | X3], each Nr x 25."""
+
+    def __init__(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim != 2 or X.shape[1] != 4 * nPntElem:
+            raise ValueError("PRT_3D expects an Nr x 100 matrix")
+        self.X = _f(np.transpose(X.reshape(X.shape[0], 4, nPntElem), (1, 0, 2)))    # [4][Nr][25]
+
+    def is1D(self):
+        return False
+
+    def checkCompatibility(self, nr):
+        if self.X.shape[1] != nr:
+            raise RuntimeError("PRT_3D::checkCompatibility || Incompatible size.")
+
+
 # ------------------------------------------------------------------------- elements
 class Element:
     def __init__(self, grad, prt, points):
-        if prt is not None:
-            raise NotImplementedError("particle relabelling (PRT) is outside the round-1 scope (SURVEY.md §8f-3)")
         if len(points) != nPntElem:
             raise ValueError("an element has 25 points")
         self.grad = grad
+        self.prt = prt
         self.points = list(points)
         self.maxNr = max(p.nr for p in points)      # Element.cpp:13-18
         self.maxNu = max(p.nu for p in points)
+        if prt is not None:
+            prt.checkCompatibility(self.maxNr)      # Element.cpp:19-21
         self.domain_tag = -1
 
     def axial(self):
@@ -357,7 +389,9 @@ class SolidElement(Element):
                 raise RuntimeError("Point::scatterDisplToElement || Incompatible point type.")
         elastic.checkCompatibility(self.maxNr)
         self.elastic = elastic
-        self.inTIso = bool(elastic.needTIso)
+        self.inTIso = bool(prt is not None or elastic.needTIso)      # SolidElement.cpp:21
+        if prt is not None and elastic.is1D() != prt.is1D():         # SolidElement.cpp:27-32
+            raise RuntimeError("SolidElement::SolidElement || Particle Relabelling and Elasticity are generated in different spaces.")
         self.elem3D = not elastic.is1D()
 
 
@@ -372,7 +406,9 @@ class FluidElement(Element):
                 raise RuntimeError("Point::scatterDisplToElement || Incompatible point type.")
         acoustic.checkCompatibility(self.maxNr)
         self.acoustic = acoustic
-        self.inTIso = False                         # only with PRT (FluidElement.cpp:21)
+        self.inTIso = prt is not None               # only with PRT (FluidElement.cpp:21)
+        if prt is not None and acoustic.is1D() != prt.is1D():        # FluidElement.cpp:27-32
+            raise RuntimeError("FluidElement::FluidElement || Particle Relabelling and Elasticity are generated in different spaces.")
         self.elem3D = not acoustic.is1D()
 
 

@@ -91,6 +91,12 @@ int ax3d_add_solid_element(ax3d_domain *dom, const int point_tags[25], const dou
 /* Domain::addElement(new FluidElement(gradient, 0, points, new Acoustic{1D,3D}(K))) (FluidElement.cpp:15). */
 int ax3d_add_fluid_element(ax3d_domain *dom, const int point_tags[25], const double *geom, int axial,
                            int rows, const float *K, int *tag);
+/* The PRT* constructor argument of SolidElement / FluidElement (SolidElement.cpp:15-34, FluidElement.cpp:15-34; built by
+ * Quad::createRelabelling, Quad.cpp:527-547): particle relabelling for undulated interfaces.  rows = 1: PRT_1D(const
+ * std::array<RMatPP, 4> &X) (PRT_1D.h:12); rows = Nr: PRT_3D(const RMatXN4 &X) (PRT_3D.cpp:13-19).  X = [4][25][rows].
+ * theta[25] = Element::formThetaMat() (Element.cpp:48-58).  Call after adding the element, before ax3d_finalize_setup.
+ * The element then takes the 9-component path (computeGrad9 / computeQuad9, Gradient.cpp:84-204). */
+int ax3d_set_element_prt(ax3d_domain *dom, int elem_tag, int rows, const float *X, const double theta[25]);
 
 /* Domain::addSourceTerm(new SourceTerm(element, force)) (SourceTerm.cpp:15-27): force of point i is
  * nrow[i] x 3 complex column-major, concatenated over the 25 points; rows beyond the point's Nu+1 are dropped. */

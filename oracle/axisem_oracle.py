@@ -124,6 +124,61 @@ class GradOps:
             f[:, M - 1] = 0                             # 316-321
         return f.astype(self.cd, copy=False)
 
+    def grad9(self, u, nyquist):
+        """Gradient::computeGrad9 (Gradient.cpp:84-141): u [E,M,3,5,5] -> u_{i,j} [E,M,9,5,5], component 3 i + j with
+        j = (d/ds, (1/s) d/dphi incl. the curvature terms, d/dz)."""
+        E, M = u.shape[:2]
+        u = u.copy()
+        u[:, 0] = u[:, 0].real
+        ia = self._ialpha(M)
+        uc = [u[:, :, 0], u[:, :, 1], u[:, :, 2]]
+        GU = [self._GU(c) for c in uc]
+        UG = [self._UG(c) for c in uc]
+        v = [uc[0] + ia * uc[1], ia * uc[0] - uc[1], ia * uc[2]]       # v0, v1, v2 (109-111)
+        e = np.zeros((E, M, 9, 5, 5), dtype=self.cd)
+        for c in range(3):
+            e[:, :, 3 * c + 0] = self.dzdeta * GU[c] + self.dzdxii * UG[c]
+            e[:, :, 3 * c + 2] = self.dsdeta * GU[c] + self.dsdxii * UG[c]
+        e[:, :, 1] = self.inv_s * v[1]
+        e[:, :, 4] = self.inv_s * v[0]
+        e[:, :, 7] = self.inv_s * v[2]
+        if self.axial:                                  # 101-104, 127-136
+            g0 = self.Gxi[:, 0]
+            row = lambda w: np.einsum("k,...kj->...j", g0, w)
+            for comp, w in ((4, v[0]), (1, v[1]), (7, v[2])):
+                e[:, :, comp, 0, :] += self.dzdeta[:, :, 0, :] * row(w)
+            if M > 1:
+                e[:, 1, 4, 0, :] += self.dzdxii[:, 0, 0, :] * (v[0][:, 1, 0, :] @ self.Geta)
+                e[:, 1, 1, 0, :] += self.dzdxii[:, 0, 0, :] * (v[1][:, 1, 0, :] @ self.Geta)
+        e[:, 0] = e[:, 0].real
+        if nyquist:
+            e[:, M - 1] = 0
+        return e.astype(self.cd, copy=False)
+
+    def quad9(self, s, nyquist):
+        """Gradient::computeQuad9 (Gradient.cpp:143-204): [E,M,9,5,5] -> force [E,M,3,5,5]."""
+        E, M = s.shape[:2]
+        s = s.copy()
+        s[:, 0] = s[:, 0].real
+        ib = -self._ialpha(M)
+        g = [s[:, :, 4] + ib * s[:, :, 1], ib * s[:, :, 4] - s[:, :, 1], ib * s[:, :, 7]]
+        f = np.zeros((E, M, 3, 5, 5), dtype=self.cd)
+        for c in range(3):
+            X = self.dzdeta * s[:, :, 3 * c] + self.dsdeta * s[:, :, 3 * c + 2]
+            Y = self.dzdxii * s[:, :, 3 * c] + self.dsdxii * s[:, :, 3 * c + 2]
+            f[:, :, c] = (np.einsum("ik,...kj->...ij", self.Gxi, X)
+                          + np.einsum("...ik,jk->...ij", Y, self.Geta)
+                          + self.inv_s * g[c])
+            if self.axial:                              # 158-161, 186-195
+                gr = self.dzdeta[:, :, 0, :] * g[c][:, :, 0, :]
+                f[:, :, c] += self.Gxi[:, 0].reshape(1, 1, 5, 1) * gr[:, :, None, :]
+                if c < 2 and M > 1:
+                    f[:, 1, c, 0, :] += (self.dzdxii[:, 0, 0, :] * g[c][:, 1, 0, :]) @ self.Geta.T
+        f[:, 0] = f[:, 0].real
+        if nyquist:
+            f[:, M - 1] = 0
+        return f.astype(self.cd, copy=False)
+
     def grad_fluid(self, u, nyquist):
         """Gradient::computeGrad (26-57).  u [E,M,5,5] -> [E,M,3,5,5]."""
         E, M = u.shape[:2]
@@ -198,6 +253,95 @@ def tiso_rtz_to_spz(u, theta, rd):
     u[:, :, 3] = c1 * u3 - s1 * u[:, :, 5]
     u[:, :, 5] = c1 * u[:, :, 5] + s1 * u3
     return u
+
+
+def _trig(theta, rd):
+    th = np.asarray(theta, dtype=np.float64).reshape(-1, 1, 5, 5)
+    return np.sin(th).astype(rd), np.cos(th).astype(rd), np.sin(2 * th).astype(rd), np.cos(2 * th).astype(rd)
+
+
+def tiso9_rotate(u, theta, rd, back):
+    """CrdTransTIsoSolid::transformSPZ_RTZ / RTZ_SPZ on 9 components (CrdTransTIsoSolid.cpp:44-83).  u [E,M,9,5,5]."""
+    s1, c1, s2, c2 = _trig(theta, rd)
+    if back:
+        s1, s2 = -s1, -s2
+    half = rd.type(0.5)
+    sum08, dif08 = u[:, :, 0] + u[:, :, 8], u[:, :, 0] - u[:, :, 8]
+    sum26, dif26 = u[:, :, 2] + u[:, :, 6], u[:, :, 2] - u[:, :, 6]
+    u1, u3 = u[:, :, 1].copy(), u[:, :, 3].copy()
+    u[:, :, 0] = half * (sum08 + c2 * dif08 - s2 * sum26)
+    u[:, :, 2] = half * (dif26 + c2 * sum26 + s2 * dif08)
+    u[:, :, 6] = u[:, :, 2] - dif26
+    u[:, :, 8] = sum08 - u[:, :, 0]
+    u[:, :, 1] = c1 * u1 - s1 * u[:, :, 7]
+    u[:, :, 7] = c1 * u[:, :, 7] + s1 * u1
+    u[:, :, 3] = c1 * u3 - s1 * u[:, :, 5]
+    u[:, :, 5] = c1 * u[:, :, 5] + s1 * u3
+    return u
+
+
+def tiso_fluid_rotate(u, theta, rd, back):
+    """CrdTransTIsoFluid::transformSPZ_RTZ / RTZ_SPZ on 3 components (CrdTransTIsoFluid.cpp:16-34).  u [E,M,3,5,5]."""
+    s1, c1, _, _ = _trig(theta, rd)
+    if back:
+        s1 = -s1
+    u0 = u[:, :, 0].copy()
+    u[:, :, 0] = c1 * u0 - s1 * u[:, :, 2]
+    u[:, :, 2] = c1 * u[:, :, 2] + s1 * u0
+    return u
+
+
+# ================================================================================= particle relabelling
+# X [4, E, rows, 25] (rows = 1: PRT_1D on Fourier coefficients, rows = Nr: PRT_3D on phi samples); fields [E, R, ncomp, 25]
+def prt_s2u_solid(sph, X):
+    """PRT_1D/3D::sphericalToUndulated(SolidResponse) (PRT_1D.cpp:32-52, PRT_3D.cpp:41-62): 9 -> 6."""
+    X0, X1, X2, X3 = X
+    c = lambda k: sph[:, :, k]
+    und = np.zeros(sph.shape[:2] + (6,) + sph.shape[3:], dtype=sph.dtype)
+    und[:, :, 0] = X0 * c(0) + X1 * c(2)
+    und[:, :, 1] = X0 * c(4) + X2 * c(5)
+    und[:, :, 2] = X3 * c(8)
+    und[:, :, 3] = X0 * c(7) + X2 * c(8) + X3 * c(5)
+    und[:, :, 4] = X0 * c(6) + X1 * c(8) + X3 * c(2)
+    und[:, :, 5] = X0 * (c(3) + c(1)) + X1 * c(5) + X2 * c(2)
+    return und
+
+
+def prt_u2s_solid(und, X):
+    """PRT_1D/3D::undulatedToSpherical(SolidResponse) (PRT_1D.cpp:54-76, PRT_3D.cpp:64-86): 6 -> 9."""
+    X0, X1, X2, X3 = X
+    c = lambda k: und[:, :, k]
+    sph = np.zeros(und.shape[:2] + (9,) + und.shape[3:], dtype=und.dtype)
+    sph[:, :, 0] = X0 * c(0)
+    sph[:, :, 1] = X0 * c(5)
+    sph[:, :, 2] = X1 * c(0) + X3 * c(4) + X2 * c(5)
+    sph[:, :, 3] = sph[:, :, 1]
+    sph[:, :, 4] = X0 * c(1)
+    sph[:, :, 5] = X2 * c(1) + X3 * c(3) + X1 * c(5)
+    sph[:, :, 6] = X0 * c(4)
+    sph[:, :, 7] = X0 * c(3)
+    sph[:, :, 8] = X3 * c(2) + X2 * c(3) + X1 * c(4)
+    return sph
+
+
+def prt_s2u_fluid(e, X):
+    """PRT_1D/3D::sphericalToUndulated(FluidResponse) (PRT_1D.cpp:9-18, PRT_3D.cpp:21-30): in place on 3 components."""
+    X0, X1, X2, X3 = X
+    out = np.empty_like(e)
+    out[:, :, 0] = X0 * e[:, :, 0] + X1 * e[:, :, 2]
+    out[:, :, 1] = X0 * e[:, :, 1] + X2 * e[:, :, 2]
+    out[:, :, 2] = X3 * e[:, :, 2]
+    return out
+
+
+def prt_u2s_fluid(s, X):
+    """PRT_1D/3D::undulatedToSpherical(FluidResponse) (PRT_1D.cpp:20-30, PRT_3D.cpp:32-39)."""
+    X0, X1, X2, X3 = X
+    out = np.empty_like(s)
+    out[:, :, 2] = X1 * s[:, :, 0] + X2 * s[:, :, 1] + X3 * s[:, :, 2]
+    out[:, :, 0] = X0 * s[:, :, 0]
+    out[:, :, 1] = X0 * s[:, :, 1]
+    return out
 
 
 # ================================================================================= FFT
@@ -401,8 +545,8 @@ class OracleDomain:
             el = e.elastic
             att = el.att
             asig = None if att is None else (att.nsls, att.cg4, att.doKappa)
-            return ("solid", e.maxNr, e.axial(), el.law, el.is3D, asig)
-        return ("fluid", e.maxNr, e.axial(), e.acoustic.is3D)
+            return ("solid", e.maxNr, e.axial(), el.law, el.is3D, asig, e.prt is not None)
+        return ("fluid", e.maxNr, e.axial(), e.acoustic.is3D, e.prt is not None)
 
     def _build_groups(self):
         rd = self.rd
@@ -428,6 +572,8 @@ class OracleDomain:
                              np.stack([x.inv_s for x in gr]), g.axial, rd)
             g.elem3D = els[0].elem3D
             rows = g.Nr if g.elem3D else 1
+            g.hasPRT = els[0].prt is not None
+            g.X = np.stack([e.prt.X for e in els], axis=1).astype(rd) if g.hasPRT else None      # [4, E, rows, 25]
             if g.kind == "solid":
                 g.law = sig[3]
                 g.inTIso = els[0].inTIso
@@ -438,6 +584,8 @@ class OracleDomain:
                 g.att = None if atts[0] is None else AttState(atts, g.Nr if g.elem3D else g.M, g.elem3D, rd)
             else:
                 g.K = np.stack([e.acoustic.K.reshape(rows, nPE) for e in els]).astype(rd)
+                g.inTIso = g.hasPRT
+                g.theta = np.stack([e.formThetaMat() for e in els]) if g.hasPRT else None
             self.groups.append(g)
         # keep reference order of first appearance irrelevant: scatter is a sum
 
@@ -463,6 +611,17 @@ class OracleDomain:
         """SolidElement::displToStiff without PRT (SolidElement.cpp:404-443)."""
         rd, cd = self.rd, self.cd
         E, M = u.shape[:2]
+        if g.hasPRT:                                                       # SolidElement.cpp:405-413, 424-432
+            e9 = tiso9_rotate(g.grad.grad9(u, g.nyq), g.theta, rd, False).reshape(E, M, 9, nPE)
+            if g.elem3D:
+                und = prt_s2u_solid(c2r(e9, g.Nr, rd), g.X).astype(rd, copy=False)
+                sph = prt_u2s_solid(self._stress(g, und), g.X).astype(rd, copy=False)
+                s9 = r2c(sph, g.Nr, cd)
+            else:
+                und = prt_s2u_solid(e9, g.X).astype(cd, copy=False)
+                s9 = prt_u2s_solid(self._stress(g, und), g.X).astype(cd, copy=False)
+            s9 = tiso9_rotate(np.ascontiguousarray(s9).reshape(E, M, 9, 5, 5), g.theta, rd, True)
+            return g.grad.quad9(s9, g.nyq)
         e = g.grad.grad6(u, g.nyq)
         if g.inTIso:
             e = tiso_spz_to_rtz(e, g.theta, rd)
@@ -491,18 +650,37 @@ class OracleDomain:
         return s
 
     def fluid_displ_to_stiff(self, g, u):
-        """FluidElement::displToStiff without PRT (FluidElement.cpp:333-355)."""
+        """FluidElement::displToStiff (FluidElement.cpp:333-355)."""
+        return g.grad.quad_fluid(self._fluid_stress(g, u), g.nyq)
+
+    def _fluid_stress(self, g, u):
+        """gather -> computeGrad -> [rotate] -> [c2r] -> [PRT] -> K -> [PRT] -> [r2c] -> [rotate back]: the part shared by
+        FluidElement::displToStiff and FluidElement::computeGroundMotion (FluidElement.cpp:163-215).  -> [E,M,3,5,5]"""
         rd, cd = self.rd, self.cd
         E, M = u.shape[:2]
         e = g.grad.grad_fluid(u, g.nyq)
         K = g.K[:, :, None, :]                             # [E,rows,1,25]
+        if g.hasPRT:
+            e = tiso_fluid_rotate(e, g.theta, rd, False)   # FluidElement.cpp:335-337
         if g.elem3D:
             eR = c2r(e.reshape(E, M, 3, nPE), g.Nr, rd)
+            if g.hasPRT:
+                eR = prt_s2u_fluid(eR, g.X).astype(rd, copy=False)
             sR = (K * eR).astype(rd, copy=False)           # Acoustic3D.cpp:9-16
+            if g.hasPRT:
+                sR = prt_u2s_fluid(sR, g.X).astype(rd, copy=False)
             s = r2c(sR, g.Nr, cd).reshape(E, M, 3, 5, 5)
         else:
-            s = (K * e.reshape(E, M, 3, nPE)).astype(cd, copy=False).reshape(E, M, 3, 5, 5)
-        return g.grad.quad_fluid(s, g.nyq)
+            ef = e.reshape(E, M, 3, nPE)
+            if g.hasPRT:
+                ef = prt_s2u_fluid(ef, g.X).astype(cd, copy=False)
+            sf = (K * ef).astype(cd, copy=False)
+            if g.hasPRT:
+                sf = prt_u2s_fluid(sf, g.X).astype(cd, copy=False)
+            s = np.ascontiguousarray(sf).reshape(E, M, 3, 5, 5)
+        if g.hasPRT:
+            s = tiso_fluid_rotate(s, g.theta, rd, True)    # FluidElement.cpp:350-352
+        return s
 
     def computeStiff(self):
         """Domain::computeStiff (Domain.cpp:82-94) -> Element::computeStiff
@@ -807,15 +985,7 @@ class OracleDomain:
                     if g.kind == "fluid" and (g.tags == e.domain_tag).any())
         M = g.M
         u = self._gather_fluid(g)                                   # [E,M,5,5]
-        E = u.shape[0]
-        ee = g.grad.grad_fluid(u, g.nyq)
-        K = g.K[:, :, None, :]
-        if g.elem3D:
-            eR = c2r(ee.reshape(E, M, 3, nPE), g.Nr, rd)
-            s = r2c((K * eR).astype(rd, copy=False), g.Nr, cd)      # [E,M,3,25]
-        else:
-            s = (K * ee.reshape(E, M, 3, nPE)).astype(cd, copy=False)
-        s = np.asarray(s).reshape(E, M, 3, nPE)[k]                  # [M,3,25]
+        s = self._fluid_stress(g, u).reshape(u.shape[0], M, 3, nPE)[k]           # [M,3,25]
         top = g.Nu - g.nyq
         al = np.arange(1, top + 1)
         ex = 2.0 * np.exp(1j * al * phi)

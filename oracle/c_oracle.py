@@ -54,6 +54,8 @@ class COracle:
         self.s_nlive = np.ascontiguousarray(live[d.s_tag])
         self.f_nlive = np.ascontiguousarray(live[d.f_tag])
         for g in d.groups:
+            if getattr(g, "hasPRT", False):
+                raise NotImplementedError("oracle.c has no particle-relabelling path: PRT elements are checked with the numpy oracle only")
             G = Group()
             G.E, G.M, G.Nr, G.axial, G.nyq = len(g.tags), g.M, g.Nr, int(g.axial), g.nyq
             G.fluid = int(g.kind == "fluid")

@@ -47,6 +47,10 @@ CASES = {
     "cfg3_aniso3d_cg4": dict(n_theta=3, n_r=8, nu=20, law="aniso", model3d=True, attenuation="cg4", fluid3d=True),
     "aniso3d_full_mass3d": dict(n_theta=3, n_r=8, nu=7, law="aniso", model3d=True, attenuation="full", fluid3d=True,
                                 perturb_rho=True),
+    # particle relabelling (9-component path): PRT_1D with 1D material, PRT_3D with 3D material, solid and fluid elements
+    "prt1d_ti1d_cg4": dict(n_theta=3, n_r=8, nu=4, law="ti", model3d=False, attenuation="cg4", prt=True),
+    "prt3d_aniso3d_full": dict(n_theta=3, n_r=8, nu=7, law="aniso", model3d=True, attenuation="full", fluid3d=True, prt=True),
+    "prt3d_iso3d": dict(n_theta=3, n_r=8, nu=12, law="iso", model3d=True, attenuation=None, fluid3d=True, prt=True),
     # cfg4: ragged per-point Nu
     "cfg4_ragged": dict(n_theta=5, n_r=8, nu_fn=ragged_nu, law="iso", model3d=True, attenuation=None),
 }

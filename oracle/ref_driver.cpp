@@ -44,6 +44,8 @@
 #include "Isotropic3D.h"
 #include "Mass1D.h"
 #include "Mass3D.h"
+#include "PRT_1D.h"
+#include "PRT_3D.h"
 #include "SFCoupling1D.h"
 #include "SFCoupling3D.h"
 #include "SolidElement.h"
@@ -169,6 +171,20 @@ int main(int argc, char **argv) {
             RDMatPP g[5];
             for (int k = 0; k < 5; ++k) std::memcpy(g[k].data(), geom.data() + 25 * k, 25 * 8);
             Gradient *grad = new Gradient(g[0], g[1], g[2], g[3], g[4], axial != 0);
+            PRT *prt = 0;                                                     // Quad::createRelabelling (Quad.cpp:527-547)
+            const int prt_rows = r.get<int32_t>();
+            if (prt_rows > 0) {
+                std::vector<float> X = r.vec<float>((size_t)4 * 25 * prt_rows);
+                if (prt_rows == 1) {
+                    std::array<RMatPP, 4> Xs;
+                    for (int k = 0; k < 4; ++k) Xs[k] = take_pp(X, k);
+                    prt = new PRT_1D(Xs);
+                } else {
+                    RMatXN4 Xf(prt_rows, 4 * nPntElem);
+                    std::memcpy(Xf.data(), X.data(), X.size() * sizeof(float));   // [k][point][row] = column-major Nr x 100
+                    prt = new PRT_3D(Xf);
+                }
+            }
             std::array<Point *, nPntElem> pts;
             for (int i = 0; i < 25; ++i) pts[i] = points[tags[i]];
             if (kind == 0) {
@@ -214,12 +230,12 @@ int main(int argc, char **argv) {
                     else el = new Anisotropic3D(C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8], C[9], C[10], C[11], C[12], C[13],
                                                 C[14], C[15], C[16], C[17], C[18], C[19], C[20], att3);
                 }
-                elements.push_back(new SolidElement(grad, 0, pts, el));
+                elements.push_back(new SolidElement(grad, prt, pts, el));
             } else {
                 const int rows = r.get<int32_t>();
                 std::vector<float> K = r.vec<float>((size_t)rows * 25);
                 Acoustic *ac = rows == 1 ? (Acoustic *)new Acoustic1D(take_pp(K, 0)) : (Acoustic *)new Acoustic3D(take_xn(K, 0, rows));
-                elements.push_back(new FluidElement(grad, 0, pts, ac));
+                elements.push_back(new FluidElement(grad, prt, pts, ac));
             }
         }
         // ---- sources (Source::release, Source.cpp:30-59)

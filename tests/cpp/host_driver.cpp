@@ -97,6 +97,20 @@ int main(int argc, char **argv) {
             RDMatPP g[5];
             for (int k = 0; k < 5; ++k) std::memcpy(g[k].data(), geom.data() + 25 * k, 25 * 8);
             Gradient *grad = new Gradient(g[0], g[1], g[2], g[3], g[4], axial != 0);
+            PRT *prt = 0;                                             // Quad::createRelabelling (Quad.cpp:527-547)
+            const int prt_rows = r.get<int32_t>();
+            if (prt_rows > 0) {
+                std::vector<float> X = r.vec<float>((size_t)4 * 25 * prt_rows);
+                if (prt_rows == 1) {
+                    std::array<RMatPP, 4> Xs;
+                    for (int k = 0; k < 4; ++k) Xs[k] = take_pp(X, k);
+                    prt = new PRT_1D(Xs);
+                } else {
+                    RMatXN4 Xf(prt_rows);
+                    Xf.v = X;
+                    prt = new PRT_3D(Xf);
+                }
+            }
             std::array<Point *, 25> pts;
             for (int i = 0; i < 25; ++i) pts[i] = domain->getPoint(tags[i]);
             if (kind == 0) {
@@ -142,12 +156,12 @@ int main(int argc, char **argv) {
                                                C[15], C[16], C[17], C[18], C[19], C[20], att);   // the reference's signature
                     }
                 }
-                domain->addElement(new SolidElement(grad, 0, pts, el));
+                domain->addElement(new SolidElement(grad, prt, pts, el));
             } else {
                 const int rows = r.get<int32_t>();
                 std::vector<float> K = r.vec<float>((size_t)rows * 25);
                 Acoustic *ac = rows == 1 ? (Acoustic *)new Acoustic1D(take_pp(K, 0)) : (Acoustic *)new Acoustic3D(take_xn(K, 0, rows));
-                domain->addElement(new FluidElement(grad, 0, pts, ac));
+                domain->addElement(new FluidElement(grad, prt, pts, ac));
             }
         }
         // ---- Source::release (Source.cpp:30-59)

@@ -100,6 +100,12 @@ class DumpDomain:
             i32(0 if e.kind == "solid" else 1, g.axial)
             arr(np.array([p.domain_tag for p in e.points], dtype=np.int32))
             arr(np.stack([g.dsdxii, g.dsdeta, g.dzdxii, g.dzdeta, g.inv_s]).reshape(-1).astype(np.float64))
+            prt = getattr(e, "prt", None)                 # rows of X: 0 = none, 1 = PRT_1D, Nr = PRT_3D; then [4][25][rows]
+            if prt is None:
+                i32(0)
+            else:
+                i32(prt.X.shape[1])
+                arr(_f32(np.transpose(prt.X, (0, 2, 1))).reshape(-1))
             if e.kind == "solid":
                 el = e.elastic
                 rows = el.coef.shape[1]

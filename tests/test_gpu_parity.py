@@ -52,6 +52,11 @@ def equator_nu500(s, z):
 
 CASES["ti3d_nu500_cluster"] = dict(n_theta=320, n_r=1, r_in=6371e3 - 80e3, nu_fn=equator_nu500, law="ti", model3d=True,
                                    attenuation="cg4", fluid_layers=())
+# particle relabelling: 9-component path (computeGrad9 / computeQuad9, 9-component rotation, PRT_1D in Fourier space, PRT_3D in
+# physical space through the split pipeline with 5 Z-form pairs per point), solid and fluid elements
+CASES["prt1d_aniso1d_full"] = dict(n_theta=6, n_r=6, nu=5, law="aniso", model3d=False, attenuation="full", prt=True)
+CASES["prt3d_ti3d_cg4_nu60"] = dict(n_theta=4, n_r=6, nu=60, law="ti", model3d=True, attenuation="cg4", fluid3d=True, prt=True)
+CASES["prt3d_ragged"] = dict(n_theta=8, n_r=6, nu_fn=ragged_nu, law="iso", model3d=True, attenuation=None, fluid3d=True, prt=True)
 CASES["cfg4_ragged"] = dict(n_theta=10, n_r=6, nu_fn=ragged_nu, law="iso", model3d=True, attenuation=None)
 
 
