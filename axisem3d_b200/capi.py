@@ -18,7 +18,7 @@ SYMBOLS = [
     "ax3d_get_field_bulk", "ax3d_set_field_bulk", "ax3d_field_size", "ax3d_record_ground_motion",
     "ax3d_launch_count", "ax3d_work_per_step", "ax3d_algorithmic_bytes", "ax3d_enable_timers",
     "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_dominant_kernel", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
-    "ax3d_halo_export", "ax3d_halo_connect", "ax3d_set_learn_parameters", "ax3d_learn_wisdom", "ax3d_get_nu_wisdom", "ax3d_set_element_prt",
+    "ax3d_halo_export", "ax3d_halo_connect", "ax3d_set_learn_parameters", "ax3d_learn_wisdom", "ax3d_get_nu_wisdom", "ax3d_set_element_prt", "ax3d_add_solid_point_ocean",
 ]
 
 
@@ -58,6 +58,7 @@ def load(build_if_missing=True):
     lib.ax3d_set_gmat.argtypes = [vp, pd, pd]
     lib.ax3d_add_solid_point.argtypes = [vp, i, i, pd, i, pf, pi_]
     lib.ax3d_add_fluid_point.argtypes = [vp, i, i, pd, i, pf, i, pi_]
+    lib.ax3d_add_solid_point_ocean.argtypes = [vp, i, i, pd, i, pd, pd, pd, pi_]
     lib.ax3d_add_solid_fluid_point.argtypes = [vp, i, i, pd, i, pf, i, pf, i, i, pf, pf, pi_]
     lib.ax3d_add_solid_element.argtypes = [vp, pi_, pd, i, pd, i, i, pf, C.POINTER(Attenuation), pi_]
     lib.ax3d_add_fluid_element.argtypes = [vp, pi_, pd, i, i, pf, pi_]

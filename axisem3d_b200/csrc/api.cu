@@ -59,6 +59,9 @@ struct HPoint {
     int nr, nu;
     bool axial, fluid_surf;
     std::vector<float> im_s, im_f;       // inverse mass (1 or nr entries)
+    int ocean = 0;                       // 0 none, 1 MassOcean1D, 3 MassOcean3D (solid points only)
+    float oc_imZ = 0, oc_sint = 0, oc_cost = 0;   // MassOcean1D (im_s[0] = 1 / m)
+    std::vector<float> oc_ns;            // MassOcean3D: normal * scal, column-major nr x 3
     int n_sf = 0;
     std::vector<float> n_un, n_as;       // SF coupling (3 or 3*nr entries, column-major nr x 3)
     int s_idx = -1, f_idx = -1;
@@ -155,6 +158,9 @@ struct ax3d_domain {
     DevBuf<float> s_invmass, f_invmass;
     PointTab s_tab{}, f_tab{};
     std::vector<Mass3DItem> h_m3d_s, h_m3d_f;
+    std::vector<Ocean1DItem> h_oc1d;
+    DevBuf<Ocean1DItem> oc1d;
+    int oc1d_max_m = 1;
     DevBuf<Mass3DItem> m3d_s, m3d_f;
     size_t m3d_smem_s = 0, m3d_smem_f = 0;
     DevBuf<float> impool;
@@ -475,14 +481,21 @@ static void finalize(ax3d_domain *d) {
             for (int a = 0; a < M; ++a) srp.push_back(p.s_idx);
             const bool m3 = p.im_s.size() > 1;
             sfl.push_back((unsigned char)((p.axial ? 1 : 0) | (m3 ? 4 : 0)));
-            sim.push_back(m3 ? 1.f : p.im_s[0]);
+            sim.push_back((m3 || p.ocean) ? 1.f : p.im_s[0]);   // Mass3D / MassOcean*: the mass kernels have already applied it
+            if (p.ocean == 1) d->h_oc1d.push_back(Ocean1DItem{p.s_idx, p.oc_imZ, p.im_s[0], p.oc_sint, p.oc_cost});
             if (m3) {
                 Mass3DItem it;
                 it.point = p.s_idx;
                 it.plan_id = get_plan(d, p.nr);
                 it.im_off = (long long)impool.size();
+                it.ns_off = -1;
                 const std::vector<int> &perm = d->h_perm[it.plan_id];
                 for (int pos = 0; pos < p.nr; ++pos) impool.push_back(p.im_s[perm[pos]]);
+                if (p.ocean == 3) {
+                    it.ns_off = (long long)impool.size();
+                    for (int c = 0; c < 3; ++c)
+                        for (int pos = 0; pos < p.nr; ++pos) impool.push_back(p.oc_ns[(size_t)c * p.nr + perm[pos]]);
+                }
                 d->h_m3d_s.push_back(it);
                 d->m3d_smem_s = std::max(d->m3d_smem_s, (size_t)3 * p.nr * sizeof(float2));
             }
@@ -782,7 +795,7 @@ static void finalize(ax3d_domain *d) {
             if (f.cls == CLS_S3D) fs = &f;
         if (d->nw_allowed && fs) {
             for (const HPoint &p : d->points)
-                if (p.kind == 0 && !p.axial && p.im_s.size() == 1) ok[p.s_idx] = 1;
+                if (p.kind == 0 && !p.axial && p.im_s.size() == 1 && !p.ocean) ok[p.s_idx] = 1;
             for (const auto &nb : d->neigh_pts)
                 for (int t : nb)
                     if (t >= 0 && t < (int)d->points.size() && d->points[t].s_idx >= 0) ok[d->points[t].s_idx] = 0;
@@ -923,6 +936,9 @@ static void finalize(ax3d_domain *d) {
     // ---------------- Mass3D + plans
     d->m3d_s.upload(d->h_m3d_s);
     d->m3d_f.upload(d->h_m3d_f);
+    d->oc1d.upload(d->h_oc1d);
+    for (const HPoint &p : d->points)
+        if (p.ocean == 1) d->oc1d_max_m = std::max(d->oc1d_max_m, p.nu + 1);
     d->impool.upload(impool);
     {
         std::vector<float2> tw;
@@ -1052,6 +1068,11 @@ static void update_newmark(ax3d_domain *d, double dt, bool special_only = false,
     if ((which & 2) && !d->h_m3d_f.empty()) {
         k_mass3d<1><<<(int)d->h_m3d_f.size(), 128, d->m3d_smem_f, d->stream>>>(d->f_tab, d->m3d_f.p, d->plans.p, d->twpool.p, d->impool.p,
                                                                               d->f_field[AX3D_STIFF].p);
+        d->launches++;
+    }
+    if ((which & 1) && !d->h_oc1d.empty()) {
+        const size_t n = d->h_oc1d.size() * (size_t)d->oc1d_max_m;
+        k_mass_ocean1d<<<nblk(n, 128), 128, 0, d->stream>>>(d->s_tab, (int)d->h_oc1d.size(), d->oc1d.p, d->oc1d_max_m, d->s_field[AX3D_STIFF].p);
         d->launches++;
     }
     const PointTab &stab = special_only ? d->s_tab_sp : d->s_tab;
@@ -1464,6 +1485,33 @@ int ax3d_add_solid_point(ax3d_domain *d, int nr, int axial, const double crds[2]
     *tag = add_point(d, 0, nr, axial, n_invmass, invmass, 0, nullptr, 0, 0, nullptr, nullptr);
     API_END
 }
+/* SolidPoint with an ocean load on top (GLLPoint.cpp:57-72): rows = 1 -> MassOcean1D(mass, massOcean, theta)
+ * (MassOcean1D.cpp:8-13), normal_or_theta[0] = theta; rows = nr -> MassOcean3D(mass[nr], massOcean[nr], unit normal [nr x 3,
+ * column-major]) (MassOcean3D.cpp:9-16).  The conversions to Real are done here, in double, as the reference does. */
+int ax3d_add_solid_point_ocean(ax3d_domain *d, int nr, int axial, const double crds[2], int rows, const double *mass, const double *mass_ocean,
+                               const double *normal_or_theta, int *tag) {
+    API_BEGIN
+    (void)crds;
+    if (rows != 1 && rows != nr) fail("MassOcean3D::checkCompatibility || Incompatible size.");
+    std::vector<float> im(rows);
+    for (int i = 0; i < rows; ++i) im[i] = (float)(1.0 / mass[i]);
+    *tag = add_point(d, 0, nr, axial, rows, im.data(), 0, nullptr, 0, 0, nullptr, nullptr);
+    HPoint &p = d->points[*tag];
+    if (rows == 1) {
+        p.ocean = 1;
+        p.oc_imZ = (float)(1.0 / (mass[0] + mass_ocean[0]));
+        p.oc_sint = (float)sin(normal_or_theta[0]);
+        p.oc_cost = (float)cos(normal_or_theta[0]);
+    } else {
+        p.ocean = 3;
+        p.oc_ns.resize((size_t)3 * nr);
+        for (int i = 0; i < nr; ++i) {
+            const float scal = (float)sqrt(mass_ocean[i] / (mass[i] * (mass[i] + mass_ocean[i])));
+            for (int c = 0; c < 3; ++c) p.oc_ns[(size_t)c * nr + i] = (float)normal_or_theta[(size_t)c * nr + i] * scal;
+        }
+    }
+    API_END
+}
 int ax3d_add_fluid_point(ax3d_domain *d, int nr, int axial, const double crds[2], int n_invmass, const float *invmass, int fluid_surf,
                          int *tag) {
     API_BEGIN
@@ -1843,6 +1891,7 @@ static long long count_step_launches(ax3d_domain *d, bool special_only, bool rec
     long long n = 0;
     if (record) for (int c = 0; c < NCLS; ++c) n += d->nrec_c[c] > 0;
     n += !d->h_m3d_s.empty();
+    n += !d->h_oc1d.empty();
     n += !d->h_m3d_f.empty();
     n += (special_only ? d->s_tab_sp.nrows : d->s_tab.nrows) > 0;
     n += d->f_tab.nrows > 0;

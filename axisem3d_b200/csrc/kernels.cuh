@@ -163,6 +163,7 @@ struct Mass3DItem {
     int point;         // index into the point table
     int plan_id;
     long long im_off;  // float [Nr] inverse mass, digit-reversed phi
+    long long ns_off;  // -1, or MassOcean3D: float [3][Nr] unit normal * sqrt(m_ocean / (m (m + m_ocean))), digit-reversed phi
 };
 template <int NCOMP>
 __global__ void __launch_bounds__(128) k_mass3d(PointTab pt, const Mass3DItem *__restrict__ items,
@@ -193,9 +194,20 @@ __global__ void __launch_bounds__(128) k_mass3d(PointTab pt, const Mass3DItem *_
     __syncthreads();
     fft_inverse_dif(pl, z, N, NCOL, tw, threadIdx.x, blockDim.x);
     const float *im = impool + it.im_off;
-    for (int idx = threadIdx.x; idx < NCOL * N; idx += blockDim.x) {
-        const int pos = idx % N;
-        z[idx] = cscale(z[idx], im[pos]);
+    if (NCOMP == 3 && it.ns_off >= 0) {   // MassOcean3D::computeAccel (MassOcean3D.cpp:18-49): a = f / m - (f . n') n'
+        const float *ns = impool + it.ns_off;
+        for (int pos = threadIdx.x; pos < N; pos += blockDim.x) {
+            const float2 z0 = z[pos], z1 = z[N + pos];
+            const float n0 = ns[pos], n1 = ns[N + pos], n2 = ns[2 * N + pos], m = im[pos];
+            const float fn = z0.x * n0 + z0.y * n1 + z1.x * n2;
+            z[pos] = make_float2(z0.x * m - fn * n0, z0.y * m - fn * n1);
+            z[N + pos] = make_float2(z1.x * m - fn * n2, 0.f);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < NCOL * N; idx += blockDim.x) {
+            const int pos = idx % N;
+            z[idx] = cscale(z[idx], im[pos]);
+        }
     }
     __syncthreads();
     fft_forward_dit(pl, z, N, NCOL, tw, threadIdx.x, blockDim.x);
@@ -211,6 +223,33 @@ __global__ void __launch_bounds__(128) k_mass3d(PointTab pt, const Mass3DItem *_
             stiff[base + 2 * st + k] = c;
         }
     }
+}
+
+// MassOcean1D::computeAccel (MassOcean1D.cpp:15-28) for the solid points with an axisymmetric ocean load: mask, rotate (s, z)
+// to (normal, tangent), scale by 1 / (m + m_ocean) and 1 / m, rotate back; phi component / m.  Overwrites stiff; the Newmark
+// kernel then sees inverse mass 1 (like the Mass3D points).  Thread = (item, mode).
+struct Ocean1DItem {
+    int point;
+    float imZ, imR, sint, cost;
+};
+__global__ void k_mass_ocean1d(PointTab pt, int nitems, const Ocean1DItem *__restrict__ items, int max_m, float2 *__restrict__ stiff) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = r / max_m, alpha = r - k * max_m;
+    if (k >= nitems) return;
+    const Ocean1DItem it = items[k];
+    const int nu = pt.nu[it.point], st = nu + 1;
+    if (alpha > nu) return;
+    const bool axial = pt.flags[it.point] & 1, nyq = (pt.nr[it.point] & 1) == 0;
+    const size_t base = (size_t)pt.off[it.point] + alpha;
+    float2 f[3] = {stiff[base], stiff[base + st], stiff[base + 2 * st]};
+    mask_solid(f, alpha, nu, axial, nyq);
+    float2 Z = cadd(cscale(f[0], it.sint), cscale(f[2], it.cost));
+    float2 R = csub(cscale(f[0], it.cost), cscale(f[2], it.sint));
+    Z = cscale(Z, it.imZ);
+    R = cscale(R, it.imR);
+    stiff[base] = cadd(cscale(Z, it.sint), cscale(R, it.cost));
+    stiff[base + 2 * st] = csub(cscale(Z, it.cost), cscale(R, it.sint));
+    stiff[base + st] = cscale(f[1], it.imR);
 }
 
 // ------------------------------------------------------------------------------------ source

@@ -78,7 +78,15 @@ class Domain:
     def addPoint(self, p):
         tag = C.c_int(-1)
         crds = np.ascontiguousarray(p.crds, dtype=np.float64)
-        if p.kind == "solid":
+        if p.kind == "solid" and getattr(p.mass, "ocean", False):
+            m = p.mass
+            if m.is3D:
+                a, b, c = np.ascontiguousarray(m.mass), np.ascontiguousarray(m.massOcean), np.ascontiguousarray(m.normal.T.reshape(-1))
+            else:
+                a, b, c = (np.array([v], dtype=np.float64) for v in (m.mass, m.massOcean, m.theta))
+            capi.check(self.lib.ax3d_add_solid_point_ocean(self.h, p.nr, int(p.axial), _pd(crds), a.size, _pd(a), _pd(b), _pd(c),
+                                                           C.byref(tag)))
+        elif p.kind == "solid":
             im = _mass(p.mass)
             capi.check(self.lib.ax3d_add_solid_point(self.h, p.nr, int(p.axial), _pd(crds), im.size, _pf(im), C.byref(tag)))
         elif p.kind == "fluid":

@@ -81,6 +81,11 @@ public:
     virtual int size() const = 0;          // 1 (Mass1D) or Nr (Mass3D)
     virtual const Real *data() const = 0;
     virtual void checkCompatibility(int nr) const {}
+    // ocean-load masses hand double-precision descriptors to the library instead (0: not an ocean mass)
+    virtual int oceanRows() const { return 0; }
+    virtual const double *oceanMass() const { return 0; }
+    virtual const double *oceanLoad() const { return 0; }
+    virtual const double *oceanNormalOrTheta() const { return 0; }
 };
 class Mass1D : public Mass {               // Mass1D.cpp:8
 public:
@@ -99,6 +104,41 @@ public:
         if ((int)mInvMass.size() != nr) throw std::runtime_error("Mass3D::checkCompatibility || Incompatible size.");
     }
 private:
+    RColX mInvMass;
+};
+
+typedef std::vector<double> RDColX;
+typedef std::vector<double> RDMatX3;         // Nr x 3, column-major
+class MassOcean1D : public Mass {            // MassOcean1D.cpp:8-13: (mass, massOcean, theta)
+public:
+    MassOcean1D(double mass, double massOcean, double theta) : mMass(mass), mOcean(massOcean), mTheta(theta), mInvMass((Real)(1. / mass)) {}
+    int size() const { return 1; }
+    const Real *data() const { return &mInvMass; }
+    int oceanRows() const { return 1; }
+    const double *oceanMass() const { return &mMass; }
+    const double *oceanLoad() const { return &mOcean; }
+    const double *oceanNormalOrTheta() const { return &mTheta; }
+private:
+    double mMass, mOcean, mTheta;
+    Real mInvMass;
+};
+class MassOcean3D : public Mass {            // MassOcean3D.cpp:9-16: (mass[Nr], massOcean[Nr], unit normal Nr x 3)
+public:
+    MassOcean3D(const RDColX &mass, const RDColX &massOcean, const RDMatX3 &normal) : mMass(mass), mOcean(massOcean), mNormal(normal) {
+        for (double m : mass) mInvMass.push_back((Real)(1. / m));
+    }
+    int size() const { return (int)mMass.size(); }
+    const Real *data() const { return mInvMass.data(); }
+    void checkCompatibility(int nr) const {
+        if ((int)mMass.size() != nr) throw std::runtime_error("MassOcean3D::checkCompatibility || Incompatible size.");
+    }
+    int oceanRows() const { return (int)mMass.size(); }
+    const double *oceanMass() const { return mMass.data(); }
+    const double *oceanLoad() const { return mOcean.data(); }
+    const double *oceanNormalOrTheta() const { return mNormal.data(); }
+private:
+    RDColX mMass, mOcean;
+    RDMatX3 mNormal;
     RColX mInvMass;
 };
 
@@ -145,7 +185,11 @@ public:
 protected:
     int release(ax3d_domain *dom) {
         int tag = -1;
-        check(ax3d_add_solid_point(dom, mNr, mAxial, mCoords.data(), mMass->size(), mMass->data(), &tag));
+        if (mMass->oceanRows())
+            check(ax3d_add_solid_point_ocean(dom, mNr, mAxial, mCoords.data(), mMass->oceanRows(), mMass->oceanMass(), mMass->oceanLoad(),
+                                             mMass->oceanNormalOrTheta(), &tag));
+        else
+            check(ax3d_add_solid_point(dom, mNr, mAxial, mCoords.data(), mMass->size(), mMass->data(), &tag));
         return tag;
     }
     std::unique_ptr<Mass> mMass;

@@ -41,7 +41,7 @@ def prem_like(r):
 class SynthMesh:
     def __init__(self, n_theta=12, n_r=8, r_in=600e3, r_out=R_EARTH, fluid_layers=None,
                  nu=2, lucky=True, law="iso", model3d=False, perturb=0.02, perturb_rho=False,
-                 fluid3d=False, attenuation=None, seed=20260101, nu_fn=None, dtype_coef=np.float64, prt=False):
+                 fluid3d=False, attenuation=None, seed=20260101, nu_fn=None, dtype_coef=np.float64, prt=False, ocean=False):
         """law: 'iso' | 'ti' | 'aniso'.  model3d: phi-dependent material in solid elements.
         attenuation: None | 'cg4' | 'full'.  nu: constant Fourier order, or nu_fn(s, z) -> nu.
         fluid_layers: (b0, b1) radial element layers [b0, b1) that are fluid; default = the layers
@@ -49,6 +49,9 @@ class SynthMesh:
         prt: every element carries a particle-relabelling transform (PRT_1D with 1D material, PRT_3D with 3D material) with
         seeded X matrices close to the identity (X0, X3 ~ 1, X1, X2 ~ 0) -- arithmetic coverage, not a physical undulation."""
         self.prt = bool(prt)
+        # ocean: solid points on the outer surface carry an ocean-load mass (MassOcean1D where the point's mass is
+        # axisymmetric, MassOcean3D otherwise; GLLPoint.cpp:57-72) with a water column of ~3 km (+-20 % in phi for 3D)
+        self.ocean = bool(ocean)
         self.nth, self.nr_ = int(n_theta), int(n_r)
         self.r_in, self.r_out = float(r_in), float(r_out)
         self.law, self.model3d, self.perturb = law, bool(model3d), float(perturb)
@@ -307,7 +310,18 @@ class SynthMesh:
             if np.ptp(m) <= 1e-12 * np.abs(m).max():     # XMath::equalRows
                 return M.Mass1D(np.float32(1.0 / m[0]))
             return M.Mass3D((1.0 / m).astype(np.float32))
-        sp = M.SolidPoint(nr, axial, crds, mk_mass(self.mass_s[t])) if is_s else None
+        ms = mk_mass(self.mass_s[t]) if is_s else None
+        if is_s and self.ocean and not is_f and np.hypot(crds[0], crds[1]) > self.r_out * (1.0 - 1e-9):
+            m = self.mass_s[t]
+            theta = float(np.arccos(np.clip(crds[1] / np.hypot(crds[0], crds[1]), -1.0, 1.0)))
+            if not ms.is3D and not self.perturb_rho:      # a phi-dependent water column makes the load 3D (GLLPoint.cpp:63-71)
+                ms = M.MassOcean1D(m[0], 0.35 * m[0], theta)
+            else:
+                phi = 2.0 * np.pi * np.arange(nr) / nr
+                nrm = np.stack([np.sin(theta) * np.ones(nr), 0.05 * np.sin(phi), np.cos(theta) * np.ones(nr)], 1)
+                nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+                ms = M.MassOcean3D(m, 0.35 * m * (1.0 + 0.2 * np.cos(phi + 0.3)), nrm)
+        sp = M.SolidPoint(nr, axial, crds, ms) if is_s else None
         fp = M.FluidPoint(nr, axial, crds, mk_mass(self.mass_f[t]), False) if is_f else None
         if sp is not None and fp is not None:
             n = self.sf_n[t]

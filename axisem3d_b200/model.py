@@ -59,6 +59,36 @@ class Mass3D:
             raise RuntimeError("Mass3D::checkCompatibility || Incompatible size.")
 
 
+class MassOcean1D:
+    """MassOcean1D(double mass, double massOcean, double theta) -- MassOcean1D.cpp:8-13 (solid surface points under an
+    axisymmetric ocean load, GLLPoint.cpp:57-62)."""
+    is3D = False
+    ocean = True
+
+    def __init__(self, mass, massOcean, theta):
+        self.mass, self.massOcean, self.theta = float(mass), float(massOcean), float(theta)
+        self.invMass = 1.0 / self.mass            # mInvMassR; mInvMassZ = 1 / (mass + massOcean)
+
+    def checkCompatibility(self, nr):
+        pass
+
+
+class MassOcean3D:
+    """MassOcean3D(const RDColX &mass, const RDColX &massOcean, const RDMatX3 &normal) -- MassOcean3D.cpp:9-16."""
+    is3D = True
+    ocean = True
+
+    def __init__(self, mass, massOcean, normal):
+        self.mass = np.asarray(mass, dtype=np.float64).reshape(-1)
+        self.massOcean = np.asarray(massOcean, dtype=np.float64).reshape(-1)
+        self.normal = np.asarray(normal, dtype=np.float64).reshape(self.mass.size, 3)
+        self.invMass = _f(1.0 / self.mass)
+
+    def checkCompatibility(self, nr):
+        if self.mass.shape[0] != nr:
+            raise RuntimeError("MassOcean3D::checkCompatibility || Incompatible size.")
+
+
 # --------------------------------------------------------------------------- points
 class Point:
     def __init__(self, nr, axial, crds):

@@ -46,6 +46,12 @@ int ax3d_set_gmat(ax3d_domain *dom, const double G_GLL[25], const double G_GLJ[2
  * Returns the domain tag (= insertion index) in *tag. */
 int ax3d_add_solid_point(ax3d_domain *dom, int nr, int axial, const double crds[2],
                          int n_invmass, const float *invmass, int *tag);
+/* Domain::addPoint(new SolidPoint(nr, axial, crds, new MassOcean1D / MassOcean3D(...))) (GLLPoint.cpp:57-72): a solid surface
+ * point under an ocean load.  rows = 1: MassOcean1D(double mass, double massOcean, double theta) (MassOcean1D.cpp:8-28),
+ * theta = normal_or_theta[0]; rows = nr: MassOcean3D(RDColX mass, RDColX massOcean, RDMatX3 unit_normal) (MassOcean3D.cpp:9-49),
+ * normal column-major nr x 3. */
+int ax3d_add_solid_point_ocean(ax3d_domain *dom, int nr, int axial, const double crds[2], int rows, const double *mass,
+                               const double *mass_ocean, const double *normal_or_theta, int *tag);
 /* Domain::addPoint(new FluidPoint(nr, axial, crds, mass, fluidSurf)) (FluidPoint.cpp:9). */
 int ax3d_add_fluid_point(ax3d_domain *dom, int nr, int axial, const double crds[2],
                          int n_invmass, const float *invmass, int fluid_surf, int *tag);

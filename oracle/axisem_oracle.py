@@ -755,13 +755,35 @@ class OracleDomain:
         """Mass1D::computeAccel (Mass1D.cpp:12-18) / Mass3D::computeAccel (Mass3D.cpp:13-57)."""
         rd, cd = self.rd, self.cd
         out = stiff
-        scal = np.array([(not m.is3D) for m in masses], dtype=bool)
-        inv = np.array([m.invMass if not m.is3D else 1.0 for m in masses], dtype=np.float64).astype(rd)
+        ocean = np.array([bool(getattr(m, "ocean", False)) for m in masses], dtype=bool)
+        scal = np.array([(not m.is3D) for m in masses], dtype=bool) & ~ocean
+        inv = np.array([m.invMass if (not m.is3D and not getattr(m, "ocean", False)) else 1.0 for m in masses], dtype=np.float64).astype(rd)
+        for i in np.nonzero(ocean)[0]:
+            m = masses[i]
+            if not m.is3D:        # MassOcean1D::computeAccel (MassOcean1D.cpp:15-28)
+                imZ, imR = rd.type(1.0 / (m.mass + m.massOcean)), rd.type(1.0 / m.mass)
+                st, ct = rd.type(np.sin(m.theta)), rd.type(np.cos(m.theta))
+                Z = (out[i, 0] * st + out[i, 2] * ct) * imZ
+                R = (out[i, 0] * ct - out[i, 2] * st) * imR
+                out[i, 0] = Z * st + R * ct
+                out[i, 2] = Z * ct - R * st
+                out[i, 1] = out[i, 1] * imR
+            else:                 # MassOcean3D::computeAccel (MassOcean3D.cpp:18-49)
+                Nr = int(self.p_nr[tags[i]])
+                Nc = Nr // 2 + 1
+                im = (1.0 / m.mass).astype(rd)
+                sc = np.sqrt(m.massOcean / (m.mass * (m.mass + m.massOcean))).astype(rd)
+                ns = (m.normal.astype(rd) * sc[:, None]).astype(rd).T               # [3, Nr]
+                xr = (np.fft.irfft(out[i, :, :Nc], n=Nr, axis=-1) * Nr).astype(rd)    # [3, Nr]
+                fn = (xr * ns).sum(axis=0).astype(rd)
+                yr = (xr * im[None, :] - fn[None, :] * ns).astype(rd)
+                y = np.fft.rfft(yr, axis=-1)
+                out[i, :, :Nc] = (y * rd.type(1.0 / Nr)).astype(cd) if rd == np.float32 else (y / Nr)
         if comps:
             out[scal] = out[scal] * inv[scal][:, None, None]
         else:
             out[scal] = out[scal] * inv[scal][:, None]
-        for i in np.nonzero(~scal)[0]:
+        for i in np.nonzero(~scal & ~ocean)[0]:
             m = masses[i]
             Nr = int(self.p_nr[tags[i]])
             Nc = Nr // 2 + 1

@@ -99,7 +99,7 @@ class COracle:
 
     def updateNewmark(self, dt):
         d = self.d
-        if any(m.is3D for m in d.s_mass) or any(m.is3D for m in d.f_mass):
+        if any(m.is3D or getattr(m, "ocean", False) for m in d.s_mass) or any(m.is3D for m in d.f_mass):
             return d.updateNewmark(dt)
         if not hasattr(self, "_pt"):
             mk = lambda tags, masses: dict(

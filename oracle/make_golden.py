@@ -51,6 +51,9 @@ CASES = {
     "prt1d_ti1d_cg4": dict(n_theta=3, n_r=8, nu=4, law="ti", model3d=False, attenuation="cg4", prt=True),
     "prt3d_aniso3d_full": dict(n_theta=3, n_r=8, nu=7, law="aniso", model3d=True, attenuation="full", fluid3d=True, prt=True),
     "prt3d_iso3d": dict(n_theta=3, n_r=8, nu=12, law="iso", model3d=True, attenuation=None, fluid3d=True, prt=True),
+    # ocean-load masses on the surface points: MassOcean1D (1D model) and MassOcean3D (phi-dependent mass)
+    "ocean1d_iso1d": dict(n_theta=3, n_r=8, nu=5, law="iso", model3d=False, attenuation=None, ocean=True),
+    "ocean3d_iso3d_rho": dict(n_theta=3, n_r=8, nu=9, law="iso", model3d=True, attenuation=None, perturb_rho=True, ocean=True),
     # cfg4: ragged per-point Nu
     "cfg4_ragged": dict(n_theta=5, n_r=8, nu_fn=ragged_nu, law="iso", model3d=True, attenuation=None),
 }

@@ -44,6 +44,8 @@
 #include "Isotropic3D.h"
 #include "Mass1D.h"
 #include "Mass3D.h"
+#include "MassOcean1D.h"
+#include "MassOcean3D.h"
 #include "PRT_1D.h"
 #include "PRT_3D.h"
 #include "SFCoupling1D.h"
@@ -90,6 +92,20 @@ static RColX take_col(const std::vector<float> &v) {
 }
 static Mass *read_mass(Reader &r) {
     const int n = r.get<int32_t>();
+    if (n <= -1000000) {                              // ocean load (GLLPoint.cpp:57-72)
+        const int rows = -n - 1000000;
+        if (rows == 1) {
+            std::vector<double> v = r.vec<double>(3);
+            return new MassOcean1D(v[0], v[1], v[2]);
+        }
+        std::vector<double> m = r.vec<double>(rows), mo = r.vec<double>(rows), nv = r.vec<double>((size_t)3 * rows);
+        RDColX mass(rows), massOcean(rows);
+        RDMatX3 normal(rows, 3);
+        std::memcpy(mass.data(), m.data(), rows * 8);
+        std::memcpy(massOcean.data(), mo.data(), rows * 8);
+        std::memcpy(normal.data(), nv.data(), (size_t)3 * rows * 8);
+        return new MassOcean3D(mass, massOcean, normal);
+    }
     std::vector<float> v = r.vec<float>(n);
     if (n == 1) return new Mass1D(v[0]);
     return new Mass3D(take_col(v));

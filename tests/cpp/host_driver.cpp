@@ -38,6 +38,15 @@ static RMatPP take_pp(const std::vector<float> &src, size_t k) {
 
 static Mass *read_mass(Reader &r) {
     const int n = r.get<int32_t>();
+    if (n <= -1000000) {                              // ocean load (GLLPoint.cpp:57-72)
+        const int rows = -n - 1000000;
+        if (rows == 1) {
+            std::vector<double> v = r.vec<double>(3);
+            return new MassOcean1D(v[0], v[1], v[2]);
+        }
+        std::vector<double> m = r.vec<double>(rows), mo = r.vec<double>(rows), nv = r.vec<double>((size_t)3 * rows);
+        return new MassOcean3D(m, mo, nv);
+    }
     std::vector<float> v = r.vec<float>(n);
     if (n == 1) return new Mass1D(v[0]);
     return new Mass3D(v);

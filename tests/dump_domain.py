@@ -68,6 +68,15 @@ class DumpDomain:
         arr = lambda a: out.append(np.ascontiguousarray(a).tobytes())
 
         def mass(m):
+            if getattr(m, "ocean", False):     # marker -1000000 - rows, then doubles: mass, massOcean, theta | normal (nr x 3, column-major)
+                rows = m.mass.size if m.is3D else 1
+                i32(-1000000 - rows)
+                if m.is3D:
+                    arr(np.asarray(m.mass, np.float64)); arr(np.asarray(m.massOcean, np.float64))
+                    arr(np.ascontiguousarray(m.normal.T.reshape(-1), dtype=np.float64))
+                else:
+                    arr(np.array([m.mass, m.massOcean, m.theta], dtype=np.float64))
+                return
             v = _mass(m)
             i32(v.size)
             arr(v)

@@ -10,7 +10,7 @@ from dump_domain import DumpDomain, build_driver, read_displacement
 from helpers import build_oracle
 from axisem3d_b200.mesh_synth import SynthMesh
 
-MESH = dict(n_theta=5, n_r=8, nu=7, law="aniso", model3d=True, attenuation="cg4", fluid3d=True, perturb_rho=True, prt=True)
+MESH = dict(n_theta=5, n_r=8, nu=7, law="aniso", model3d=True, attenuation="cg4", fluid3d=True, perturb_rho=True, prt=True, ocean=True)
 
 
 def _dump(tmp_path, nstep=40):
