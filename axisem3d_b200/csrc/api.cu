@@ -1116,11 +1116,14 @@ static void unscramble_record(const ax3d_domain *d, const float *row, float *out
 
 // Domain::record -> PointwiseRecorder::record (Domain.cpp:207-220): one sample per registered receiver into row
 // `*slot` of the device ring (slot == nullptr: row 0 of `out`).
-static void launch_record(ax3d_domain *d, float *out, const int *slot, int stride) {
+// which: 1 = receivers in solid elements, 2 = in fluid elements (they read different displacement fields, which the dual-stream
+// step updates on different streams), 3 = both
+static void launch_record(ax3d_domain *d, float *out, const int *slot, int stride, int which = 3) {
     int row = 0;
     for (int c = 0; c < NCLS; ++c) {
         const int n = d->nrec_c[c];
         if (!n) continue;
+        if (!(which & ((c == CLS_S1D || c == CLS_S3D) ? 1 : 2))) { row += n; continue; }
         if (c == CLS_S1D || c == CLS_S3D)
             k_ground_motion<<<n, AX_REC_NT, 0, d->stream>>>(d->desc[c].p, d->rec_items_c[c].p, d->rec_w_c[c].p, d->s_field[AX3D_DISPL].p,
                                                            out + (size_t)3 * row, slot, stride);
@@ -1859,13 +1862,14 @@ static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool
             CK(cudaStreamWaitEvent(d->stream2, d->ev_fork, 0));
             d->stream = d->stream2;
             update_newmark(d, dt, special_only, 2);
+            if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * d->nrec_total(), 2);
             compute_stiff(d, nw_on, dt, 2);
             CK(cudaEventRecord(d->ev_join, d->stream2));
             d->stream = s;
         };
         if (d->dual_mode == 1) fluid_chain();          // fork at the top of the step
         update_newmark(d, dt, special_only, 1);
-        if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * d->nrec_total());
+        if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * d->nrec_total(), 1);
         launch_source(d);
         if (d->dual_mode == 2) fluid_chain();          // fork just before the solid elements: the fluid chain fills their tail
         compute_stiff(d, nw_on, dt, 1);

@@ -9,7 +9,9 @@
 // Mesh.cpp:177-208), axisem.cpp:219-232 (static initialisation) and the serial Newmark::solve / Domain verbs
 // (Newmark.cpp:47-93, Domain.cpp:82-109,165-191) -- Domain.cpp itself drags in the recorders, NetCDF and Boost.
 //
-//   usage: ref_driver <dump.bin> <out.bin> [kick.bin|-] [recv.in recv.out] [wisdom.out cutoff]
+//   usage: ref_driver <dump.bin> <out.bin> [kick.bin|-] [recv.in recv.out] [wisdom.out|- cutoff] [series.out]
+// series.out (optional, needs recv.in): Domain::record after the update of every step (Newmark.cpp:64-70) -- float
+// [nsteps][nrec][3] seismograms from Element::computeGroundMotion, the quantity BASELINE.json's 2000-step check is about.
 // wisdom.out (optional): Point::learnWisdom(cutoff) is called on every point after every step (Domain::learnWisdom with
 // interval 1, Domain.cpp:384-402); the file receives int32 getNuWisdom() per point (Domain::dumpWisdom, Domain.cpp:404-440).
 // recv.in (optional): int32 nrec, then per receiver int32 element tag, float phi, float weights[25] (ipol-major);
@@ -285,15 +287,37 @@ int main(int argc, char **argv) {
                 p->extractBuffer(buf, row);
             }
         }
+        struct Recv { int etag; float phi; RMatPP w; };
+        std::vector<Recv> recvs;
+        std::ofstream series;
+        if (argc > 8) {
+            Reader rr(argv[4]);
+            const int nrec = rr.get<int32_t>();
+            for (int ir = 0; ir < nrec; ++ir) {
+                Recv q;
+                q.etag = rr.get<int32_t>();
+                q.phi = rr.get<float>();
+                q.w = take_pp(rr.vec<float>(25), 0);
+                recvs.push_back(q);
+            }
+            series.open(argv[8], std::ios::binary);
+        }
+        const bool learn = argc > 7 && std::string(argv[6]) != "-";
         for (int tstep = 1; tstep <= nsteps; ++tstep) {
             for (Point *p : points) p->updateNewmark(dt);                     // Domain.cpp:165-176
+            for (const Recv &q : recvs) {                                     // Domain::record (Domain.cpp:207-220)
+                RRow3 u;
+                elements[q.etag]->computeGroundMotion(q.phi, q.w, u);
+                const float o[3] = {u(0), u(1), u(2)};
+                series.write(reinterpret_cast<const char *>(o), sizeof(o));
+            }
             for (SourceTerm *s : sources) s->apply(stf[tstep - 1]);          // Domain.cpp:96-109
             for (Element *e : elements) e->computeStiff();                    // Domain.cpp:82-94
             for (SolidFluidPoint *sf : sfpoints) sf->coupleSolidFluid();      // Domain.cpp:178-191
-            if (argc > 7)
+            if (learn)
                 for (Point *p : points) p->learnWisdom((Real)std::atof(argv[7]));   // Domain.cpp:384-402
         }
-        if (argc > 7) {
+        if (learn) {
             std::ofstream wo(argv[6], std::ios::binary);
             for (Point *p : points) {
                 const int32_t nw = p->getNuWisdom();
