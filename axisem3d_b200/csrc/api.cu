@@ -1846,6 +1846,8 @@ int ax3d_reset_zero(ax3d_domain *d) {
     }
     d->attstate1d.zero();
     d->attstate3d.zero();
+    d->tstep = 0;              // Newmark::solve restarts its step counter after Domain::resetZero (Newmark.cpp:30-47)
+    d->plain_advanced = false;
     API_END
 }
 

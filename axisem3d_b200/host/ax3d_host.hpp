@@ -351,31 +351,40 @@ protected:
     RColX mAlpha, mBeta, mGamma, mDKappa, mDMu;
     bool mDoKappa;
 };
+// the two intermediate bases of the reference (Attenuation1D.h:10, Attenuation3D.h:10): what the 1D / 3D elastic classes take
+class Attenuation1D : public Attenuation {
+protected:
+    using Attenuation::Attenuation;
+};
+class Attenuation3D : public Attenuation {
+protected:
+    using Attenuation::Attenuation;
+};
 // Attenuation1D_Full.h / _CG4.h: (nsls, alpha, beta, gamma, Nu, dkappa, dmu, doKappa) with RMatPP / RRow4 moduli
-class Attenuation1D_Full : public Attenuation {
+class Attenuation1D_Full : public Attenuation1D {
 public:
     Attenuation1D_Full(int nsls, const RColX &alpha, const RColX &beta, const RColX &gamma, int /*Nu*/, const RMatPP &dkappa,
                        const RMatPP &dmu, bool doKappa)
-        : Attenuation(AX3D_ATT_FULL, nsls, alpha, beta, gamma, 1, 25, dkappa.data(), dmu.data(), doKappa) {}
+        : Attenuation1D(AX3D_ATT_FULL, nsls, alpha, beta, gamma, 1, 25, dkappa.data(), dmu.data(), doKappa) {}
 };
-class Attenuation1D_CG4 : public Attenuation {
+class Attenuation1D_CG4 : public Attenuation1D {
 public:
     Attenuation1D_CG4(int nsls, const RColX &alpha, const RColX &beta, const RColX &gamma, int /*Nu*/, const RRow4 &dkappa,
                       const RRow4 &dmu, bool doKappa)
-        : Attenuation(AX3D_ATT_CG4, nsls, alpha, beta, gamma, 1, 4, dkappa.data(), dmu.data(), doKappa) {}
+        : Attenuation1D(AX3D_ATT_CG4, nsls, alpha, beta, gamma, 1, 4, dkappa.data(), dmu.data(), doKappa) {}
 };
 // Attenuation3D_Full.h / _CG4.h: (nsls, alpha, beta, gamma, dkappa, dmu, doKappa) with RMatXN / RMatX4 moduli
-class Attenuation3D_Full : public Attenuation {
+class Attenuation3D_Full : public Attenuation3D {
 public:
     Attenuation3D_Full(int nsls, const RColX &alpha, const RColX &beta, const RColX &gamma, const RMatXN &dkappa, const RMatXN &dmu,
                        bool doKappa)
-        : Attenuation(AX3D_ATT_FULL, nsls, alpha, beta, gamma, dkappa.rows, 25, dkappa.data(), dmu.data(), doKappa) {}
+        : Attenuation3D(AX3D_ATT_FULL, nsls, alpha, beta, gamma, dkappa.rows, 25, dkappa.data(), dmu.data(), doKappa) {}
 };
-class Attenuation3D_CG4 : public Attenuation {
+class Attenuation3D_CG4 : public Attenuation3D {
 public:
     Attenuation3D_CG4(int nsls, const RColX &alpha, const RColX &beta, const RColX &gamma, const RMatX4 &dkappa, const RMatX4 &dmu,
                       bool doKappa)
-        : Attenuation(AX3D_ATT_CG4, nsls, alpha, beta, gamma, dkappa.rows, 4, dkappa.data(), dmu.data(), doKappa) {}
+        : Attenuation3D(AX3D_ATT_CG4, nsls, alpha, beta, gamma, dkappa.rows, 4, dkappa.data(), dmu.data(), doKappa) {}
 };
 
 class Elastic {                             // S/core/element/material/elastic; owns its Attenuation (Elastic1D.cpp:13-17)

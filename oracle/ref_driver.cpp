@@ -6,7 +6,7 @@
 // SolverFFTW_{1,3,N3,N6,N9}, CrdTransTIso*, every Elastic/Acoustic/Attenuation class, SolidElement/FluidElement,
 // SourceTerm.  What is NOT the reference: Eigen and FFTW (absent from the image; oracle/shim/ provides plain-loop
 // stand-ins with the documented semantics) and this file, which plays the part of Mesh::release (construction,
-// Mesh.cpp:177-208), axisem.cpp:219-232 (static initialisation) and the serial Newmark::solve / Domain verbs
+// Mesh.cpp:177-208: the text of tests/cpp/release_domain.inc, shared with the facade's test driver), axisem.cpp:219-232 (static initialisation) and the serial Newmark::solve / Domain verbs
 // (Newmark.cpp:47-93, Domain.cpp:82-109,165-191) -- Domain.cpp itself drags in the recorders, NetCDF and Boost.
 //
 //   usage: ref_driver <dump.bin> <out.bin> [kick.bin|-] [recv.in recv.out] [wisdom.out|- cutoff] [series.out]
@@ -77,90 +77,91 @@ struct Reader {
     }
 };
 
-static RMatXN take_xn(const std::vector<float> &src, size_t k, int rows) {
+// matrix adapters of this side: raw floats / doubles -> the Eigen typedefs of S/core/eigenc.h and S/preloop/eigenp.h
+static RMatXN mk_xn(const std::vector<float> &src, size_t k, int rows) {
     RMatXN m(rows, nPntElem);
     std::memcpy(m.data(), src.data() + k * (size_t)rows * 25, (size_t)rows * 25 * sizeof(float));
     return m;
 }
-static RMatPP take_pp(const std::vector<float> &src, size_t k) {
+static RMatPP mk_pp(const std::vector<float> &src, size_t k) {
     RMatPP m;
     std::memcpy(m.data(), src.data() + k * 25, 25 * sizeof(float));
     return m;
 }
-static RColX take_col(const std::vector<float> &v) {
+static RMatPP take_pp(const std::vector<float> &src, size_t k) { return mk_pp(src, k); }
+static RDMatPP mk_dpp(const double *p) { RDMatPP m; std::memcpy(m.data(), p, 25 * 8); return m; }
+static RDCol2 mk_crds(double s, double z) { RDCol2 c; c(0) = s; c(1) = z; return c; }
+static RColX mk_col(const std::vector<float> &v) {
     RColX c((int)v.size());
     std::memcpy(c.data(), v.data(), v.size() * sizeof(float));
     return c;
 }
-static Mass *read_mass(Reader &r) {
-    const int n = r.get<int32_t>();
-    if (n <= -1000000) {                              // ocean load (GLLPoint.cpp:57-72)
-        const int rows = -n - 1000000;
-        if (rows == 1) {
-            std::vector<double> v = r.vec<double>(3);
-            return new MassOcean1D(v[0], v[1], v[2]);
-        }
-        std::vector<double> m = r.vec<double>(rows), mo = r.vec<double>(rows), nv = r.vec<double>((size_t)3 * rows);
-        RDColX mass(rows), massOcean(rows);
-        RDMatX3 normal(rows, 3);
-        std::memcpy(mass.data(), m.data(), rows * 8);
-        std::memcpy(massOcean.data(), mo.data(), rows * 8);
-        std::memcpy(normal.data(), nv.data(), (size_t)3 * rows * 8);
-        return new MassOcean3D(mass, massOcean, normal);
-    }
-    std::vector<float> v = r.vec<float>(n);
-    if (n == 1) return new Mass1D(v[0]);
-    return new Mass3D(take_col(v));
+static RDColX mk_dcol(const std::vector<double> &v) {
+    RDColX c((int)v.size());
+    std::memcpy(c.data(), v.data(), v.size() * 8);
+    return c;
+}
+static RDMatX3 mk_dx3(const std::vector<double> &v, int rows) {
+    RDMatX3 m(rows, 3);
+    std::memcpy(m.data(), v.data(), v.size() * 8);
+    return m;
+}
+static RMatX3 mk_x3(const std::vector<float> &v, int rows) {
+    RMatX3 m(rows, 3);
+    std::memcpy(m.data(), v.data(), v.size() * sizeof(float));
+    return m;
+}
+static RMatX4 mk_x4(const std::vector<float> &v, int rows) {
+    RMatX4 m(rows, 4);
+    std::memcpy(m.data(), v.data(), v.size() * sizeof(float));
+    return m;
+}
+static RMatXN4 mk_xn4(const std::vector<float> &v, int rows) {
+    RMatXN4 m(rows, 4 * nPntElem);
+    std::memcpy(m.data(), v.data(), v.size() * sizeof(float));   // [k][point][row] = column-major Nr x 100
+    return m;
+}
+static RRow4 mk_row4(const float *p) {
+    RRow4 r;
+    for (int i = 0; i < 4; ++i) r(i) = p[i];
+    return r;
+}
+static CMatX3 mk_cx3(const std::vector<float> &v, int nrow) {
+    CMatX3 m(nrow, 3);
+    std::memcpy(static_cast<void *>(m.data()), v.data(), v.size() * sizeof(float));
+    return m;
 }
 
+// the part of Domain that Mesh::release talks to (Domain.h:30-39, Domain.cpp:46-56): containers only
+struct RefDomain {
+    std::vector<Point *> points;
+    std::vector<SolidFluidPoint *> sfpoints;
+    std::vector<Element *> elements;
+    std::vector<SourceTerm *> sources;
+    int addPoint(Point *p) { points.push_back(p); return (int)points.size() - 1; }
+    void addSFPoint(SolidFluidPoint *p) { sfpoints.push_back(p); }
+    int addElement(Element *e) { elements.push_back(e); return (int)elements.size() - 1; }
+    void addSourceTerm(SourceTerm *s) { sources.push_back(s); }
+    Point *getPoint(int i) const { return points[i]; }
+    Element *getElement(int i) const { return elements[i]; }
+};
+
+#include "../tests/cpp/release_domain.inc"
+
 int main(int argc, char **argv) {
-    if (argc < 3) { std::fprintf(stderr, "usage: ref_driver dump.bin out.bin [kick.bin]\n"); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: ref_driver dump.bin out.bin [kick.bin|-] [recv.in recv.out] [wisdom.out|- cutoff] [series.out]\n"); return 2; }
     try {
         Reader r(argv[1]);
-        char magic[4];
-        r.f.read(magic, 4);
-        if (std::memcmp(magic, "AX3D", 4) != 0) throw std::runtime_error("ref_driver || bad magic");
-        RDMatPP G_GLL, G_GLJ;
-        r.f.read(reinterpret_cast<char *>(G_GLL.data()), 25 * 8);
-        r.f.read(reinterpret_cast<char *>(G_GLJ.data()), 25 * 8);
-        Gradient::setGMat(G_GLL, G_GLJ);
-
-        // ---- points (GLLPoint::release, GLLPoint.cpp:48-128)
-        std::vector<Point *> points;
-        std::vector<SolidFluidPoint *> sfpoints;
-        const int npoints = r.get<int32_t>();
-        int maxNr = 1;
-        struct PendingPoint { int kind, nr, axial, surf; RDCol2 crds; Mass *m0, *m1; SFCoupling *c; };
-        std::vector<PendingPoint> pend;
-        for (int ip = 0; ip < npoints; ++ip) {
-            PendingPoint q;
-            q.kind = r.get<int32_t>(); q.nr = r.get<int32_t>(); q.axial = r.get<int32_t>();
-            q.surf = 0; q.m0 = q.m1 = 0; q.c = 0;
-            r.f.read(reinterpret_cast<char *>(q.crds.data()), 16);
-            maxNr = std::max(maxNr, q.nr);
-            pend.push_back(q);
-            PendingPoint &p = pend.back();
-            if (p.kind == 0) {
-                p.m0 = read_mass(r);
-            } else if (p.kind == 1) {
-                p.m0 = read_mass(r);
-                p.surf = r.get<int32_t>();
-            } else {
-                p.m0 = read_mass(r);
-                p.m1 = read_mass(r);
-                p.surf = r.get<int32_t>();
-                const int nsf = r.get<int32_t>();
-                std::vector<float> un = r.vec<float>(3 * (size_t)nsf), as = r.vec<float>(3 * (size_t)nsf);
-                if (nsf == 1) {
-                    p.c = new SFCoupling1D(un[0], un[2], as[0], as[2]);
-                } else {
-                    RMatX3 a(nsf, 3), b(nsf, 3);
-                    std::memcpy(a.data(), un.data(), un.size() * sizeof(float));
-                    std::memcpy(b.data(), as.data(), as.size() * sizeof(float));
-                    p.c = new SFCoupling3D(a, b);
-                }
-            }
-        }
+        RefDomain dom;
+        ReleaseInfo info;
+        release_domain(r, &dom, info);                          // the construction text shared with tests/cpp/host_driver.cpp
+        std::vector<Point *> &points = dom.points;
+        std::vector<SolidFluidPoint *> &sfpoints = dom.sfpoints;
+        std::vector<Element *> &elements = dom.elements;
+        std::vector<SourceTerm *> &sources = dom.sources;
+        const int npoints = info.npoints, nelems = info.nelems, nsteps = info.nsteps, maxNr = info.maxNr;
+        const double dt = info.dt;
+        const std::vector<float> &stf = info.stf;
         // ---- static solver state (axisem.cpp:219-232); wisdom import/export is file IO only and skipped
         SolverFFTW_1::initialize(maxNr);
         SolverFFTW_3::initialize(maxNr);
@@ -169,110 +170,6 @@ int main(int argc, char **argv) {
         SolverFFTW_N9::initialize(maxNr);
         SolidElement::initWorkspace(maxNr / 2);
         FluidElement::initWorkspace(maxNr / 2);
-        for (PendingPoint &p : pend) {
-            if (p.kind == 0) points.push_back(new SolidPoint(p.nr, p.axial != 0, p.crds, p.m0));
-            else if (p.kind == 1) points.push_back(new FluidPoint(p.nr, p.axial != 0, p.crds, p.m0, p.surf != 0));
-            else {
-                SolidFluidPoint *sf = new SolidFluidPoint(new SolidPoint(p.nr, p.axial != 0, p.crds, p.m0),
-                                                          new FluidPoint(p.nr, p.axial != 0, p.crds, p.m1, p.surf != 0), p.c);
-                points.push_back(sf);
-                sfpoints.push_back(sf);
-            }
-        }
-        // ---- elements (Quad::release, Quad.cpp:378-420)
-        std::vector<Element *> elements;
-        const int nelems = r.get<int32_t>();
-        for (int ie = 0; ie < nelems; ++ie) {
-            const int kind = r.get<int32_t>(), axial = r.get<int32_t>();
-            std::vector<int32_t> tags = r.vec<int32_t>(25);
-            std::vector<double> geom = r.vec<double>(125);
-            RDMatPP g[5];
-            for (int k = 0; k < 5; ++k) std::memcpy(g[k].data(), geom.data() + 25 * k, 25 * 8);
-            Gradient *grad = new Gradient(g[0], g[1], g[2], g[3], g[4], axial != 0);
-            PRT *prt = 0;                                                     // Quad::createRelabelling (Quad.cpp:527-547)
-            const int prt_rows = r.get<int32_t>();
-            if (prt_rows > 0) {
-                std::vector<float> X = r.vec<float>((size_t)4 * 25 * prt_rows);
-                if (prt_rows == 1) {
-                    std::array<RMatPP, 4> Xs;
-                    for (int k = 0; k < 4; ++k) Xs[k] = take_pp(X, k);
-                    prt = new PRT_1D(Xs);
-                } else {
-                    RMatXN4 Xf(prt_rows, 4 * nPntElem);
-                    std::memcpy(Xf.data(), X.data(), X.size() * sizeof(float));   // [k][point][row] = column-major Nr x 100
-                    prt = new PRT_3D(Xf);
-                }
-            }
-            std::array<Point *, nPntElem> pts;
-            for (int i = 0; i < 25; ++i) pts[i] = points[tags[i]];
-            if (kind == 0) {
-                const int law = r.get<int32_t>(), rows = r.get<int32_t>();
-                const int ncoef = law == 0 ? 2 : law == 1 ? 5 : 21;
-                std::vector<float> coef = r.vec<float>((size_t)ncoef * rows * 25);
-                const int att_kind = r.get<int32_t>();
-                Attenuation1D *att1 = 0;
-                Attenuation3D *att3 = 0;
-                if (att_kind != 0) {
-                    const int nsls = r.get<int32_t>(), dok = r.get<int32_t>();
-                    RColX al = take_col(r.vec<float>(nsls)), be = take_col(r.vec<float>(nsls)), ga = take_col(r.vec<float>(nsls));
-                    const int P = att_kind == 2 ? 4 : 25;
-                    std::vector<float> dk = r.vec<float>((size_t)rows * P), dm = r.vec<float>((size_t)rows * P);
-                    int maxNu = 0;
-                    for (int i = 0; i < 25; ++i) maxNu = std::max(maxNu, pts[i]->getNu());
-                    if (rows == 1 && P == 25) att1 = new Attenuation1D_Full(nsls, al, be, ga, maxNu, take_pp(dk, 0), take_pp(dm, 0), dok != 0);
-                    else if (rows == 1) {
-                        RRow4 a, b;
-                        for (int i = 0; i < 4; ++i) { a(i) = dk[i]; b(i) = dm[i]; }
-                        att1 = new Attenuation1D_CG4(nsls, al, be, ga, maxNu, a, b, dok != 0);
-                    } else if (P == 25) att3 = new Attenuation3D_Full(nsls, al, be, ga, take_xn(dk, 0, rows), take_xn(dm, 0, rows), dok != 0);
-                    else {
-                        RMatX4 a(rows, 4), b(rows, 4);
-                        std::memcpy(a.data(), dk.data(), dk.size() * sizeof(float));
-                        std::memcpy(b.data(), dm.data(), dm.size() * sizeof(float));
-                        att3 = new Attenuation3D_CG4(nsls, al, be, ga, a, b, dok != 0);
-                    }
-                }
-                Elastic *el;
-                if (rows == 1) {
-                    RMatPP C[21];
-                    for (int k = 0; k < ncoef; ++k) C[k] = take_pp(coef, k);
-                    if (law == 0) el = new Isotropic1D(C[0], C[1], att1);
-                    else if (law == 1) el = new TransverselyIsotropic1D(C[0], C[1], C[2], C[3], C[4], att1);
-                    else el = new Anisotropic1D(C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8], C[9], C[10], C[11], C[12], C[13],
-                                                C[14], C[15], C[16], C[17], C[18], C[19], C[20], att1);
-                } else {
-                    std::vector<RMatXN> C;
-                    for (int k = 0; k < ncoef; ++k) C.push_back(take_xn(coef, k, rows));
-                    if (law == 0) el = new Isotropic3D(C[0], C[1], att3);
-                    else if (law == 1) el = new TransverselyIsotropic3D(C[0], C[1], C[2], C[3], C[4], att3);
-                    else el = new Anisotropic3D(C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8], C[9], C[10], C[11], C[12], C[13],
-                                                C[14], C[15], C[16], C[17], C[18], C[19], C[20], att3);
-                }
-                elements.push_back(new SolidElement(grad, prt, pts, el));
-            } else {
-                const int rows = r.get<int32_t>();
-                std::vector<float> K = r.vec<float>((size_t)rows * 25);
-                Acoustic *ac = rows == 1 ? (Acoustic *)new Acoustic1D(take_pp(K, 0)) : (Acoustic *)new Acoustic3D(take_xn(K, 0, rows));
-                elements.push_back(new FluidElement(grad, prt, pts, ac));
-            }
-        }
-        // ---- sources (Source::release, Source.cpp:30-59)
-        std::vector<SourceTerm *> sources;
-        const int nsrc = r.get<int32_t>();
-        for (int is = 0; is < nsrc; ++is) {
-            const int etag = r.get<int32_t>();
-            std::vector<int32_t> nrow = r.vec<int32_t>(25);
-            arPP_CMatX3 force;
-            for (int i = 0; i < 25; ++i) {
-                force[i] = CMatX3(nrow[i], 3);
-                std::vector<float> v = r.vec<float>((size_t)6 * nrow[i]);
-                std::memcpy(static_cast<void *>(force[i].data()), v.data(), v.size() * sizeof(float));
-            }
-            sources.push_back(new SourceTerm(elements[etag], force));
-        }
-        const int nsteps = r.get<int32_t>();
-        const double dt = r.get<double>();
-        std::vector<float> stf = r.vec<float>(nsteps);
 
         // ---- Newmark::solve (Newmark.cpp:19-93), serial: Domain::resetZero, then the step verbs in order
         for (Element *e : elements) e->resetZero();
@@ -328,11 +225,11 @@ int main(int argc, char **argv) {
         std::ofstream out(argv[2], std::ios::binary);
         for (size_t ip = 0; ip < points.size(); ++ip) {
             Point *p = points[ip];
-            if (pend[ip].kind != 1) {
+            if (info.point_kind[ip] != 1) {
                 const CMatX3 &u = p->getDispFourierSolid();
                 out.write(reinterpret_cast<const char *>(u.data()), (size_t)u.size() * sizeof(Complex));
             }
-            if (pend[ip].kind != 0) {
+            if (info.point_kind[ip] != 0) {
                 const CColX &u = p->getDispFourierFluid();
                 out.write(reinterpret_cast<const char *>(u.data()), (size_t)u.size() * sizeof(Complex));
             }

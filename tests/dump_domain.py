@@ -18,7 +18,8 @@ _LAW = {"iso": 0, "ti": 1, "aniso": 2}
 def build_driver(force=False):
     """g++ the facade test driver against the in-tree library (no nvcc needed: the facade is plain C++)."""
     lib_dir = os.path.join(ROOT, "axisem3d_b200")
-    deps = [DRIVER_SRC, os.path.join(lib_dir, "host", "ax3d_host.hpp"), os.path.join(ROOT, "include", "axisem3d_b200.h")]
+    deps = [DRIVER_SRC, os.path.join(ROOT, "tests", "cpp", "release_domain.inc"), os.path.join(lib_dir, "host", "ax3d_host.hpp"),
+            os.path.join(ROOT, "include", "axisem3d_b200.h")]
     if not force and os.path.exists(DRIVER) and all(os.path.getmtime(DRIVER) >= os.path.getmtime(d) for d in deps):
         return DRIVER
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", DRIVER, DRIVER_SRC, "-L" + lib_dir, "-laxisem3d_b200",
