@@ -18,7 +18,7 @@ SYMBOLS = [
     "ax3d_get_field_bulk", "ax3d_set_field_bulk", "ax3d_field_size", "ax3d_record_ground_motion",
     "ax3d_launch_count", "ax3d_work_per_step", "ax3d_algorithmic_bytes", "ax3d_enable_timers",
     "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_dominant_kernel", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
-    "ax3d_halo_export", "ax3d_halo_connect", "ax3d_set_learn_parameters", "ax3d_learn_wisdom", "ax3d_get_nu_wisdom", "ax3d_set_element_prt", "ax3d_add_solid_point_ocean",
+    "ax3d_halo_export", "ax3d_halo_connect", "ax3d_set_learn_parameters", "ax3d_learn_wisdom", "ax3d_get_nu_wisdom", "ax3d_set_element_prt", "ax3d_add_solid_point_ocean", "ax3d_record_strain", "ax3d_record_curl",
 ]
 
 
@@ -92,6 +92,8 @@ def load(build_if_missing=True):
     lib.ax3d_set_field_bulk.argtypes = [vp, i, i, pf, C.c_size_t]
     lib.ax3d_field_size.argtypes = [vp, i, C.POINTER(C.c_size_t)]
     lib.ax3d_record_ground_motion.argtypes = [vp, i, pi_, pf, pf, pf]
+    lib.ax3d_record_strain.argtypes = [vp, i, pi_, pf, pf, pf]
+    lib.ax3d_record_curl.argtypes = [vp, i, pi_, pf, pf, pf]
     lib.ax3d_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.ax3d_work_per_step.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.ax3d_algorithmic_bytes.argtypes = [vp, pd]

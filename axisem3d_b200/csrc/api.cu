@@ -59,6 +59,7 @@ struct HPoint {
     int nr, nu;
     bool axial, fluid_surf;
     std::vector<float> im_s, im_f;       // inverse mass (1 or nr entries)
+    double crds[2] = {0, 0};             // (s, z): Point::getCoords, used by Element::formThetaMat (Element.cpp:48-58)
     int ocean = 0;                       // 0 none, 1 MassOcean1D, 3 MassOcean3D (solid points only)
     float oc_imZ = 0, oc_sint = 0, oc_cost = 0;   // MassOcean1D (im_s[0] = 1 / m)
     std::vector<float> oc_ns;            // MassOcean3D: normal * scal, column-major nr x 3
@@ -377,6 +378,9 @@ static void set_mass(std::vector<float> &dst, int nr, int n, const float *im, co
     dst.assign(im, im + n);
 }
 
+static void set_crds(ax3d_domain *d, int tag, const double crds[2]) {
+    if (crds) { d->points[tag].crds[0] = crds[0]; d->points[tag].crds[1] = crds[1]; }
+}
 static int add_point(ax3d_domain *d, int kind, int nr, int axial, int n_s, const float *im_s, int n_f, const float *im_f,
                      int fluid_surf, int n_sf, const float *n_un, const float *n_as) {
     check_open(d);
@@ -631,7 +635,8 @@ static void finalize(ax3d_domain *d) {
             }
             D.geom_off = (long long)geom.size();
             for (int i = 0; i < 5 * AX_NPE; ++i) geom.push_back((float)E.geom[i]);
-            if (D.tiso || D.prt) {   // fluid elements rotate only with PRT (FluidElement.cpp:21)
+            if (D.tiso || D.prt || !fluid) {   // fluid elements rotate only with PRT (FluidElement.cpp:21); every solid element
+                                               // keeps its trig for the strain / curl read-back (forceTIso, SolidElement.cpp:347-352)
                 D.trig_off = (long long)geom.size();
                 for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)sin(E.theta[i]));
                 for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)cos(E.theta[i]));
@@ -1484,8 +1489,8 @@ int ax3d_set_gmat(ax3d_domain *d, const double G_GLL[25], const double G_GLJ[25]
 
 int ax3d_add_solid_point(ax3d_domain *d, int nr, int axial, const double crds[2], int n_invmass, const float *invmass, int *tag) {
     API_BEGIN
-    (void)crds;
     *tag = add_point(d, 0, nr, axial, n_invmass, invmass, 0, nullptr, 0, 0, nullptr, nullptr);
+    set_crds(d, *tag, crds);
     API_END
 }
 /* SolidPoint with an ocean load on top (GLLPoint.cpp:57-72): rows = 1 -> MassOcean1D(mass, massOcean, theta)
@@ -1494,11 +1499,11 @@ int ax3d_add_solid_point(ax3d_domain *d, int nr, int axial, const double crds[2]
 int ax3d_add_solid_point_ocean(ax3d_domain *d, int nr, int axial, const double crds[2], int rows, const double *mass, const double *mass_ocean,
                                const double *normal_or_theta, int *tag) {
     API_BEGIN
-    (void)crds;
     if (rows != 1 && rows != nr) fail("MassOcean3D::checkCompatibility || Incompatible size.");
     std::vector<float> im(rows);
     for (int i = 0; i < rows; ++i) im[i] = (float)(1.0 / mass[i]);
     *tag = add_point(d, 0, nr, axial, rows, im.data(), 0, nullptr, 0, 0, nullptr, nullptr);
+    set_crds(d, *tag, crds);
     HPoint &p = d->points[*tag];
     if (rows == 1) {
         p.ocean = 1;
@@ -1518,15 +1523,15 @@ int ax3d_add_solid_point_ocean(ax3d_domain *d, int nr, int axial, const double c
 int ax3d_add_fluid_point(ax3d_domain *d, int nr, int axial, const double crds[2], int n_invmass, const float *invmass, int fluid_surf,
                          int *tag) {
     API_BEGIN
-    (void)crds;
     *tag = add_point(d, 1, nr, axial, 0, nullptr, n_invmass, invmass, fluid_surf, 0, nullptr, nullptr);
+    set_crds(d, *tag, crds);
     API_END
 }
 int ax3d_add_solid_fluid_point(ax3d_domain *d, int nr, int axial, const double crds[2], int n_s, const float *im_s, int n_f,
                                const float *im_f, int fluid_surf, int n_sf, const float *n_un, const float *n_as, int *tag) {
     API_BEGIN
-    (void)crds;
     *tag = add_point(d, 2, nr, axial, n_s, im_s, n_f, im_f, fluid_surf, n_sf, n_un, n_as);
+    set_crds(d, *tag, crds);
     API_END
 }
 
@@ -1541,9 +1546,14 @@ int ax3d_add_solid_element(ax3d_domain *d, const int tags[25], const double *geo
     e.rows = rows;
     e.ncoef = law == AX3D_ISO ? 2 : law == AX3D_TI ? 5 : 21;
     e.coef.assign(coef, coef + (size_t)e.ncoef * rows * AX_NPE);
-    if (law != AX3D_ISO) {
-        if (!theta) fail("SolidElement::SolidElement || theta is required for TI / anisotropic elements");
+    if (theta) {
         memcpy(e.theta, theta, sizeof(e.theta));
+    } else {   // Element::formThetaMat (Element.cpp:48-58) with Geodesy::theta of the points' (s, z)
+        for (int i = 0; i < AX_NPE; ++i) {
+            const double *c = d->points[e.pt[i]].crds;
+            const double r = sqrt(c[0] * c[0] + c[1] * c[1]);
+            e.theta[i] = r < 1e-10 ? 0.0 : acos(std::max(-1.0, std::min(1.0, c[1] / r)));
+        }
     }
     if (att && att->kind != AX3D_ATT_NONE) {
         if (att->kind != AX3D_ATT_FULL && att->kind != AX3D_ATT_CG4) fail("Attenuation || unknown kind");
@@ -2182,6 +2192,62 @@ int ax3d_record_ground_motion(ax3d_domain *d, int nrec, const int *elem_tags, co
         for (size_t k = 0; k < sub.size(); ++k)
             for (int cc = 0; cc < 3; ++cc) out[where[k] * 3 + cc] = d->rec_host[k * 3 + cc];
     }
+    API_END
+}
+
+/* Element::computeStrain (which = 0: out[nrec][6], Voigt strain in RTZ) / computeCurl (which = 1: out[nrec][3]) after
+ * Element::forceTIso, as PointwiseRecorder::record uses them (PointwiseRecorder.cpp:96-135); SolidElement.cpp:219-345. */
+static void record_strain_curl(ax3d_domain *d, int which, int nrec, const int *elem_tags, const float *phi, const float *weights, float *out) {
+    check_final(d);
+    if (nrec <= 0) return;
+    const int nout = which ? 3 : 6;
+    const char *fn = which ? "computeCurl" : "computeStrain";
+    std::vector<RecvItem> items(nrec);
+    for (int i = 0; i < nrec; ++i) {
+        if (elem_tags[i] < 0 || elem_tags[i] >= (int)d->elems.size()) fail("PointwiseRecorder::record || invalid element tag");
+        const HElem &E = d->elems[elem_tags[i]];
+        if (E.fluid) fail(std::string("FluidElement::") + fn + " || strain / curl receivers in fluid elements are not supported by the B200 path.");
+        if (E.prt_rows) fail(std::string("SolidElement::") + fn + " || strain / curl receivers in elements with particle relabelling are not supported by the B200 path.");
+        items[i].elem = E.idx | (E.cls << 28);
+        items[i].phi = phi[i];
+    }
+    DevBuf<RecvItem> di;
+    DevBuf<float> dw, dout;
+    for (int c : {CLS_S1D, CLS_S3D}) {
+        std::vector<RecvItem> sub;
+        std::vector<int> where;
+        std::vector<float> w;
+        for (int i = 0; i < nrec; ++i)
+            if ((items[i].elem >> 28) == c) {
+                RecvItem r = items[i];
+                r.elem &= 0x0fffffff;
+                sub.push_back(r);
+                where.push_back(i);
+                w.insert(w.end(), weights + (size_t)i * AX_NPE, weights + (size_t)(i + 1) * AX_NPE);
+            }
+        if (sub.empty()) continue;
+        di.upload(sub);
+        dw.upload(w);
+        dout.alloc(sub.size() * nout);
+        if (which) k_strain_curl<true><<<(int)sub.size(), AX_TILE * AX_NPE, 0, d->stream>>>(d->desc[c].p, di.p, dw.p, d->geom.p, d->s_field[AX3D_DISPL].p, dout.p);
+        else k_strain_curl<false><<<(int)sub.size(), AX_TILE * AX_NPE, 0, d->stream>>>(d->desc[c].p, di.p, dw.p, d->geom.p, d->s_field[AX3D_DISPL].p, dout.p);
+        d->launches++;
+        CK(cudaGetLastError());
+        std::vector<float> h(sub.size() * nout);
+        CK(cudaStreamSynchronize(d->stream));
+        CK(cudaMemcpy(h.data(), dout.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < sub.size(); ++k)
+            for (int cc = 0; cc < nout; ++cc) out[where[k] * nout + cc] = h[k * nout + cc];
+    }
+}
+int ax3d_record_strain(ax3d_domain *d, int nrec, const int *elem_tags, const float *phi, const float *weights, float *out) {
+    API_BEGIN
+    record_strain_curl(d, 0, nrec, elem_tags, phi, weights, out);
+    API_END
+}
+int ax3d_record_curl(ax3d_domain *d, int nrec, const int *elem_tags, const float *phi, const float *weights, float *out) {
+    API_BEGIN
+    record_strain_curl(d, 1, nrec, elem_tags, phi, weights, out);
     API_END
 }
 

@@ -851,6 +851,73 @@ __global__ void __launch_bounds__(AX_REC_NT) k_ground_motion(const ElemDesc *__r
     }
 }
 
+// SolidElement::computeStrain (SolidElement.cpp:219-279) and computeCurl (281-345) without PRT: gather -> computeGrad6 /
+// computeGrad9 -> transformSPZ_RTZ (the recorder has called forceTIso, SolidElement.cpp:347-352, so every receiver element
+// rotates) -> evaluation at azimuth phi with the 25 interpolation weights.  One CTA of 16 modes x 25 points per receiver,
+// mode tiles staged like k_grad3d.  out: 6 Voigt strains (RTZ) or 3 curl components per receiver.
+template <bool CURL>
+__global__ void __launch_bounds__(AX_TILE *AX_NPE) k_strain_curl(const ElemDesc *__restrict__ elems, const RecvItem *__restrict__ rec,
+                                                                 const float *__restrict__ weights, const float *__restrict__ geom,
+                                                                 const float2 *__restrict__ displ, float *__restrict__ out) {
+    constexpr int NOUT = CURL ? 3 : 6;
+    __shared__ float2 sU[3 * AX_NPE * AX_TILE];
+    __shared__ float red[NOUT][AX_TILE * AX_NPE / 32 + 1];
+    const RecvItem R = rec[blockIdx.x];
+    const ElemDesc &E = elems[R.elem];
+    const int t = threadIdx.x % AX_TILE, p = threadIdx.x / AX_TILE;
+    const int i = p / 5, j = p % 5;
+    const int top = E.nu - E.nyq;
+    GCoef gc;
+    load_gcoef(gc, E.axial, i, j);
+    const PointGeom g = load_geom(geom, E.geom_off, p);
+    const bool ax0 = E.axial && i == 0;
+    float tr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+    const float wp = weights[(size_t)blockIdx.x * AX_NPE + p];
+    float acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) acc[k] = 0.f;
+    for (int a0 = 0; a0 <= top; a0 += AX_TILE) {
+        const int alpha = a0 + t;
+        __syncthreads();
+        gather_tile<3>(E, displ, sU, t, p, alpha <= E.nu ? alpha : (1 << 30));
+        __syncthreads();
+        if (alpha > top || fabsf(wp) < 1e-10f) continue;
+        float sn, cs;
+        sincosf((float)alpha * R.phi, &sn, &cs);
+        const float f = (alpha == 0 ? 1.f : 2.f) * wp;
+        auto ev = [&](float2 v) { return f * (alpha == 0 ? v.x : cs * v.x - sn * v.y); };
+        if constexpr (CURL) {
+            float2 e9[9];
+            grad9_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e9);
+            rot9(e9, tr[0], tr[1], tr[2], tr[3], false);
+            acc[0] += ev(csub(e9[7], e9[5]));      // dUZdT - dUTdZ
+            acc[1] += ev(csub(e9[2], e9[6]));      // dURdZ - dUZdR
+            acc[2] += ev(csub(e9[3], e9[1]));      // dUTdR - dURdT
+        } else {
+            float2 e[6];
+            grad6_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
+            rot_spz_to_rtz(e, tr[0], tr[1], tr[2], tr[3]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[k] += ev(e[k]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NOUT) {
+        float s = 0.f;
+        for (int k = 0; k < (AX_TILE * AX_NPE + 31) / 32; ++k) s += red[threadIdx.x][k];
+        out[blockIdx.x * NOUT + threadIdx.x] = s;
+    }
+}
+
 // FluidElement::computeGroundMotion (FluidElement.cpp:163-215): the fluid "displacement" is the acoustic stress of the
 // potential, u = K grad(chi) -- gather -> Gradient::computeGrad -> [c2r -> K(phi) -> r2c for 3D material] -- evaluated at
 // azimuth phi and interpolated with the receiver's 25 weights.  One CTA per receiver, one GLL row (5 points) at a time so

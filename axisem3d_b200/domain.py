@@ -344,6 +344,22 @@ class Domain:
         capi.check(self.lib.ax3d_record_ground_motion(self.h, len(et), _pi(et), _pf(ph), _pf(w), _pf(out)))
         return out
 
+    def strain(self, elem_tags, phi, weights):
+        """Element::computeStrain after forceTIso (SolidElement.cpp:219-279): [nrec][6] Voigt strain in RTZ."""
+        return self._strain_curl(self.lib.ax3d_record_strain, 6, elem_tags, phi, weights)
+
+    def curl(self, elem_tags, phi, weights):
+        """Element::computeCurl after forceTIso (SolidElement.cpp:281-345): [nrec][3]."""
+        return self._strain_curl(self.lib.ax3d_record_curl, 3, elem_tags, phi, weights)
+
+    def _strain_curl(self, fn, nout, elem_tags, phi, weights):
+        et = np.ascontiguousarray(elem_tags, dtype=np.int32)
+        ph = _f32(phi)
+        w = _f32(np.asarray(weights).reshape(len(et), 25))
+        out = np.zeros((len(et), nout), dtype=np.float32)
+        capi.check(fn(self.h, len(et), _pi(et), _pf(ph), _pf(w), _pf(out)))
+        return out
+
     # ------------------------------------------------------------------ measurement
     def launch_count(self):
         n = C.c_longlong(0)

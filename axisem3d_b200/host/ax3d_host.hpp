@@ -34,6 +34,7 @@ typedef std::array<double, 2> RDCol2;
 typedef std::array<double, 25> RDMatPP;   // row-major (ipol, jpol)
 typedef std::array<Real, 25> RMatPP;      // row-major (ipol, jpol)
 typedef std::array<Real, 3> RRow3;
+typedef std::array<Real, 6> RRow6;
 typedef std::array<Real, 4> RRow4;        // eigen_cg4.h: the four CG4 points (1,1) (1,3) (3,1) (3,3)
 typedef std::vector<Real> RColX;
 struct RMatXN {                           // Nr x 25, column-major: (j, ipnt) at [ipnt * rows + j]
@@ -509,6 +510,14 @@ public:
     void computeGroundMotion(Real phi, const RMatPP &weights, RRow3 &u_spz) const {
         check(ax3d_record_ground_motion(mDom, 1, &mDomainTag, &phi, weights.data(), u_spz.data()));
     }
+    // Element.h:26-32 (SolidElement.cpp:219-352): the library applies forceTIso itself for strain / curl receivers
+    void computeStrain(Real phi, const RMatPP &weights, RRow6 &strain) const {
+        check(ax3d_record_strain(mDom, 1, &mDomainTag, &phi, weights.data(), strain.data()));
+    }
+    void computeCurl(Real phi, const RMatPP &weights, RRow3 &curl) const {
+        check(ax3d_record_curl(mDom, 1, &mDomainTag, &phi, weights.data(), curl.data()));
+    }
+    void forceTIso() {}
 protected:
     friend class Domain;
     virtual int release(ax3d_domain *dom) = 0;

@@ -183,6 +183,13 @@ int ax3d_field_size(ax3d_domain *dom, int fluid_part, size_t *n_complex);
 int ax3d_record_ground_motion(ax3d_domain *dom, int nrec, const int *elem_tags, const float *phi,
                               const float *weights /* nrec x 25 */, float *out /* nrec x 3 */);
 
+/* Element::computeStrain(phi, weights, RRow6&) and Element::computeCurl(phi, weights, RRow3&) after Element::forceTIso, as
+ * PointwiseRecorder::record uses them for stations that dump strain / curl (PointwiseRecorder.cpp:96-135; SolidElement.cpp:
+ * 219-345, 347-352): 6 Voigt strains resp. 3 curl components in the (R, T, Z) frame per receiver.  Solid elements without
+ * particle relabelling. */
+int ax3d_record_strain(ax3d_domain *dom, int nrec, const int *elem_tags, const float *phi, const float *weights, float *out /* nrec x 6 */);
+int ax3d_record_curl(ax3d_domain *dom, int nrec, const int *elem_tags, const float *phi, const float *weights, float *out /* nrec x 3 */);
+
 /* Domain::setPointwiseRecorder (Domain.h:34; ReceiverCollection.cpp:135-223): registers nrec receivers
  * (element, azimuth, 25 interpolation weights each) once ... */
 int ax3d_set_receivers(ax3d_domain *dom, int nrec, const int *elem_tags, const float *phi, const float *weights);

@@ -999,6 +999,40 @@ class OracleDomain:
                 out[t] = v
         return out
 
+    def _solid_group_of(self, e):
+        return next((g, int(np.nonzero(g.tags == e.domain_tag)[0][0])) for g in self.groups
+                    if g.kind == "solid" and (g.tags == e.domain_tag).any())
+
+    def _eval_phi(self, s, g, phi, w):
+        """sum_p w_p (s_0 + 2 Re sum_{alpha >= 1} s_alpha e^{i alpha phi}) for s [M, ncomp, 25]"""
+        top = g.Nu - g.nyq
+        ex = 2.0 * np.exp(1j * np.arange(1, top + 1) * phi)
+        up = s[0].real + (ex[:, None, None] * s[1:top + 1]).real.sum(axis=0)
+        return (up * np.where(np.abs(w) < 1e-10, 0.0, w)[None, :]).sum(axis=1)
+
+    def strain(self, elem_tag, phi, weights):
+        """SolidElement::computeStrain (SolidElement.cpp:219-279) after forceTIso, no PRT: grad6 -> SPZ_RTZ -> evaluation."""
+        e = self.elements[elem_tag]
+        if e.kind != "solid" or e.prt is not None:
+            raise NotImplementedError("strain receivers: solid elements without PRT")
+        g, k = self._solid_group_of(e)
+        u = self._gather_solid(g)
+        th = np.stack([self.elements[t].formThetaMat() for t in g.tags])
+        s = tiso_spz_to_rtz(g.grad.grad6(u, g.nyq), th, self.rd)
+        return self._eval_phi(s.reshape(u.shape[0], g.M, 6, nPE)[k], g, phi, np.asarray(weights, float).reshape(nPE))
+
+    def curl(self, elem_tag, phi, weights):
+        """SolidElement::computeCurl (SolidElement.cpp:281-345) after forceTIso, no PRT: grad9 -> SPZ_RTZ -> curl."""
+        e = self.elements[elem_tag]
+        if e.kind != "solid" or e.prt is not None:
+            raise NotImplementedError("curl receivers: solid elements without PRT")
+        g, k = self._solid_group_of(e)
+        u = self._gather_solid(g)
+        th = np.stack([self.elements[t].formThetaMat() for t in g.tags])
+        s = tiso9_rotate(g.grad.grad9(u, g.nyq), th, self.rd, False).reshape(u.shape[0], g.M, 9, nPE)[k]
+        v = self._eval_phi(s, g, phi, np.asarray(weights, float).reshape(nPE))
+        return np.array([v[7] - v[5], v[2] - v[6], v[3] - v[1]])
+
     def _ground_motion_fluid(self, e, phi, w):
         """FluidElement::computeGroundMotion (FluidElement.cpp:163-215): gather, Gradient::computeGrad, [c2r, K, r2c | K],
         then the same azimuthal evaluation on the acoustic stress (= the fluid displacement)."""

@@ -147,12 +147,15 @@ def main():
             displ, stiff = split_output(np.fromfile(out, dtype=np.complex64), d.points)
             meta = dict(case=name, params={k: (v.__name__ if callable(v) else v) for k, v in CASES[name].items()}, nstep=NSTEP,
                         kick_seed=KICK_SEED, dt=dt, source="oracle/_ref/ref_driver (reference sources + oracle/shim)")
-            ground = np.fromfile(rout, dtype=np.float32).reshape(-1, 3)
+            raw_r = np.fromfile(rout, dtype=np.float32)
+            nrec = raw_r.size // 12
+            ground = raw_r[:3 * nrec].reshape(nrec, 3)
+            strain_curl = raw_r[3 * nrec:].reshape(nrec, 9)      # 6 strains (RTZ, Voigt) + 3 curl; zeros where not applicable
             meta["recv_seed"] = RECV_SEED
             meta["wisdom_cutoff"] = WISDOM_CUTOFF
             nu_wisdom = np.fromfile(wout, dtype=np.int32)
             assert nu_wisdom.size == len(d.points)
-            np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_%s.npz" % name), displ=displ, stiff=stiff, ground=ground, nu_wisdom=nu_wisdom,
+            np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_%s.npz" % name), displ=displ, stiff=stiff, ground=ground, strain_curl=strain_curl, nu_wisdom=nu_wisdom,
                                 meta=np.array(json.dumps(meta)))
             print("%-24s %5d points %5d elements  |u| %.3e  |f| %.3e  %s" % (
                 name, len(d.points), len(d.elements), np.abs(displ).max(), np.abs(stiff).max(), r.stdout.strip()))

@@ -241,6 +241,7 @@ int main(int argc, char **argv) {
             out.write(reinterpret_cast<const char *>(buf.data()), (size_t)buf.size() * sizeof(Complex));
         }
         if (argc > 5) {
+            const bool has_prt = info.has_prt;
             Reader rr(argv[4]);
             std::ofstream ro(argv[5], std::ios::binary);
             const int nrec = rr.get<int32_t>();
@@ -252,6 +253,26 @@ int main(int argc, char **argv) {
                 RRow3 u;
                 elements[etag]->computeGroundMotion(phi, w, u);
                 const float o[3] = {u(0), u(1), u(2)};
+                ro.write(reinterpret_cast<const char *>(o), sizeof(o));
+            }
+            // ... then strain and curl at the same receivers (PointwiseRecorder.cpp:96-135), solid elements without PRT only;
+            // forceTIso first, as ReceiverCollection::release does for stations that dump them
+            rr.f.seekg(4);
+            for (int ir = 0; ir < nrec; ++ir) {
+                const int etag = rr.get<int32_t>();
+                const float phi = rr.get<float>();
+                std::vector<float> wv = rr.vec<float>(25);
+                float o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (dynamic_cast<SolidElement *>(elements[etag]) && !has_prt) {
+                    RMatPP w = take_pp(wv, 0);
+                    elements[etag]->forceTIso();
+                    RRow6 st;
+                    RRow3 cu;
+                    elements[etag]->computeStrain(phi, w, st);
+                    elements[etag]->computeCurl(phi, w, cu);
+                    for (int k = 0; k < 6; ++k) o[k] = st(k);
+                    for (int k = 0; k < 3; ++k) o[6 + k] = cu(k);
+                }
                 ro.write(reinterpret_cast<const char *>(o), sizeof(o));
             }
         }
