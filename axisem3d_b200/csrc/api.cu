@@ -195,6 +195,7 @@ struct ax3d_domain {
     DevBuf<float2> attstate1d;
     DevBuf<int> w_elem[NCLS], w_a0[NCLS];
     int n_work[NCLS] = {0, 0, 0, 0};
+    bool cls_prt[NCLS] = {false, false, false, false};   // the class has elements with particle relabelling (1D classes: kernel instance)
     DevBuf<FftItem> fft_items[NCLS];
     std::vector<Chunk> chunks;
     std::vector<ClusterLaunch> clusters;
@@ -430,10 +431,15 @@ typedef void (*fft_kernel_t)(const ElemDesc *, const FftItem *, const FftPlan *,
                              float2 *);
 static fft_kernel_t fft_kernel(const Chunk &ch) {
     const bool fluid = ch.cls == CLS_F3D;
-    if (ch.prt && !fluid) {
-        if (ch.fft_np == 1) return k_fft3d_v2<false, 1, 256, 5>;
-        if (ch.fft_nt == 256) return k_fft3d_v2<false, 5, 256, 5>;
-        return k_fft3d_v2<false, 5, 512, 5>;
+    if (ch.prt && !fluid) {   // solid elements with PRT: 5 Z-form pairs per point
+        if (ch.fft_np == 1) return k_fft3d_v2<false, 1, 256, 5, true>;
+        if (ch.fft_nt == 256) return k_fft3d_v2<false, 5, 256, 5, true>;
+        return k_fft3d_v2<false, 5, 512, 5, true>;
+    }
+    if (ch.prt && fluid) {    // fluid elements with PRT: same 2 pairs, PRT applied around Acoustic3D
+        if (ch.fft_np == 1) return k_fft3d_v2<true, 1, 256, 0, true>;
+        if (ch.fft_nt == 256) return k_fft3d_v2<true, 5, 256, 0, true>;
+        return k_fft3d_v2<true, 5, 512, 0, true>;
     }
     if (ch.fft_np == 1) return fluid ? k_fft3d_v2<true, 1, 256> : k_fft3d_v2<false, 1, 256>;
     if (ch.fft_nt == 256) return fluid ? k_fft3d_v2<true, 5, 256> : k_fft3d_v2<false, 5, 256>;
@@ -621,6 +627,7 @@ static void finalize(ax3d_domain *d) {
             D.axial = E.axial ? 1 : 0;
             D.law = E.law;
             D.prt = E.prt_rows > 0 ? 1 : 0;
+            if (D.prt) d->cls_prt[c] = true;
             D.tiso = (!fluid && (E.law != AX3D_ISO || D.prt)) ? 1 : 0;   // SolidElement.cpp:21: mInTIso = mHasPRT || needTIso
             D.is3d = is3d ? 1 : 0;
             D.att_kind = E.att.kind;
@@ -745,8 +752,8 @@ static void finalize(ax3d_domain *d) {
                     // one k_fft3d_v2 instance per chunk: same pair count and same points per CTA (5, or 1 when five points of
                     // this Nr do not fit in shared memory; elements come in descending Nr)
                     const int my_np = ((size_t)enp * 5 * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2) <= (size_t)220 * 1024 ? 5 : 1;
-                    if (ch.w_count > 0 && ((D.prt && !fluid) != (ch.prt != 0) || my_np != ch.fft_np)) close_chunk();
-                    ch.prt = (D.prt && !fluid) ? 1 : 0;
+                    if (ch.w_count > 0 && ((D.prt != 0) != (ch.prt != 0) || my_np != ch.fft_np)) close_chunk();
+                    ch.prt = D.prt ? 1 : 0;
                     (void)cls_np;
                     D.ppb = my_np;
                     const size_t need_sc = (size_t)enp * AX_NPE * N;
@@ -1298,13 +1305,13 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, i
     TimerScope ts(d, 1);
     const int TB = AX_TILE * AX_NPE;
     if ((which & 1) && d->n_work[CLS_S1D]) {
-        k_elem1d<false><<<d->n_work[CLS_S1D], TB, 0, d->stream>>>(d->desc[CLS_S1D].p, d->w_elem[CLS_S1D].p, d->w_a0[CLS_S1D].p, d->geom.p,
+        (d->cls_prt[CLS_S1D] ? k_elem1d<false, true> : k_elem1d<false, false>)<<<d->n_work[CLS_S1D], TB, 0, d->stream>>>(d->desc[CLS_S1D].p, d->w_elem[CLS_S1D].p, d->w_a0[CLS_S1D].p, d->geom.p,
                                                                   d->coef.p, d->attpar.p, d->attstate1d.p, d->s_field[AX3D_DISPL].p,
                                                                   d->s_field[AX3D_STIFF].p);
         d->launches++;
     }
     if ((which & 2) && d->n_work[CLS_F1D]) {
-        k_elem1d<true><<<d->n_work[CLS_F1D], TB, 0, d->stream>>>(d->desc[CLS_F1D].p, d->w_elem[CLS_F1D].p, d->w_a0[CLS_F1D].p, d->geom.p,
+        (d->cls_prt[CLS_F1D] ? k_elem1d<true, true> : k_elem1d<true, false>)<<<d->n_work[CLS_F1D], TB, 0, d->stream>>>(d->desc[CLS_F1D].p, d->w_elem[CLS_F1D].p, d->w_a0[CLS_F1D].p, d->geom.p,
                                                                  d->coef.p, d->attpar.p, d->attstate1d.p, d->f_field[AX3D_DISPL].p,
                                                                  d->f_field[AX3D_STIFF].p);
         d->launches++;
@@ -1313,18 +1320,18 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, i
         const int c = ch.cls;
         if (!(which & (c == CLS_S3D ? 1 : 2))) continue;
         if (c == CLS_S3D) {
-            k_grad3d<false><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
+            (ch.prt ? k_grad3d<false, true> : k_grad3d<false, false>)<<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                               d->s_field[AX3D_DISPL].p, d->scratch.p);
             fft_kernel(ch)<<<ch.f_count, ch.fft_np == 1 ? 256 : ch.fft_nt, ch.fft_smem, d->stream>>>(
                 d->desc[c].p, d->fft_items[c].p + ch.f_begin, d->plans.p, d->stwpool.p, d->coef.p, d->attpar.p, d->attstate3d.p, d->scratch.p);
-            k_quad3d<false><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
+            (ch.prt ? k_quad3d<false, true> : k_quad3d<false, false>)<<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                               d->scratch.p, d->s_field[AX3D_STIFF].p);
         } else {
-            k_grad3d<true><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
+            (ch.prt ? k_grad3d<true, true> : k_grad3d<true, false>)<<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                              d->f_field[AX3D_DISPL].p, d->scratch.p);
             fft_kernel(ch)<<<ch.f_count, ch.fft_np == 1 ? 256 : ch.fft_nt, ch.fft_smem, d->stream>>>(
                 d->desc[c].p, d->fft_items[c].p + ch.f_begin, d->plans.p, d->stwpool.p, d->coef.p, d->attpar.p, d->attstate3d.p, d->scratch.p);
-            k_quad3d<true><<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
+            (ch.prt ? k_quad3d<true, true> : k_quad3d<true, false>)<<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                              d->scratch.p, d->f_field[AX3D_STIFF].p);
         }
         d->launches += 3;

@@ -269,7 +269,7 @@ __device__ __forceinline__ void stress_batch(int law, float2 *__restrict__ Z, co
 // Physical space of `np` points [p0, p0 + np) of element E: stress (+ SLS attenuation) on the c2r output, in place
 // (Isotropic3D.cpp:10-27, TransverselyIsotropic3D.cpp:10-28, Anisotropic3D.cpp:10-54, Attenuation3D_{Full,CG4}.cpp,
 // Acoustic3D.cpp:9-16).  Phi positions are in the digit-reversed order of the plan, like the uploaded moduli.
-template <bool FLUID, int NT>
+template <bool FLUID, int NT, bool PRT = false>
 __device__ __forceinline__ void physical_space(const ElemDesc &E, const float *__restrict__ coef, const float *__restrict__ attpar,
                                                float *__restrict__ attstate, float2 *__restrict__ Z, int N, int ldz, int p0, int np,
                                                int tid, int cs_in = 0) {
@@ -278,7 +278,7 @@ __device__ __forceinline__ void physical_space(const ElemDesc &E, const float *_
     const float *cf0 = coef + E.coef_off + (size_t)p0 * N;
     const int law = E.law;
     if constexpr (!FLUID) {
-        if (E.att_kind == ATT_NONE && E.prt == 0) {
+        if (E.att_kind == ATT_NONE && !(PRT && E.prt != 0)) {
             if (law == LAW_ISO) stress_batch<2, 4, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
             else if (law == LAW_TI) stress_batch<5, 2, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
             else stress_batch<21, 1, NT>(law, Z, cf0, total, cf_stride, cs, ldz, N, tid);
@@ -288,7 +288,7 @@ __device__ __forceinline__ void physical_space(const ElemDesc &E, const float *_
     int idx = tid;
     int pl = idx / N, pos = idx - pl * N;
     const int dp = NT / N, dpos = NT - dp * N;
-    const bool prt = E.prt != 0;
+    const bool prt = PRT && E.prt != 0;
     const float *px0 = coef + E.prt_off + (size_t)p0 * N;   // X [4][25][N], digit-reversed phi like the moduli
     for (; idx < total; idx += NT) {
         float2 *zc = Z + pl * ldz + pos;
@@ -552,7 +552,7 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
 // space part for NP consecutive GLL points of one element (the constitutive law couples the 6 components of one point,
 // never two points): load NPAIR * NP columns, c2r, stress (+SLS), r2c, store -- the same stage and stress code as the
 // fused kernel, on a tile that is 1/5 (NP = 5) or 1/25 (NP = 1) of an element, so that even Nr = 2016 fits.
-template <bool FLUID, int NP, int NT, int NPAIR_ = 0>
+template <bool FLUID, int NP, int NT, int NPAIR_ = 0, bool PRT = false>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_fft3d_v2(const ElemDesc *__restrict__ elems, const FftItem *__restrict__ items,
                                                  const FftPlan *__restrict__ plans, const float2 *__restrict__ stwpool,
                                                  const float *__restrict__ coef, const float *__restrict__ attpar,
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_fft3d_v2(const ElemDe
             __syncthreads();
         }
     }
-    physical_space<FLUID, NT>(E, coef, attpar, attstate, Z, N, ldz, p0, NP, tid);
+    physical_space<FLUID, NT, PRT>(E, coef, attpar, attstate, Z, N, ldz, p0, NP, tid);
     __syncthreads();
     {
         int L = 1;

@@ -301,7 +301,8 @@ static __device__ __forceinline__ int cg4_index(int p) {   // (1,1),(1,3),(3,1),
 
 // ------------------------------------------------------------------------------------ 1D-material element kernel
 // grid: one CTA per work item (element, first mode of the tile); block: AX_TILE x 25 threads, lane = mode.
-template <bool FLUID>
+// PRT: instance that also handles elements with particle relabelling (only launched when the class has any)
+template <bool FLUID, bool PRT = false>
 __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
                                                             const int *__restrict__ w_a0, const float *__restrict__ geom,
                                                             const float *__restrict__ coef, const float *__restrict__ attpar,
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
             for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
         }
         float px[4] = {1.f, 0.f, 0.f, 1.f};
-        if (E.prt) {   // SolidElement.cpp:405-413: grad9 -> rotate -> sphericalToUndulated (PRT_1D, Fourier space)
+        if (PRT && E.prt) {   // SolidElement.cpp:405-413: grad9 -> rotate -> sphericalToUndulated (PRT_1D, Fourier space)
 #pragma unroll
             for (int k = 0; k < 4; ++k) px[k] = coef[E.prt_off + k * AX_NPE + p];
             float2 e9[9];
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
                     [&](int c) -> float2 & { return stt[E.nsls * sl + (size_t)c * P * M + cell]; });
             }
         }
-        if (E.prt) {   // SolidElement.cpp:424-432: undulatedToSpherical -> rotate back -> quad9
+        if (PRT && E.prt) {   // SolidElement.cpp:424-432: undulatedToSpherical -> rotate back -> quad9
             float2 s9[9];
             prt_u2s_solid(s, px, s9);
             rot9(s9, tr[0], tr[1], tr[2], tr[3], true);
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
         grad_fluid_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
         const float K = dead ? 0.f : coef[E.coef_off + p];
         float px[4] = {1.f, 0.f, 0.f, 1.f}, s1 = 0.f, c1 = 1.f;
-        if (E.prt) {   // FluidElement.cpp:335-343: rotate -> sphericalToUndulated
+        if (PRT && E.prt) {   // FluidElement.cpp:335-343: rotate -> sphericalToUndulated
 #pragma unroll
             for (int k = 0; k < 4; ++k) px[k] = coef[E.prt_off + k * AX_NPE + p];
             s1 = geom[E.trig_off + p];
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) s[c] = cscale(e[c], K);   // Acoustic1D.cpp:8-16
-        if (E.prt) {   // FluidElement.cpp:345-352
+        if (PRT && E.prt) {   // FluidElement.cpp:345-352
             prt_u2s_fluid(s, px);
             rot3_fluid(s, s1, c1, true);
         }
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
 }
 
 // ------------------------------------------------------------------------------------ 3D material: stage A (grad)
-template <bool FLUID>
+template <bool FLUID, bool PRT = false>
 __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
                                                             const int *__restrict__ w_a0, const float *__restrict__ geom,
                                                             const float2 *__restrict__ displ, float2 *__restrict__ scratch) {
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__re
     const bool dead = E.nyq && alpha == E.nu;
     float2 *z = scratch + E.scratch_off + (size_t)p * N;
     if constexpr (!FLUID) {
-        if (E.prt) {   // 9 components -> 5 Z-form pairs (the last one half empty)
+        if (PRT && E.prt) {   // 9 components -> 5 Z-form pairs (the last one half empty)
             float2 e9[9];
             grad9_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e9);
             if (dead) {
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__re
     } else {
         float2 e[3];
         grad_fluid_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
-        if (E.prt) rot3_fluid(e, geom[E.trig_off + p], geom[E.trig_off + AX_NPE + p], false);
+        if (PRT && E.prt) rot3_fluid(e, geom[E.trig_off + p], geom[E.trig_off + AX_NPE + p], false);
         if (dead) e[0] = e[1] = e[2] = czero();
         zform_store(z, N, alpha, e[0], e[1]);
         zform_store(z + (size_t)AX_NPE * N, N, alpha, e[2], czero());
@@ -488,7 +489,7 @@ struct FftItem {
     int p0;
 };
 // ------------------------------------------------------------------------------------ 3D material: stage C (quad)
-template <bool FLUID>
+template <bool FLUID, bool PRT = false>
 __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
                                                             const int *__restrict__ w_a0, const float *__restrict__ geom,
                                                             const float2 *__restrict__ scratch, float2 *__restrict__ stiff) {
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__re
     float2 r[NC];
     if constexpr (!FLUID) {
         float2 s[6], X[3], Y[3];
-        if (E.prt) {
+        if (PRT && E.prt) {
             float2 s9[9], dummy;
             if (!dead) {
 #pragma unroll
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__re
         if (!dead) {
             zform_load(z, N, beta, sc, s[0], s[1]);
             zform_load(z + (size_t)AX_NPE * N, N, beta, sc, s[2], dummy);
-            if (E.prt) rot3_fluid(s, geom[E.trig_off + p], geom[E.trig_off + AX_NPE + p], true);
+            if (PRT && E.prt) rot3_fluid(s, geom[E.trig_off + p], geom[E.trig_off + AX_NPE + p], true);
         } else {
             s[0] = s[1] = s[2] = czero();
         }
