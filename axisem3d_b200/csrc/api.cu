@@ -581,6 +581,8 @@ static void finalize(ax3d_domain *d) {
     const int cluster_nt = env_clnt ? atoi(env_clnt) : AX_CLUSTER_NT_DEFAULT;
     if (cluster_nt != 0 && cluster_nt != 128 && cluster_nt != 192 && cluster_nt != 256 && cluster_nt != 512)
         fail("ax3d::cluster || AX3D_CL_NT must be 0 (by shared-memory class), 128, 192, 256 or 512");
+    const char *env_pk = getenv("AX3D_PACK_SMALL");
+    const bool pack_small = env_pk ? atoi(env_pk) != 0 : true;
     const char *env_nf = getenv("AX3D_NO_FUSED");
     const bool use_fused = !(env_nf && atoi(env_nf) != 0);
     {
@@ -769,7 +771,18 @@ static void finalize(ax3d_domain *d) {
                     ch.fft_nt = ch.fft_smem <= (size_t)110 * 1024 ? 256 : 512;
                 }
             } else {
-                for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); }
+                // 1D classes, small expansions (cfg1: M = 3): the 16 mode lanes of a CTA take up to 16 / Mpad consecutive
+                // elements of the same M (Mpad = 4 or 8); such an item carries a0 = -(number of elements)
+                const int Mpad = M <= 4 ? 4 : M <= 8 ? 8 : 0;
+                if (pack_small && Mpad && !w_elem.empty() && w_a0.back() < 0 && -w_a0.back() < AX_TILE / Mpad &&
+                    d->h_desc[c][w_elem.back()].nu + 1 == M && w_elem.back() - w_a0.back() == (int)k) {
+                    w_a0.back() -= 1;                         // extend the open pack by this element
+                } else if (pack_small && Mpad) {
+                    w_elem.push_back((int)k);
+                    w_a0.push_back(-1);
+                } else {
+                    for (int a0 = 0; a0 < M; a0 += AX_TILE) { w_elem.push_back((int)k); w_a0.push_back(a0); }
+                }
             }
             d->h_desc[c].push_back(D);
         }

@@ -312,12 +312,23 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__re
     __shared__ float2 sU[NC * AX_NPE * AX_TILE];
     __shared__ float2 sX[NC * AX_NPE * AX_TILE];
     __shared__ float2 sY[NC * AX_NPE * AX_TILE];
-    const ElemDesc &E = elems[w_elem[blockIdx.x]];
     const int t = threadIdx.x % AX_TILE, p = threadIdx.x / AX_TILE;
     const int i = p / 5, j = p % 5;
-    const int alpha = w_a0[blockIdx.x] + t;
+    // work item: (element, first mode of a 16-mode tile), or a pack of -a0 consecutive small elements of equal M sharing
+    // the 16 lanes (lane = sub-element * Mpad + mode); all tiles below are indexed by lane, so a pack needs no other change
+    const int e0 = w_elem[blockIdx.x], a0 = w_a0[blockIdx.x];
+    int sub = 0, alpha = a0 + t;
+    bool lane_on = true;
+    if (a0 < 0) {
+        const int Mpad = elems[e0].nu + 1 <= 4 ? 4 : 8;
+        sub = t / Mpad;
+        alpha = t - sub * Mpad;
+        lane_on = sub < -a0;
+        if (!lane_on) sub = 0;
+    }
+    const ElemDesc &E = elems[e0 + sub];
     const int M = E.nu + 1;
-    const bool active = alpha < M;
+    const bool active = lane_on && alpha < M;
     gather_tile<NC>(E, displ, sU, t, p, active ? alpha : (1 << 30));
     GCoef gc;
     load_gcoef(gc, E.axial, i, j);
