@@ -301,9 +301,13 @@ static __device__ __forceinline__ int cg4_index(int p) {   // (1,1),(1,3),(3,1),
 
 // ------------------------------------------------------------------------------------ 1D-material element kernel
 // grid: one CTA per work item (element, first mode of the tile); block: AX_TILE x 25 threads, lane = mode.
+#ifndef AX_ELEM1D_MIN_CTAS
+#define AX_ELEM1D_MIN_CTAS 3   // resident 400-thread CTAs per SM the register allocation must allow for the solid instance; B200, cfg1
+                               // (profiles/microbench/elem1d_ab.sh): 1 -> 0.0472, 2 -> 0.0403, 3 -> 0.0371, 4 -> 0.0437 ms per step
+#endif
 // PRT: instance that also handles elements with particle relabelling (only launched when the class has any)
 template <bool FLUID, bool PRT = false>
-__global__ void __launch_bounds__(AX_TILE *AX_NPE) k_elem1d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
+__global__ void __launch_bounds__(AX_TILE *AX_NPE, FLUID ? 4 : AX_ELEM1D_MIN_CTAS) k_elem1d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
                                                             const int *__restrict__ w_a0, const float *__restrict__ geom,
                                                             const float *__restrict__ coef, const float *__restrict__ attpar,
                                                             float2 *__restrict__ attstate, const float2 *__restrict__ displ,
