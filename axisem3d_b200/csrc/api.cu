@@ -106,6 +106,13 @@ struct HSource {
 #ifndef AX_CLUSTER_NT_DEFAULT
 #define AX_CLUSTER_NT_DEFAULT 0
 #endif
+// k_fft3d_v2 instance by shared-memory residency: every instance is compiled for 1024 resident threads per SM (64 registers;
+// the kernel is latency-bound and prefers warps to registers, profiles/microbench/occ_ab*.sh): four 256-thread CTAs when four
+// tiles fit, two 512-thread CTAs when two or three fit, one 1024-thread CTA otherwise
+static int fft_threads(size_t smem_bytes) {
+    const size_t per_sm = (size_t)(228 * 1024) / (smem_bytes + 1024);
+    return per_sm >= 4 ? 256 : per_sm >= 2 ? 512 : 1024;
+}
 enum { CLS_S1D = 0, CLS_F1D = 1, CLS_S3D = 2, CLS_F3D = 3, NCLS = 4 };
 
 struct Chunk {   // a run of 3D elements of one class whose spectra fit the scratch ring together
@@ -434,16 +441,19 @@ static fft_kernel_t fft_kernel(const Chunk &ch) {
     if (ch.prt && !fluid) {   // solid elements with PRT: 5 Z-form pairs per point
         if (ch.fft_np == 1) return k_fft3d_v2<false, 1, 256, 5, true>;
         if (ch.fft_nt == 256) return k_fft3d_v2<false, 5, 256, 5, true>;
-        return k_fft3d_v2<false, 5, 512, 5, true>;
+        if (ch.fft_nt == 512) return k_fft3d_v2<false, 5, 512, 5, true>;
+        return k_fft3d_v2<false, 5, 1024, 5, true>;
     }
     if (ch.prt && fluid) {    // fluid elements with PRT: same 2 pairs, PRT applied around Acoustic3D
         if (ch.fft_np == 1) return k_fft3d_v2<true, 1, 256, 0, true>;
         if (ch.fft_nt == 256) return k_fft3d_v2<true, 5, 256, 0, true>;
-        return k_fft3d_v2<true, 5, 512, 0, true>;
+        if (ch.fft_nt == 512) return k_fft3d_v2<true, 5, 512, 0, true>;
+        return k_fft3d_v2<true, 5, 1024, 0, true>;
     }
     if (ch.fft_np == 1) return fluid ? k_fft3d_v2<true, 1, 256> : k_fft3d_v2<false, 1, 256>;
     if (ch.fft_nt == 256) return fluid ? k_fft3d_v2<true, 5, 256> : k_fft3d_v2<false, 5, 256>;
-    return fluid ? k_fft3d_v2<true, 5, 512> : k_fft3d_v2<false, 5, 512>;
+    if (ch.fft_nt == 512) return fluid ? k_fft3d_v2<true, 5, 512> : k_fft3d_v2<false, 5, 512>;
+    return fluid ? k_fft3d_v2<true, 5, 1024> : k_fft3d_v2<false, 5, 1024>;
 }
 
 static void finalize(ax3d_domain *d) {
@@ -755,6 +765,12 @@ static void finalize(ax3d_domain *d) {
                     // this Nr do not fit in shared memory; elements come in descending Nr)
                     const int my_np = ((size_t)enp * 5 * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2) <= (size_t)220 * 1024 ? 5 : 1;
                     if (ch.w_count > 0 && ((D.prt != 0) != (ch.prt != 0) || my_np != ch.fft_np)) close_chunk();
+                    {   // elements come in descending Nr: start a new chunk where one more k_fft3d_v2 CTA per SM becomes resident
+                        // (its 256-thread instance is compiled for AX_FFT_MIN_CTAS CTAs per SM), instead of running the whole class
+                        // at the shared-memory footprint of its largest element
+                        const size_t mine = ((size_t)enp * my_np * fused_ldz(N) + (size_t)((stw_len + 1) & ~1)) * sizeof(float2);
+                        if (ch.w_count > 0 && fft_threads(mine) != fft_threads(ch.fft_smem)) close_chunk();
+                    }
                     ch.prt = D.prt ? 1 : 0;
                     (void)cls_np;
                     D.ppb = my_np;
@@ -768,7 +784,7 @@ static void finalize(ax3d_domain *d) {
                     for (int p0 = 0; p0 < AX_NPE; p0 += D.ppb) { fitems.push_back(FftItem{(int)k, p0}); ch.f_count++; }
                     ch.fft_smem = std::max(ch.fft_smem, ((size_t)enp * D.ppb * fused_ldz(N) + (size_t)((stw_len + 1) & ~1)) * sizeof(float2));
                     ch.fft_np = D.ppb;
-                    ch.fft_nt = ch.fft_smem <= (size_t)110 * 1024 ? 256 : 512;
+                    ch.fft_nt = fft_threads(ch.fft_smem);
                 }
             } else {
                 // 1D classes, small expansions (cfg1: M = 3): the 16 mode lanes of a CTA take up to 16 / Mpad consecutive

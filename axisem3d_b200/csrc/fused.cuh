@@ -552,8 +552,12 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
 // space part for NP consecutive GLL points of one element (the constitutive law couples the 6 components of one point,
 // never two points): load NPAIR * NP columns, c2r, stress (+SLS), r2c, store -- the same stage and stress code as the
 // fused kernel, on a tile that is 1/5 (NP = 5) or 1/25 (NP = 1) of an element, so that even Nr = 2016 fits.
+#ifndef AX_FFT_MIN_CTAS
+#define AX_FFT_MIN_CTAS 4   // resident 256-thread CTAs per SM the register allocation of k_fft3d_v2 must allow (64 registers, 76 B
+                            // of spills).  B200, cfg3 (profiles/microbench/occ_ab*.sh): 2 -> 1.271, 3 -> 1.108, 4 -> 1.099 ms per step
+#endif
 template <bool FLUID, int NP, int NT, int NPAIR_ = 0, bool PRT = false>
-__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_fft3d_v2(const ElemDesc *__restrict__ elems, const FftItem *__restrict__ items,
+__global__ void __launch_bounds__(NT, NT <= 256 ? AX_FFT_MIN_CTAS : NT <= 512 ? AX_FFT_MIN_CTAS / 2 : 1) k_fft3d_v2(const ElemDesc *__restrict__ elems, const FftItem *__restrict__ items,
                                                  const FftPlan *__restrict__ plans, const float2 *__restrict__ stwpool,
                                                  const float *__restrict__ coef, const float *__restrict__ attpar,
                                                  float *__restrict__ attstate, float2 *__restrict__ scratch) {
