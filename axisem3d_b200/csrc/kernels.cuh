@@ -434,9 +434,12 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE, FLUID ? 4 : AX_ELEM1D_MIN_CTA
     }
 }
 
+#ifndef AX_GQ3D_MIN_CTAS
+#define AX_GQ3D_MIN_CTAS 3   // resident 400-thread CTAs per SM the register allocation of k_grad3d / k_quad3d must allow
+#endif
 // ------------------------------------------------------------------------------------ 3D material: stage A (grad)
 template <bool FLUID, bool PRT = false>
-__global__ void __launch_bounds__(AX_TILE *AX_NPE) k_grad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
+__global__ void __launch_bounds__(AX_TILE *AX_NPE, AX_GQ3D_MIN_CTAS) k_grad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
                                                             const int *__restrict__ w_a0, const float *__restrict__ geom,
                                                             const float2 *__restrict__ displ, float2 *__restrict__ scratch) {
     constexpr int NC = FLUID ? 1 : 3;
@@ -505,7 +508,7 @@ struct FftItem {
 };
 // ------------------------------------------------------------------------------------ 3D material: stage C (quad)
 template <bool FLUID, bool PRT = false>
-__global__ void __launch_bounds__(AX_TILE *AX_NPE) k_quad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
+__global__ void __launch_bounds__(AX_TILE *AX_NPE, AX_GQ3D_MIN_CTAS) k_quad3d(const ElemDesc *__restrict__ elems, const int *__restrict__ w_elem,
                                                             const int *__restrict__ w_a0, const float *__restrict__ geom,
                                                             const float2 *__restrict__ scratch, float2 *__restrict__ stiff) {
     constexpr int NC = FLUID ? 1 : 3;
