@@ -151,9 +151,10 @@ def cpu_arm(steps, warmup, stride=9, min_seconds=0.0, max_seconds=25.0):
         if el > max_seconds or (done >= steps and el >= min_seconds):
             break
     return dict(value=work * done / el, unit=UNIT, cores=co.threads(), kind="port",
-                sample="%d of %d quads (every %s theta-column of the cfg2 mesh), %d point-modes per step, %d steps, %.1f s of "
-                       "C/OpenMP oracle on %d threads" % (len(rel["elements"]), mesh.nelem, "" if stride == 1 else "%d-th" % stride,
-                                                          work, done, el, co.threads()),
+                sample="%d of %d quads (%s of the %s mesh), %d point-modes per step, %d steps, %.1f s of "
+                       "C/OpenMP oracle on %d threads" % (len(rel["elements"]), mesh.nelem,
+                                                          "every theta-column" if stride == 1 else "every %d-th theta-column" % stride,
+                                                          CFG, work, done, el, co.threads()),
                 ms_per_step=1e3 * el / done, steps=done)
 
 
