@@ -17,7 +17,7 @@ SYMBOLS = [
     "ax3d_run_steps", "ax3d_synchronize", "ax3d_get_point_field", "ax3d_set_point_field",
     "ax3d_get_field_bulk", "ax3d_set_field_bulk", "ax3d_field_size", "ax3d_record_ground_motion",
     "ax3d_launch_count", "ax3d_work_per_step", "ax3d_algorithmic_bytes", "ax3d_enable_timers",
-    "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_dominant_kernel", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
+    "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_kernel_stats", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
     "ax3d_halo_export", "ax3d_halo_connect", "ax3d_set_learn_parameters", "ax3d_learn_wisdom", "ax3d_get_nu_wisdom", "ax3d_set_element_prt", "ax3d_add_solid_point_ocean", "ax3d_record_strain", "ax3d_record_curl",
 ]
 
@@ -46,7 +46,11 @@ def load(build_if_missing=True):
     # The library links libnccl.so.2.  torch bundles a newer NCCL under the same SONAME than the system one; whichever is
     # mapped first wins for the whole process, and libtorch_cuda does not load against the older system copy.  Import
     # torch first so that one NCCL (torch's) serves both.
-    import torch  # noqa: F401
+    # torch is optional for this binding: without it the system libnccl serves the library alone.
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
     lib = C.CDLL(path)
     lib.ax3d_last_error.restype = C.c_char_p
     for s in SYMBOLS:
@@ -80,7 +84,7 @@ def load(build_if_missing=True):
     lib.ax3d_synchronize.argtypes = [vp]
     lib.ax3d_run_steps_timed.argtypes = [vp, i, d, pf, pf]
     lib.ax3d_run_steps_record.argtypes = [vp, i, d, pf, pf]
-    lib.ax3d_dominant_kernel.argtypes = [vp, pd, pd, i]
+    lib.ax3d_kernel_stats.argtypes = [vp, i, C.c_char_p, i, pd, C.POINTER(C.c_longlong), pd, pi_, i]
     lib.ax3d_set_receivers.argtypes = [vp, i, pi_, pf, pf]
     lib.ax3d_record.argtypes = [vp, pf]
     lib.ax3d_nccl_unique_id.argtypes = [vp]

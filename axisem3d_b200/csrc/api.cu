@@ -38,12 +38,21 @@ struct DevBuf {
         n = count;
         if (count) CK(cudaMalloc(&p, count * sizeof(T)));
     }
+    // The domain's streams are non-blocking: they do not synchronise with the legacy stream these set-up copies use, a
+    // pageable H2D cudaMemcpy may return before its DMA has landed and cudaMemset is asynchronous.  Every set-up copy
+    // therefore drains the legacy stream before returning, so that work enqueued afterwards on any stream sees the data.
     void upload(const std::vector<T> &h) {
         alloc(h.size());
-        if (n) CK(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+        if (n) {
+            CK(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+            CK(cudaStreamSynchronize(cudaStreamLegacy));
+        }
     }
     void zero() {
-        if (n) CK(cudaMemset(p, 0, n * sizeof(T)));
+        if (n) {
+            CK(cudaMemset(p, 0, n * sizeof(T)));
+            CK(cudaStreamSynchronize(cudaStreamLegacy));
+        }
     }
     void release() {
         if (p) cudaFree(p);
@@ -122,6 +131,7 @@ struct Chunk {   // a run of 3D elements of one class whose spectra fit the scra
     size_t fft_smem;
     int fft_np, fft_nt;         // k_fft3d_v2 instance: points per CTA (5 or 1), threads (256: two CTAs per SM, or 512)
     int prt;                    // 1: solid elements with particle relabelling (5 Z-form pairs per point instead of 3)
+    double alg_b;               // algorithmic bytes of the elements of the chunk
 };
 
 struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_elem3d_fused<FLUID, 512, nct> launch
@@ -197,6 +207,7 @@ struct ax3d_domain {
     bool plain_advanced = false;    // the plain points already hold the state of the step about to start
     // ---- elements
     std::vector<ElemDesc> h_desc[NCLS];
+    std::vector<double> h_alg_b[NCLS];   // algorithmic bytes of every element, in class order
     DevBuf<ElemDesc> desc[NCLS];
     DevBuf<float> geom, coef, attpar, attstate3d;
     DevBuf<float2> attstate1d;
@@ -245,9 +256,13 @@ struct ax3d_domain {
     DevBuf<int> bad_flag;
     bool timers = false;
     double timer_ms[4] = {0, 0, 0, 0};
-    // dominant kernel (solid k_elem3d_fused launch): its own event pair, algorithmic bytes {elements, in-kernel Newmark points}
-    double dom_ms = 0, dom_bytes[2] = {0, 0};
-    long long dom_launches = 0;
+    // per-kernel statistics while the timers are on (eager steps): name -> summed device time, launches, summed algorithmic
+    // bytes of those launches.  bench.py takes the entry with the largest summed time as the dominant kernel.
+    struct KStat { double ms = 0; long long n = 0; double bytes = 0; };
+    std::map<std::string, KStat> kstats;
+    double dom_bytes[2] = {0, 0};       // solid fused launch: algorithmic bytes {elements, in-kernel Newmark points}
+    double pts_bytes[2] = {0, 0};       // algorithmic bytes of all solid / all fluid points
+    double cls_bytes[4] = {0, 0, 0, 0}; // algorithmic bytes of the elements of each class that go through k_elem1d / the fused launch
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // fluid chain of a step on its own stream (step_body)
@@ -521,6 +536,7 @@ static void finalize(ax3d_domain *d) {
             }
             s_len += (size_t)3 * M;
             bytes_pts += 192.0 * M + (m3 ? 4.0 * p.nr : 4.0);
+            d->pts_bytes[0] += 192.0 * M + (m3 ? 4.0 * p.nr : 4.0);
         }
         if (p.kind == 1 || p.kind == 2) {
             p.f_idx = (int)fo.size();
@@ -545,6 +561,7 @@ static void finalize(ax3d_domain *d) {
             }
             f_len += (size_t)M;
             bytes_pts += 64.0 * M + (m3 ? 4.0 * p.nr : 4.0);
+            d->pts_bytes[1] += 64.0 * M + (m3 ? 4.0 * p.nr : 4.0);
         }
     }
     if (s_len >= (1ull << 31) || f_len >= (1ull << 31)) fail("ax3d::finalize || field arrays exceed 2^31 complex entries per GPU");
@@ -605,12 +622,12 @@ static void finalize(ax3d_domain *d) {
         const int npair = fluid ? 2 : 3;
         std::vector<int> w_elem, w_a0;
         std::vector<FftItem> fitems;
-        Chunk ch{c, 0, 0, 0, 0, 0, 5, 256, 0};
+        Chunk ch{c, 0, 0, 0, 0, 0, 5, 256, 0, 0.0};
         int cls_np = 0;   // points per k_fft3d_v2 CTA for this class: fixed by its largest split element
         size_t ch_scratch = 0;
         auto close_chunk = [&]() {
             if (ch.w_count > 0) d->chunks.push_back(ch);
-            ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0, 5, 256, 0};
+            ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0, 5, 256, 0, 0.0};
             ch_scratch = 0;
         };
         std::vector<int> cl_elems;
@@ -785,6 +802,7 @@ static void finalize(ax3d_domain *d) {
                     ch.fft_smem = std::max(ch.fft_smem, ((size_t)enp * D.ppb * fused_ldz(N) + (size_t)((stw_len + 1) & ~1)) * sizeof(float2));
                     ch.fft_np = D.ppb;
                     ch.fft_nt = fft_threads(ch.fft_smem);
+                    ch.alg_b += E.alg_b;
                 }
             } else {
                 // 1D classes, small expansions (cfg1: M = 3): the 16 mode lanes of a CTA take up to 16 / Mpad consecutive
@@ -801,6 +819,8 @@ static void finalize(ax3d_domain *d) {
                 }
             }
             d->h_desc[c].push_back(D);
+            d->h_alg_b[c].push_back(E.alg_b);
+            if (!is3d) d->cls_bytes[c] += E.alg_b;
         }
         if (is3d) { close_chunk(); close_fused(); }
         if (!cl_elems.empty()) {
@@ -1094,6 +1114,28 @@ struct TimerScope {
     }
 };
 
+// one kernel (or one back-to-back group of kernels) under its own event pair, nested inside the family's TimerScope
+struct KTimer {
+    ax3d_domain *d;
+    const char *name;
+    double bytes;
+    KTimer(ax3d_domain *d_, const char *name_, double bytes_) : d(d_), name(name_), bytes(bytes_) {
+        if (d->timers) cudaEventRecord(d->ev2, d->stream);
+    }
+    ~KTimer() {
+        if (d->timers) {
+            cudaEventRecord(d->ev3, d->stream);
+            cudaEventSynchronize(d->ev3);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, d->ev2, d->ev3);
+            ax3d_domain::KStat &k = d->kstats[name];
+            k.ms += ms;
+            k.n += 1;
+            k.bytes += bytes;
+        }
+    }
+};
+
 static inline int nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
 
 // special_only: the plain solid points were already advanced by the previous step's element kernel (fused.cuh)
@@ -1118,11 +1160,13 @@ static void update_newmark(ax3d_domain *d, double dt, bool special_only = false,
     }
     const PointTab &stab = special_only ? d->s_tab_sp : d->s_tab;
     if ((which & 1) && stab.nrows) {
+        KTimer kt(d, "k_newmark_solid", d->pts_bytes[0] - (special_only ? d->dom_bytes[1] : 0.0));
         k_newmark_solid<<<nblk(stab.nrows, 256), 256, 0, d->stream>>>(stab, d->s_field[0].p, d->s_field[1].p, d->s_field[2].p,
                                                                      d->s_field[3].p, (float)half_dt, (float)dt, (float)half_dt_dt);
         d->launches++;
     }
     if ((which & 2) && d->f_tab.nrows) {
+        KTimer kt(d, "k_newmark_fluid", d->pts_bytes[1]);
         k_newmark_fluid<<<nblk(d->f_tab.nrows, 256), 256, 0, d->stream>>>(d->f_tab, d->f_field[0].p, d->f_field[1].p, d->f_field[2].p,
                                                                          d->f_field[3].p, (float)half_dt, (float)dt, (float)half_dt_dt);
         d->launches++;
@@ -1271,19 +1315,14 @@ static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool n
         nw.half_dt_dt = (float)half_dt_dt;
     }
     if (!fluid && d->nw_dbg.p && nw.on) nw.dbg = d->nw_dbg.p;
-    const bool time_it = d->timers && !fluid;
-    if (time_it) cudaEventRecord(d->ev2, d->stream);
+    double kbytes = 0;
+    for (int k = f.first; k < f.first + f.count; ++k) kbytes += d->h_alg_b[c][k];
+    if (nw.on) kbytes += d->dom_bytes[1];
+    KTimer kt(d, fluid ? "k_elem3d_fused<fluid>" : (nw.on ? "k_elem3d_fused<solid> + in-kernel Newmark" : "k_elem3d_fused<solid>"), kbytes);
     fused_kernel(f)<<<f.grid, fused_nt(f), f.smem, d->stream>>>(
         d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
         fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
         f.u_cap, f.tw_cap, f.z_cap, d->fused_work.p + 2 * which, nw);
-    if (time_it) {
-        cudaEventRecord(d->ev3, d->stream);
-        cudaEventSynchronize(d->ev3);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, d->ev2, d->ev3);
-        if (nw.on || d->n_plain == 0) { d->dom_ms += ms; d->dom_launches++; }   // launches that do the whole job of the kernel
-    }
 }
 
 static void set_fused_smem(int device, const FusedLaunch &f) {
@@ -1334,12 +1373,14 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, i
     TimerScope ts(d, 1);
     const int TB = AX_TILE * AX_NPE;
     if ((which & 1) && d->n_work[CLS_S1D]) {
+        KTimer kt(d, "k_elem1d<solid>", d->cls_bytes[CLS_S1D]);
         (d->cls_prt[CLS_S1D] ? k_elem1d<false, true> : k_elem1d<false, false>)<<<d->n_work[CLS_S1D], TB, 0, d->stream>>>(d->desc[CLS_S1D].p, d->w_elem[CLS_S1D].p, d->w_a0[CLS_S1D].p, d->geom.p,
                                                                   d->coef.p, d->attpar.p, d->attstate1d.p, d->s_field[AX3D_DISPL].p,
                                                                   d->s_field[AX3D_STIFF].p);
         d->launches++;
     }
     if ((which & 2) && d->n_work[CLS_F1D]) {
+        KTimer kt(d, "k_elem1d<fluid>", d->cls_bytes[CLS_F1D]);
         (d->cls_prt[CLS_F1D] ? k_elem1d<true, true> : k_elem1d<true, false>)<<<d->n_work[CLS_F1D], TB, 0, d->stream>>>(d->desc[CLS_F1D].p, d->w_elem[CLS_F1D].p, d->w_a0[CLS_F1D].p, d->geom.p,
                                                                  d->coef.p, d->attpar.p, d->attstate1d.p, d->f_field[AX3D_DISPL].p,
                                                                  d->f_field[AX3D_STIFF].p);
@@ -1348,6 +1389,7 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, i
     for (const Chunk &ch : d->chunks) {
         const int c = ch.cls;
         if (!(which & (c == CLS_S3D ? 1 : 2))) continue;
+        KTimer kt(d, c == CLS_S3D ? "split pipeline <solid>: k_grad3d + k_fft3d_v2 + k_quad3d" : "split pipeline <fluid>: k_grad3d + k_fft3d_v2 + k_quad3d", ch.alg_b);
         if (c == CLS_S3D) {
             (ch.prt ? k_grad3d<false, true> : k_grad3d<false, false>)<<<ch.w_count, TB, 0, d->stream>>>(d->desc[c].p, d->w_elem[c].p + ch.w_begin, d->w_a0[c].p + ch.w_begin, d->geom.p,
                                                               d->s_field[AX3D_DISPL].p, d->scratch.p);
@@ -1905,15 +1947,20 @@ static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool
         // runs on a second, lower-priority stream next to the solid chain and fills the SMs the persistent solid element
         // kernel leaves idle at its start and in its tail (fork / join by events: capturable into the step graph).
         cudaStream_t s = d->stream;
+        struct StreamSwap {   // the launch helpers enqueue on d->stream: restored on every exit path, exceptions included
+            ax3d_domain *d;
+            cudaStream_t keep;
+            StreamSwap(ax3d_domain *d_, cudaStream_t to) : d(d_), keep(d_->stream) { d->stream = to; }
+            ~StreamSwap() { d->stream = keep; }
+        };
         auto fluid_chain = [&]() {
             CK(cudaEventRecord(d->ev_fork, s));
             CK(cudaStreamWaitEvent(d->stream2, d->ev_fork, 0));
-            d->stream = d->stream2;
+            StreamSwap on_stream2(d, d->stream2);
             update_newmark(d, dt, special_only, 2);
             if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * d->nrec_total(), 2);
             compute_stiff(d, nw_on, dt, 2);
             CK(cudaEventRecord(d->ev_join, d->stream2));
-            d->stream = s;
         };
         if (d->dual_mode == 1) fluid_chain();          // fork at the top of the step
         update_newmark(d, dt, special_only, 1);
@@ -1989,7 +2036,16 @@ static void run_steps(ax3d_domain *d, int nsteps, double dt, const float *stf, b
             if (!d->graph_exec[v]) {
                 const long long before = d->launches;
                 CK(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
-                step_body(d, dt, special_only, nw_on, record);
+                try {
+                    step_body(d, dt, special_only, nw_on, record);
+                } catch (...) {   // never leave the stream capturing: end (and discard) the capture, then report
+                    cudaGraph_t broken = nullptr;
+                    cudaStreamEndCapture(d->stream, &broken);
+                    if (broken) cudaGraphDestroy(broken);
+                    cudaGetLastError();
+                    d->launches = before;
+                    throw;
+                }
                 CK(cudaStreamEndCapture(d->stream, &d->graph[v]));
                 CK(cudaGraphInstantiate(&d->graph_exec[v], d->graph[v], 0));
                 d->launches = before;   // capture enqueues nothing
@@ -2060,6 +2116,14 @@ int ax3d_run_steps_timed(ax3d_domain *d, int nsteps, double dt, const float *stf
 int ax3d_set_receivers(ax3d_domain *d, int nrec, const int *elem_tags, const float *phi, const float *weights) {
     API_BEGIN
     check_final(d);
+    // A second registration replaces the first: the recording graphs bake in the old item / weight pointers, grid sizes and
+    // ring row stride, and the ring was sized for the old receiver count -- drain the stream, drop them and start over.
+    CK(cudaStreamSynchronize(d->stream));
+    for (int v = 4; v < 8; ++v) {
+        if (d->graph_exec[v]) { cudaGraphExecDestroy(d->graph_exec[v]); d->graph_exec[v] = nullptr; }
+        if (d->graph[v]) { cudaGraphDestroy(d->graph[v]); d->graph[v] = nullptr; }
+    }
+    d->rec_ring_steps = 0;
     std::vector<RecvItem> it[NCLS];
     std::vector<float> w[NCLS];
     for (int c = 0; c < NCLS; ++c) d->rec_where_c[c].clear();
@@ -2146,6 +2210,7 @@ int ax3d_set_point_field(ax3d_domain *d, int tag, int field, int fluid_part, con
     if ((size_t)n_in != n) fail("ax3d_set_point_field || size mismatch");
     CK(cudaStreamSynchronize(d->stream));
     CK(cudaMemcpy(b, in, n * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaStreamSynchronize(cudaStreamLegacy));   // pageable H2D: landed before anything later on the (non-blocking) compute streams
     API_END
 }
 int ax3d_field_size(ax3d_domain *d, int fluid_part, size_t *n) {
@@ -2172,6 +2237,7 @@ int ax3d_set_field_bulk(ax3d_domain *d, int field, int fluid_part, const float *
     if (n_in != n) fail("ax3d_set_field_bulk || size mismatch");
     CK(cudaStreamSynchronize(d->stream));
     if (n) CK(cudaMemcpy(fluid_part ? d->f_field[field].p : d->s_field[field].p, in, n * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
     API_END
 }
 
@@ -2309,13 +2375,25 @@ int ax3d_enable_timers(ax3d_domain *d, int on) {
     d->timers = on != 0;
     API_END
 }
-int ax3d_dominant_kernel(ax3d_domain *d, double *ms_per_launch, double bytes[2], int reset) {
+/* Per-kernel statistics gathered while the timers are on (ax3d_enable_timers): entry `index` in name order -> name, summed
+ * device time (ms), launches, summed algorithmic bytes of those launches.  *count = number of entries (index < 0: only that).
+ * reset != 0 clears the table after the read of the LAST entry (index == count - 1) or when index < 0. */
+int ax3d_kernel_stats(ax3d_domain *d, int index, char *name, int name_cap, double *ms_total, long long *launches, double *bytes_total,
+                      int *count, int reset) {
     API_BEGIN
     check_final(d);
-    *ms_per_launch = d->dom_launches ? d->dom_ms / (double)d->dom_launches : 0.0;
-    bytes[0] = d->dom_bytes[0];
-    bytes[1] = d->n_plain > 0 ? d->dom_bytes[1] : 0.0;
-    if (reset) { d->dom_ms = 0; d->dom_launches = 0; }
+    const int n = (int)d->kstats.size();
+    if (count) *count = n;
+    if (index >= 0) {
+        if (index >= n) fail("ax3d_kernel_stats || index out of range");
+        auto it = d->kstats.begin();
+        std::advance(it, index);
+        if (name && name_cap > 0) { strncpy(name, it->first.c_str(), (size_t)name_cap - 1); name[name_cap - 1] = 0; }
+        if (ms_total) *ms_total = it->second.ms;
+        if (launches) *launches = it->second.n;
+        if (bytes_total) *bytes_total = it->second.bytes;
+    }
+    if (reset && (index < 0 || index == n - 1)) d->kstats.clear();
     API_END
 }
 int ax3d_get_timers(ax3d_domain *d, double out_ms[4], int reset) {

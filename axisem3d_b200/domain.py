@@ -287,12 +287,18 @@ class Domain:
         capi.check(self.lib.ax3d_record(self.h, _pf(out)))
         return out
 
-    def dominant_kernel(self, reset=True):
-        """(ms per launch, algorithmic bytes [elements, in-kernel Newmark points]) of the solid fused element kernel."""
-        ms = C.c_double(0)
-        b = np.zeros(2, dtype=np.float64)
-        capi.check(self.lib.ax3d_dominant_kernel(self.h, C.byref(ms), b.ctypes.data_as(C.POINTER(C.c_double)), 1 if reset else 0))
-        return ms.value, b
+    def kernel_stats(self, reset=True):
+        """{kernel name: (summed ms, launches, summed algorithmic bytes)} gathered while the timers were on."""
+        n = C.c_int(0)
+        capi.check(self.lib.ax3d_kernel_stats(self.h, -1, None, 0, None, None, None, C.byref(n), 0))
+        out = {}
+        for k in range(n.value):
+            name = C.create_string_buffer(160)
+            ms, nl, by = C.c_double(0), C.c_longlong(0), C.c_double(0)
+            capi.check(self.lib.ax3d_kernel_stats(self.h, k, name, 160, C.byref(ms), C.byref(nl), C.byref(by), None,
+                                                  1 if (reset and k == n.value - 1) else 0))
+            out[name.value.decode()] = (ms.value, nl.value, by.value)
+        return out
 
     def synchronize(self):
         capi.check(self.lib.ax3d_synchronize(self.h))

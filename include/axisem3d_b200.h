@@ -90,7 +90,7 @@ typedef struct ax3d_attenuation {
  *  law/rows/coef: Isotropic{1D,3D}(lambda, mu) (2 arrays), TransverselyIsotropic{1D,3D}(A, C, F, L, N)
  *  (5), Anisotropic{1D,3D}(C11, C12, ..., C66) (21, upper triangle row by row); each array rows x 25
  *  column-major, rows = 1 (1D classes) or the element's Nr (3D classes);
- *  att: NULL or attenuation living in the same space.  Particle relabelling (PRT) is not supported. */
+ *  att: NULL or attenuation living in the same space.  Particle relabelling: ax3d_set_element_prt below. */
 int ax3d_add_solid_element(ax3d_domain *dom, const int point_tags[25], const double *geom, int axial,
                            const double *theta, int law, int rows, const float *coef,
                            const ax3d_attenuation *att, int *tag);
@@ -217,11 +217,14 @@ int ax3d_algorithmic_bytes(ax3d_domain *dom, double out[3]);
  * events on the launching stream when profiling is enabled: out[0] newmark, [1] elements(stiff),
  * [2] solid-fluid + source, [3] halo. */
 int ax3d_enable_timers(ax3d_domain *dom, int on);
-/* the dominant kernel of the step (the solid k_elem3d_fused launch, which also advances the "plain" solid points to the
- * next step): average device time per launch [ms] over the timed launches (CUDA events on the launching stream, timers
- * enabled, steps issued through ax3d_run_steps) and its algorithmic bytes per launch: bytes[0] elements of the launch,
- * bytes[1] points updated in-kernel (192 B per mode + mass). */
-int ax3d_dominant_kernel(ax3d_domain *dom, double *ms_per_launch, double bytes[2], int reset);
+/* Per-kernel statistics gathered while the timers are on (steps issued through ax3d_run_steps run eagerly then): one
+ * CUDA-event pair on the launching stream around every hot kernel (the three launches of a split-pipeline chunk count as
+ * one entry).  Entry `index` (name order) -> name, summed device time [ms], launches, summed ALGORITHMIC bytes of those
+ * launches (elements of the launch; + 192 B per mode + mass for points advanced in-kernel).  *count = number
+ * of entries; index < 0 reads only the count.  reset != 0 clears the table once the last entry (or the count) is read.
+ * The caller picks the dominant kernel = the entry with the largest summed time (bench.py). */
+int ax3d_kernel_stats(ax3d_domain *dom, int index, char *name, int name_cap, double *ms_total, long long *launches,
+                      double *bytes_total, int *count, int reset);
 int ax3d_get_timers(ax3d_domain *dom, double out_ms[4], int reset);
 
 #ifdef __cplusplus

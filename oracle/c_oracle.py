@@ -86,6 +86,11 @@ class COracle:
     def threads(self):
         return self.lib.orc_num_threads()
 
+    def set_threads(self, n):
+        """explicit OpenMP thread count (launchers such as torchrun export OMP_NUM_THREADS=1)"""
+        self.lib.orc_set_num_threads(C.c_int(int(n)))
+        return self.threads()
+
     def computeStiff(self):
         d = self.d
         for g, G, att in self.groups:

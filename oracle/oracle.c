@@ -588,3 +588,12 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* bench.py's CPU arm sets the thread count explicitly: launchers such as torchrun export OMP_NUM_THREADS=1 */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

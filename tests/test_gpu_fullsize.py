@@ -107,3 +107,43 @@ def test_stiffness_operator_properties_at_full_size(cfg):
         scale = np.sqrt(_dot(w, ua, fa) * _dot(w, ub, fb))
         assert _dot(w, ua, fa) > 0 and _dot(w, ub, fb) > 0
         assert abs(ab - ba) <= 1e-5 * scale, (cfg, ab, ba, scale)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The bench's own domains against the CPU oracle.  oracle/oracle.c (C/OpenMP, fp32; pinned to the reference's golden
+# vectors by tests/test_golden_reference.py::test_c_oracle_matches_reference_sources) steps the whole 2016-quad mesh in
+# about a second, so the full-size CUDA path -- the exact kernel instances, shared-memory plans, work queues and chunking
+# bench.py times -- is compared entry by entry: per-step stiffness forces of each field family to rel. L2 <= 1e-5
+# (BASELINE.json's force tolerance), for three steps from a random admissible displacement, once verb by verb and once
+# through ax3d_run_steps (CUDA graph replay + in-kernel Newmark).
+@pytest.mark.timeout(1500)
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4"])
+def test_full_size_forces_match_c_oracle(cfg):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    from helpers import build_oracle, build_gpu, randomize_displ, push_fields, compare_field
+    from c_oracle import COracle
+    bench.CFG = cfg
+    m = bench.make_mesh(bench.N_THETA)
+    assert m.nelem == 2016
+    dt = m.estimate_dt()
+    ora, _ = build_oracle(m, dt, np.float32, source=False)
+    co = COracle(ora)
+    randomize_displ(ora, seed=11)
+    g1, _ = build_gpu(m, dt, source=False)
+    g2, _ = build_gpu(m, dt, source=False)
+    push_fields(ora, g1)
+    push_fields(ora, g2)
+    nstep = 3
+    for i in range(nstep):
+        co.step(dt, 0.0)
+        g1.step(dt, 0.0)
+        for which in ("stiff", "displ"):
+            err = compare_field(ora, g1, which)
+            assert err and all(v <= 1e-5 for v in err.values()), (cfg, "verbs", i, which, err)
+    g2.runSteps(dt, np.zeros(nstep, np.float32))
+    assert g2.checkStability()
+    for which in ("stiff", "displ", "veloc"):
+        err = compare_field(ora, g2, which)
+        assert err and all(v <= 1e-5 for v in err.values()), (cfg, "run_steps", which, err)

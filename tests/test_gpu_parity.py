@@ -216,3 +216,26 @@ def test_cluster_kernel_matches_oracle(name, monkeypatch):
     g.coupleSolidFluid()
     for k, v in compare_field(d, g, "stiff").items():
         assert v <= TOL_FORCE, (name, k, v)
+
+
+def test_check_stability_reports_non_finite_displacement():
+    """Domain::checkStability (Domain.cpp:237-275): Point::stable() = mDispl.allFinite() (SolidPoint.h:21, FluidPoint.h:21).
+    A NaN or an infinity anywhere in the solid or the fluid displacement must come back as `*stable == 0`; a clean field as 1."""
+    m = SynthMesh(n_theta=6, n_r=8, nu=8, law="iso", model3d=True, attenuation=None)
+    dt = m.estimate_dt()
+    g, _ = build_gpu(m, dt)
+    g.runSteps(dt, np.exp(-((np.arange(8) - 3) / 2.0) ** 2).astype(np.float32))
+    assert g.checkStability()
+    for fluid, bad in ((False, np.nan), (True, np.inf), (False, -np.inf), (True, np.nan)):
+        u = g.get_bulk("displ", fluid).copy()
+        keep = u.copy()
+        k = u.size - 3 if fluid else u.size // 2        # anywhere in the array, including the tail the last CTA covers
+        u[k] = complex(bad, 0.0) if fluid else complex(0.0, bad)
+        g.set_bulk("displ", fluid, u)
+        assert not g.checkStability(), (fluid, bad)
+        g.set_bulk("displ", fluid, keep)
+        assert g.checkStability()
+    # an unstable time step must be caught by the loop itself: dt far above the CFL limit blows up within a few hundred steps
+    g2, _ = build_gpu(m, dt)
+    g2.runSteps(50.0 * dt, np.ones(400, np.float32))
+    assert not g2.checkStability()
