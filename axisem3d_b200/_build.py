@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libaxisem3d_b200.so")
 SRC = os.path.join(HERE, "csrc", "api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cuh", "elem.cuh", "fft.cuh", "fused.cuh", "fused_wp.cuh", "cluster.cuh")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cuh", "elem.cuh", "fft.cuh", "fused.cuh")] + [
     os.path.join(ROOT, "include", "axisem3d_b200.h")]
 
 

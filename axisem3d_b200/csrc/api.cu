@@ -4,7 +4,6 @@
 #include "../../include/axisem3d_b200.h"
 #include "kernels.cuh"
 #include "fused.cuh"
-#include "cluster.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -106,15 +105,6 @@ struct HSource {
 #ifndef AX_DUAL_DEFAULT
 #define AX_DUAL_DEFAULT 2   // fluid chain of a step on a second stream (step_body): 0 off, 1 fork at the top of the step, 2 fork before the solid elements (B200, cfg2: 0.318 / 0.313 / 0.311 ms per step); AX3D_DUAL overrides
 #endif
-#define AX_CLUSTER_DYN_MAX (232448 - 1024)   // 227 KB per CTA minus the cluster kernel's static shared memory (plan, row geometry)
-#ifndef AX_CLUSTER_DEFAULT
-#define AX_CLUSTER_DEFAULT 0      // 0: off (split pipeline), 1: elements that do not fit the single-CTA kernel, 2: every 3D element; AX3D_CLUSTER overrides.
-                                  // Measured on B200 (profiles/r1_cluster_experiment.md): parity green, but DSMEM-latency- and cluster-barrier-bound --
-                                  // cfg2 elements 0.53 ms vs 0.31 ms single-CTA, cfg4 1.05 ms vs 0.84 ms split pipeline -- so it stays opt-in
-#endif
-#ifndef AX_CLUSTER_NT_DEFAULT
-#define AX_CLUSTER_NT_DEFAULT 0
-#endif
 // k_fft3d_v2 instance by shared-memory residency: every instance is compiled for 1024 resident threads per SM (64 registers;
 // the kernel is latency-bound and prefers warps to registers, profiles/microbench/occ_ab*.sh): four 256-thread CTAs when four
 // tiles fit, two 512-thread CTAs when two or three fit, one 1024-thread CTA otherwise
@@ -134,22 +124,13 @@ struct Chunk {   // a run of 3D elements of one class whose spectra fit the scra
     double alg_b;               // algorithmic bytes of the elements of the chunk
 };
 
-struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_elem3d_fused<FLUID, 512, nct> launch
+struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_elem3d_fused<FLUID, ...> launch
     int cls, first, count;
-    int nct;                     // > 0: kernel instance with a compile-time specialised body for Nr == nct
-    int u_cap, tw_cap, ldz_max;  // shared-memory regions (float2 units)
-    int nr_max;                  // largest Nr of the launch (fixes the Z and twiddle regions)
-    int nww;                     // Newmark warps per CTA (0: none; the solid launch uses 2 when the domain has plain points)
-    int z_cap;
+    int nww;                     // Newmark warps per CTA (0: none; the solid launch uses AX_NWW when the domain has plain points)
+    int tile_cap;                // float2 capacity R of the tile region (U | TW | Z, laid out per element by plan_fused_element)
     size_t smem;
     int grid;
-    std::map<int, int> nr_hist;  // Nr -> element count (to pick nct)
-};
-
-struct ClusterLaunch {   // a run of 3D elements of one class that go through k_elem3d_cluster (cluster.cuh), one 5-CTA cluster each
-    int cls, begin, count;       // window into cl_list[cls]
-    int nt;                      // threads per CTA
-    size_t smem;                 // dynamic shared memory per CTA = that of the largest element of the run
+    double alg_b;                // algorithmic bytes of the elements of the launch
 };
 
 struct ax3d_domain {
@@ -216,8 +197,6 @@ struct ax3d_domain {
     bool cls_prt[NCLS] = {false, false, false, false};   // the class has elements with particle relabelling (1D classes: kernel instance)
     DevBuf<FftItem> fft_items[NCLS];
     std::vector<Chunk> chunks;
-    std::vector<ClusterLaunch> clusters;
-    DevBuf<int> cl_list[NCLS];
     DevBuf<float2> scratch;
     // ---- source, solid-fluid
     DevBuf<unsigned> src_off;
@@ -304,15 +283,7 @@ struct ax3d_domain {
 static void fail(const std::string &m) { throw std::runtime_error(m); }
 
 // ------------------------------------------------------------------------------------------ FFT plans
-// Largest power-of-two radix of the plans of this process: 8 when the warp-per-point element kernel is in use (AX3D_WP=1),
-// 16 otherwise (thread-per-(mode, point) kernel, the default).  Every phi-dependent array is uploaded in the digit-reversed order
-// of these plans, so all kernels of a process share them.
-static bool use_wp() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("AX3D_WP"); v = (e && atoi(e) != 0) ? 1 : 0; }
-    return v != 0;
-}
-static int plan_maxr2() { return use_wp() ? 8 : 16; }
+static int plan_maxr2() { return 16; }
 
 static std::vector<int> choose_radices(int N) {
     const RadixList rl = choose_radices_ct(N, plan_maxr2());   // fft.cuh: the one definition host and kernels share
@@ -447,8 +418,6 @@ static void common_elem(ax3d_domain *d, HElem &e, const int tags[25], const doub
 
 // ------------------------------------------------------------------------------------------ finalize
 static void set_fused_smem(int device, const FusedLaunch &f);
-static void set_cluster_smem(const ClusterLaunch &cl);
-static bool fused_specialised(bool fluid, int N);
 typedef void (*fft_kernel_t)(const ElemDesc *, const FftItem *, const FftPlan *, const float2 *, const float *, const float *, float *,
                              float2 *);
 static fft_kernel_t fft_kernel(const Chunk &ch) {
@@ -594,8 +563,14 @@ static void finalize(ax3d_domain *d) {
         E.cls = E.fluid ? (is3d ? CLS_F3D : CLS_F1D) : (is3d ? CLS_S3D : CLS_S1D);
         order[E.cls].push_back((int)e);
     }
+    // 3D classes: elements with particle relabelling first (split pipeline only), then by Nr descending -- the fused launch
+    // takes the tail of this order (everything below the largest Nr whose single GLL row still fits in shared memory)
     for (int c : {CLS_S3D, CLS_F3D})
-        std::stable_sort(order[c].begin(), order[c].end(), [&](int a, int b) { return d->elems[a].nr > d->elems[b].nr; });
+        std::stable_sort(order[c].begin(), order[c].end(), [&](int a, int b) {
+            const HElem &A = d->elems[a], &B = d->elems[b];
+            if ((A.prt_rows > 0) != (B.prt_rows > 0)) return A.prt_rows > 0;
+            return A.nr > B.nr;
+        });
 
     std::vector<float> geom, coef, attpar;
     size_t att1d_len = 0, att3d_len = 0;
@@ -603,11 +578,6 @@ static void finalize(ax3d_domain *d) {
     const char *env_sc = getenv("AX3D_SCRATCH_MB");
     const size_t scratch_cap = (size_t)((env_sc ? atof(env_sc) : 256.0) * 1024.0 * 1024.0 / sizeof(float2));
     size_t scratch_need = 0;
-    const char *env_cl = getenv("AX3D_CLUSTER"), *env_clnt = getenv("AX3D_CL_NT");
-    const int cluster_mode = env_cl ? atoi(env_cl) : AX_CLUSTER_DEFAULT;
-    const int cluster_nt = env_clnt ? atoi(env_clnt) : AX_CLUSTER_NT_DEFAULT;
-    if (cluster_nt != 0 && cluster_nt != 128 && cluster_nt != 192 && cluster_nt != 256 && cluster_nt != 512)
-        fail("ax3d::cluster || AX3D_CL_NT must be 0 (by shared-memory class), 128, 192, 256 or 512");
     const char *env_pk = getenv("AX3D_PACK_SMALL");
     const bool pack_small = env_pk ? atoi(env_pk) != 0 : true;
     const char *env_nf = getenv("AX3D_NO_FUSED");
@@ -630,18 +600,46 @@ static void finalize(ax3d_domain *d) {
             ch = Chunk{c, (int)w_elem.size(), 0, (int)fitems.size(), 0, 0, 5, 256, 0, 0.0};
             ch_scratch = 0;
         };
-        std::vector<int> cl_elems;
-        std::vector<size_t> cl_smem;
         FusedLaunch fl{};
         fl.cls = c;
+        // tile region of the one resident CTA per SM (the solid launch keeps room for its Newmark warps' stages behind it)
+        const size_t fused_lim = (size_t)AX_FUSED_DYN_MAX - ((c == CLS_S3D && d->nw_allowed) ? (size_t)AX_NWW * NW_WARP_SMEM + 8 : 0);
+        fl.tile_cap = (int)((fused_lim / sizeof(float2)) & ~(size_t)1);
+        // per-element shared-memory plan (fused.cuh): the smallest number of row groups ng in {1, 2, 3, 5} whose Z-form columns
+        // fit next to the twiddle tables and a gather tile of >= 16 modes; Z sits at the end of the tile region, the twiddle
+        // tables below it, the gather tile U = [0, twoff) in front
+        auto plan_fused_element = [&](int N, int M, int stw_len, ElemDesc &D) -> bool {
+            const int nc = fluid ? 1 : 3, us = nc * AX_NPE;
+            static const int ngs[4] = {1, 2, 3, 5};
+            for (int ng : ngs) {
+                const long long zsz = (long long)npair * 5 * fused_rows_per_group(ng) * fused_ldz(N);
+                const long long zoff = ((long long)fl.tile_cap - zsz) & ~1ll;
+                const long long twoff = (zoff - ((stw_len + 1) & ~1)) & ~1ll;
+                if (twoff < (long long)us * 16) continue;
+                const int cap = (int)((twoff / us) & ~15ll);     // modes per gather tile
+                D.ng = ng;
+                D.zoff = (int)zoff;
+                D.twoff = (int)twoff;
+                D.mt = std::min(cap, M);
+                return true;
+            }
+            return false;
+        };
+        // the fused launch takes the tail of the class order: everything behind the last element that cannot be fused
+        int first_fused = (int)order[c].size();
+        if (is3d && use_fused) {
+            first_fused = 0;
+            for (size_t k = 0; k < order[c].size(); ++k) {
+                const HElem &E = d->elems[order[c][k]];
+                ElemDesc tmp;
+                const int pid = get_plan(d, E.nr);
+                if (E.prt_rows > 0 || !plan_fused_element(E.nr, E.nu + 1, d->h_plans[pid].stw_len, tmp)) first_fused = (int)k + 1;
+            }
+        }
         auto close_fused = [&]() {
             if (fl.count > 0) {
-                fl.tw_cap = 2 * fl.nr_max;
-                fl.smem = ((size_t)fl.u_cap + fl.tw_cap + (size_t)fl.z_cap) * sizeof(float2);
+                fl.smem = (size_t)AX_FUSED_DYN_MAX;   // tile region + (solid launch) the Newmark warps' stage buffers
                 fl.grid = std::min(fl.count, d->num_sm);
-                int best = 0;
-                for (const auto &kv : fl.nr_hist)
-                    if (kv.second > best && fused_specialised(fluid, kv.first)) { best = kv.second; fl.nct = kv.first; }
                 d->fused.push_back(fl);
             }
         };
@@ -737,44 +735,16 @@ static void finalize(ax3d_domain *d) {
             D.bucket = -1;
             D.mt = M;
             if (is3d) {
-                // fused one-CTA-per-element kernel when the element's spectrum fits in shared memory (fused.cuh)
-                const int nc = fluid ? 1 : 3;
-                // dynamic smem of the one resident CTA per SM (the solid launch keeps room for its Newmark warps' stages)
-                const size_t lim[1] = {(size_t)AX_FUSED_DYN_MAX - ((!fluid && d->nw_allowed) ? (size_t)AX_NWW * NW_WARP_SMEM + 8 : 0)};
+                // fused one-CTA-per-element kernel (fused.cuh) when one row group of the element fits in shared memory
                 D.plan_id = get_plan(d, N);
                 const int stw_len = d->h_plans[D.plan_id].stw_len;
-                // One shared-memory layout per launch: elements are sorted by Nr (descending), so the first element that
-                // fits fixes the Z and twiddle regions; what is left is the gather tile of every element of the launch.
-                const size_t fixed = fl.count ? ((size_t)fl.z_cap + 2 * (size_t)fl.nr_max) * sizeof(float2)
-                                              : ((size_t)npair * AX_NPE * fused_ldz(N) + 2 * (size_t)N) * sizeof(float2);   // twiddle tables <= 2 N
-                bool can_fuse = use_fused && !D.prt;   // the 9-component path runs through the split pipeline only
-                if (can_fuse && fixed + (size_t)nc * AX_NPE * M * sizeof(float2) > lim[0]) {
-                    const long long room = ((long long)lim[0] - (long long)fixed) / (long long)(nc * AX_NPE * sizeof(float2));
-                    D.mt = (int)(room / 16) * 16;
-                    if (D.mt < 16) can_fuse = false;
-                }
-                // cluster kernel (cluster.cuh): mode 1 = elements too large for one SM's shared memory, 2 = every 3D element
-                const size_t cl_bytes = (size_t)cl_layout(fluid, N, stw_len).total * sizeof(float2);
-                const bool can_cluster = !D.prt && cluster_mode > 0 && cl_bytes <= (size_t)AX_CLUSTER_DYN_MAX && (cluster_mode == 2 || !can_fuse);
-                if (can_cluster) can_fuse = false;
-                if (can_fuse && fl.count == 0) {
-                    fl.nr_max = N;
-                    fl.z_cap = npair * AX_NPE * fused_ldz(N);
-                }
+                const bool can_fuse = (int)k >= first_fused;
                 if (can_fuse) {
+                    if (!plan_fused_element(N, M, stw_len, D)) fail("ax3d::fused || internal: element does not fit its launch");
                     D.bucket = 0;
                     if (fl.count == 0) fl.first = (int)k;
                     fl.count++;
-                    fl.nr_hist[N]++;
-                    fl.u_cap = std::max(fl.u_cap, nc * AX_NPE * D.mt);
-                    fl.tw_cap = std::max(fl.tw_cap, stw_len);
-                    fl.ldz_max = std::max(fl.ldz_max, fused_ldz(N));
-                    if (stw_len > 2 * fl.nr_max) fail("ax3d::fused || twiddle table larger than its bound");
-                } else if (can_cluster) {
-                    D.mt = M;
-                    D.bucket = 1;
-                    cl_elems.push_back((int)k);
-                    cl_smem.push_back(cl_bytes);
+                    fl.alg_b += E.alg_b;
                 } else {
                     D.mt = M;
                     const int enp = (D.prt && !fluid) ? 5 : npair;   // Z-form pairs per point of this element
@@ -823,23 +793,6 @@ static void finalize(ax3d_domain *d) {
             if (!is3d) d->cls_bytes[c] += E.alg_b;
         }
         if (is3d) { close_chunk(); close_fused(); }
-        if (!cl_elems.empty()) {
-            // elements are sorted by Nr (descending); cut the list where one more resident CTA per SM becomes possible
-            auto per_sm = [](size_t bytes) { return (int)std::min<size_t>(8, (size_t)(228 * 1024) / (bytes + 1024)); };
-            // threads per CTA by residency: the warps of an SM come from 1, 2 or >= 3 CTAs (126 registers: <= 512 threads per SM)
-            auto nt_for = [&](size_t bytes) { return cluster_nt ? cluster_nt : per_sm(bytes) <= 1 ? 512 : per_sm(bytes) == 2 ? 256 : 128; };
-            ClusterLaunch cl{c, 0, 0, nt_for(cl_smem[0]), cl_smem[0]};
-            for (size_t k = 0; k < cl_elems.size(); ++k) {
-                if (cl.count > 0 && per_sm(cl_smem[k]) > per_sm(cl.smem)) {
-                    d->clusters.push_back(cl);
-                    cl = ClusterLaunch{c, (int)k, 0, nt_for(cl_smem[k]), cl_smem[k]};
-                }
-                cl.count++;
-                cl.smem = std::max(cl.smem, cl_smem[k]);   // not monotone in Nr: the twiddle tables depend on the factorisation
-            }
-            d->clusters.push_back(cl);
-            d->cl_list[c].upload(cl_elems);
-        }
         d->desc[c].upload(d->h_desc[c]);
         d->w_elem[c].upload(w_elem);
         d->w_a0[c].upload(w_a0);
@@ -908,8 +861,7 @@ static void finalize(ax3d_domain *d) {
                 }
             }
             d->desc[CLS_S3D].upload(d->h_desc[CLS_S3D]);
-            fs->nww = AX_NWW;
-            fs->smem += (size_t)AX_NWW * NW_WARP_SMEM + 8;   // + 8: the stages start on a 16-byte boundary behind the tile
+            fs->nww = AX_NWW;                                // their stages sit behind the tile region (plan_fused_element left the room)
             d->nw_cnt.alloc(ns);
             d->nw_cnt.zero();
             std::vector<int> q((size_t)n_plain, -1);
@@ -1071,7 +1023,6 @@ static void finalize(ax3d_domain *d) {
         if (ch.fft_smem > (size_t)224 * 1024) fail("ax3d::finalize || Nr too large for the FFT stage (needs > 224 KB shared memory per point)");
         CK(cudaFuncSetAttribute((const void *)fft_kernel(ch), cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     }
-    for (const ClusterLaunch &cl : d->clusters) set_cluster_smem(cl);
     {
         std::vector<unsigned> w;
         for (const FusedLaunch &f : d->fused) {
@@ -1236,57 +1187,20 @@ static void apply_source(ax3d_domain *d, float stf) {
     launch_source(d);
 }
 
-// kernel instances with a compile-time specialised body: (fluid, Nr).  Add a line to specialise another size.
-// (none is instantiated by default: on B200 the specialised body measured no faster than the generic one -- the kernel
-//  is latency-, not instruction-bound -- while doubling the code size; profiles/r1_fused_kernel_history.md)
-#define AX_FUSED_SPECIALISATIONS(X)
-// the same for the warp-per-point body (fused_wp.cuh), where compile-time strides and trip counts do pay: Nr = 208 is
-// Nu = 100 (configs[1]) after the lucky-number rounding of PreloopFFTW.cpp:59-99
-#define AX_WP_SPECIALISATIONS(X) X(false, 208)
-
-static bool fused_specialised(bool fluid, int N) {
-    const char *env = getenv("AX3D_NO_SPECIALISED");
-    if (env && atoi(env) != 0) return false;
-    if (use_wp()) {
-#define X(F, NCT) if (fluid == F && N == NCT) return true;
-        AX_WP_SPECIALISATIONS(X)
-#undef X
-        return false;
-    }
-#define X(F, NCT) if (fluid == F && N == NCT) return true;
-    AX_FUSED_SPECIALISATIONS(X)
-#undef X
-    return false;
-}
-
 // 512 threads = 128 registers/thread.  Measured on B200 (cfg2, elements family): 416 -> 0.270 ms, 448 -> 0.266, 512 -> 0.259,
 // 640 (96 regs) -> 0.289, 768 (80 regs) -> 0.310: the kernel is not occupancy-limited.  With Newmark warps the CTA is
 // 448 compute + 64 Newmark threads.
 static int fused_nt(const FusedLaunch &f) {
-    if (use_wp()) return AX_WP_NT + 32 * f.nww;
     return f.nww ? AX_NW_NT + 32 * AX_NWW : 512;
 }
 
 typedef void (*fused_kernel_t)(const ElemDesc *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
-                               float *, const float2 *, float2 *, int, int, int, unsigned *, const NwArgs);
+                               float *, const float2 *, float2 *, int, unsigned *, const NwArgs);
 
 static fused_kernel_t fused_kernel(const FusedLaunch &f) {
     const bool fluid = f.cls == CLS_F3D;
-#define X(F, NCT) if (fluid == F && f.nct == NCT && f.nww == 0) return k_elem3d_fused<F, 512, 0, NCT>;
-    AX_FUSED_SPECIALISATIONS(X)
-#undef X
-    if (use_wp()) {
-#define X(F, NCT) if (fluid == F && f.nct == NCT) return f.nww ? k_elem3d_fused<F, AX_WP_NT, F ? 0 : AX_NWW, NCT, true> : k_elem3d_fused<F, AX_WP_NT, 0, NCT, true>;
-        AX_WP_SPECIALISATIONS(X)
-#undef X
-    }
-    if (f.nct != 0) fail("ax3d::fused || no specialised kernel for this launch");
-    if (use_wp()) {
-        if (fluid) return k_elem3d_fused<true, AX_WP_NT, 0, 0, true>;
-        return f.nww ? k_elem3d_fused<false, AX_WP_NT, AX_NWW, 0, true> : k_elem3d_fused<false, AX_WP_NT, 0, 0, true>;
-    }
-    if (fluid) return k_elem3d_fused<true, 512, 0, 0>;
-    return f.nww ? k_elem3d_fused<false, AX_NW_NT, AX_NWW, 0> : k_elem3d_fused<false, 512, 0, 0>;
+    if (fluid) return k_elem3d_fused<true, 512, 0>;
+    return f.nww ? k_elem3d_fused<false, AX_NW_NT, AX_NWW> : k_elem3d_fused<false, 512, 0>;
 }
 
 // nw_on: this launch also advances the plain solid points to the next step (its dt is the step being integrated)
@@ -1315,14 +1229,12 @@ static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool n
         nw.half_dt_dt = (float)half_dt_dt;
     }
     if (!fluid && d->nw_dbg.p && nw.on) nw.dbg = d->nw_dbg.p;
-    double kbytes = 0;
-    for (int k = f.first; k < f.first + f.count; ++k) kbytes += d->h_alg_b[c][k];
-    if (nw.on) kbytes += d->dom_bytes[1];
+    const double kbytes = f.alg_b + (nw.on ? d->dom_bytes[1] : 0.0);
     KTimer kt(d, fluid ? "k_elem3d_fused<fluid>" : (nw.on ? "k_elem3d_fused<solid> + in-kernel Newmark" : "k_elem3d_fused<solid>"), kbytes);
     fused_kernel(f)<<<f.grid, fused_nt(f), f.smem, d->stream>>>(
         d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
         fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
-        f.u_cap, f.tw_cap, f.z_cap, d->fused_work.p + 2 * which, nw);
+        f.tile_cap, d->fused_work.p + 2 * which, nw);
 }
 
 static void set_fused_smem(int device, const FusedLaunch &f) {
@@ -1330,42 +1242,6 @@ static void set_fused_smem(int device, const FusedLaunch &f) {
     if (f.smem > AX_FUSED_DYN_MAX) fail("ax3d::fused || shared-memory plan exceeds 227 KB");
     // several launches (and domains) may share one kernel instance: opt in to the maximum once
     CK(cudaFuncSetAttribute((const void *)fused_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, AX_FUSED_DYN_MAX));
-}
-
-typedef void (*cluster_kernel_t)(const ElemDesc *, const int *, const FftPlan *, const float2 *, const float *, const float *, const float *,
-                                 float *, const float2 *, float2 *);
-static cluster_kernel_t cluster_kernel(bool fluid, int nt) {
-    if (nt == 128) return fluid ? k_elem3d_cluster<true, 128> : k_elem3d_cluster<false, 128>;
-    if (nt == 192) return fluid ? k_elem3d_cluster<true, 192> : k_elem3d_cluster<false, 192>;
-    if (nt == 512) return fluid ? k_elem3d_cluster<true, 512> : k_elem3d_cluster<false, 512>;
-    return fluid ? k_elem3d_cluster<true, 256> : k_elem3d_cluster<false, 256>;
-}
-
-static void set_cluster_smem(const ClusterLaunch &cl) {
-    CK(cudaFuncSetAttribute((const void *)cluster_kernel(cl.cls == CLS_F3D, cl.nt), cudaFuncAttributeMaxDynamicSharedMemorySize, AX_CLUSTER_DYN_MAX));
-}
-
-static void launch_cluster(ax3d_domain *d, const ClusterLaunch &cl) {
-    const int c = cl.cls;
-    const bool fluid = c == CLS_F3D;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(AX_CL * cl.count), 1, 1);
-    cfg.blockDim = dim3((unsigned)cl.nt, 1, 1);
-    cfg.dynamicSmemBytes = cl.smem;
-    cfg.stream = d->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = AX_CL;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, cluster_kernel(fluid, cl.nt), (const ElemDesc *)d->desc[c].p, (const int *)(d->cl_list[c].p + cl.begin),
-                          (const FftPlan *)d->plans.p, (const float2 *)d->stwpool.p, (const float *)d->geom.p, (const float *)d->coef.p,
-                          (const float *)d->attpar.p, d->attstate3d.p,
-                          (const float2 *)(fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p),
-                          fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p));
 }
 
 // which: 1 = solid elements, 2 = fluid elements, 3 = both
@@ -1406,11 +1282,6 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, i
                                                              d->scratch.p, d->f_field[AX3D_STIFF].p);
         }
         d->launches += 3;
-    }
-    for (const ClusterLaunch &cl : d->clusters) {
-        if (!(which & (cl.cls == CLS_S3D ? 1 : 2))) continue;
-        launch_cluster(d, cl);
-        d->launches++;
     }
     for (size_t k = 0; k < d->fused.size(); ++k) {
         if (!(which & (d->fused[k].cls == CLS_S3D ? 1 : 2))) continue;

@@ -1,25 +1,30 @@
-// fused.cuh -- persistent one-CTA-per-element kernel for elements with 3D (phi-dependent) material whose whole
-// strain spectrum fits in shared memory: SolidElement::computeStiff / FluidElement::computeStiff
-// (SolidElement.cpp:43-65, 404-443; FluidElement.cpp:43-65, 333-355) with no HBM/L2 round trip between
-// gather -> grad -> [rotate] -> c2r -> stress(+SLS) -> r2c -> [rotate^-1] -> quad -> scatter.
+// fused.cuh -- persistent one-CTA-per-element kernel for elements with 3D (phi-dependent) material:
+// SolidElement::computeStiff / FluidElement::computeStiff (SolidElement.cpp:43-65, 404-443; FluidElement.cpp:43-65, 333-355)
+// with no HBM/L2 round trip between gather -> grad -> [rotate] -> c2r -> stress(+SLS) -> r2c -> [rotate^-1] -> quad -> scatter.
 //
-// Shared memory of one CTA (float2 units), fixed offsets for every element of a launch:
-//   U  [u_cap]             gathered displacement, mode-major: U[a * NC*25 + c * 25 + point] (all contraction operands
-//                           of one thread sit at immediate offsets; the odd row stride keeps lanes = modes conflict free);
-//   TW [tw_cap]            per-stage twiddle tables of the plan;
-//   Z  [NPAIR * 25][ldz]   "Z-form" columns: two real strain/stress components of one GLL point as one complex
-//                           column of length N = Nr.  ldz = (N + 1) | 1 is odd, so lanes that run over columns are
-//                           bank-conflict free, and slot N of every column is a spare.
-// One CTA takes elements off a device-side work counter (elements are sorted by cost, largest first, so the queue is
-// LPT-like).  While element e is in its FFT/stress/quad phases the displacement of the NEXT element streams into U
-// with cp.async (U is dead after grad: the quad phase keeps its pointwise term in registers), its descriptor and plan
-// are prefetched, and the moduli of e are prefetched into L2 at the top of e.  Phases of one element:
-//   grad (thread = (mode, point), writes Z-form) | DIF stages (thread = (column, butterfly), column fastest)
+// An element is processed in `ng` passes over groups of GLL rows (xi index): ng = 1 (all 25 points at once) while the whole
+// strain spectrum fits in shared memory, 2 (rows 0-2 | 3-4), 3 (0-1 | 2-3 | 4) or 5 (one row per pass) for longer azimuthal
+// expansions -- a pass holds the Z-form columns of its np = 5 * rows points only, so that one GLL row of Nr <= ~1300 fits.
+// What couples the rows is cheap to repeat: the xi-derivative of the gradient needs the displacement of all 25 points, so
+// every pass gathers it again (L2 hits), and the xi-part of the quadrature of a pass is a partial sum for all 25 points,
+// scattered with one more RED per point (f = G_xi X + Y G_eta^T + r is linear in the rows of X).
+//
+// Shared memory of one CTA (float2 units), tile region [0, R) laid out per element (host: plan_fused_element):
+//   U  [0, twoff)          gathered displacement of a tile of `mt` modes, mode-major: U[a * NC*25 + c * 25 + point] (all
+//                           contraction operands of one thread sit at immediate offsets; the odd row stride keeps lanes =
+//                           modes conflict free);
+//   TW [twoff, zoff)       per-stage twiddle tables of the plan;
+//   Z  [zoff, R)           "Z-form" columns of the pass, [pair][local point][ldz]: two real strain/stress components of one
+//                           GLL point as one complex column of length N = Nr.  ldz = (N + 1) | 1 is odd, so lanes that run
+//                           over columns are bank-conflict free, and slot N of every column is a spare.
+// Behind the tile region: the stage buffers of the in-kernel Newmark warps.
+// One CTA takes elements off a device-side work counter (elements are sorted by Nr, largest first, so the queue is
+// LPT-like).  While a pass is in its FFT/stress/quad phases the first displacement tile of the NEXT pass streams into U
+// with cp.async (U is dead after grad: the quad phase keeps its pointwise term in registers), the next element's
+// descriptor and plan are prefetched, and the moduli of an element are prefetched into L2 at its top.  Phases of one pass:
+//   grad (thread = (mode, point of the group), writes Z-form) | DIF stages (thread = (column, butterfly), column fastest)
 //   | stress (thread = (point, phi)) | DIT stages | quad-pre (in place: slot beta <- X, slot N - beta <- Y)
-//   | quad-post + scatter (RED.ADD.F32x2).
-// The element body exists twice in a kernel instance: generic (driven by the FftPlan at run time) and, when NCT1 > 0,
-// specialised for the one compile-time Nr = NCT1 (strides, radices and twiddle offsets become immediates) -- the host
-// picks the instance whose NCT1 is the most frequent Nr of the domain.
+//   | quad-post + scatter (RED.ADD.F32x2; the points outside the group receive the xi-partial sums only).
 #pragma once
 #include "kernels.cuh"
 
@@ -45,18 +50,15 @@ __device__ __forceinline__ void cta_sync() {
 
 // ---------------------------------------------------------------- one FFT stage over all columns
 // DIF (c2r, SIGN = +1): butterfly, then twiddle T[j][p].  DIT (r2c, SIGN = -1): conj twiddle, then butterfly.
-// NCT > 0: N = NCT and L = LCT are compile-time.
-template <int R, int SIGN, bool DIF, int NT, int NCOLS, int NCT, int LCT>
-__device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int N_rt, int L_rt, const float2 *__restrict__ T, int tid) {
-    const int N = NCT ? NCT : N_rt;
-    const int L = NCT ? LCT : L_rt;
+template <int R, int SIGN, bool DIF, int NT>
+__device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int N, int L, int ncols, const float2 *__restrict__ T, int tid) {
     const int ldz = fused_ldz(N);
     const int Ls = L / R;
     const int nb = N / R;
-    const int total = NCOLS * nb;
+    const int total = ncols * nb;
     int idx = tid;
-    int b = idx / NCOLS, col = idx - b * NCOLS;
-    constexpr int db = NT / NCOLS, dc = NT - db * NCOLS;
+    int b = idx / ncols, col = idx - b * ncols;
+    const int db = NT / ncols, dc = NT - db * ncols;
     for (; idx < total; idx += NT) {
         int blk, j;
         if (Ls == 1) { blk = b; j = 0; }
@@ -84,48 +86,25 @@ __device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int N_rt, in
         for (int q = 0; q < R; ++q) x[q * Ls] = a[q];
         col += dc;
         b += db;
-        if (col >= NCOLS) { col -= NCOLS; ++b; }
+        if (col >= ncols) { col -= ncols; ++b; }
     }
 }
 
-template <int SIGN, bool DIF, int NT, int NCOLS>
-__device__ __forceinline__ void fused_stage_dispatch(int R, float2 *z, int N, int L, const float2 *T, int tid) {
+template <int SIGN, bool DIF, int NT>
+__device__ __forceinline__ void fused_stage_dispatch(int R, float2 *z, int N, int L, int ncols, const float2 *T, int tid) {
     switch (R) {
-        case 2: fused_stage<2, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
-        case 3: fused_stage<3, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
-        case 4: fused_stage<4, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
-        case 5: fused_stage<5, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
-        case 7: fused_stage<7, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
-        case 8: fused_stage<8, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
-        case 11: fused_stage<11, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
-        case 13: fused_stage<13, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
-        case 16: fused_stage<16, SIGN, DIF, NT, NCOLS, 0, 0>(z, N, L, T, tid); break;
+        case 2: fused_stage<2, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 3: fused_stage<3, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 4: fused_stage<4, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 5: fused_stage<5, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 7: fused_stage<7, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 8: fused_stage<8, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 11: fused_stage<11, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 13: fused_stage<13, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 16: fused_stage<16, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
         default: break;
     }
 }
-
-// compile-time plan: stage S of length-NCT transform has block length L; TWOFF = offset of its twiddle table
-template <int NT, int NWW, int NCOLS, int NCT, int S, int L, int TWOFF>
-struct CtFft {
-    static __device__ __forceinline__ void inverse(float2 *Z, const float2 *TW, int tid) {
-        if constexpr (S < choose_radices_ct(NCT).n) {
-            constexpr int R = choose_radices_ct(NCT).r[S];
-            constexpr int Ls = L / R;
-            fused_stage<R, +1, true, NT, NCOLS, NCT, L>(Z, NCT, L, TW + TWOFF, tid);
-            cta_sync<NT, NWW>();
-            CtFft<NT, NWW, NCOLS, NCT, S + 1, Ls, TWOFF + (Ls > 1 ? L : 0)>::inverse(Z, TW, tid);
-        }
-    }
-    static __device__ __forceinline__ void forward(float2 *Z, const float2 *TW, int tid) {
-        if constexpr (S < choose_radices_ct(NCT).n) {
-            constexpr int R = choose_radices_ct(NCT).r[S];
-            constexpr int Ls = L / R;
-            CtFft<NT, NWW, NCOLS, NCT, S + 1, Ls, TWOFF + (Ls > 1 ? L : 0)>::forward(Z, TW, tid);
-            fused_stage<R, -1, false, NT, NCOLS, NCT, L>(Z, NCT, L, TW + TWOFF, tid);
-            cta_sync<NT, NWW>();
-        }
-    }
-};
 
 // ---------------------------------------------------------------- grad / quad on the mode-major tile
 // um = U + a * NC*25: the displacement of one mode, [c * 25 + point].
@@ -359,29 +338,35 @@ __device__ __forceinline__ void physical_space(const ElemDesc &E, const float *_
     }
 }
 
-// E, P: descriptor and plan of this element (shared memory).  On entry the first gather tile of this element is in
-// flight (cp.async); `after_first_sync` runs behind the first barrier (every thread has left the previous element: its
-// descriptor slot is free), `after_grad` once U is dead (it starts the next element's gather).
-template <bool FLUID, int NT, int NWW, int NCT, typename GatherFn, typename AfterSyncFn, typename AfterGradFn>
-__device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const ElemDesc &E, const FftPlan &P, int tid,
-                                              GatherFn gather, AfterSyncFn after_first_sync, AfterGradFn after_grad) {
+// Row groups of an element processed in ng passes: rows [row_begin(ng, g), row_begin(ng, g + 1)); ng in {1, 2, 3, 5}.
+__host__ __device__ __forceinline__ constexpr int fused_rows_per_group(int ng) { return (5 + ng - 1) / ng; }
+__host__ __device__ __forceinline__ constexpr int fused_row_begin(int ng, int g) {
+    return g * fused_rows_per_group(ng) < 5 ? g * fused_rows_per_group(ng) : 5;
+}
+
+// One pass = one row group of one element.  E, P: descriptor and plan of this element (shared memory).  On entry the
+// first gather tile of this pass (`first_mt` modes) is in flight (cp.async); `after_first_sync` runs behind the first
+// barrier of the pass, `after_grad` once U is dead (it starts the next pass's gather).
+template <bool FLUID, int NT, int NWW, typename GatherFn, typename AfterSyncFn, typename AfterGradFn>
+__device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const ElemDesc &E, const FftPlan &P, int g, int first_mt, int tid,
+                                           GatherFn gather, AfterSyncFn after_first_sync, AfterGradFn after_grad) {
     constexpr int NC = FLUID ? 1 : 3, NPAIR = FLUID ? 2 : 3;
     constexpr int US = NC * AX_NPE;                   // row stride of U (odd)
-    constexpr int NCOLS = NPAIR * AX_NPE;
     constexpr int NHW = NT / 16;
-    constexpr int PP = (AX_NPE + NHW - 1) / NHW;      // point passes per thread
-    constexpr int QIT = NT >= 256 ? 4 : 2;   // 16-mode chunks per quad tile (the pointwise term r lives in registers)
+    constexpr int QIT = 4;                            // in-group (point, 16-mode chunk) items per half-warp and quad tile: their pointwise term r lives in registers
     float2 *const U = cx.U, *const TW = cx.TW, *const Z = cx.Z;
     const int hw = tid >> 4, t = tid & 15;
-    const int N = NCT ? NCT : E.nr, nu = N / 2, M = nu + 1, Mt = E.mt;
+    const int N = E.nr, nu = N / 2, M = nu + 1, Mt = E.mt;
     const int ldz = fused_ldz(N);
     const bool nyq = (N & 1) == 0;
     const bool axial = E.axial != 0, tiso = !FLUID && E.tiso != 0;
-    const int law = E.law;
+    const int ng = E.ng;
+    const int r0 = fused_row_begin(ng, g), r1 = fused_row_begin(ng, g + 1);
+    const int p0 = 5 * r0, np = 5 * (r1 - r0);       // points of this pass: [p0, p0 + np)
+    const int ncols = NPAIR * np, cs = np * ldz;      // column of (pair pr, local point pl) = Z + (pr * np + pl) * ldz
 
-    // ------------------------------------------------------------ gather (prefetched) + grad, Mt modes at a time   @phase gather wait + grad
-    for (int a0 = 0; a0 < M; a0 += Mt) {
-        const int mt = min(Mt, M - a0);
+    // ------------------------------------------------------------ gather (prefetched) + grad, one tile of modes at a time   @phase gather wait + grad
+    for (int a0 = 0, mt = first_mt; a0 < M; a0 += mt, mt = min(Mt, M - a0)) {
         if (a0) {
             cta_sync<NT, NWW>();
             gather(E, a0, mt, -1);
@@ -391,120 +376,128 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
             for (int row = hw; row < US; row += NHW) U[row].y = 0.f;
         cta_sync<NT, NWW>();
         if (a0 == 0) after_first_sync();
-#pragma unroll
-        for (int pp = 0; pp < PP; ++pp) {
-            const int p = pp * NHW + hw;
-            if (p < AX_NPE) {
-                const int i = p / 5, j = p - 5 * i;
-                GCoef gc;
+        // items = (local point, 16-mode chunk of the tile), point-major; a half-warp takes a contiguous run of items
+        const int nch = (mt + 15) >> 4, nitem = np * nch, ipw = (nitem + NHW - 1) / NHW;
+        int pl_cur = -1;
+        GCoef gc;
+        PointGeom gm;
+        float tr[4] = {0.f, 1.f, 0.f, 1.f};
+        bool ax0 = false;
+        int i = 0, j = 0;
+        for (int it = hw * ipw, ie = min(nitem, hw * ipw + ipw); it < ie; ++it) {
+            const int pl = it / nch, ch = it - pl * nch;
+            if (pl != pl_cur) {
+                pl_cur = pl;
+                const int p = p0 + pl;
+                i = p / 5;
+                j = p - 5 * i;
                 load_gcoef(gc, axial, i, j);
-                const PointGeom g = load_geom(cx.sgeom, 0, p);
-                const bool ax0 = axial && i == 0;
-                float tr[4] = {0.f, 1.f, 0.f, 1.f};
+                gm = load_geom(cx.sgeom, 0, p);
+                ax0 = axial && i == 0;
                 if (tiso) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tr[k] = cx.sgeom[(5 + k) * AX_NPE + p];
                 }
-                float2 *zp = Z + p * ldz;
-                for (int a = t; a < mt; a += 16) {
-                    const int alpha = a0 + a;
-                    const bool dead = nyq && alpha == nu;
-                    if constexpr (!FLUID) {
-                        float2 ee[6];
-                        grad6_mm(U + a * US, i, j, gc, g, (float)alpha, ax0, ee);
-                        if (dead) {
+            }
+            const int a = ch * 16 + t;
+            if (a < mt) {
+                const int alpha = a0 + a;
+                const bool dead = nyq && alpha == nu;
+                float2 *zp = Z + pl * ldz;
+                if constexpr (!FLUID) {
+                    float2 ee[6];
+                    grad6_mm(U + a * US, i, j, gc, gm, (float)alpha, ax0, ee);
+                    if (dead) {
 #pragma unroll
-                            for (int c = 0; c < 6; ++c) ee[c] = czero();
-                        }
-                        if (tiso) rot_spz_to_rtz(ee, tr[0], tr[1], tr[2], tr[3]);
-#pragma unroll
-                        for (int pr = 0; pr < 3; ++pr) zform_store(zp + pr * AX_NPE * ldz, N, alpha, ee[2 * pr], ee[2 * pr + 1]);
-                    } else {
-                        float2 ee[3];
-                        grad_fluid_mm(U + a * US, i, j, gc, g, (float)alpha, ax0, ee);
-                        if (dead) ee[0] = ee[1] = ee[2] = czero();
-                        zform_store(zp, N, alpha, ee[0], ee[1]);
-                        zform_store(zp + AX_NPE * ldz, N, alpha, ee[2], czero());
+                        for (int c = 0; c < 6; ++c) ee[c] = czero();
                     }
+                    if (tiso) rot_spz_to_rtz(ee, tr[0], tr[1], tr[2], tr[3]);
+#pragma unroll
+                    for (int pr = 0; pr < 3; ++pr) zform_store(zp + pr * cs, N, alpha, ee[2 * pr], ee[2 * pr + 1]);
+                } else {
+                    float2 ee[3];
+                    grad_fluid_mm(U + a * US, i, j, gc, gm, (float)alpha, ax0, ee);
+                    if (dead) ee[0] = ee[1] = ee[2] = czero();
+                    zform_store(zp, N, alpha, ee[0], ee[1]);
+                    zform_store(zp + cs, N, alpha, ee[2], czero());
                 }
             }
         }
     }
     cta_sync<NT, NWW>();   // Z complete, U dead
-    after_grad();      // @phase next-element gather issue
+    after_grad();      // @phase next-pass gather issue
 
     // ------------------------------------------------------------ c2r (SolverFFTW_N6::computeC2R, unnormalised, sign +)   @phase c2r
-    if constexpr (NCT != 0) {
-        CtFft<NT, NWW, NCOLS, NCT, 0, NCT, 0>::inverse(Z, TW, tid);
-    } else {
+    {
         int L = N;
         for (int s = 0; s < P.nstages; ++s) {
             const int R = P.radix[s];
-            fused_stage_dispatch<+1, true, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+            fused_stage_dispatch<+1, true, NT>(R, Z, N, L, ncols, TW + (P.stw_off[s] - P.stw_base), tid);
             L /= R;
             cta_sync<NT, NWW>();
         }
     }
 
     // ------------------------------------------------------------ physical space: stress (+ SLS attenuation)   @phase stress
-    physical_space<FLUID, NT>(E, cx.coef, cx.attpar, cx.attstate, Z, N, ldz, 0, AX_NPE, tid);
+    physical_space<FLUID, NT>(E, cx.coef, cx.attpar, cx.attstate, Z, N, ldz, p0, np, tid);
     cta_sync<NT, NWW>();
 
     // ------------------------------------------------------------ r2c (computeR2C; the 1/Nr is applied at load below)   @phase r2c
-    if constexpr (NCT != 0) {
-        CtFft<NT, NWW, NCOLS, NCT, 0, NCT, 0>::forward(Z, TW, tid);
-    } else {
+    {
         int L = 1;
         for (int s = P.nstages - 1; s >= 0; --s) {
             const int R = P.radix[s];
             L *= R;
-            fused_stage_dispatch<-1, false, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+            fused_stage_dispatch<-1, false, NT>(R, Z, N, L, ncols, TW + (P.stw_off[s] - P.stw_base), tid);
             cta_sync<NT, NWW>();
         }
     }
 
-    // ------------------------------------------------------------ quad + scatter, 16 * QIT modes at a time   @phase quad-pre
+    // ------------------------------------------------------------ quad + scatter, a tile of 16-mode chunks at a time   @phase quad-pre
+    // In-group items (local point, chunk): half-warp hw owns items [QIT * hw, QIT * hw + QIT) of the tile, pre and post, so
+    // that the pointwise term r never leaves its registers.  A tile has `sch` chunks with np * sch <= QIT * NHW items.
     const float sc = 1.f / (float)N;   // SolverFFTW_N6::computeR2C scaling (SolverFFTW_N6.cpp:47-48)
-    for (int a0 = 0; a0 < M; a0 += 16 * QIT) {
-        float2 r[PP][QIT][NC];
-        // pointwise half, in place: slot beta <- X, slot N - beta <- Y (beta = 0: the spare slot N); r stays in registers
+    const int nchq = (M + 15) >> 4;
+    const int sch = max(1, min(nchq, (QIT * NHW) / np));
+    const int nout = AX_NPE - np;      // points outside the group: xi-partial sums only
+    for (int c0 = 0; c0 < nchq; c0 += sch) {
+        const int nchs = min(sch, nchq - c0), nin = np * nchs;
+        float2 r[QIT][NC];
+        // pointwise half, in place: slot beta <- X, slot N - beta <- Y (beta = 0: the spare slot N)
 #pragma unroll
-        for (int pp = 0; pp < PP; ++pp) {
-            const int p = pp * NHW + hw;
-            if (p < AX_NPE) {
-                const int i = p / 5;
-                const PointGeom g = load_geom(cx.sgeom, 0, p);
-                const bool ax0 = axial && i == 0;
-                float tr[4] = {0.f, 1.f, 0.f, 1.f};
-                if (tiso) {
+        for (int q = 0; q < QIT; ++q) {
+            const int it = hw * QIT + q;
+            if (it < nin) {
+                const int pl = it / nchs, ch = it - pl * nchs;
+                const int p = p0 + pl, i = p / 5;
+                const int beta = (c0 + ch) * 16 + t;
+                if (beta < M && !(nyq && beta == nu)) {
+                    const PointGeom gm = load_geom(cx.sgeom, 0, p);
+                    const bool ax0 = axial && i == 0;
+                    float2 *zp = Z + pl * ldz;
+                    if constexpr (!FLUID) {
+                        float2 s[6], X[3], Y[3];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tr[k] = cx.sgeom[(5 + k) * AX_NPE + p];
-                }
-                float2 *zp = Z + p * ldz;
+                        for (int pr = 0; pr < 3; ++pr) zform_load(zp + pr * cs, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
+                        if (tiso) {
+                            float tr[4];
 #pragma unroll
-                for (int q = 0; q < QIT; ++q) {
-                    const int beta = a0 + 16 * q + t;
-                    if (beta < M && !(nyq && beta == nu)) {
-                        if constexpr (!FLUID) {
-                            float2 s[6], X[3], Y[3];
-#pragma unroll
-                            for (int pr = 0; pr < 3; ++pr)
-                                zform_load(zp + pr * AX_NPE * ldz, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
-                            if (tiso) rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
-                            quad6_pre(s, g, (float)beta, ax0, X, Y, r[pp][q]);
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                zp[c * AX_NPE * ldz + beta] = X[c];
-                                zp[c * AX_NPE * ldz + N - beta] = Y[c];
-                            }
-                        } else {
-                            float2 s[3], X, Y, dummy;
-                            zform_load(zp, N, beta, sc, s[0], s[1]);
-                            zform_load(zp + AX_NPE * ldz, N, beta, sc, s[2], dummy);
-                            quad_fluid_pre(s, g, (float)beta, ax0, X, Y, r[pp][q][0]);
-                            zp[beta] = X;
-                            zp[N - beta] = Y;
+                            for (int k = 0; k < 4; ++k) tr[k] = cx.sgeom[(5 + k) * AX_NPE + p];
+                            rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
                         }
+                        quad6_pre(s, gm, (float)beta, ax0, X, Y, r[q]);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            zp[c * cs + beta] = X[c];
+                            zp[c * cs + N - beta] = Y[c];
+                        }
+                    } else {
+                        float2 s[3], X, Y, dummy;
+                        zform_load(zp, N, beta, sc, s[0], s[1]);
+                        zform_load(zp + cs, N, beta, sc, s[2], dummy);
+                        quad_fluid_pre(s, gm, (float)beta, ax0, X, Y, r[q][0]);
+                        zp[beta] = X;
+                        zp[N - beta] = Y;
                     }
                 }
             }
@@ -512,38 +505,58 @@ __device__ __forceinline__ void fused_element(const FusedCtx<FLUID> &cx, const E
         cta_sync<NT, NWW>();
         // tensor-product half + Point::gatherStiffFromElement (SolidPoint.cpp:197-209)   @phase quad-post + scatter
 #pragma unroll
-        for (int pp = 0; pp < PP; ++pp) {
-            const int p = pp * NHW + hw;
-            if (p < AX_NPE) {
-                const int i = p / 5, j = p - 5 * i;
-                GCoef gc;
-                load_gcoef(gc, axial, i, j);
-                const int nlive = E.pt_nlive[p];
-                float2 *const dst = cx.stiff + (size_t)E.pt_off[p];
-                const int st = E.pt_stride[p];
+        for (int q = 0; q < QIT; ++q) {
+            const int it = hw * QIT + q;
+            if (it < nin) {
+                const int pl = it / nchs, ch = it - pl * nchs;
+                const int p = p0 + pl, i = p / 5, j = p - 5 * i;
+                const int beta = (c0 + ch) * 16 + t;
+                if (beta < M && !(nyq && beta == nu) && beta < E.pt_nlive[p]) {
+                    GCoef gc;
+                    load_gcoef(gc, axial, i, j);
+                    float2 *const dst = cx.stiff + (size_t)E.pt_off[p];
+                    const int st = E.pt_stride[p];
 #pragma unroll
-                for (int q = 0; q < QIT; ++q) {
-                    const int beta = a0 + 16 * q + t;
-                    if (beta < M && !(nyq && beta == nu) && beta < nlive) {
+                    for (int c = 0; c < NC; ++c) {
+                        float2 f = r[q][c];
+                        const float2 *zx = Z + c * cs + j * ldz + beta;                         // X(k, j), k = r0 .. r1 - 1
+                        const float2 *zy = Z + c * cs + (i - r0) * 5 * ldz + N - beta;          // Y(i, k), k = 0 .. 4
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            float2 f = r[pp][q][c];
-                            const float2 *zx = Z + (c * AX_NPE + j) * ldz + beta;           // X(k, j), k = 0..4
-                            const float2 *zy = Z + (c * AX_NPE + i * 5) * ldz + N - beta;   // Y(i, k)
-#pragma unroll
-                            for (int k = 0; k < 5; ++k) {
-                                f = cfma(gc.gxi_row[k], zx[k * 5 * ldz], f);
-                                f = cfma(gc.geta_row[k], zy[k * ldz], f);
-                            }
-                            if (beta == 0) f.y = 0.f;
-                            atomicAdd(dst + (size_t)c * st + beta, make_float2(-f.x, -f.y));   // stiff -= f (RED.ADD.F32x2)
+                        for (int k = 0; k < 5; ++k) {   // static register indices: the row range is a (warp-uniform) predicate
+                            if (k >= r0 && k < r1) f = cfma(gc.gxi_row[k], zx[(k - r0) * 5 * ldz], f);
+                            f = cfma(gc.geta_row[k], zy[k * ldz], f);
                         }
+                        if (beta == 0) f.y = 0.f;
+                        atomicAdd(dst + (size_t)c * st + beta, make_float2(-f.x, -f.y));   // stiff -= f (RED.ADD.F32x2)
                     }
                 }
             }
         }
+        // points of the other rows: f(i', j) += sum_{k in group} G_xi(i', k) X(k, j)
+        for (int it = hw; it < nout * nchs; it += NHW) {
+            const int po = it / nchs, ch = it - po * nchs;
+            const int p = po < p0 ? po : po + np;          // skip [p0, p0 + np)
+            const int i = p / 5, j = p - 5 * i;
+            const int beta = (c0 + ch) * 16 + t;
+            if (beta < M && !(nyq && beta == nu) && beta < E.pt_nlive[p]) {
+                GCoef gc;
+                load_gcoef(gc, axial, i, j);
+                float2 *const dst = cx.stiff + (size_t)E.pt_off[p];
+                const int st = E.pt_stride[p];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float2 f = czero();
+                    const float2 *zx = Z + c * cs + j * ldz + beta;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+                        if (k >= r0 && k < r1) f = cfma(gc.gxi_row[k], zx[(k - r0) * 5 * ldz], f);
+                    if (beta == 0) f.y = 0.f;
+                    atomicAdd(dst + (size_t)c * st + beta, make_float2(-f.x, -f.y));
+                }
+            }
+        }
     }
-    // the barrier after cp_async_wait_all at the top of the next element separates these reads of Z from its grad
+    // the barrier after cp_async_wait_all at the top of the next pass separates these reads of Z from its grad
 }
 
 // ---------------------------------------------------------------- split pipeline, middle kernel
@@ -588,7 +601,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? AX_FFT_MIN_CTAS : NT <= 512 ? 
         int L = N;
         for (int s = 0; s < P.nstages; ++s) {
             const int R = P.radix[s];
-            fused_stage_dispatch<+1, true, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+            fused_stage_dispatch<+1, true, NT>(R, Z, N, L, NCOLS, TW + (P.stw_off[s] - P.stw_base), tid);
             L /= R;
             __syncthreads();
         }
@@ -600,7 +613,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? AX_FFT_MIN_CTAS : NT <= 512 ? 
         for (int s = P.nstages - 1; s >= 0; --s) {
             const int R = P.radix[s];
             L *= R;
-            fused_stage_dispatch<-1, false, NT, NCOLS>(R, Z, N, L, TW + (P.stw_off[s] - P.stw_base), tid);
+            fused_stage_dispatch<-1, false, NT>(R, Z, N, L, NCOLS, TW + (P.stw_off[s] - P.stw_base), tid);
             __syncthreads();
         }
     }
@@ -643,7 +656,9 @@ struct NwArgs {
 #ifndef AX_NW_NT
 #define AX_NW_NT (512 - 32 * AX_NWW)   // compute threads of that launch
 #endif
-#define NW_CHR 160             // rows (complex entries) per chunk
+#ifndef NW_CHR
+#define NW_CHR 96              // rows (complex entries) per chunk (160: 31 KB of stages per CTA, 96: 19 KB)
+#endif
 #define NW_CHS (NW_CHR + 2)    // stage row capacity: the 16-byte aligned superset of a chunk
 #ifndef NW_NSTAGE
 #define NW_NSTAGE 3
@@ -699,9 +714,10 @@ __device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, uns
                 if (p >= 0) break;
                 service();
                 __nanosleep(200);
-                if (spins > (1u << 22)) {                 // ~1 s: never hang the GPU on a bookkeeping error
-                    if (lane == 0) nw.ctl[3] = 1u;
-                    return false;
+                if (spins > (1u << 24)) {                 // ~4 s of waiting for a producer: a bookkeeping error.  Never hang the GPU,
+                    if (lane == 0) nw.ctl[3] = 1u;        // never carry on with a point that was not advanced: flag it and abort the
+                    __threadfence_system();               // launch (the next API call reports the failed launch)
+                    __trap();
                 }
             }
             if (lane == 0) {
@@ -780,19 +796,18 @@ __device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, uns
     }
 }
 
-#include "fused_wp.cuh"
-
 // ---------------------------------------------------------------- the kernel   @phase kernel loop
 // grid: persistent, one CTA per SM; block NT compute threads (+ 32 * NWW Newmark threads).  work[0] = next element index
 // (starts at gridDim.x), work[1] = number of warps that have finished; the last one re-arms the counters for the next
-// launch (graph replay).
-// WP: warp-per-point element body (fused_wp.cuh; NT = 800) instead of the thread-per-(mode, point) body above.
-template <bool FLUID, int NT, int NWW, int NCT1, bool WP = false>
+// launch (graph replay).  tile_cap: float2 capacity R of the tile region (the per-element offsets twoff / zoff of the
+// descriptors refer to it); the Newmark warps' stage buffers start right behind it.
+#define NW_RING 8   // arrival-code ring (elements finished by the compute warps, not yet posted by Newmark warp 0)
+template <bool FLUID, int NT, int NWW>
 __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
                    const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
                    const float *__restrict__ attpar, float *__restrict__ attstate, const float2 *__restrict__ displ,
-                   float2 *__restrict__ stiff, int u_cap, int tw_cap, int z_cap, unsigned *__restrict__ work, const NwArgs nw) {
+                   float2 *__restrict__ stiff, int tile_cap, unsigned *__restrict__ work, const NwArgs nw) {
     constexpr int NC = FLUID ? 1 : 3;
     constexpr int US = NC * AX_NPE;
     constexpr int NHW = NT / 16;
@@ -802,12 +817,13 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     extern __shared__ __align__(16) float2 smem[];
     __shared__ ElemDesc sE[2];
     __shared__ FftPlan sP[2];
-    __shared__ float sGeom[2][9 * AX_NPE];   // geometry (+ trig) of the current / next element, staged with its gather
+    __shared__ float sGeom[2][9 * AX_NPE];   // geometry (+ trig) of the current / next element, staged with its first gather
     __shared__ int sIdx[3];   // ring of element indices: current, next, next-next
     __shared__ unsigned long long sBar[NWARP][NW_NSTAGE];
-    __shared__ int sArrCode[4][AX_NPE];   // ring: pt_nw codes of the elements whose scatter is complete ...
-    __shared__ volatile int sArrHead;     // ... up to this count (written by compute thread 0 behind a barrier)
-    __shared__ volatile int sCtaDone;     // the compute warps have handed over their last element
+    __shared__ int sArrCode[NW_RING][AX_NPE];   // ring: pt_nw codes of the elements whose scatter is complete ...
+    __shared__ volatile int sArrHead;           // ... up to this count (written by compute thread 0 behind a barrier)
+    __shared__ volatile int sArrSeen;           // ... of which Newmark warp 0 has posted this many (back-pressure for the ring)
+    __shared__ volatile int sCtaDone;           // the compute warps have handed over their last element
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const bool nw_on = NWW > 0 && nw.on != 0;
@@ -817,7 +833,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
         for (int s = 0; s < NW_NSTAGE; ++s) mbar_init(&sBar[warp][s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (tid == 0) { sArrHead = 0; sCtaDone = 0; }
+    if (tid == 0) { sArrHead = 0; sArrSeen = 0; sCtaDone = 0; }
     auto stamp = [&](int k) {
         if (nw.dbg) {
             unsigned long long t;
@@ -830,8 +846,8 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
 
     if (tid < NT) {
         const int hw = tid >> 4, t = tid & 15;
-        FusedCtx<FLUID> cx{geom, coef, attpar, attstate, displ, stiff, smem, smem + u_cap, smem + u_cap + tw_cap, sGeom[0]};
-        float2 *const U = cx.U;
+        FusedCtx<FLUID> cx{geom, coef, attpar, attstate, displ, stiff, smem, smem, smem, sGeom[0]};
+        float2 *const U = smem;
 
         // descriptor + plan of element el -> slot s (plain loads; visible after the next barrier)
         auto load_desc = [&](int s, int el) {
@@ -844,7 +860,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
         // Point::scatterDisplToElement (SolidPoint.cpp:175-195) for modes [a0, a0 + mt): half-warp per (component, point)
         // slot >= 0: first tile of an element -- its geometry goes to sGeom[slot] with the same cp.async group
         auto gather = [&](const ElemDesc &E, int a0, int mt, int slot) {
-            if (AX_SGEOM && slot >= 0) {
+            if (slot >= 0) {
                 const bool ti = !FLUID && E.tiso != 0;
                 if (tid < 5 * AX_NPE || (ti && tid >= 128 && tid < 128 + 4 * AX_NPE)) {
                     const float *src = tid < 128 ? geom + E.geom_off + tid : geom + E.trig_off + (tid - 128);
@@ -871,52 +887,68 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
             load_desc(0, e);
             if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
             cta_sync<NT, NWW>();
-            gather(sE[0], 0, min(sE[0].mt, sE[0].nu + 1), 0);
-            float gv = 0.f, gv_next = 0.f;   // WP: geometry of the current / next element (wp_load_geom)
-            if constexpr (WP) gv = wp_load_geom(sE[0], geom, tid, FLUID);
-            int tw_plan = -1;
+            int first_mt = min(sE[0].mt, sE[0].nu + 1);   // modes of the gather tile in flight (first tile of the coming pass)
+            gather(sE[0], 0, first_mt, 0);
+            int tw_plan = -1, tw_at = -1;
             for (int it = 0, k = 0; e < nelem; it ^= 1, k = (k == 2 ? 0 : k + 1)) {
                 const ElemDesc &E = sE[it];
                 const FftPlan &P = sP[it];
-                cx.sgeom = AX_SGEOM ? sGeom[it] : geom + E.geom_off;
+                cx.sgeom = sGeom[it];
+                cx.TW = smem + E.twoff;
+                cx.Z = smem + E.zoff;
                 const int kn = k == 2 ? 0 : k + 1, knn = kn == 2 ? 0 : kn + 1;   // ring slots of the next two elements
-                if (tw_plan != E.plan_id) {   // TW is idle here: the FFT stages of the previous element are barrier-separated
-                    const int tb = P.stw_base + (WP ? P.stw2_delta : 0);   // WP: the p-major copies of the stage tables
-                    for (int k = tid; k < P.stw_len; k += NT) cx.TW[k] = stwpool[tb + k];
-                    tw_plan = E.plan_id;
-                }
                 // moduli of this element -> L2 while gather/grad/c2r run
                 {
                     const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
                     const float *cb = coef + E.coef_off;
                     const int nline = (ncoef * AX_NPE * E.nr + 31) / 32;
-                    for (int k = tid; k < nline; k += NT) prefetch_l2(cb + (size_t)k * 32);
+                    for (int q = tid; q < nline; q += NT) prefetch_l2(cb + (size_t)q * 32);
                 }
-                // next element: descriptor behind the first barrier, displacement (cp.async into the dead U) behind grad
-                auto after_first_sync = [&]() {
-                    if (nw_on && tid == 0) {   // the previous element's scatter is complete (barrier): hand it to Newmark warp 0
-                        __threadfence_block();
-                        sArrHead = n_done;
-                    }
-                    const int en = sIdx[kn];   // fetched during the previous element
-                    if (en < nelem) load_desc(it ^ 1, en);
-                };
-                auto after_grad = [&]() {
-                    if (tid == 0) sIdx[knn] = (int)atomicAdd(&work[0], 1u);   // needed one element from now: latency hidden
-                    if (sIdx[kn] < nelem) {
-                        const ElemDesc &En = sE[it ^ 1];
-                        gather(En, 0, min(En.mt, En.nu + 1), it ^ 1);
-                        if constexpr (WP) gv_next = wp_load_geom(En, geom, tid, FLUID);
-                    }
-                };
-                if constexpr (WP) {
-                    if (NCT1 != 0 && E.nr == NCT1) wp_element<FLUID, NT, NWW, NCT1>(cx, E, P, tid, gv, gather, after_first_sync, after_grad);
-                    else wp_element<FLUID, NT, NWW, 0>(cx, E, P, tid, gv, gather, after_first_sync, after_grad);
-                    gv = gv_next;
-                } else if (NCT1 != 0 && E.nr == NCT1) fused_element<FLUID, NT, NWW, NCT1>(cx, E, P, tid, gather, after_first_sync, after_grad);
-                else fused_element<FLUID, NT, NWW, 0>(cx, E, P, tid, gather, after_first_sync, after_grad);
+                const int ng = E.ng;
+                for (int g = 0; g < ng; ++g) {
+                    const bool last = g + 1 == ng;
+                    int next_mt = 0;
+                    // next element: descriptor behind the first barrier of the element, displacement (cp.async into the dead U) behind grad
+                    auto after_first_sync = [&]() {
+                        if (g != 0) return;
+                        if (nw_on && tid == 0) {   // the previous element's scatter is complete (barrier): hand it to Newmark warp 0
+                            __threadfence_block();
+                            sArrHead = n_done;
+                        }
+                        const int en = sIdx[kn];   // fetched during the previous element
+                        if (en < nelem) load_desc(it ^ 1, en);
+                        // twiddle tables of this element's plan.  Its TW region may overlap the previous element's Z: written only
+                        // now, behind the barrier every thread passes after the previous element's last read of Z; the
+                        // barrier behind grad publishes it before the first FFT stage
+                        if (tw_plan != E.plan_id || tw_at != E.twoff) {
+                            const int tb = P.stw_base;
+                            for (int q = tid; q < P.stw_len; q += NT) cx.TW[q] = stwpool[tb + q];
+                            tw_plan = E.plan_id;
+                            tw_at = E.twoff;
+                        }
+                    };
+                    auto after_grad = [&]() {
+                        if (!last) {               // next row group of this element: same displacement again
+                            next_mt = min(E.mt, E.nu + 1);
+                            gather(E, 0, next_mt, -1);
+                            return;
+                        }
+                        if (tid == 0) sIdx[knn] = (int)atomicAdd(&work[0], 1u);   // needed one element from now: latency hidden
+                        if (sIdx[kn] < nelem) {
+                            const ElemDesc &En = sE[it ^ 1];
+                            // the first tile of the next element lands in U while this element's TW / Z are live: stay below both
+                            next_mt = min(min(En.mt, En.nu + 1), (E.twoff / US) & ~15);
+                            gather(En, 0, next_mt, it ^ 1);
+                        }
+                    };
+                    fused_pass<FLUID, NT, NWW>(cx, E, P, g, first_mt, tid, gather, after_first_sync, after_grad);
+                    first_mt = next_mt;
+                }
                 if (nw_on) {
-                    if (tid < AX_NPE) sArrCode[n_done & 3][tid] = E.pt_nw[tid];
+                    if (tid < AX_NPE) {
+                        while (n_done - sArrSeen >= NW_RING) __nanosleep(100);   // ring full: Newmark warp 0 is behind
+                        sArrCode[n_done & (NW_RING - 1)][tid] = E.pt_nw[tid];
+                    }
                     ++n_done;
                 }
                 e = sIdx[kn];
@@ -935,13 +967,13 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
         }
         if (tid == 0) stamp(1);
         // element queue empty: the compute warps join the Newmark consumers (their stages live in the now idle tile memory)
-        if (nw_on && (warp + 1) * NW_WARP_SMEM <= (u_cap + tw_cap + z_cap) * (int)sizeof(float2)) {
+        if (nw_on && (warp + 1) * NW_WARP_SMEM <= tile_cap * (int)sizeof(float2)) {
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy tile traffic before the TMA writes
             nw_consumer(nw, smem + warp * (NW_WARP_SMEM / 8), sBar[warp], lane, [] {});
         }
     } else if (NWW > 0) {
         if (nw_on) {
-            float2 *stage = smem + ((u_cap + tw_cap + z_cap + 1) & ~1) + (warp - NT / 32) * (NW_WARP_SMEM / 8);
+            float2 *stage = smem + ((tile_cap + 1) & ~1) + (warp - NT / 32) * (NW_WARP_SMEM / 8);
             if (warp == NT / 32) {
                 // Newmark warp 0 posts the arrivals: a point whose last element has scattered goes to the ready queue.
                 // (Kept off the compute warps: the release fence would sit on their critical path once per element.)
@@ -952,7 +984,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                         __threadfence_block();
                         __threadfence();   // release: the CTA's forces (ordered before sArrHead by its barrier) before the counts
                         for (; seen < h; ++seen) {
-                            const int code = lane < AX_NPE ? sArrCode[seen & 3][lane] : -1;
+                            const int code = lane < AX_NPE ? sArrCode[seen & (NW_RING - 1)][lane] : -1;
                             if (code >= 0) {
                                 const int p = code & 0xffffff, need = code >> 24;
                                 if (atomicAdd(&nw.cnt[p], 1) + 1 == need) {
@@ -963,6 +995,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                             }
                         }
                         __syncwarp();
+                        if (lane == 0) sArrSeen = seen;
                     }
                 };
                 nw_consumer(nw, stage, sBar[warp], lane, service);

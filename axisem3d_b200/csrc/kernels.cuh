@@ -30,7 +30,9 @@ struct ElemDesc {
     long long att_state_off;   // 1D: float2 [nsls+1][6][P][M]   3D: float [nsls+1][6][P][Nr]; slot nsls = stressR
     long long scratch_off;     // float2 [NPAIR][25][Nr] inside the scratch ring
     long long prt_off;         // float  particle relabelling X: 1D [4][25], 3D [4][25][Nr] (digit-reversed phi), in the moduli pool
-    int prt, pad_;             // 1: the element carries a PRT (9-component path; trig_off is valid for fluid elements too)
+    int prt;                   // 1: the element carries a PRT (9-component path; trig_off is valid for fluid elements too)
+    int ng;                    // fused kernel: number of row-group passes (1, 2, 3 or 5)
+    int zoff, twoff;           // fused kernel: float2 offsets of the Z-form columns and of the twiddle tables in the tile region
 };
 
 struct PointTab {              // one per field family (solid: ncomp = 3, fluid: ncomp = 1)

@@ -1,13 +1,15 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json's metric on the cfg2 workload: GLL-point x Fourier-mode Newmark steps / second.
+"""bench.py -- BASELINE.json's metric: GLL-point x Fourier-mode Newmark steps / second, % of the HBM roofline.
 
 A "step" is one iteration of Newmark::solve's loop body (Newmark.cpp:47-93: updateNewmark, applySource,
-computeStiff, coupleSolidFluid[, assembleStiff]) over the whole mesh.  Workload at N = 1 = configs[1]:
-the 50 s-period mesh size (2016 quads, ~32.7 k GLL points), 3D isotropic elastic model, constant Nu = 100
-(Nr = 208, capped by the circumference near the axis), no attenuation, fluid outer core with solid-fluid
-coupling -- on the synthetic structured mesh of axisem3d_b200/mesh_synth.py (the Exodus reader is out of the
-hot-path scope).  At N > 1 the mesh grows with N (72 N x 28 quads, weak scaling) and is cut into N
-contiguous parts with an NCCL halo sum per step.
+computeStiff, coupleSolidFluid, assembleStiff) over the whole mesh.  The default workload is the configuration the
+north star's target is quoted on, configs[3] = "cfg4": the 50 s-period mesh size (2016 quads, ~32.7 k GLL points), 3D
+model, per-point Nu 20 ... 500 (ragged FFT sizes), fluid outer core with solid-fluid coupling -- on the synthetic
+structured mesh of axisem3d_b200/mesh_synth.py.  cfg1 / cfg2 / cfg3 / cfg5 are selected with --config.
+
+Weak scaling (default): at N > 1 the mesh grows with N (72 N x 28 quads) and is cut into N parts by METIS k-way on the
+element dual graph (axisem3d_b200/partition.py; DualGraph.cpp:35-94), boundary-point stiffness summed over NVLink every
+step.  --scaling strong keeps the N = 8 mesh (576 x 28 = 16128 quads) for every N.
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one JSON line on rank 0)
     python bench.py --impl reference --steps K --warmup W    # CPU arm: oracle/oracle.c on the host cores
@@ -30,11 +32,18 @@ sys.path.insert(0, ROOT)
 METRIC = "GLL-point x Fourier-mode Newmark steps per second"
 UNIT = "point-modes/s"
 N_THETA, N_R, NU = 72, 28, 100
+STRONG_N = 8            # --scaling strong: the mesh every N runs is the N = 8 weak-scaling mesh
 
 
 def cfg4_nu(s, z):
     """configs[3]: per-point Nu 20 ... 500, growing with the distance from the axis (wisdom-style ragged expansion)."""
     return int(20 + 480 * min(1.0, s / 6371e3))
+
+
+def cfg5_nu(s, z):
+    """configs[4]: empirical Nu law in the spirit of EmpNrField (preloop/nrfield/EmpNrField.cpp:22-53): Nu grows with the
+    distance from the axis (the wavefield needs ~ 2 pi s / lambda_min azimuthal samples), capped at 1000."""
+    return int(min(1000, 24 + 1100 * (s / 6371e3) ** 0.85))
 
 
 CONFIGS = {
@@ -46,14 +55,25 @@ CONFIGS = {
     "cfg3": (dict(nu=200, law="aniso", model3d=True, attenuation="cg4", fluid3d=False),
              "cfg3: 3D anisotropic (21 C_ij) + CG4 SLS attenuation, Nu=200 (Nr=416), SF coupling through the outer core"),
     "cfg4": (dict(nu_fn=cfg4_nu, law="iso", model3d=True, attenuation=None),
-             "cfg4: 3D isotropic, per-point Nu 20..500 (Nr 42..1008), ragged FFT sizes"),
+             "cfg4: 3D isotropic, per-point Nu 20..500 (Nr up to 672 on this mesh), ragged FFT sizes, fluid core + SF coupling"),
+    # ~5 s-period mesh: 100 x the element count of the 50 s mesh (720 x 280 = 201600 quads), anisotropic + CG4 SLS, Nu <= 1000;
+    # only meaningful partitioned over 8 GPUs (bench.py --config cfg5 --gpus 8)
+    "cfg5": (dict(nu_fn=cfg5_nu, law="aniso", model3d=True, attenuation="cg4", fluid3d=False),
+             "cfg5: ~5 s-period synthetic mesh, 3D anisotropic + CG4 SLS attenuation, empirical Nu <= 1000 (Nr <= 2016)"),
 }
-CFG = "cfg2"
+CFG = "cfg4"
+CFG5_THETA, CFG5_R = 720, 280
 
 
-def make_mesh(n_theta, **kw):
+def mesh_shape(world, scaling):
+    if CFG == "cfg5":
+        return CFG5_THETA, CFG5_R
+    return N_THETA * (STRONG_N if scaling == "strong" else world), N_R
+
+
+def make_mesh(n_theta, n_r=None, **kw):
     from axisem3d_b200.mesh_synth import SynthMesh
-    args = dict(n_theta=n_theta, n_r=N_R, dtype_coef=np.float32)
+    args = dict(n_theta=n_theta, n_r=n_r or N_R, dtype_coef=np.float32)
     args.update(CONFIGS[CFG][0])
     args.update(kw)
     return SynthMesh(**args)
@@ -64,8 +84,14 @@ def stf_series(n):
     return np.exp(-((t - 40.0) / 12.0) ** 2).astype(np.float32)
 
 
-def workload_name(n_theta):
-    return "%s; 50 s-mesh-size synthetic meridional mesh (%d x %d = %d quads)" % (CONFIGS[CFG][1], n_theta, N_R, n_theta * N_R)
+def workload_name(n_theta, n_r=N_R):
+    return "%s; synthetic meridional mesh %d x %d = %d quads" % (CONFIGS[CFG][1], n_theta, n_r, n_theta * n_r)
+
+
+def element_weights(mesh):
+    """first-pass element cost for the partitioner (the reference starts from Nr, Mesh.cpp:88-101): Nr log Nr"""
+    nr = mesh.e_nr.astype(np.float64)
+    return nr * np.log2(np.maximum(nr, 2.0)) + 16.0
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -81,7 +107,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -94,13 +120,13 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -109,30 +135,37 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for k, nm in enumerate(names):
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_median": float(np.median(pw)) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_arm(steps, warmup, stride=9, min_seconds=0.0, max_seconds=25.0):
+def cpu_arm(steps, warmup, stride=9, min_seconds=0.0, max_seconds=25.0, n_theta=N_THETA):
     """Times oracle/oracle.c (C + OpenMP restatement on all host cores; the reference itself cannot be built here) on a
-    bounded sample of the cfg2 workload: every `stride`-th theta-column of the 72 x 28 mesh (same Nr distribution;
-    stride 1 = the whole mesh).  Runs `steps` steps, keeps going until `min_seconds` of CPU work, stops at `max_seconds`."""
+    bounded sample of the workload: every `stride`-th theta-column of the n_theta x 28 mesh (same Nr distribution;
+    stride 1 = the whole mesh).  Runs `steps` steps, keeps going until `min_seconds` of CPU work, stops at `max_seconds`.
+    The OpenMP thread count is set explicitly to the host's core count (torchrun exports OMP_NUM_THREADS=1)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from axisem_oracle import OracleDomain
     from c_oracle import COracle
-    mesh = make_mesh(N_THETA)
+    mesh = make_mesh(n_theta)
     dt = mesh.estimate_dt()
     e2p = np.where(mesh.ab[:, 0] % stride == stride // 2, 0, 1)
     d = OracleDomain(np.float32)
     rel = mesh.release(d, dt, rank=0, elem_to_proc=e2p)
     d.finalize()
     co = COracle(d)
+    try:
+        ncore = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncore = os.cpu_count() or 1
+    threads = co.set_threads(ncore)
     rng = np.random.default_rng(1)
     for fld in (d.S, d.F):
         a = fld["displ"]
@@ -150,32 +183,60 @@ def cpu_arm(steps, warmup, stride=9, min_seconds=0.0, max_seconds=25.0):
         el = time.perf_counter() - t0
         if el > max_seconds or (done >= steps and el >= min_seconds):
             break
-    return dict(value=work * done / el, unit=UNIT, cores=co.threads(), kind="port",
-                sample="%d of %d quads (%s of the %s mesh), %d point-modes per step, %d steps, %.1f s of "
-                       "C/OpenMP oracle on %d threads" % (len(rel["elements"]), mesh.nelem,
-                                                          "every theta-column" if stride == 1 else "every %d-th theta-column" % stride,
-                                                          CFG, work, done, el, co.threads()),
-                ms_per_step=1e3 * el / done, steps=done)
+    return dict(value=work * done / el, unit=UNIT, cores=threads, kind="port",
+                sample="%d of %d quads (%s of the %s mesh, %d x %d), %d point-modes per step, %d steps, %.1f s of "
+                       "C/OpenMP oracle on %d threads (of %d host cores)" % (
+                           len(rel["elements"]), mesh.nelem, "every theta-column" if stride == 1 else "every %d-th theta-column" % stride,
+                           CFG, n_theta, N_R, work, done, el, threads, ncore),
+                ms_per_step=1e3 * el / done, steps=done, elements=len(rel["elements"]), mesh_elements=int(mesh.nelem))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_arm(args.steps, args.warmup, stride=1, max_seconds=150.0)   # whole cfg2 mesh per step
+    if CFG == "cfg5":
+        print(json.dumps({"impl": "reference", "unavailable": "cfg5 (201600 quads, Nu <= 1000) does not fit the CPU arm's time budget; use cfg1-cfg4"}))
+        return
+    n_theta, n_r = mesh_shape(args.gpus, args.scaling)
+    # the same N x mesh the GPU arm steps at --gpus N, whole mesh per step, all host threads
+    r = cpu_arm(args.steps, args.warmup, stride=1, max_seconds=150.0, n_theta=n_theta)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
-            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(N_THETA), "note": "whole cfg2 mesh per step on the host cores (C/OpenMP restatement of the reference path; the reference binary cannot be built in this image)"},
+            "config": {"workload": workload_name(n_theta), "elements": r["mesh_elements"],
+                       "note": "whole mesh per step on the host cores (C/OpenMP restatement of the reference path; the reference binary cannot be built in this image)"},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------- our arm
+def global_receivers(mesh, nrec=128, seed=5):
+    """128 receivers (the template STATIONS file has 128) in the outermost solid layer of the GLOBAL mesh: element id,
+    azimuth, interpolation weights -- the same on every rank, so that an N-rank run and a 1-rank run record the same stations."""
+    surf = np.nonzero((mesh.ab[:, 1] == mesh.nr_ - 1) & ~mesh.is_fluid)[0]
+    rng = np.random.default_rng(seed)
+    eg = surf[rng.integers(0, len(surf), nrec)]
+    phi = rng.uniform(0, 2 * np.pi, nrec)
+    w = rng.uniform(0, 1, (nrec, 25))
+    w /= w.sum(axis=1, keepdims=True)
+    return eg, phi, w
+
+
+def register_receivers(dom, rel, eg, phi, w):
+    """registers the receivers that lie in this rank's elements; returns their indices in the global list"""
+    loc = {int(g): il for il, g in enumerate(rel["dec"].local_elems)}
+    mine = [k for k, g in enumerate(eg) if int(g) in loc]
+    if mine:
+        dom.setReceivers([rel["elements"][loc[int(eg[k])]].domain_tag for k in mine], phi[mine], w[mine])
+    return mine
+
+
 def run_ours(args):
     import torch
     from axisem3d_b200 import connectivity as CN
+    from axisem3d_b200 import partition as PT
     from axisem3d_b200.domain import Domain, nccl_unique_id
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,13 +254,18 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    n_theta = N_THETA * world
-    mesh = make_mesh(n_theta)
+    n_theta, n_r = mesh_shape(world, args.scaling)
+    mesh = make_mesh(n_theta, n_r)
     dt = mesh.estimate_dt()
     dom = Domain(local)
-    e2p = None
+    e2p, part_info = None, None
     if world > 1:
-        e2p = CN.partition_contiguous(mesh.e_nr.astype(np.float64), world)
+        if args.partition == "metis":
+            e2p, part_info = PT.partition_kway(mesh.conn, element_weights(mesh), world, imbalance=0.01, ntrials=4)
+        else:
+            e2p = CN.partition_contiguous(element_weights(mesh), world)
+            part_info = {"method": "contiguous weighted cuts of the element order"}
+        part_info.update(PT.halo_stats(mesh.conn, e2p))
     rel = mesh.release(dom, dt, rank=rank, elem_to_proc=e2p)
     src = mesh.make_source(rel["elements"], rel["dec"], amp=1e18)
     if src is not None:
@@ -216,19 +282,14 @@ def run_ours(args):
         halo = "nccl send/recv (eager steps)"
         if os.environ.get("AX3D_HALO", "peer") == "peer":
             dom.connectHalo(rel["msg"], rank, dist)     # NVLink peer-memory windows; steps replay as CUDA graphs
-            halo = "peer-memory windows over NVLink (k_halo_put / k_halo_wait_add), steps replayed as CUDA graphs"
+            halo = "peer-memory windows over NVLink (k_halo_put / k_halo_wait_add inside the step graph)"
 
-    # 128 receivers (the template STATIONS file has 128) in the outermost solid layer
-    surf = [e.domain_tag for e in rel["elements"] if e.kind == "solid"]
-    rng = np.random.default_rng(5)
-    nrec = 128
-    etags = [surf[i] for i in rng.integers(0, len(surf), nrec)]
-    w = rng.uniform(0, 1, (nrec, 25))
-    w /= w.sum(axis=1, keepdims=True)
-    dom.setReceivers(etags, rng.uniform(0, 2 * np.pi, nrec), w)
+    eg, phi, w = global_receivers(mesh)
+    mine = register_receivers(dom, rel, eg, phi, w)
 
     K, W = args.steps, max(args.warmup, 3)
-    stf = stf_series(W + 2 * K + 64)
+    NPAR = 10            # steps of the N-rank vs 1-rank parity check
+    stf = stf_series(NPAR + W + 2 * K + 64)
     work_local = dom.work_per_step()
     alg = dom.algorithmic_bytes()
 
@@ -238,66 +299,143 @@ def run_ours(args):
         dom.synchronize()
         torch.cuda.synchronize()
 
-    # ---- device-timed region: inputs resident in HBM
-    dom.runSteps(dt, stf[:W])
+    # ---- parity of the partitioned run (N > 1): the first NPAR steps from rest, seismograms at the 128 global receivers,
+    #      compared below with a single-domain run of the same global mesh on rank 0's GPU
+    seis_par = None
+    if world > 1 and not args.no_parity:
+        seis_par = dom.runStepsRecord(dt, stf[:NPAR]) if mine else np.zeros((NPAR, 0, 3), np.float32)
+        barrier()
+
+    # ---- device-timed region: inputs resident in HBM.  K steps per region (CUDA events on the launching stream, max over
+    #      ranks); the region is repeated until >= args.min_seconds of GPU time so that the clock sampler sees the load,
+    #      the median region is reported
+    dom.runSteps(dt, stf[NPAR:NPAR + W])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = dom.launch_count()
-    barrier()
-    ms = dom.runStepsTimed(dt, stf[W:W + K])
-    barrier()
-    launches = dom.launch_count() - l0
+    regions = []
+    t_start = time.perf_counter()
+    while True:
+        barrier()
+        regions.append(dom.runStepsTimed(dt, stf[NPAR + W:NPAR + W + K]))
+        barrier()
+        go = (time.perf_counter() - t_start) < args.min_seconds and len(regions) < 400
+        if dist is not None:
+            flag = torch.tensor([1.0 if go else 0.0], device="cuda")
+            dist.broadcast(flag, 0)
+            go = bool(flag.item() > 0)
+        if not go:
+            break
+    launches = (dom.launch_count() - l0) // len(regions)
     clocks = sampler.stop() if rank == 0 else None
     stable = dom.checkStability()
+    regions = np.array(regions, dtype=np.float64)
 
     # ---- end-to-end through the C-ABI with host buffers: ax3d_run_steps_record = Newmark::solve with the pointwise
     #      recorder (Newmark.cpp:49-70 order: update, record, source, stiff, couple, assemble).  Per step the host source
-    #      factor goes H2D through a pinned slot (8 bytes) and the 128 receiver samples come back D2H (one copy per batch of
+    #      factor goes H2D through a pinned slot (8 bytes) and the receiver samples come back D2H (one copy per batch of
     #      BATCH steps = the recorder's dump interval; the call returns only when the samples are in host memory).
     BATCH = 25
-    dom.runStepsRecord(dt, stf[:BATCH])      # graph variants of the recording path, record ring sized for a batch
-    dom.runStepsRecord(dt, stf[:3])
+    e2e_regions, seis_bytes_per_step = [], 0
+    if mine:
+        dom.runStepsRecord(dt, stf[:BATCH])      # graph variants of the recording path, record ring sized for a batch
+        dom.runStepsRecord(dt, stf[:3])
     barrier()
-    t0 = time.perf_counter()
-    done = 0
-    while done < K:
-        nb = min(BATCH, K - done)
-        seis = dom.runStepsRecord(dt, stf[W + K + done:W + K + done + nb])   # returns with the samples in host memory
-        done += nb
-    e2e_s = time.perf_counter() - t0         # per rank; the max over ranks is taken below
+    t_e2e = time.perf_counter()
+    while True:
+        barrier()
+        t0 = time.perf_counter()
+        done = 0
+        while done < K:
+            nb = min(BATCH, K - done)
+            s_ = stf[NPAR + W + K + done:NPAR + W + K + done + nb]
+            if mine:
+                seis = dom.runStepsRecord(dt, s_)   # returns with the samples in host memory
+                seis_bytes_per_step = int(seis[0].nbytes)
+            else:
+                dom.runSteps(dt, s_)
+                dom.synchronize()
+            done += nb
+        e2e_regions.append(time.perf_counter() - t0)         # per rank; the max over ranks is taken below
+        go = (time.perf_counter() - t_e2e) < 0.5 * args.min_seconds and len(e2e_regions) < 100
+        if dist is not None:
+            flag = torch.tensor([1.0 if go else 0.0], device="cuda")
+            dist.broadcast(flag, 0)
+            go = bool(flag.item() > 0)
+        if not go:
+            break
     barrier()
-    seis_bytes_per_step = int(seis[0].nbytes)
+    e2e_regions = np.array(e2e_regions, dtype=np.float64)
 
-    # ---- per-family device times and the dominant kernel's launch time: CUDA events on the launching stream around each
-    #      family / around the solid k_elem3d_fused launch, steps issued through ax3d_run_steps (eager, not the graph), so
-    #      the in-kernel Newmark is active exactly as in the timed region above
+    # ---- per-family and per-kernel device times: CUDA events on the launching stream around each family / each hot kernel,
+    #      steps issued through ax3d_run_steps (eager, not the graph), so the in-kernel Newmark is active exactly as above
     dom.enable_timers(True)
     dom.get_timers(reset=True)
-    dom.dominant_kernel(reset=True)
+    dom.kernel_stats(reset=True)
     nt = max(min(K, 12), 4)
     dom.runSteps(dt, stf[:nt])
     fam = dom.get_timers(reset=True) / nt          # ms: newmark, elements, sf+source, halo
-    dk_ms, dk_bytes = dom.dominant_kernel(reset=True)
+    kst = dom.kernel_stats(reset=True)
     dom.enable_timers(False)
 
     if dist is not None:
-        t = torch.tensor([ms, e2e_s, float(work_local), float(launches)], dtype=torch.float64, device="cuda")
+        t = torch.tensor(np.concatenate([regions, e2e_regions, [float(work_local), float(launches), float(seis_bytes_per_step)]]),
+                         dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, e2e_s = float(tmax[0]), float(tmax[1])
+        regions = tmax[:len(regions)].cpu().numpy()
+        e2e_regions = tmax[len(regions):len(regions) + len(e2e_regions)].cpu().numpy()
         work = mesh.work_per_step()          # global GLL points (shared points counted once)
-        launches = int(tsum[3])
+        launches = int(tsum[-2])
+        seis_bytes_per_step = int(tsum[-1])
+        alg_all = torch.tensor(alg, dtype=torch.float64, device="cuda")
+        dist.all_reduce(alg_all, op=dist.ReduceOp.SUM)
+        alg_job = alg_all.cpu().numpy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine, seis_par))
     else:
         work = work_local
+        alg_job = alg
+        gathered = None
+    ms = float(np.median(regions))
+    e2e_s = float(np.median(e2e_regions))
 
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return
+
+    # ---- parity: the same global mesh as ONE domain on this GPU, same source and receivers, first NPAR steps from rest
+    parity = None
+    if gathered is not None and not args.no_parity:
+        try:
+            one = Domain(local)
+            rel1 = mesh.release(one, dt)
+            s1 = mesh.make_source(rel1["elements"], rel1["dec"], amp=1e18)
+            if s1 is not None:
+                one.addSourceTerm(s1)
+            one.finalize()
+            register_receivers(one, rel1, eg, phi, w)
+            ref = one.runStepsRecord(dt, stf[:NPAR]).astype(np.float64)
+            got = np.zeros_like(ref)
+            seen = np.zeros(len(eg), dtype=bool)
+            for idx, sp in gathered:
+                if idx:
+                    got[:, idx, :] = sp
+                    seen[idx] = True
+            den = float(np.linalg.norm(ref))
+            parity = {"what": "seismograms at the %d receivers, first %d steps from rest: %d-rank run vs one domain holding the whole mesh" % (len(eg), NPAR, world),
+                      "rel_l2": float(np.linalg.norm(got - ref) / den) if den > 0 else None, "tolerance": 1e-4,
+                      "receivers_recorded": int(seen.sum())}
+            parity["ok"] = bool(parity["rel_l2"] is not None and parity["rel_l2"] <= 1e-4 and seen.all())
+            del one
+        except Exception as ex:
+            parity = {"ok": False, "error": repr(ex)}
 
     peaks = {}
     try:
@@ -306,47 +444,54 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # dominant kernel = the entry with the largest summed device time over the timed eager steps (rank 0's GPU)
+    el_ms = float(fam[1])
+    kernels = {k: {"ms_per_step": v[0] / nt, "launches_per_step": v[1] / nt, "algorithmic_bytes_per_step": v[2] / nt,
+                   "GBps": (v[2] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else None} for k, v in kst.items()}
+    dk_name = max(kst, key=lambda k: kst[k][0]) if kst else "none"
+    dk_ms_total, dk_n, dk_bytes_total = kst.get(dk_name, (0.0, 0, 0.0))
+    dk_ms = dk_ms_total / dk_n if dk_n else 0.0
+    dk_bytes = dk_bytes_total / dk_n if dk_n else 0.0
+    achieved = dk_bytes / (dk_ms * 1e-3) / 1e9 if dk_ms > 0 else 0.0
     traffic = None
     try:
-        if CFG == "cfg2" and world == 1:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_elem3d_fused_dram_bytes_per_launch_cfg2")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get("%s|%s" % (CFG, dk_name.split(" ")[0])) if world == 1 else None
+        if ent:
+            traffic = ent.get("dram_bytes_per_launch")
     except Exception:
         pass
-    el_ms = float(fam[1])
-    if dk_ms > 0:
-        dk_name = "k_elem3d_fused<solid> (gather+grad+c2r+stress+r2c+quad+scatter of the 3D solid elements" + \
-                  (" + in-kernel Newmark of the plain solid points)" if dk_bytes[1] > 0 else ")")
-        dk_total = float(dk_bytes.sum())
-        achieved = dk_total / (dk_ms * 1e-3) / 1e9
-    else:   # no fused launch in this configuration (e.g. cfg1: all elements 1D): fall back to the element family
-        dk_name = "element stiffness family (k_elem1d)"
-        dk_total = float(alg[1])
-        achieved = alg[1] / (el_ms * 1e-3) / 1e9 if el_ms > 0 else 0.0
-        dk_ms = el_ms
-    step_bytes = float(alg.sum())
+    step_bytes = float(alg_job.sum())
+    ws_mb = (4 * 8 * (dom.field_size(False) + dom.field_size(True)) + alg[1] * 0.2) / 1e6
     line = {
         "metric": METRIC, "value": work * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(n_theta), "elements": int(mesh.nelem), "gll_points": int(mesh.ngll),
-                   "point_modes_per_step": int(work), "parallelism": "dd%d" % world, "halo": halo,
-                   "l2": "working set %.0f MB of point fields + moduli per GPU exceeds the 126 MB L2; no explicit flush" %
-                         ((4 * 8 * (dom.field_size(False) + dom.field_size(True)) + alg[1] * 0.2) / 1e6),
+        "config": {"workload": workload_name(n_theta, n_r), "elements": int(mesh.nelem), "gll_points": int(mesh.ngll),
+                   "point_modes_per_step": int(work), "parallelism": "dd%d" % world, "halo": halo, "partition": part_info,
+                   "timing": "median of %d regions of %d steps (CUDA events, max over ranks); min %.4f max %.4f ms/step" % (
+                       len(regions), K, regions.min() / K, regions.max() / K),
+                   "l2": "working set %.0f MB of point fields + moduli per GPU %s the 126 MB L2; no explicit flush" % (
+                       ws_mb, "exceeds" if ws_mb > 126 else "DOES NOT exceed"),
                    "stable": bool(stable)},
         "clocks": clocks,
-        "e2e": {"value": work * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": seis_bytes_per_step, "batch_steps": BATCH,
-                "ms_per_step": 1e3 * e2e_s / K},
+        "e2e": {"value": work * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * world, "d2h_bytes_per_step": seis_bytes_per_step,
+                "batch_steps": BATCH, "ms_per_step": 1e3 * e2e_s / K, "regions": int(len(e2e_regions))},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dk_name,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel_ms_per_launch": dk_ms, "kernel_algorithmic_bytes_per_launch": dk_total,
-                     "kernel_bytes_split": {"elements": float(dk_bytes[0]), "points_in_kernel": float(dk_bytes[1])},
-                     "algorithmic_bytes_per_step": {"points": alg[0], "elements": alg[1], "halo": alg[2]},
+                     "kernel_ms_per_launch": dk_ms, "kernel_algorithmic_bytes_per_launch": dk_bytes,
+                     "kernel_share_of_step": (dk_ms_total / nt) / float(fam.sum()) if fam.sum() > 0 else None,
+                     "kernels": kernels,
+                     "algorithmic_bytes_per_step": {"points": float(alg_job[0]), "elements": float(alg_job[1]), "halo": float(alg_job[2])},
                      "family_ms": {"newmark": float(fam[0]), "elements": el_ms, "sf_source": float(fam[2]), "halo": float(fam[3])},
-                     "whole_step": {"achieved": step_bytes / (ms / K * 1e-3) / 1e9, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak}},
+                     "whole_step": {"achieved": step_bytes / (ms / K * 1e-3) / 1e9,
+                                    "frac": step_bytes / (ms / K * 1e-3) / 1e9 / (peak * world)}},
     }
-    if world == 1 and not args.no_cpu:
+    if parity is not None:
+        line["parity"] = parity
+    if world == 1 and not args.no_cpu and CFG != "cfg5":
         try:
             c = cpu_arm(6, 1, stride=3, min_seconds=12.0, max_seconds=25.0)
             line["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -357,6 +502,7 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     os.dup2(2, 1)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -367,8 +513,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS),
-                    help="BASELINE.json config (cfg2 = configs[1] is the headline; the others are extra measurements)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank seismogram check (N > 1)")
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS),
+                    help="BASELINE.json config (cfg4 = configs[3], the variable-Nu config the target is quoted on, is the headline)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 72 N x 28 quads on N GPUs; strong: the N = 8 mesh (576 x 28) on every N")
+    ap.add_argument("--partition", default="metis", choices=["metis", "contiguous"])
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="the K-step region is repeated until this much time has passed")
     args = ap.parse_args()
     global CFG
     CFG = args.config
