@@ -92,6 +92,7 @@ struct HElem {
     int prt_rows = 0;         // particle relabelling: 0 none, 1 PRT_1D, Nr PRT_3D
     std::vector<float> prtX;  // [4][25][prt_rows]
     int cls = -1, idx = -1;   // class and index inside the class after finalize
+    bool bnd = false;         // touches a point shared with another rank
     double alg_b = 0;         // algorithmic bytes of one stiffness evaluation of this element
 };
 struct HSource {
@@ -226,6 +227,17 @@ struct ax3d_domain {
     std::vector<unsigned *> peer_count;      // per neighbour: its arrival counter for me
     std::vector<void *> peer_mapped;         // bases returned by cudaIpcOpenMemHandle (closed at destroy)
     bool peer_halo = false;
+    // in-kernel put (fused.cuh: halo_put_cta): the solid element kernel sends the boundary forces itself
+    std::vector<char> is_halo_point;        // per point tag
+    SFTab sf_tab_halo{}, sf_tab_rest{};     // 1D-coupled solid-fluid points on / off the halo
+    DevBuf<unsigned> sfh_s_off, sfh_f_off, sfr_s_off, sfr_f_off;
+    DevBuf<int> sfh_nu, sfh_row_point, sfh_row_start, sfr_nu, sfr_row_point, sfr_row_start;
+    DevBuf<float> sfh_cpl, sfr_cpl;
+    bool halo_sf3d = false;                 // a 3D-coupled solid-fluid point lies on the halo: no in-kernel put
+    DevBuf<HaloTab> halo_tab;
+    DevBuf<unsigned> halo_bcnt;
+    int n_bnd_fused = 0;                    // boundary elements in the solid fused launch
+    bool inkernel_put = false;
     bool have_uid = false;
     unsigned char uid[128];
 #ifdef AX3D_WITH_NCCL
@@ -283,7 +295,10 @@ struct ax3d_domain {
 static void fail(const std::string &m) { throw std::runtime_error(m); }
 
 // ------------------------------------------------------------------------------------------ FFT plans
-static int plan_maxr2() { return 16; }
+#ifndef AX_PLAN_MAXR2
+#define AX_PLAN_MAXR2 16   // largest power-of-two radix of the FFT plans (16: 32 data registers per butterfly; 8 for kernels compiled for < 96 registers)
+#endif
+static int plan_maxr2() { return AX_PLAN_MAXR2; }
 
 static std::vector<int> choose_radices(int N) {
     const RadixList rl = choose_radices_ct(N, plan_maxr2());   // fft.cuh: the one definition host and kernels share
@@ -556,22 +571,20 @@ static void finalize(ax3d_domain *d) {
     d->alg_bytes[0] = bytes_pts;
 
     // ---------------- elements: classify, sort 3D classes by Nr (descending) for load balance / chunking
+    d->is_halo_point.assign(d->points.size(), 0);
+    for (const auto &nb : d->neigh_pts)
+        for (int t : nb) {
+            if (t < 0 || t >= (int)d->points.size()) fail("Domain::setMessaging || invalid point tag");
+            d->is_halo_point[t] = 1;
+        }
     std::vector<int> order[NCLS];
     for (size_t e = 0; e < d->elems.size(); ++e) {
         HElem &E = d->elems[e];
+        for (int i = 0; i < AX_NPE; ++i) E.bnd = E.bnd || d->is_halo_point[E.pt[i]];
         const bool is3d = E.rows > 1;
         E.cls = E.fluid ? (is3d ? CLS_F3D : CLS_F1D) : (is3d ? CLS_S3D : CLS_S1D);
         order[E.cls].push_back((int)e);
     }
-    // 3D classes: elements with particle relabelling first (split pipeline only), then by Nr descending -- the fused launch
-    // takes the tail of this order (everything below the largest Nr whose single GLL row still fits in shared memory)
-    for (int c : {CLS_S3D, CLS_F3D})
-        std::stable_sort(order[c].begin(), order[c].end(), [&](int a, int b) {
-            const HElem &A = d->elems[a], &B = d->elems[b];
-            if ((A.prt_rows > 0) != (B.prt_rows > 0)) return A.prt_rows > 0;
-            return A.nr > B.nr;
-        });
-
     std::vector<float> geom, coef, attpar;
     size_t att1d_len = 0, att3d_len = 0;
     double bytes_el = 0;
@@ -583,8 +596,11 @@ static void finalize(ax3d_domain *d) {
     const char *env_nf = getenv("AX3D_NO_FUSED");
     const bool use_fused = !(env_nf && atoi(env_nf) != 0);
     {
-        const char *env_nw = getenv("AX3D_NO_NW");
-        d->nw_allowed = !(env_nw && atoi(env_nw) != 0) && so.size() < (1u << 24);
+        // In-kernel Newmark (fused.cuh) is opt-in (AX3D_NW=1).  Measured on B200 (profiles/r2_nw_ab.md): the element kernel is
+        // issue-bound, so the Newmark warps' polling and update instructions slow it down by more than the stand-alone,
+        // HBM-bound k_newmark_solid costs (cfg4: 0.934 ms per step with, 0.820 ms without).
+        const char *env_nw = getenv("AX3D_NW");
+        d->nw_allowed = (env_nw && atoi(env_nw) != 0) && so.size() < (1u << 24);
     }
 
     for (int c = 0; c < NCLS; ++c) {
@@ -625,16 +641,27 @@ static void finalize(ax3d_domain *d) {
             }
             return false;
         };
-        // the fused launch takes the tail of the class order: everything behind the last element that cannot be fused
+        // 3D classes: the fused launch takes the tail of the class order.  In front: what cannot be fused (particle relabelling,
+        // one GLL row larger than shared memory; split pipeline), Nr descending; then the fused elements -- boundary elements
+        // first (their forces go to the neighbours while the interior ones are computed), each part by Nr descending (LPT)
         int first_fused = (int)order[c].size();
-        if (is3d && use_fused) {
-            first_fused = 0;
-            for (size_t k = 0; k < order[c].size(); ++k) {
-                const HElem &E = d->elems[order[c][k]];
+        if (is3d) {
+            std::vector<char> fit(d->elems.size(), 0);
+            for (int e : order[c]) {
+                const HElem &E = d->elems[e];
                 ElemDesc tmp;
                 const int pid = get_plan(d, E.nr);
-                if (E.prt_rows > 0 || !plan_fused_element(E.nr, E.nu + 1, d->h_plans[pid].stw_len, tmp)) first_fused = (int)k + 1;
+                fit[e] = use_fused && E.prt_rows == 0 && plan_fused_element(E.nr, E.nu + 1, d->h_plans[pid].stw_len, tmp);
             }
+            std::stable_sort(order[c].begin(), order[c].end(), [&](int a, int b) {
+                const HElem &A = d->elems[a], &B = d->elems[b];
+                if (fit[a] != fit[b]) return fit[a] < fit[b];
+                if (!fit[a] && (A.prt_rows > 0) != (B.prt_rows > 0)) return A.prt_rows > 0;
+                if (fit[a] && A.bnd != B.bnd) return A.bnd;
+                return A.nr > B.nr;
+            });
+            first_fused = 0;
+            while (first_fused < (int)order[c].size() && !fit[order[c][first_fused]]) ++first_fused;
         }
         auto close_fused = [&]() {
             if (fl.count > 0) {
@@ -654,6 +681,7 @@ static void finalize(ax3d_domain *d) {
             D.axial = E.axial ? 1 : 0;
             D.law = E.law;
             D.prt = E.prt_rows > 0 ? 1 : 0;
+            D.bnd = E.bnd ? 1 : 0;
             if (D.prt) d->cls_prt[c] = true;
             D.tiso = (!fluid && (E.law != AX3D_ISO || D.prt)) ? 1 : 0;   // SolidElement.cpp:21: mInTIso = mHasPRT || needTIso
             D.is3d = is3d ? 1 : 0;
@@ -745,6 +773,7 @@ static void finalize(ax3d_domain *d) {
                     if (fl.count == 0) fl.first = (int)k;
                     fl.count++;
                     fl.alg_b += E.alg_b;
+                    if (c == CLS_S3D && E.bnd) d->n_bnd_fused++;
                 } else {
                     D.mt = M;
                     const int enp = (D.prt && !fluid) ? 5 : npair;   // Z-form pairs per point of this element
@@ -908,23 +937,29 @@ static void finalize(ax3d_domain *d) {
         d->src_off.upload(off);
         d->src_val.upload(val);
     }
-    // ---------------- solid-fluid points
+    // ---------------- solid-fluid points: the whole 1D-coupled table, and the same split into points on / off the halo
     {
-        std::vector<unsigned> a, b;
-        std::vector<int> nu, rp, rs;
-        std::vector<float> cpl, pool;
-        for (const HPoint &p : d->points) {
+        struct Tab { std::vector<unsigned> a, b; std::vector<int> nu, rp, rs; std::vector<float> cpl; };
+        Tab all, onh, off;
+        std::vector<float> pool;
+        auto push = [](Tab &t, const HPoint &p) {
+            const int q = (int)t.a.size();
+            t.a.push_back((unsigned)p.s_off);
+            t.b.push_back((unsigned)p.f_off);
+            t.nu.push_back(p.nu);
+            t.rs.push_back((int)t.rp.size());
+            for (int k = 0; k <= p.nu; ++k) t.rp.push_back(q);
+            t.cpl.push_back(p.n_un[0]); t.cpl.push_back(p.n_un[2]);
+            t.cpl.push_back(p.n_as[0]); t.cpl.push_back(p.n_as[2]);
+        };
+        for (size_t tg = 0; tg < d->points.size(); ++tg) {
+            const HPoint &p = d->points[tg];
             if (p.kind != 2) continue;
             if (p.n_sf == 1) {
-                const int q = (int)a.size();
-                a.push_back((unsigned)p.s_off);
-                b.push_back((unsigned)p.f_off);
-                nu.push_back(p.nu);
-                rs.push_back((int)rp.size());
-                for (int k = 0; k <= p.nu; ++k) rp.push_back(q);
-                cpl.push_back(p.n_un[0]); cpl.push_back(p.n_un[2]);
-                cpl.push_back(p.n_as[0]); cpl.push_back(p.n_as[2]);
+                push(all, p);
+                push(d->is_halo_point[tg] ? onh : off, p);
             } else {
+                if (d->is_halo_point[tg]) d->halo_sf3d = true;
                 SF3DItem it;
                 it.s_off = (unsigned)p.s_off;
                 it.f_off = (unsigned)p.f_off;
@@ -940,9 +975,15 @@ static void finalize(ax3d_domain *d) {
                 d->sf3d_smem = std::max(d->sf3d_smem, (size_t)3 * p.nr * sizeof(float2));
             }
         }
-        d->sf_s_off.upload(a); d->sf_f_off.upload(b); d->sf_nu.upload(nu);
-        d->sf_row_point.upload(rp); d->sf_row_start.upload(rs); d->sf_cpl.upload(cpl);
-        d->sf_tab = SFTab{d->sf_s_off.p, d->sf_f_off.p, d->sf_nu.p, d->sf_cpl.p, d->sf_row_point.p, d->sf_row_start.p, (int)rp.size()};
+        d->sf_s_off.upload(all.a); d->sf_f_off.upload(all.b); d->sf_nu.upload(all.nu);
+        d->sf_row_point.upload(all.rp); d->sf_row_start.upload(all.rs); d->sf_cpl.upload(all.cpl);
+        d->sf_tab = SFTab{d->sf_s_off.p, d->sf_f_off.p, d->sf_nu.p, d->sf_cpl.p, d->sf_row_point.p, d->sf_row_start.p, (int)all.rp.size()};
+        d->sfh_s_off.upload(onh.a); d->sfh_f_off.upload(onh.b); d->sfh_nu.upload(onh.nu);
+        d->sfh_row_point.upload(onh.rp); d->sfh_row_start.upload(onh.rs); d->sfh_cpl.upload(onh.cpl);
+        d->sf_tab_halo = SFTab{d->sfh_s_off.p, d->sfh_f_off.p, d->sfh_nu.p, d->sfh_cpl.p, d->sfh_row_point.p, d->sfh_row_start.p, (int)onh.rp.size()};
+        d->sfr_s_off.upload(off.a); d->sfr_f_off.upload(off.b); d->sfr_nu.upload(off.nu);
+        d->sfr_row_point.upload(off.rp); d->sfr_row_start.upload(off.rs); d->sfr_cpl.upload(off.cpl);
+        d->sf_tab_rest = SFTab{d->sfr_s_off.p, d->sfr_f_off.p, d->sfr_nu.p, d->sfr_cpl.p, d->sfr_row_point.p, d->sfr_row_start.p, (int)off.rp.size()};
         d->sf3d.upload(d->h_sf3d);
         d->sf3d_pool.upload(pool);
     }
@@ -1191,20 +1232,20 @@ static void apply_source(ax3d_domain *d, float stf) {
 // 640 (96 regs) -> 0.289, 768 (80 regs) -> 0.310: the kernel is not occupancy-limited.  With Newmark warps the CTA is
 // 448 compute + 64 Newmark threads.
 static int fused_nt(const FusedLaunch &f) {
-    return f.nww ? AX_NW_NT + 32 * AX_NWW : 512;
+    return f.nww ? AX_NW_NT + 32 * AX_NWW : AX_FUSED_NT;
 }
 
 typedef void (*fused_kernel_t)(const ElemDesc *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
-                               float *, const float2 *, float2 *, int, unsigned *, const NwArgs);
+                               float *, const float2 *, float2 *, int, unsigned *, const NwArgs, const HaloArgs);
 
 static fused_kernel_t fused_kernel(const FusedLaunch &f) {
     const bool fluid = f.cls == CLS_F3D;
-    if (fluid) return k_elem3d_fused<true, 512, 0>;
-    return f.nww ? k_elem3d_fused<false, AX_NW_NT, AX_NWW> : k_elem3d_fused<false, 512, 0>;
+    if (fluid) return k_elem3d_fused<true, AX_FUSED_NT, 0>;
+    return f.nww ? k_elem3d_fused<false, AX_NW_NT, AX_NWW> : k_elem3d_fused<false, AX_FUSED_NT, 0>;
 }
 
 // nw_on: this launch also advances the plain solid points to the next step (its dt is the step being integrated)
-static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool nw_on, double dt) {
+static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool nw_on, double dt, bool put) {
     const int c = f.cls;
     const bool fluid = c == CLS_F3D;
     NwArgs nw;
@@ -1230,11 +1271,13 @@ static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool n
     }
     if (!fluid && d->nw_dbg.p && nw.on) nw.dbg = d->nw_dbg.p;
     const double kbytes = f.alg_b + (nw.on ? d->dom_bytes[1] : 0.0);
+    HaloArgs halo{nullptr, nullptr, 0};
+    if (put && !fluid) halo = HaloArgs{d->halo_tab.p, d->halo_bcnt.p, d->n_bnd_fused};
     KTimer kt(d, fluid ? "k_elem3d_fused<fluid>" : (nw.on ? "k_elem3d_fused<solid> + in-kernel Newmark" : "k_elem3d_fused<solid>"), kbytes);
     fused_kernel(f)<<<f.grid, fused_nt(f), f.smem, d->stream>>>(
         d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
         fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
-        f.tile_cap, d->fused_work.p + 2 * which, nw);
+        f.tile_cap, d->fused_work.p + 2 * which, nw, halo);
 }
 
 static void set_fused_smem(int device, const FusedLaunch &f) {
@@ -1245,7 +1288,8 @@ static void set_fused_smem(int device, const FusedLaunch &f) {
 }
 
 // which: 1 = solid elements, 2 = fluid elements, 3 = both
-static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, int which = 3) {
+// put: the solid fused launch sends the halo itself (in-kernel put; run_steps only)
+static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, int which = 3, bool put = false) {
     TimerScope ts(d, 1);
     const int TB = AX_TILE * AX_NPE;
     if ((which & 1) && d->n_work[CLS_S1D]) {
@@ -1283,19 +1327,23 @@ static void compute_stiff(ax3d_domain *d, bool nw_on = false, double dt = 0.0, i
         }
         d->launches += 3;
     }
-    for (size_t k = 0; k < d->fused.size(); ++k) {
-        if (!(which & (d->fused[k].cls == CLS_S3D ? 1 : 2))) continue;
-        launch_fused(d, d->fused[k], (int)k, nw_on, dt);
-        d->launches++;
-    }
+    for (int pass = 0; pass < 2; ++pass)   // the solid launch last: it may send the halo once every boundary force is in memory
+        for (size_t k = 0; k < d->fused.size(); ++k) {
+            const bool solid = d->fused[k].cls == CLS_S3D;
+            if (solid != (pass == 1) || !(which & (solid ? 1 : 2))) continue;
+            launch_fused(d, d->fused[k], (int)k, nw_on, dt, put);
+            d->launches++;
+        }
     CK(cudaGetLastError());
 }
 
-static void couple_solid_fluid(ax3d_domain *d) {
+// rest_only: the solid-fluid points on the halo have been coupled by the in-kernel put already
+static void couple_solid_fluid(ax3d_domain *d, bool rest_only = false) {
     TimerScope ts(d, 2);
-    if (d->sf_tab.nrows) {
-        k_sf_couple<<<nblk(d->sf_tab.nrows, 128), 128, 0, d->stream>>>(d->sf_tab, d->s_field[AX3D_DISPL].p, d->s_field[AX3D_STIFF].p,
-                                                                      d->f_field[AX3D_STIFF].p);
+    const SFTab &tab = rest_only ? d->sf_tab_rest : d->sf_tab;
+    if (tab.nrows) {
+        k_sf_couple<<<nblk(tab.nrows, 128), 128, 0, d->stream>>>(tab, d->s_field[AX3D_DISPL].p, d->s_field[AX3D_STIFF].p,
+                                                                d->f_field[AX3D_STIFF].p);
         d->launches++;
     }
     if (!d->h_sf3d.empty()) {
@@ -1640,6 +1688,36 @@ int ax3d_halo_connect(ax3d_domain *d, int nneigh, const void *handles, void *con
         d->peer_count[n] = (unsigned *)((float2 *)base + 2 * peer_total[n]) + peer_slot[n];
     }
     d->peer_halo = true;
+    // in-kernel put (fused.cuh: halo_put_cta): needs a solid fused launch to carry it, at most AX_MAX_NEIGH neighbours and no
+    // 3D-coupled solid-fluid point on the halo (its coupling is an FFT per point: k_sf_couple3d); otherwise k_halo_put kernels
+    {
+        bool solid_fused = false;
+        for (const FusedLaunch &f : d->fused) solid_fused = solid_fused || f.cls == CLS_S3D;
+        const char *env = getenv("AX3D_NO_INKERNEL_PUT");
+        d->inkernel_put = solid_fused && nneigh <= AX_MAX_NEIGH && !d->halo_sf3d && !(env && atoi(env) != 0);
+        if (d->inkernel_put) {
+            HaloTab ht;
+            memset(&ht, 0, sizeof(ht));
+            ht.nneigh = nneigh;
+            for (int n = 0; n < nneigh; ++n) {
+                const size_t b = d->neigh_begin[n], cnt = d->neigh_begin[n + 1] - b;
+                ht.peer[n] = HaloPeer{d->halo_idx.p + b, d->peer_win[n], (unsigned long long)d->peer_stride[n], d->peer_count[n], (int)cnt,
+                                      nblk(cnt, 256)};
+            }
+            ht.step = d->halo_step.p;
+            ht.f_stiff = d->f_field[AX3D_STIFF].p;
+            ht.sf_halo = d->sf_tab_halo;
+            std::vector<HaloTab> v(1, ht);
+            d->halo_tab.upload(v);
+            d->halo_bcnt.alloc(1);
+            d->halo_bcnt.zero();
+            d->dual_chain = false;   // every other element kernel of the step must be complete when the solid launch sends
+        }
+    }
+    for (int v = 0; v < 8; ++v) {   // step graphs captured before the connection do not contain the exchange
+        if (d->graph_exec[v]) { cudaGraphExecDestroy(d->graph_exec[v]); d->graph_exec[v] = nullptr; }
+        if (d->graph[v]) { cudaGraphDestroy(d->graph[v]); d->graph[v] = nullptr; }
+    }
     API_END
 }
 
@@ -1851,9 +1929,10 @@ static void step_body(ax3d_domain *d, double dt, bool special_only = false, bool
     // kernel, which already advances the plain points to the next step
     if (record) launch_record(d, d->rec_ring.p, reinterpret_cast<const int *>(d->stf_dev.p + 1), 3 * d->nrec_total());
     launch_source(d);
-    compute_stiff(d, nw_on, dt);
-    couple_solid_fluid(d);
-    assemble_stiff(d, -1);   // no-ops on a single rank
+    const bool put = d->inkernel_put && d->nproc > 1 && !d->neigh_rank.empty();
+    compute_stiff(d, nw_on, dt, 3, put);
+    couple_solid_fluid(d, put);
+    if (!put) assemble_stiff(d, -1);   // no-ops on a single rank
     assemble_stiff(d, 1);
 }
 
@@ -1875,7 +1954,7 @@ static long long count_step_launches(ax3d_domain *d, bool special_only, bool rec
     if (d->nproc > 1 && !d->neigh_rank.empty()) {
         n += 1;   // k_pack (NCCL path) / k_halo_advance (peer path)
         for (size_t k = 0; k < d->neigh_rank.size(); ++k)
-            n += (d->peer_halo ? 2 : 1) * (d->neigh_begin[k + 1] > d->neigh_begin[k]);   // [k_halo_put +] k_unpack_add / k_halo_wait_add
+            n += (d->peer_halo && !d->inkernel_put ? 2 : 1) * (d->neigh_begin[k + 1] > d->neigh_begin[k]);   // [k_halo_put +] k_unpack_add / k_halo_wait_add
     }
     return n;
 }

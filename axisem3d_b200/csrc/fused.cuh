@@ -365,6 +365,19 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
     const int p0 = 5 * r0, np = 5 * (r1 - r0);       // points of this pass: [p0, p0 + np)
     const int ncols = NPAIR * np, cs = np * ldz;      // column of (pair pr, local point pl) = Z + (pr * np + pl) * ldz
 
+    // Static thread mapping of the pass: kpp = NHW / np half-warps share one point of the group and interleave its 16-mode
+    // chunks (np = 25: one half-warp per point; 15: two; 10: three; 5: six, at NHW = 32), lanes run over the 16 modes of a chunk.
+    // Everything that depends on the point only (G coefficients, geometry, rotation) is loaded once per pass.
+    const int kpp = max(1, NHW / np);
+    const int pl = hw / kpp, sub = hw - pl * kpp;
+    const bool act = pl < np;
+    const int p = p0 + (act ? pl : 0), i = p / 5, j = p - 5 * i;
+    const bool ax0 = axial && i == 0;
+    GCoef gc;
+    load_gcoef(gc, axial, i, j);
+    PointGeom gm = {0.f, 0.f, 0.f, 0.f, 0.f};   // geometry / rotation of the point: read behind the first barrier of the pass (the
+    float tr[4] = {0.f, 1.f, 0.f, 1.f};          // geometry tile of a new element arrives with its first gather)
+
     // ------------------------------------------------------------ gather (prefetched) + grad, one tile of modes at a time   @phase gather wait + grad
     for (int a0 = 0, mt = first_mt; a0 < M; a0 += mt, mt = min(Mt, M - a0)) {
         if (a0) {
@@ -375,35 +388,19 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
         if (a0 == 0 && t == 0)   // Im(u) of mode 0 is not used (Gradient.cpp:209-224): this thread copied these entries
             for (int row = hw; row < US; row += NHW) U[row].y = 0.f;
         cta_sync<NT, NWW>();
-        if (a0 == 0) after_first_sync();
-        // items = (local point, 16-mode chunk of the tile), point-major; a half-warp takes a contiguous run of items
-        const int nch = (mt + 15) >> 4, nitem = np * nch, ipw = (nitem + NHW - 1) / NHW;
-        int pl_cur = -1;
-        GCoef gc;
-        PointGeom gm;
-        float tr[4] = {0.f, 1.f, 0.f, 1.f};
-        bool ax0 = false;
-        int i = 0, j = 0;
-        for (int it = hw * ipw, ie = min(nitem, hw * ipw + ipw); it < ie; ++it) {
-            const int pl = it / nch, ch = it - pl * nch;
-            if (pl != pl_cur) {
-                pl_cur = pl;
-                const int p = p0 + pl;
-                i = p / 5;
-                j = p - 5 * i;
-                load_gcoef(gc, axial, i, j);
-                gm = load_geom(cx.sgeom, 0, p);
-                ax0 = axial && i == 0;
-                if (tiso) {
+        if (a0 == 0) {
+            after_first_sync();
+            gm = load_geom(cx.sgeom, 0, p);
+            if (tiso) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tr[k] = cx.sgeom[(5 + k) * AX_NPE + p];
-                }
+                for (int k = 0; k < 4; ++k) tr[k] = cx.sgeom[(5 + k) * AX_NPE + p];
             }
-            const int a = ch * 16 + t;
-            if (a < mt) {
+        }
+        if (act) {
+            float2 *zp = Z + pl * ldz;
+            for (int a = sub * 16 + t; a < mt; a += 16 * kpp) {
                 const int alpha = a0 + a;
                 const bool dead = nyq && alpha == nu;
-                float2 *zp = Z + pl * ldz;
                 if constexpr (!FLUID) {
                     float2 ee[6];
                     grad6_mm(U + a * US, i, j, gc, gm, (float)alpha, ax0, ee);
@@ -453,49 +450,39 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
         }
     }
 
-    // ------------------------------------------------------------ quad + scatter, a tile of 16-mode chunks at a time   @phase quad-pre
-    // In-group items (local point, chunk): half-warp hw owns items [QIT * hw, QIT * hw + QIT) of the tile, pre and post, so
-    // that the pointwise term r never leaves its registers.  A tile has `sch` chunks with np * sch <= QIT * NHW items.
+    // ------------------------------------------------------------ quad + scatter, QIT * kpp 16-mode chunks at a time   @phase quad-pre
+    // Same mapping as grad: the half-warp keeps its point; chunk q of its tile is c0 + q * kpp + sub, pre and post, so that the
+    // pointwise term r never leaves its registers.
     const float sc = 1.f / (float)N;   // SolverFFTW_N6::computeR2C scaling (SolverFFTW_N6.cpp:47-48)
     const int nchq = (M + 15) >> 4;
-    const int sch = max(1, min(nchq, (QIT * NHW) / np));
     const int nout = AX_NPE - np;      // points outside the group: xi-partial sums only
-    for (int c0 = 0; c0 < nchq; c0 += sch) {
-        const int nchs = min(sch, nchq - c0), nin = np * nchs;
+    const int nlive = E.pt_nlive[p], st = E.pt_stride[p];
+    float2 *const dst = cx.stiff + (size_t)E.pt_off[p];
+    float2 *const zp = Z + pl * ldz;
+    for (int c0 = 0; c0 < nchq; c0 += QIT * kpp) {
         float2 r[QIT][NC];
         // pointwise half, in place: slot beta <- X, slot N - beta <- Y (beta = 0: the spare slot N)
+        if (act) {
 #pragma unroll
-        for (int q = 0; q < QIT; ++q) {
-            const int it = hw * QIT + q;
-            if (it < nin) {
-                const int pl = it / nchs, ch = it - pl * nchs;
-                const int p = p0 + pl, i = p / 5;
-                const int beta = (c0 + ch) * 16 + t;
+            for (int q = 0; q < QIT; ++q) {
+                const int beta = (c0 + q * kpp + sub) * 16 + t;
                 if (beta < M && !(nyq && beta == nu)) {
-                    const PointGeom gm = load_geom(cx.sgeom, 0, p);
-                    const bool ax0 = axial && i == 0;
-                    float2 *zp = Z + pl * ldz;
                     if constexpr (!FLUID) {
-                        float2 s[6], X[3], Y[3];
+                        float2 sg[6], X[3], Y[3];
 #pragma unroll
-                        for (int pr = 0; pr < 3; ++pr) zform_load(zp + pr * cs, N, beta, sc, s[2 * pr], s[2 * pr + 1]);
-                        if (tiso) {
-                            float tr[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) tr[k] = cx.sgeom[(5 + k) * AX_NPE + p];
-                            rot_rtz_to_spz(s, tr[0], tr[1], tr[2], tr[3]);
-                        }
-                        quad6_pre(s, gm, (float)beta, ax0, X, Y, r[q]);
+                        for (int pr = 0; pr < 3; ++pr) zform_load(zp + pr * cs, N, beta, sc, sg[2 * pr], sg[2 * pr + 1]);
+                        if (tiso) rot_rtz_to_spz(sg, tr[0], tr[1], tr[2], tr[3]);
+                        quad6_pre(sg, gm, (float)beta, ax0, X, Y, r[q]);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             zp[c * cs + beta] = X[c];
                             zp[c * cs + N - beta] = Y[c];
                         }
                     } else {
-                        float2 s[3], X, Y, dummy;
-                        zform_load(zp, N, beta, sc, s[0], s[1]);
-                        zform_load(zp + cs, N, beta, sc, s[2], dummy);
-                        quad_fluid_pre(s, gm, (float)beta, ax0, X, Y, r[q][0]);
+                        float2 sg[3], X, Y, dummy;
+                        zform_load(zp, N, beta, sc, sg[0], sg[1]);
+                        zform_load(zp + cs, N, beta, sc, sg[2], dummy);
+                        quad_fluid_pre(sg, gm, (float)beta, ax0, X, Y, r[q][0]);
                         zp[beta] = X;
                         zp[N - beta] = Y;
                     }
@@ -504,27 +491,28 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
         }
         cta_sync<NT, NWW>();
         // tensor-product half + Point::gatherStiffFromElement (SolidPoint.cpp:197-209)   @phase quad-post + scatter
+        if (act) {
 #pragma unroll
-        for (int q = 0; q < QIT; ++q) {
-            const int it = hw * QIT + q;
-            if (it < nin) {
-                const int pl = it / nchs, ch = it - pl * nchs;
-                const int p = p0 + pl, i = p / 5, j = p - 5 * i;
-                const int beta = (c0 + ch) * 16 + t;
-                if (beta < M && !(nyq && beta == nu) && beta < E.pt_nlive[p]) {
-                    GCoef gc;
-                    load_gcoef(gc, axial, i, j);
-                    float2 *const dst = cx.stiff + (size_t)E.pt_off[p];
-                    const int st = E.pt_stride[p];
+            for (int q = 0; q < QIT; ++q) {
+                const int beta = (c0 + q * kpp + sub) * 16 + t;
+                if (beta < M && !(nyq && beta == nu) && beta < nlive) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         float2 f = r[q][c];
                         const float2 *zx = Z + c * cs + j * ldz + beta;                         // X(k, j), k = r0 .. r1 - 1
                         const float2 *zy = Z + c * cs + (i - r0) * 5 * ldz + N - beta;          // Y(i, k), k = 0 .. 4
+                        if (ng == 1) {
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) {   // static register indices: the row range is a (warp-uniform) predicate
-                            if (k >= r0 && k < r1) f = cfma(gc.gxi_row[k], zx[(k - r0) * 5 * ldz], f);
-                            f = cfma(gc.geta_row[k], zy[k * ldz], f);
+                            for (int k = 0; k < 5; ++k) {
+                                f = cfma(gc.gxi_row[k], zx[k * 5 * ldz], f);
+                                f = cfma(gc.geta_row[k], zy[k * ldz], f);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {   // static register indices: the row range is a (warp-uniform) predicate
+                                if (k >= r0 && k < r1) f = cfma(gc.gxi_row[k], zx[(k - r0) * 5 * ldz], f);
+                                f = cfma(gc.geta_row[k], zy[k * ldz], f);
+                            }
                         }
                         if (beta == 0) f.y = 0.f;
                         atomicAdd(dst + (size_t)c * st + beta, make_float2(-f.x, -f.y));   // stiff -= f (RED.ADD.F32x2)
@@ -533,25 +521,25 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
             }
         }
         // points of the other rows: f(i', j) += sum_{k in group} G_xi(i', k) X(k, j)
-        for (int it = hw; it < nout * nchs; it += NHW) {
-            const int po = it / nchs, ch = it - po * nchs;
-            const int p = po < p0 ? po : po + np;          // skip [p0, p0 + np)
-            const int i = p / 5, j = p - 5 * i;
-            const int beta = (c0 + ch) * 16 + t;
-            if (beta < M && !(nyq && beta == nu) && beta < E.pt_nlive[p]) {
-                GCoef gc;
-                load_gcoef(gc, axial, i, j);
-                float2 *const dst = cx.stiff + (size_t)E.pt_off[p];
-                const int st = E.pt_stride[p];
+        if (nout) {
+            const int nchs = min(QIT * kpp, nchq - c0);
+            for (int it = hw; it < nout * nchs; it += NHW) {
+                const int po = it / nchs, ch = it - po * nchs;
+                const int p2 = po < p0 ? po : po + np;          // skip [p0, p0 + np)
+                const int i2 = p2 / 5, j2 = p2 - 5 * i2;
+                const int beta = (c0 + ch) * 16 + t;
+                if (beta < M && !(nyq && beta == nu) && beta < E.pt_nlive[p2]) {
+                    const float *Gxi = c_G[axial ? 1 : 0];
+                    float2 *const dst2 = cx.stiff + (size_t)E.pt_off[p2];
+                    const int st2 = E.pt_stride[p2];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    float2 f = czero();
-                    const float2 *zx = Z + c * cs + j * ldz + beta;
-#pragma unroll
-                    for (int k = 0; k < 5; ++k)
-                        if (k >= r0 && k < r1) f = cfma(gc.gxi_row[k], zx[(k - r0) * 5 * ldz], f);
-                    if (beta == 0) f.y = 0.f;
-                    atomicAdd(dst + (size_t)c * st + beta, make_float2(-f.x, -f.y));
+                    for (int c = 0; c < NC; ++c) {
+                        float2 f = czero();
+                        const float2 *zx = Z + c * cs + j2 * ldz + beta;
+                        for (int k = r0; k < r1; ++k) f = cfma(Gxi[i2 * 5 + k], zx[(k - r0) * 5 * ldz], f);
+                        if (beta == 0) f.y = 0.f;
+                        atomicAdd(dst2 + (size_t)c * st2 + beta, make_float2(-f.x, -f.y));
+                    }
                 }
             }
         }
@@ -650,11 +638,14 @@ struct NwArgs {
     unsigned long long *dbg;   // optional [grid][4] globaltimer stamps: start, elements done, consumers done (AX3D_NW_DEBUG)
 };
 
+#ifndef AX_FUSED_NT
+#define AX_FUSED_NT 512        // compute threads of the fused element kernel (one CTA per SM: 512 -> 128 registers per thread)
+#endif
 #ifndef AX_NWW
 #define AX_NWW 2               // Newmark warps per CTA of the solid launch
 #endif
 #ifndef AX_NW_NT
-#define AX_NW_NT (512 - 32 * AX_NWW)   // compute threads of that launch
+#define AX_NW_NT (AX_FUSED_NT - 32 * AX_NWW)   // compute threads of that launch
 #endif
 #ifndef NW_CHR
 #define NW_CHR 96              // rows (complex entries) per chunk (160: 31 KB of stages per CTA, 96: 19 KB)
@@ -796,6 +787,40 @@ __device__ __forceinline__ void nw_consumer(const NwArgs &nw, float2 *stage, uns
     }
 }
 
+// ---------------------------------------------------------------- in-kernel halo put   @phase halo put
+// Domain::assembleStiff, send half (Domain.cpp:111-131), overlapped with the interior elements: boundary elements (those that
+// touch a point shared with another rank) are first in the work queue of the solid launch; every CTA that finishes one bumps
+// `bcnt`, and the CTA that brings it to `nb` -- every boundary force of the rank is then in memory: the other element
+// kernels of the step were launched before this one -- couples the solid-fluid points on the halo
+// (SolidFluidPoint::coupleSolidFluid comes before the exchange, Newmark.cpp:57-59) and stores every neighbour's segment
+// into that neighbour's window over NVLink, then goes back to the element queue.  k_halo_wait_add runs behind the kernel.
+struct HaloArgs {
+    const HaloTab *tab;   // nullptr: no in-kernel put in this launch
+    unsigned *bcnt;       // boundary elements finished in this launch (re-armed by the CTA that sends)
+    int nb;               // boundary elements of the launch (0: CTA 0 sends before its first element)
+};
+
+template <int NT, int NWW>
+__device__ __forceinline__ void halo_put_cta(const HaloTab &ht, const float2 *__restrict__ s_displ, float2 *__restrict__ s_stiff, int tid) {
+    __threadfence();   // acquire: the forces every other CTA fenced before its bump of bcnt
+    for (int r = tid; r < ht.sf_halo.nrows; r += NT) sf_couple_row(ht.sf_halo, r, s_displ, s_stiff, ht.f_stiff);
+    __threadfence();
+    cta_sync<NT, NWW>();
+    const unsigned s = __ldcg(ht.step);
+    for (int n = 0; n < ht.nneigh; ++n) {
+        const HaloPeer &P = ht.peer[n];
+        float2 *dst = P.win + (size_t)(s & 1u) * P.stride;
+        for (int i = tid; i < P.n; i += NT) {
+            const unsigned k = P.idx[i];
+            const float2 v = (k >> 31) ? __ldcg(ht.f_stiff + (k & 0x7fffffffu)) : __ldcg(s_stiff + k);
+            __stcg(dst + i, v);
+        }
+    }
+    __threadfence_system();
+    cta_sync<NT, NWW>();
+    if (tid < ht.nneigh) atomicAdd_system(ht.peer[tid].count, (unsigned)ht.peer[tid].nblocks);
+}
+
 // ---------------------------------------------------------------- the kernel   @phase kernel loop
 // grid: persistent, one CTA per SM; block NT compute threads (+ 32 * NWW Newmark threads).  work[0] = next element index
 // (starts at gridDim.x), work[1] = number of warps that have finished; the last one re-arms the counters for the next
@@ -807,7 +832,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
                    const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
                    const float *__restrict__ attpar, float *__restrict__ attstate, const float2 *__restrict__ displ,
-                   float2 *__restrict__ stiff, int tile_cap, unsigned *__restrict__ work, const NwArgs nw) {
+                   float2 *__restrict__ stiff, int tile_cap, unsigned *__restrict__ work, const NwArgs nw, const HaloArgs halo) {
     constexpr int NC = FLUID ? 1 : 3;
     constexpr int US = NC * AX_NPE;
     constexpr int NHW = NT / 16;
@@ -824,6 +849,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     __shared__ volatile int sArrHead;           // ... up to this count (written by compute thread 0 behind a barrier)
     __shared__ volatile int sArrSeen;           // ... of which Newmark warp 0 has posted this many (back-pressure for the ring)
     __shared__ volatile int sCtaDone;           // the compute warps have handed over their last element
+    __shared__ int sPut;                        // this CTA finished the rank's last boundary element: it sends the halo
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const bool nw_on = NWW > 0 && nw.on != 0;
@@ -883,6 +909,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
         };
         int e = blockIdx.x;
         int n_done = 0;     // elements of this CTA whose scatter has been issued (their codes are in the ring)
+        if (!FLUID && halo.tab != nullptr && halo.nb == 0 && blockIdx.x == 0) halo_put_cta<NT, NWW>(*halo.tab, displ, stiff, tid);
         if (e < nelem) {
             load_desc(0, e);
             if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
@@ -943,6 +970,17 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                     };
                     fused_pass<FLUID, NT, NWW>(cx, E, P, g, first_mt, tid, gather, after_first_sync, after_grad);
                     first_mt = next_mt;
+                }
+                if (!FLUID && halo.tab != nullptr && E.bnd) {
+                    __threadfence();          // this thread's scatter of the element before the count
+                    cta_sync<NT, NWW>();
+                    if (tid == 0) {
+                        const unsigned old = atomicAdd(halo.bcnt, 1u);
+                        sPut = (old + 1u == (unsigned)halo.nb) ? 1 : 0;
+                        if (sPut) *halo.bcnt = 0u;   // re-arm for the next launch (graph replay)
+                    }
+                    cta_sync<NT, NWW>();
+                    if (sPut) halo_put_cta<NT, NWW>(*halo.tab, displ, stiff, tid);
                 }
                 if (nw_on) {
                     if (tid < AX_NPE) {

@@ -33,6 +33,7 @@ struct ElemDesc {
     int prt;                   // 1: the element carries a PRT (9-component path; trig_off is valid for fluid elements too)
     int ng;                    // fused kernel: number of row-group passes (1, 2, 3 or 5)
     int zoff, twoff;           // fused kernel: float2 offsets of the Z-form columns and of the twiddle tables in the tile region
+    int bnd, pad_;             // 1: the element touches a point shared with another rank (boundary element: first in the work queue)
 };
 
 struct PointTab {              // one per field family (solid: ncomp = 3, fluid: ncomp = 1)
@@ -603,25 +604,31 @@ struct SFTab {
     const int *row_point, *row_start;
     int nrows;
 };
-__global__ void k_sf_couple(SFTab sf, const float2 *__restrict__ s_displ, float2 *__restrict__ s_stiff,
-                            float2 *__restrict__ f_stiff) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= sf.nrows) return;
+// one (sf point, mode) row.  L2-only accesses (ld.cg / st.cg): the in-kernel caller (fused.cuh: halo_put_cta) reads forces that
+// other SMs have just RED-added
+__device__ __forceinline__ void sf_couple_row(const SFTab &sf, int r, const float2 *__restrict__ s_displ, float2 *__restrict__ s_stiff,
+                                              float2 *__restrict__ f_stiff) {
     const int q = sf.row_point[r];
     const int alpha = r - sf.row_start[q];
     const int st = sf.nu[q] + 1;
     const float *c = sf.cpl + 4 * q;
     const size_t so = (size_t)sf.s_off[q] + alpha, fo = (size_t)sf.f_off[q] + alpha;
-    float2 us = s_displ[so], uz = s_displ[so + 2 * (size_t)st];
-    float2 ff = f_stiff[fo];
+    float2 us = __ldcg(s_displ + so), uz = __ldcg(s_displ + so + 2 * (size_t)st);
+    float2 ff = __ldcg(f_stiff + fo);
     ff.x += c[0] * us.x + c[1] * uz.x;
     ff.y += c[0] * us.y + c[1] * uz.y;
-    f_stiff[fo] = ff;
-    float2 a = s_stiff[so], b = s_stiff[so + 2 * (size_t)st];
+    __stcg(f_stiff + fo, ff);
+    float2 a = __ldcg(s_stiff + so), b = __ldcg(s_stiff + so + 2 * (size_t)st);
     a.x -= c[2] * ff.x; a.y -= c[2] * ff.y;
     b.x -= c[3] * ff.x; b.y -= c[3] * ff.y;
-    s_stiff[so] = a;
-    s_stiff[so + 2 * (size_t)st] = b;
+    __stcg(s_stiff + so, a);
+    __stcg(s_stiff + so + 2 * (size_t)st, b);
+}
+__global__ void k_sf_couple(SFTab sf, const float2 *__restrict__ s_displ, float2 *__restrict__ s_stiff,
+                            float2 *__restrict__ f_stiff) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= sf.nrows) return;
+    sf_couple_row(sf, r, s_displ, s_stiff, f_stiff);
 }
 
 // SFCoupling3D (SFCoupling3D.cpp:9-54): one CTA per 3D solid-fluid point.
@@ -738,16 +745,17 @@ __global__ void k_halo_wait_add(int n, const unsigned *__restrict__ idx, const f
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned s = *step;
     if (threadIdx.x == 0) {
-        const unsigned want = (s + 1u) * gridDim.x;   // the matching put has the same grid
+        const unsigned want = (s + 1u) * gridDim.x;   // the matching put announces the same number of blocks
         unsigned long long spins = 0;
         for (;;) {
             unsigned c;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(c) : "l"(count) : "memory");
             if ((int)(c - want) >= 0) break;
             __nanosleep(100);
-            if (++spins > (1ull << 26)) {   // ~10 s: never hang the GPU on a lost neighbour
-                *timeout_flag = 1;
-                break;
+            if (++spins > (1ull << 27)) {   // ~20 s without the neighbour's boundary forces: never add stale data, never hang the
+                *timeout_flag = 1;          // GPU -- flag it and abort the launch (the next API call reports the failure)
+                __threadfence_system();
+                __trap();
             }
         }
         __threadfence_system();
@@ -761,6 +769,23 @@ __global__ void k_halo_wait_add(int n, const unsigned *__restrict__ idx, const f
         d->y += v.y;
     }
 }
+// In-kernel form of k_halo_put (fused.cuh: halo_put_cta): one CTA of the solid element kernel sends the boundary forces of every
+// neighbour as soon as the last boundary element of the rank has scattered, while the interior elements are still being computed.
+#define AX_MAX_NEIGH 16
+struct HaloPeer {
+    const unsigned *idx;          // pack list of this neighbour (k_halo_put order)
+    float2 *win;                  // my segment in the neighbour's window (parity 0)
+    unsigned long long stride;    // its parity stride
+    unsigned *count;              // its arrival counter for me
+    int n, nblocks;               // entries; blocks the matching k_halo_wait_add expects per exchange (= its grid)
+};
+struct HaloTab {
+    int nneigh;
+    HaloPeer peer[AX_MAX_NEIGH];
+    const unsigned *step;         // exchange number (k_halo_advance)
+    float2 *f_stiff;              // fluid stiffness (the kernel's own arrays are the solid ones)
+    SFTab sf_halo;                // (sf point, mode) rows of the solid-fluid points on the halo: coupled before they are sent
+};
 __global__ void k_halo_advance(unsigned *step) { *step += 1u; }
 
 // ------------------------------------------------------------------------------------ stability

@@ -26,7 +26,7 @@ def src_line(path, n):
 def pick_outer(chain):
     """outermost frame that is not merely the call of an inlined element body (so phases inside it are seen)"""
     for f in reversed(chain):
-        if "fused_element<" not in src_line(*f) and "wp_element<" not in src_line(*f):
+        if "fused_pass<" not in src_line(*f) and "fused_element<" not in src_line(*f):
             return f
     return chain[-1]
 loc_of, chain, fresh = {}, [("?", 0)], True
