@@ -238,6 +238,9 @@ struct ax3d_domain {
     DevBuf<unsigned> halo_bcnt;
     int n_bnd_fused = 0;                    // boundary elements in the solid fused launch
     bool inkernel_put = false;
+    // ax3d_measure_costs: per-element SM cycles recorded by the fused launches ([class offset + index in launch])
+    DevBuf<unsigned> cost_buf;
+    size_t cost_off[NCLS] = {0, 0, 0, 0};
     bool have_uid = false;
     unsigned char uid[128];
 #ifdef AX3D_WITH_NCCL
@@ -1271,8 +1274,9 @@ static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool n
     }
     if (!fluid && d->nw_dbg.p && nw.on) nw.dbg = d->nw_dbg.p;
     const double kbytes = f.alg_b + (nw.on ? d->dom_bytes[1] : 0.0);
-    HaloArgs halo{nullptr, nullptr, 0};
-    if (put && !fluid) halo = HaloArgs{d->halo_tab.p, d->halo_bcnt.p, d->n_bnd_fused};
+    HaloArgs halo{nullptr, nullptr, 0, nullptr};
+    if (put && !fluid) halo = HaloArgs{d->halo_tab.p, d->halo_bcnt.p, d->n_bnd_fused, nullptr};
+    if (d->cost_buf.p) halo.cost = d->cost_buf.p + d->cost_off[c];
     KTimer kt(d, fluid ? "k_elem3d_fused<fluid>" : (nw.on ? "k_elem3d_fused<solid> + in-kernel Newmark" : "k_elem3d_fused<solid>"), kbytes);
     fused_kernel(f)<<<f.grid, fused_nt(f), f.smem, d->stream>>>(
         d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
@@ -2300,6 +2304,69 @@ int ax3d_record_strain(ax3d_domain *d, int nrec, const int *elem_tags, const flo
 int ax3d_record_curl(ax3d_domain *d, int nrec, const int *elem_tags, const float *phi, const float *weights, float *out) {
     API_BEGIN
     record_strain_curl(d, 1, nrec, elem_tags, phi, weights, out);
+    API_END
+}
+
+/* Measured element costs (the reference's cost-measure pass, Mesh.cpp:412-588: each element's computeStiff is timed and the
+ * times weight the second METIS partition).  One Domain::computeStiff is run `repeats` times with the clocks on:
+ * elements of the fused launches report the SM cycles their CTA spent on them (clock64 around the element, gather prefetch
+ * of the next one included); elements that go through k_elem1d or the split pipeline share the event-timed duration of
+ * their launches in proportion to their number of 16-mode tiles (x Nr for 3D).  cost_us[elem tag] = microseconds of ONE SM. */
+int ax3d_measure_costs(ax3d_domain *d, int repeats, double *cost_us, int nelem) {
+    API_BEGIN
+    check_final(d);
+    if (nelem != (int)d->elems.size()) fail("Mesh::measure || size mismatch");
+    if (repeats < 1) repeats = 1;
+    int khz = 0;
+    CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d->device));
+    size_t tot = 0;
+    for (int c = 0; c < NCLS; ++c) { d->cost_off[c] = tot; tot += d->h_desc[c].size(); }
+    d->cost_buf.alloc(tot);
+    std::vector<double> acc(d->elems.size(), 0.0);
+    std::vector<unsigned> h(tot);
+    const bool timers_were = d->timers;
+    for (int r = 0; r <= repeats; ++r) {   // r = 0: warm-up
+        d->cost_buf.zero();
+        d->kstats.clear();
+        d->timers = true;
+        compute_stiff(d);
+        d->timers = timers_were;
+        CK(cudaStreamSynchronize(d->stream));
+        if (r == 0) continue;
+        CK(cudaMemcpy(h.data(), d->cost_buf.p, tot * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        // launches without in-kernel clocks: event time x resident CTAs share, split by work units
+        double ms1d[NCLS] = {0, 0, 0, 0};
+        for (const auto &kv : d->kstats) {
+            if (kv.first == "k_elem1d<solid>") ms1d[CLS_S1D] += kv.second.ms;
+            if (kv.first == "k_elem1d<fluid>") ms1d[CLS_F1D] += kv.second.ms;
+            if (kv.first.rfind("split pipeline <solid>", 0) == 0) ms1d[CLS_S3D] += kv.second.ms;
+            if (kv.first.rfind("split pipeline <fluid>", 0) == 0) ms1d[CLS_F3D] += kv.second.ms;
+        }
+        double units[NCLS] = {0, 0, 0, 0};
+        auto unit_of = [&](const HElem &E) {
+            const double tiles = (double)((E.nu + 1 + AX_TILE - 1) / AX_TILE);
+            return E.rows > 1 ? tiles * E.nr : tiles;
+        };
+        for (const HElem &E : d->elems) {
+            const bool in_fused = E.rows > 1 && d->h_desc[E.cls][E.idx].bucket == 0;
+            if (!in_fused) units[E.cls] += unit_of(E);
+        }
+        for (size_t e = 0; e < d->elems.size(); ++e) {
+            const HElem &E = d->elems[e];
+            const bool in_fused = E.rows > 1 && d->h_desc[E.cls][E.idx].bucket == 0;
+            if (in_fused) {
+                // the fused launch indexes its elements from its first one
+                int first = 0;
+                for (const FusedLaunch &f : d->fused) if (f.cls == E.cls) first = f.first;
+                acc[e] += (double)h[d->cost_off[E.cls] + (size_t)(E.idx - first)] / (double)khz * 1e3;
+            } else if (units[E.cls] > 0) {
+                acc[e] += ms1d[E.cls] * 1e3 * (double)d->num_sm * unit_of(E) / units[E.cls];
+            }
+        }
+    }
+    for (size_t e = 0; e < d->elems.size(); ++e) cost_us[e] = acc[e] / repeats;
+    d->cost_buf.release();
+    d->kstats.clear();
     API_END
 }
 

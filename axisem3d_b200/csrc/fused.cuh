@@ -798,6 +798,8 @@ struct HaloArgs {
     const HaloTab *tab;   // nullptr: no in-kernel put in this launch
     unsigned *bcnt;       // boundary elements finished in this launch (re-armed by the CTA that sends)
     int nb;               // boundary elements of the launch (0: CTA 0 sends before its first element)
+    unsigned *cost;       // nullptr, or [nelem]: SM clock cycles this launch spent on every element (ax3d_measure_costs: the
+                          // measured element costs that weight the partition, Mesh.cpp:412-588)
 };
 
 template <int NT, int NWW>
@@ -932,6 +934,8 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                     for (int q = tid; q < nline; q += NT) prefetch_l2(cb + (size_t)q * 32);
                 }
                 const int ng = E.ng;
+                long long t_el = 0;
+                if (halo.cost != nullptr && tid == 0) t_el = clock64();
                 for (int g = 0; g < ng; ++g) {
                     const bool last = g + 1 == ng;
                     int next_mt = 0;
@@ -971,6 +975,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                     fused_pass<FLUID, NT, NWW>(cx, E, P, g, first_mt, tid, gather, after_first_sync, after_grad);
                     first_mt = next_mt;
                 }
+                if (halo.cost != nullptr && tid == 0) halo.cost[e] = (unsigned)(clock64() - t_el);
                 if (!FLUID && halo.tab != nullptr && E.bnd) {
                     __threadfence();          // this thread's scatter of the element before the count
                     cta_sync<NT, NWW>();

@@ -89,9 +89,36 @@ def workload_name(n_theta, n_r=N_R):
 
 
 def element_weights(mesh):
-    """first-pass element cost for the partitioner (the reference starts from Nr, Mesh.cpp:88-101): Nr log Nr"""
+    """Element cost for the partitioner.  The reference measures every element's computeStiff and repartitions with the
+    times as METIS vertex weights (Mesh.cpp:412-588); here the weights come from the cost model calibrated on costs
+    measured on the device (ax3d_measure_costs; axisem3d_b200/cost_model.json, profiles/scripts/calibrate_costs.py):
+    a Nr log2 Nr + b Nr + c per element kind, plus the Newmark update of the element's share of points.  Without the
+    model file: Nr log2 Nr for 3D solid elements, a tenth of it for the cheap kinds."""
     nr = mesh.e_nr.astype(np.float64)
-    return nr * np.log2(np.maximum(nr, 2.0)) + 16.0
+    nlog = nr * np.log2(np.maximum(nr, 2.0))
+    fluid = np.asarray(mesh.is_fluid, dtype=bool)
+    skey = "solid|%s|%s|%s" % ("3d" if mesh.model3d else "1d", mesh.law, mesh.att_kind or "none")
+    fkey = "fluid|%s" % ("3d" if mesh.fluid3d else "1d")
+    try:
+        model = json.load(open(os.path.join(ROOT, "axisem3d_b200", "cost_model.json")))
+        w = np.zeros_like(nr)
+        for key, mask in ((skey, ~fluid), (fkey, fluid)):
+            c = model[key]
+            fit = np.maximum(c["a_nr_log2nr"] * nlog[mask] + c["b_nr"] * nr[mask] + c["c"], 0.05)
+            if "table_nr" in c:      # inside the measured range: the measured mean cost per Nr, interpolated
+                tn, tu = np.asarray(c["table_nr"], dtype=np.float64), np.asarray(c["table_us"], dtype=np.float64)
+                inside = (nr[mask] >= tn[0]) & (nr[mask] <= tn[-1])
+                fit = np.where(inside, np.interp(nr[mask], tn, tu), fit)
+            w[mask] = fit
+        # Newmark: ~16 unique points per element, (Nu + 1) modes each, 3 components for solid points
+        w += model["_point_us_per_mode"] * 16.0 * (nr / 2 + 1) * np.where(fluid, 1.0 / 3.0, 1.0)
+        return w
+    except (OSError, KeyError):
+        w = nlog + 16.0
+        cheap = fluid if not mesh.fluid3d else np.zeros_like(fluid)
+        if not mesh.model3d:
+            cheap = np.ones_like(fluid)
+        return np.where(cheap, 0.1 * w, w)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -224,6 +251,26 @@ def global_receivers(mesh, nrec=128, seed=5):
     return eg, phi, w
 
 
+def apply_kick(dom, rel, amp=1e12):
+    """A broadband force on every GLL point and Fourier mode, a function of the GLOBAL point tag only, so that a partitioned
+    run and a single-domain run start from the same state and the whole wavefield -- across every partition boundary -- is
+    in motion from the first step of the parity check (the first Newmark update masks and mass-scales it)."""
+    l2g = rel["dec"].local_to_global_gll
+    ks, kf = [], []
+    for t, p in enumerate(rel["points"]):
+        g = float(l2g[t])
+        a = np.arange(p.nu + 1, dtype=np.float64)
+        if p.kind != "fluid":
+            for c in range(3):
+                ks.append(amp * (np.sin(0.37 * g + 1.3 * c + 0.11 * a) + 1j * np.cos(0.23 * g + 0.7 * c + 0.05 * a)) / (1.0 + a))
+        if p.kind != "solid":
+            kf.append(amp * (np.cos(0.41 * g + 0.13 * a) + 1j * np.sin(0.29 * g + 0.07 * a)) / (1.0 + a))
+    if ks:
+        dom.set_bulk("stiff", False, np.concatenate(ks).astype(np.complex64))
+    if kf:
+        dom.set_bulk("stiff", True, np.concatenate(kf).astype(np.complex64))
+
+
 def register_receivers(dom, rel, eg, phi, w):
     """registers the receivers that lie in this rank's elements; returns their indices in the global list"""
     loc = {int(g): il for il, g in enumerate(rel["dec"].local_elems)}
@@ -303,7 +350,12 @@ def run_ours(args):
     #      compared below with a single-domain run of the same global mesh on rank 0's GPU
     seis_par = None
     if world > 1 and not args.no_parity:
-        seis_par = dom.runStepsRecord(dt, stf[:NPAR]) if mine else np.zeros((NPAR, 0, 3), np.float32)
+        apply_kick(dom, rel)
+        if mine:
+            seis_par = dom.runStepsRecord(dt, stf[:NPAR])
+        else:
+            dom.runSteps(dt, stf[:NPAR])
+            seis_par = np.zeros((NPAR, 0, 3), np.float32)
         barrier()
 
     # ---- device-timed region: inputs resident in HBM.  K steps per region (CUDA events on the launching stream, max over
@@ -421,6 +473,7 @@ def run_ours(args):
                 one.addSourceTerm(s1)
             one.finalize()
             register_receivers(one, rel1, eg, phi, w)
+            apply_kick(one, rel1)
             ref = one.runStepsRecord(dt, stf[:NPAR]).astype(np.float64)
             got = np.zeros_like(ref)
             seen = np.zeros(len(eg), dtype=bool)
@@ -429,7 +482,7 @@ def run_ours(args):
                     got[:, idx, :] = sp
                     seen[idx] = True
             den = float(np.linalg.norm(ref))
-            parity = {"what": "seismograms at the %d receivers, first %d steps from rest: %d-rank run vs one domain holding the whole mesh" % (len(eg), NPAR, world),
+            parity = {"what": "seismograms at the %d receivers, first %d steps after a broadband kick on every point and mode (+ the source): %d-rank run vs one domain holding the whole mesh" % (len(eg), NPAR, world),
                       "rel_l2": float(np.linalg.norm(got - ref) / den) if den > 0 else None, "tolerance": 1e-4,
                       "receivers_recorded": int(seen.sum())}
             parity["ok"] = bool(parity["rel_l2"] is not None and parity["rel_l2"] <= 1e-4 and seen.all())

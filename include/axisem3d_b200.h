@@ -226,6 +226,12 @@ int ax3d_enable_timers(ax3d_domain *dom, int on);
 int ax3d_kernel_stats(ax3d_domain *dom, int index, char *name, int name_cap, double *ms_total, long long *launches,
                       double *bytes_total, int *count, int reset);
 int ax3d_get_timers(ax3d_domain *dom, double out_ms[4], int reset);
+/* Measured element costs = the reference's cost-measure pass before its second partition (Mesh::measure,
+ * Mesh.cpp:412-588: every element's computeStiff is timed, the times become the METIS vertex weights).  Runs
+ * Domain::computeStiff `repeats` times with the device clocks on and returns cost_us[element tag] = microseconds of one
+ * SM spent on the element (fused launches: clock64 around the element inside the kernel; k_elem1d / split pipeline:
+ * event-timed launch duration shared by work units). */
+int ax3d_measure_costs(ax3d_domain *dom, int repeats, double *cost_us, int nelem);
 
 #ifdef __cplusplus
 }
