@@ -812,10 +812,19 @@ __device__ __forceinline__ void halo_put_cta(const HaloTab &ht, const float2 *__
     for (int n = 0; n < ht.nneigh; ++n) {
         const HaloPeer &P = ht.peer[n];
         float2 *dst = P.win + (size_t)(s & 1u) * P.stride;
-        for (int i = tid; i < P.n; i += NT) {
-            const unsigned k = P.idx[i];
-            const float2 v = (k >> 31) ? __ldcg(ht.f_stiff + (k & 0x7fffffffu)) : __ldcg(s_stiff + k);
-            __stcg(dst + i, v);
+        for (int i0 = tid; i0 < P.n; i0 += 4 * NT) {   // four independent index -> force -> remote store chains per thread
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * NT;
+                if (i < P.n) {
+                    const unsigned k = P.idx[i];
+                    v[u] = (k >> 31) ? __ldcg(ht.f_stiff + (k & 0x7fffffffu)) : __ldcg(s_stiff + k);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * NT < P.n) __stcg(dst + i0 + u * NT, v[u]);
         }
     }
     __threadfence_system();

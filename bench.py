@@ -71,11 +71,39 @@ def mesh_shape(world, scaling):
     return N_THETA * (STRONG_N if scaling == "strong" else world), N_R
 
 
+def _iso_work_nu(base_nu, base_fn):
+    """Weak scaling keeps the work per GPU fixed: the N-GPU mesh refines the N = 1 mesh in theta, and the circumference cap of
+    the Fourier order (Quad.cpp:562-566: Nr <= 2 pi s / GLL spacing) would loosen with the finer spacing and give the near-axis
+    points of the larger meshes more modes.  The order field of the weak-scaling meshes is therefore the N = 1 field: the
+    configured order capped with the N = 1 mesh's GLL spacing."""
+    from axisem3d_b200.mesh_synth import R_EARTH
+    dth1, dr = np.pi / N_THETA, (R_EARTH - 600e3) / N_R
+
+    def fn(s, z):
+        nu = base_fn(s, z) if base_fn is not None else base_nu
+        spacing = 0.5 * (np.hypot(s, z) * dth1 + dr) / 4.0
+        upper = max(int(2 * np.pi * s / spacing), 3)
+        return min(int(nu), (upper - 1) // 2)
+    return fn
+
+
+MESH = "synth"          # --mesh exodus: the shipped 50 s Exodus mesh itself (tests/golden/AxiSEM_prem_ani_one_crust_50.e), N = 1
+EXODUS_FILE = os.path.join(ROOT, "tests", "golden", "AxiSEM_prem_ani_one_crust_50.e")
+
+
 def make_mesh(n_theta, n_r=None, **kw):
+    if MESH == "exodus":
+        from axisem3d_b200.exodus_mesh import ExodusMesh
+        c = CONFIGS[CFG][0]
+        # the elastic law comes from the file (PREM: transversely isotropic in the upper mantle, isotropic elsewhere)
+        return ExodusMesh(EXODUS_FILE, nu=c.get("nu", 2), nu_fn=c.get("nu_fn"), attenuation=c.get("attenuation"),
+                          model3d=c.get("model3d", False), fluid3d=c.get("fluid3d", False), dtype_coef=np.float32)
     from axisem3d_b200.mesh_synth import SynthMesh
     args = dict(n_theta=n_theta, n_r=n_r or N_R, dtype_coef=np.float32)
     args.update(CONFIGS[CFG][0])
     args.update(kw)
+    if CFG != "cfg5" and n_theta != N_THETA and (n_r or N_R) == N_R:
+        args["nu_fn"] = _iso_work_nu(args.get("nu", 2), args.get("nu_fn"))
     return SynthMesh(**args)
 
 
@@ -85,6 +113,8 @@ def stf_series(n):
 
 
 def workload_name(n_theta, n_r=N_R):
+    if MESH == "exodus":
+        return "%s; on the shipped mesh template/input/AxiSEM_prem_ani_one_crust_50.e (2016 quads; elastic law from the file)" % CONFIGS[CFG][1]
     return "%s; synthetic meridional mesh %d x %d = %d quads" % (CONFIGS[CFG][1], n_theta, n_r, n_theta * n_r)
 
 
@@ -242,7 +272,10 @@ def run_reference(args):
 def global_receivers(mesh, nrec=128, seed=5):
     """128 receivers (the template STATIONS file has 128) in the outermost solid layer of the GLOBAL mesh: element id,
     azimuth, interpolation weights -- the same on every rank, so that an N-rank run and a 1-rank run record the same stations."""
-    surf = np.nonzero((mesh.ab[:, 1] == mesh.nr_ - 1) & ~mesh.is_fluid)[0]
+    if hasattr(mesh, "surf_side"):
+        surf = np.nonzero((mesh.surf_side >= 0) & ~mesh.is_fluid)[0]
+    else:
+        surf = np.nonzero((mesh.ab[:, 1] == mesh.nr_ - 1) & ~mesh.is_fluid)[0]
     rng = np.random.default_rng(seed)
     eg = surf[rng.integers(0, len(surf), nrec)]
     phi = rng.uniform(0, 2 * np.pi, nrec)
@@ -519,7 +552,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": work * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
+        "data": "synthetic" if MESH == "synth" else "template/input Exodus mesh (1D PREM from the file%s), synthetic source and receivers" % (
+            " + synthetic azimuthal perturbation" if CONFIGS[CFG][0].get("model3d") else ""),
         "config": {"workload": workload_name(n_theta, n_r), "elements": int(mesh.nelem), "gll_points": int(mesh.ngll),
                    "point_modes_per_step": int(work), "parallelism": "dd%d" % world, "halo": halo, "partition": part_info,
                    "timing": "median of %d regions of %d steps (CUDA events, max over ranks); min %.4f max %.4f ms/step" % (
@@ -573,9 +607,14 @@ def main():
                     help="weak: 72 N x 28 quads on N GPUs; strong: the N = 8 mesh (576 x 28) on every N")
     ap.add_argument("--partition", default="metis", choices=["metis", "contiguous"])
     ap.add_argument("--min-seconds", type=float, default=2.0, help="the K-step region is repeated until this much time has passed")
+    ap.add_argument("--mesh", default="synth", choices=["synth", "exodus"],
+                    help="exodus: run the configuration on the shipped 50 s Exodus mesh (read with axisem3d_b200/h5lite.py; N = 1)")
     args = ap.parse_args()
-    global CFG
+    global CFG, MESH
     CFG = args.config
+    MESH = args.mesh
+    if MESH == "exodus" and (args.gpus > 1 or CFG == "cfg5"):
+        ap.error("--mesh exodus runs cfg1-cfg4 on one GPU")
     if args.impl == "reference":
         run_reference(args)
     else:
