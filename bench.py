@@ -56,13 +56,16 @@ CONFIGS = {
              "cfg3: 3D anisotropic (21 C_ij) + CG4 SLS attenuation, Nu=200 (Nr=416), SF coupling through the outer core"),
     "cfg4": (dict(nu_fn=cfg4_nu, law="iso", model3d=True, attenuation=None),
              "cfg4: 3D isotropic, per-point Nu 20..500 (Nr up to 672 on this mesh), ragged FFT sizes, fluid core + SF coupling"),
-    # ~5 s-period mesh: 100 x the element count of the 50 s mesh (720 x 280 = 201600 quads), anisotropic + CG4 SLS, Nu <= 1000;
-    # only meaningful partitioned over 8 GPUs (bench.py --config cfg5 --gpus 8)
+    # configs[4]: the large anisotropic + SLS mesh with Nu up to 1000, partitioned over 8 GPUs (bench.py --config cfg5 --gpus 8).
+    # Element count used: 240 x 96 = 23 040 quads (11.4 x the 50 s mesh, ~370 k GLL points, 166 M point-modes per step,
+    # 52 GB of fields + moduli + memory variables in total).  The ~200 k-quad mesh BASELINE.md sketches (720 x 280) would fit
+    # the 8 x 180 GB as well (~470 GB), but the per-element Python set-up of the synthetic generator would take ~10 min per
+    # rank on the GPU box; the per-element work, the Nr range and the partition shape are the same.
     "cfg5": (dict(nu_fn=cfg5_nu, law="aniso", model3d=True, attenuation="cg4", fluid3d=False),
-             "cfg5: ~5 s-period synthetic mesh, 3D anisotropic + CG4 SLS attenuation, empirical Nu <= 1000 (Nr <= 2016)"),
+             "cfg5: synthetic mesh of 23 040 quads, 3D anisotropic (21 C_ij) + CG4 SLS attenuation, empirical Nu <= 1000 (Nr <= 2016)"),
 }
 CFG = "cfg4"
-CFG5_THETA, CFG5_R = 720, 280
+CFG5_THETA, CFG5_R = 240, 96
 
 
 def mesh_shape(world, scaling):
@@ -253,7 +256,7 @@ def run_reference(args):
     if rank != 0:
         return
     if CFG == "cfg5":
-        print(json.dumps({"impl": "reference", "unavailable": "cfg5 (201600 quads, Nu <= 1000) does not fit the CPU arm's time budget; use cfg1-cfg4"}))
+        print(json.dumps({"impl": "reference", "unavailable": "cfg5 (23040 quads, Nu <= 1000: ~20 s of CPU work per step) does not fit the CPU arm's time budget; use cfg1-cfg4"}))
         return
     n_theta, n_r = mesh_shape(args.gpus, args.scaling)
     # the same N x mesh the GPU arm steps at --gpus N, whole mesh per step, all host threads
@@ -382,6 +385,8 @@ def run_ours(args):
     # ---- parity of the partitioned run (N > 1): the first NPAR steps from rest, seismograms at the 128 global receivers,
     #      compared below with a single-domain run of the same global mesh on rank 0's GPU
     seis_par = None
+    if CFG == "cfg5":
+        args.no_parity = True            # a single domain holding the whole cfg5 mesh is a set-up of its own
     if world > 1 and not args.no_parity:
         apply_kick(dom, rel)
         if mine:
