@@ -700,7 +700,7 @@ static void finalize(ax3d_domain *d) {
             }
             D.geom_off = (long long)geom.size();
             for (int i = 0; i < 5 * AX_NPE; ++i) geom.push_back((float)E.geom[i]);
-            if (D.tiso || D.prt || !fluid) {   // fluid elements rotate only with PRT (FluidElement.cpp:21); every solid element
+            {                                  // fluid elements rotate only with PRT (FluidElement.cpp:21); every element
                                                // keeps its trig for the strain / curl read-back (forceTIso, SolidElement.cpp:347-352)
                 D.trig_off = (long long)geom.size();
                 for (int i = 0; i < AX_NPE; ++i) geom.push_back((float)sin(E.theta[i]));
@@ -1582,6 +1582,11 @@ int ax3d_add_fluid_element(ax3d_domain *d, const int tags[25], const double *geo
     e.rows = rows;
     e.ncoef = 1;
     e.coef.assign(K, K + (size_t)rows * AX_NPE);
+    for (int i = 0; i < AX_NPE; ++i) {   // Element::formThetaMat (Element.cpp:48-58): the strain read-back rotates to RTZ (forceTIso)
+        const double *c = d->points[e.pt[i]].crds;
+        const double r = sqrt(c[0] * c[0] + c[1] * c[1]);
+        e.theta[i] = r < 1e-10 ? 0.0 : acos(std::max(-1.0, std::min(1.0, c[1] / r)));
+    }
     d->elems.push_back(std::move(e));
     *tag = (int)d->elems.size() - 1;
     API_END
@@ -2262,14 +2267,19 @@ static void record_strain_curl(ax3d_domain *d, int which, int nrec, const int *e
     for (int i = 0; i < nrec; ++i) {
         if (elem_tags[i] < 0 || elem_tags[i] >= (int)d->elems.size()) fail("PointwiseRecorder::record || invalid element tag");
         const HElem &E = d->elems[elem_tags[i]];
-        if (E.fluid) fail(std::string("FluidElement::") + fn + " || strain / curl receivers in fluid elements are not supported by the B200 path.");
-        if (E.prt_rows) fail(std::string("SolidElement::") + fn + " || strain / curl receivers in elements with particle relabelling are not supported by the B200 path.");
+        // FluidElement::computeCurl is identically zero (FluidElement.cpp:308-311); computeStrain is built for Acoustic1D elements
+        if (E.fluid && !which && E.rows > 1) fail("FluidElement::computeStrain || strain receivers in fluid elements with 3D material are not supported by the B200 path.");
+        if (E.prt_rows) fail(std::string(E.fluid ? "FluidElement::" : "SolidElement::") + fn + " || strain / curl receivers in elements with particle relabelling are not supported by the B200 path.");
         items[i].elem = E.idx | (E.cls << 28);
         items[i].phi = phi[i];
     }
     DevBuf<RecvItem> di;
     DevBuf<float> dw, dout;
-    for (int c : {CLS_S1D, CLS_S3D}) {
+    for (int i = 0; i < nrec; ++i)   // fluid receivers: zero curl; the strain rows are filled by the fluid launch below
+        if (d->elems[elem_tags[i]].fluid && which)
+            for (int cc = 0; cc < nout; ++cc) out[i * nout + cc] = 0.f;
+    for (int c : {CLS_S1D, CLS_S3D, CLS_F1D}) {
+        if (c == CLS_F1D && which) continue;
         std::vector<RecvItem> sub;
         std::vector<int> where;
         std::vector<float> w;
@@ -2285,7 +2295,8 @@ static void record_strain_curl(ax3d_domain *d, int which, int nrec, const int *e
         di.upload(sub);
         dw.upload(w);
         dout.alloc(sub.size() * nout);
-        if (which) k_strain_curl<true><<<(int)sub.size(), AX_TILE * AX_NPE, 0, d->stream>>>(d->desc[c].p, di.p, dw.p, d->geom.p, d->s_field[AX3D_DISPL].p, dout.p);
+        if (c == CLS_F1D) k_strain_fluid1d<<<(int)sub.size(), AX_TILE * AX_NPE, 0, d->stream>>>(d->desc[c].p, di.p, dw.p, d->geom.p, d->coef.p, d->f_field[AX3D_DISPL].p, dout.p);
+        else if (which) k_strain_curl<true><<<(int)sub.size(), AX_TILE * AX_NPE, 0, d->stream>>>(d->desc[c].p, di.p, dw.p, d->geom.p, d->s_field[AX3D_DISPL].p, dout.p);
         else k_strain_curl<false><<<(int)sub.size(), AX_TILE * AX_NPE, 0, d->stream>>>(d->desc[c].p, di.p, dw.p, d->geom.p, d->s_field[AX3D_DISPL].p, dout.p);
         d->launches++;
         CK(cudaGetLastError());

@@ -964,6 +964,74 @@ __global__ void __launch_bounds__(AX_TILE *AX_NPE) k_strain_curl(const ElemDesc 
     }
 }
 
+// FluidElement::computeStrain (FluidElement.cpp:219-306) for Acoustic1D elements without particle relabelling: the fluid
+// displacement u = K grad(chi) of a mode tile is formed for all 25 points in shared memory (with a 1D K the SPZ <-> RTZ
+// rotations around Acoustic1D::strainToStress cancel), then Gradient::computeGrad6 of it, rotated to RTZ (forceTIso) and
+// evaluated at azimuth phi with the 25 interpolation weights -- the second half is k_strain_curl's.
+__global__ void __launch_bounds__(AX_TILE *AX_NPE) k_strain_fluid1d(const ElemDesc *__restrict__ elems, const RecvItem *__restrict__ rec,
+                                                                    const float *__restrict__ weights, const float *__restrict__ geom,
+                                                                    const float *__restrict__ coef, const float2 *__restrict__ displ,
+                                                                    float *__restrict__ out) {
+    __shared__ float2 sC[AX_NPE * AX_TILE];
+    __shared__ float2 sU[3 * AX_NPE * AX_TILE];
+    __shared__ float red[6][AX_TILE * AX_NPE / 32 + 1];
+    const RecvItem R = rec[blockIdx.x];
+    const ElemDesc &E = elems[R.elem];
+    const int t = threadIdx.x % AX_TILE, p = threadIdx.x / AX_TILE;
+    const int i = p / 5, j = p % 5;
+    const int top = E.nu - E.nyq;
+    GCoef gc;
+    load_gcoef(gc, E.axial, i, j);
+    const PointGeom g = load_geom(geom, E.geom_off, p);
+    const bool ax0 = E.axial && i == 0;
+    float tr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tr[k] = geom[E.trig_off + k * AX_NPE + p];
+    const float K = coef[E.coef_off + p];
+    const float wp = weights[(size_t)blockIdx.x * AX_NPE + p];
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int a0 = 0; a0 <= top; a0 += AX_TILE) {
+        const int alpha = a0 + t;
+        __syncthreads();
+        gather_tile<1>(E, displ, sC, t, p, alpha <= E.nu ? alpha : (1 << 30));
+        __syncthreads();
+        {
+            float2 e3[3];
+            grad_fluid_point(sC, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e3);
+            if (alpha > top) e3[0] = e3[1] = e3[2] = czero();
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float2 u = cscale(e3[c], K);
+                if (alpha == 0) u.y = 0.f;
+                sU[(c * AX_NPE + p) * AX_TILE + t] = u;
+            }
+        }
+        __syncthreads();
+        if (alpha > top || fabsf(wp) < 1e-10f) continue;
+        float sn, cs;
+        sincosf((float)alpha * R.phi, &sn, &cs);
+        const float f = (alpha == 0 ? 1.f : 2.f) * wp;
+        float2 e[6];
+        grad6_point(sU, AX_TILE, t, i, j, gc, g, (float)alpha, ax0, e);
+        rot_spz_to_rtz(e, tr[0], tr[1], tr[2], tr[3]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[k] += f * (alpha == 0 ? e[k].x : cs * e[k].x - sn * e[k].y);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float sm = 0.f;
+        for (int k = 0; k < (AX_TILE * AX_NPE + 31) / 32; ++k) sm += red[threadIdx.x][k];
+        out[blockIdx.x * 6 + threadIdx.x] = sm;
+    }
+}
+
 // FluidElement::computeGroundMotion (FluidElement.cpp:163-215): the fluid "displacement" is the acoustic stress of the
 // potential, u = K grad(chi) -- gather -> Gradient::computeGrad -> [c2r -> K(phi) -> r2c for 3D material] -- evaluated at
 // azimuth phi and interpolated with the receiver's 25 weights.  One CTA per receiver, one GLL row (5 points) at a time so

@@ -429,9 +429,17 @@ def run_ours(args):
     #      BATCH steps = the recorder's dump interval; the call returns only when the samples are in host memory).
     BATCH = 25
     e2e_regions, seis_bytes_per_step = [], 0
-    if mine:
-        dom.runStepsRecord(dt, stf[:BATCH])      # graph variants of the recording path, record ring sized for a batch
-        dom.runStepsRecord(dt, stf[:3])
+    def steps_rec(series):
+        """K steps through the recording entry point; a rank without receivers steps through ax3d_run_steps and synchronises
+        (every rank must take the same number of steps: the halo exchange pairs them)"""
+        if mine:
+            return dom.runStepsRecord(dt, series)
+        dom.runSteps(dt, series)
+        dom.synchronize()
+        return None
+
+    steps_rec(stf[:BATCH])      # graph variants of the recording path, record ring sized for a batch
+    steps_rec(stf[:3])
     barrier()
     t_e2e = time.perf_counter()
     while True:
@@ -441,12 +449,9 @@ def run_ours(args):
         while done < K:
             nb = min(BATCH, K - done)
             s_ = stf[NPAR + W + K + done:NPAR + W + K + done + nb]
-            if mine:
-                seis = dom.runStepsRecord(dt, s_)   # returns with the samples in host memory
+            seis = steps_rec(s_)                    # returns with the samples in host memory
+            if seis is not None:
                 seis_bytes_per_step = int(seis[0].nbytes)
-            else:
-                dom.runSteps(dt, s_)
-                dom.synchronize()
             done += nb
         e2e_regions.append(time.perf_counter() - t0)         # per rank; the max over ranks is taken below
         go = (time.perf_counter() - t_e2e) < 0.5 * args.min_seconds and len(e2e_regions) < 100
@@ -487,10 +492,16 @@ def run_ours(args):
         alg_job = alg_all.cpu().numpy()
         gathered = [None] * world
         dist.all_gather_object(gathered, (mine, seis_par))
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"rank": rank, "elements": len(rel["elements"]), "point_modes": int(work_local),
+                                          "family_ms": [round(float(x), 4) for x in fam],
+                                          "kernels_ms": {k: round(v[0] / nt, 4) for k, v in kst.items()},
+                                          "neighbours": len(rel["msg"].mIProcComm)})
     else:
         work = work_local
         alg_job = alg
         gathered = None
+        per_rank = None
     ms = float(np.median(regions))
     e2e_s = float(np.median(e2e_regions))
 
@@ -583,6 +594,8 @@ def run_ours(args):
     }
     if parity is not None:
         line["parity"] = parity
+    if per_rank is not None:
+        line["per_rank"] = per_rank           # eager-step (timers on) family times of every rank: the load balance of the partition
     if world == 1 and not args.no_cpu and CFG != "cfg5":
         try:
             c = cpu_arm(6, 1, stride=3, min_seconds=12.0, max_seconds=25.0)

@@ -1011,10 +1011,22 @@ class OracleDomain:
         return (up * np.where(np.abs(w) < 1e-10, 0.0, w)[None, :]).sum(axis=1)
 
     def strain(self, elem_tag, phi, weights):
-        """SolidElement::computeStrain (SolidElement.cpp:219-279) after forceTIso, no PRT: grad6 -> SPZ_RTZ -> evaluation."""
+        """SolidElement::computeStrain (SolidElement.cpp:219-279) after forceTIso, no PRT: grad6 -> SPZ_RTZ -> evaluation.
+        Fluid elements (FluidElement::computeStrain, FluidElement.cpp:219-306, no PRT): the fluid displacement (acoustic stress of
+        the potential, as in computeGroundMotion) goes through the same computeGrad6 -> transformSPZ_RTZ -> evaluation."""
         e = self.elements[elem_tag]
-        if e.kind != "solid" or e.prt is not None:
-            raise NotImplementedError("strain receivers: solid elements without PRT")
+        if e.prt is not None:
+            raise NotImplementedError("strain receivers: elements without PRT")
+        if e.kind == "fluid":
+            g, k = next((g, int(np.nonzero(g.tags == e.domain_tag)[0][0])) for g in self.groups
+                        if g.kind == "fluid" and (g.tags == e.domain_tag).any())
+            u = self._fluid_stress(g, self._gather_fluid(g)).reshape(len(g.tags), g.M, 3, 5, 5)[k:k + 1]
+            th = e.formThetaMat()[None]
+            x = e.grad
+            grad = GradOps(self.G_GLL, self.G_GLJ, x.dsdxii[None], x.dsdeta[None], x.dzdxii[None], x.dzdeta[None], x.inv_s[None],
+                           g.axial, self.rd)
+            s = tiso_spz_to_rtz(grad.grad6(u.astype(self.cd), g.nyq), th, self.rd)
+            return self._eval_phi(s.reshape(1, g.M, 6, nPE)[0], g, phi, np.asarray(weights, float).reshape(nPE))
         g, k = self._solid_group_of(e)
         u = self._gather_solid(g)
         th = np.stack([self.elements[t].formThetaMat() for t in g.tags])
@@ -1022,9 +1034,12 @@ class OracleDomain:
         return self._eval_phi(s.reshape(u.shape[0], g.M, 6, nPE)[k], g, phi, np.asarray(weights, float).reshape(nPE))
 
     def curl(self, elem_tag, phi, weights):
-        """SolidElement::computeCurl (SolidElement.cpp:281-345) after forceTIso, no PRT: grad9 -> SPZ_RTZ -> curl."""
+        """SolidElement::computeCurl (SolidElement.cpp:281-345) after forceTIso, no PRT: grad9 -> SPZ_RTZ -> curl.
+        FluidElement::computeCurl is identically zero (FluidElement.cpp:308-311)."""
         e = self.elements[elem_tag]
-        if e.kind != "solid" or e.prt is not None:
+        if e.kind == "fluid":
+            return np.zeros(3)
+        if e.prt is not None:
             raise NotImplementedError("curl receivers: solid elements without PRT")
         g, k = self._solid_group_of(e)
         u = self._gather_solid(g)

@@ -286,3 +286,29 @@ def test_real_mesh_matches_oracle(kw):
     for k, v in compare_field(d2, g2, "displ").items():
         if k == "solid":          # the wave has not reached the fluid core in 40 steps
             assert v <= 1e-4, (kw, k, v)
+
+
+def test_fluid_strain_and_curl_receivers():
+    """FluidElement::computeStrain (FluidElement.cpp:219-306; Acoustic1D elements: k_strain_fluid1d) against the numpy oracle, and
+    FluidElement::computeCurl == 0 (FluidElement.cpp:308-311); a 3D fluid is rejected with the reference-style message."""
+    m = SynthMesh(n_theta=6, n_r=8, nu=9, law="iso", model3d=True, attenuation=None)       # 3D solid, 1D fluid
+    dt = m.estimate_dt()
+    d, rel = build_oracle(m, dt, np.float64)
+    g, _ = build_gpu(m, dt)
+    randomize_displ(d, seed=4)
+    push_fields(d, g, ("displ",))
+    fl = [e.domain_tag for e in rel["elements"] if e.kind == "fluid"]
+    rng = np.random.default_rng(2)
+    tags = [fl[i] for i in rng.integers(0, len(fl), 7)] + [fl[0], fl[-1]]      # includes axial fluid elements
+    phi = rng.uniform(0, 2 * np.pi, len(tags))
+    w = rng.uniform(0, 1, (len(tags), 25))
+    w /= w.sum(axis=1, keepdims=True)
+    ref = np.array([d.strain(t, p, ww) for t, p, ww in zip(tags, phi, w)])
+    got = g.strain(tags, phi, w)
+    assert np.abs(ref).max() > 0 and rel_l2(ref, got) <= 1e-4
+    assert np.all(g.curl(tags, phi, w) == 0.0)
+    m3 = SynthMesh(n_theta=5, n_r=8, nu=7, law="iso", model3d=True, attenuation=None, fluid3d=True)
+    g3, rel3 = build_gpu(m3, m3.estimate_dt())
+    f3 = [e.domain_tag for e in rel3["elements"] if e.kind == "fluid" and e.acoustic.K.shape[0] > 1][:1]
+    with pytest.raises(RuntimeError, match="FluidElement::computeStrain"):
+        g3.strain(f3, phi[:1], w[:1])
