@@ -129,6 +129,7 @@ struct FusedLaunch {   // all fused 3D elements of one class: one persistent k_e
     int cls, first, count;
     int nww;                     // Newmark warps per CTA (0: none; the solid launch uses AX_NWW when the domain has plain points)
     int tile_cap;                // float2 capacity R of the tile region (U | TW | Z, laid out per element by plan_fused_element)
+    int nitems, nb_items;        // work items (element, row-group pass) of the launch; boundary items among them (first in the list)
     size_t smem;
     int grid;
     double alg_b;                // algorithmic bytes of the elements of the launch
@@ -173,7 +174,8 @@ struct ax3d_domain {
     std::vector<float2> h_stw;      // per-stage twiddle tables of all plans (fused kernel)
     DevBuf<float2> stwpool;
     std::vector<FusedLaunch> fused;
-    DevBuf<unsigned> fused_work;    // per launch: {next element index, finished warps}
+    DevBuf<unsigned> fused_work;    // per launch: {next work-item index, finished warps}
+    DevBuf<int> fused_items[NCLS];  // per class: (element index in launch << 3) | pass, boundary items first, then by cost
     // ---- in-kernel Newmark (fused.cuh): "plain" solid points are advanced by the element kernel of the previous step
     bool nw_allowed = true;         // AX3D_NO_NW=1 switches the mechanism off
     int n_plain = 0;
@@ -668,8 +670,53 @@ static void finalize(ax3d_domain *d) {
         }
         auto close_fused = [&]() {
             if (fl.count > 0) {
+                // work items: one per (element, row-group pass) -- passes are independent, and a pass is a finer scheduling
+                // quantum than a large element -- or one per element (code 7 = all passes) when the in-kernel Newmark counts
+                // arrivals per element.  Boundary items first, then by estimated cost (Nr log Nr x rows of the pass), largest first.
+                struct It { int code; bool bnd; double cost; };
+                std::vector<It> its;
+                // Pass-level items cost a few per cent on their own (consecutive passes of one element no longer share a CTA's
+                // warm descriptor / twiddles / L2 lines; B200 cfg4: 0.848 -> 0.875 ms per step), so they are used only where the
+                // element-level queue would lose more to the quantisation: LPT makespan of the element costs over num_sm
+                // bins more than 2.5 % above the ideal.  AX3D_PASS_ITEMS=0 / 1 forces the choice.
+                auto lpt_excess = [&]() {
+                    std::vector<double> cost;
+                    double tot = 0;
+                    for (int k = fl.first; k < fl.first + fl.count; ++k) {
+                        const ElemDesc &D = d->h_desc[c][k];
+                        // measured shape of the element cost (cost_model.json): ~ Nr log2 Nr, steeper once the element needs several passes
+                        const double x = (double)D.nr * std::log2((double)std::max(D.nr, 2)) * (1.0 + 0.15 * (D.ng - 1)) + 150.0;
+                        cost.push_back(x);
+                        tot += x;
+                    }
+                    std::sort(cost.begin(), cost.end(), std::greater<double>());
+                    std::vector<double> bin((size_t)d->num_sm, 0.0);
+                    for (double x : cost) *std::min_element(bin.begin(), bin.end()) += x;
+                    return *std::max_element(bin.begin(), bin.end()) / (tot / d->num_sm) - 1.0;
+                };
+                const char *env_pi = getenv("AX3D_PASS_ITEMS");
+                const bool pass_items = env_pi ? atoi(env_pi) != 0 : lpt_excess() > 0.025;
+                const bool per_element = (c == CLS_S3D && d->nw_allowed) || !pass_items;
+                for (int k = fl.first; k < fl.first + fl.count; ++k) {
+                    const ElemDesc &D = d->h_desc[c][k];
+                    const double full = (double)D.nr * std::log2((double)std::max(D.nr, 2)) + 64.0;
+                    if (per_element) { its.push_back(It{((k - fl.first) << 3) | 7, D.bnd != 0, full}); continue; }
+                    for (int g = 0; g < D.ng; ++g) {
+                        const int rows = fused_row_begin(D.ng, g + 1) - fused_row_begin(D.ng, g);
+                        its.push_back(It{((k - fl.first) << 3) | g, D.bnd != 0, full * rows / 5.0 + 16.0});
+                    }
+                }
+                std::stable_sort(its.begin(), its.end(), [](const It &a, const It &b) {
+                    if (a.bnd != b.bnd) return a.bnd;
+                    return a.cost > b.cost;
+                });
+                std::vector<int> codes;
+                fl.nb_items = 0;
+                for (const It &x : its) { codes.push_back(x.code); fl.nb_items += x.bnd ? 1 : 0; }
+                fl.nitems = (int)codes.size();
+                d->fused_items[c].upload(codes);
                 fl.smem = (size_t)AX_FUSED_DYN_MAX;   // tile region + (solid launch) the Newmark warps' stage buffers
-                fl.grid = std::min(fl.count, d->num_sm);
+                fl.grid = std::min(fl.nitems, d->num_sm);
                 d->fused.push_back(fl);
             }
         };
@@ -1238,7 +1285,7 @@ static int fused_nt(const FusedLaunch &f) {
     return f.nww ? AX_NW_NT + 32 * AX_NWW : AX_FUSED_NT;
 }
 
-typedef void (*fused_kernel_t)(const ElemDesc *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
+typedef void (*fused_kernel_t)(const ElemDesc *, const int *, int, const FftPlan *, const float2 *, const float *, const float *, const float *,
                                float *, const float2 *, float2 *, int, unsigned *, const NwArgs, const HaloArgs);
 
 static fused_kernel_t fused_kernel(const FusedLaunch &f) {
@@ -1275,11 +1322,11 @@ static void launch_fused(ax3d_domain *d, const FusedLaunch &f, int which, bool n
     if (!fluid && d->nw_dbg.p && nw.on) nw.dbg = d->nw_dbg.p;
     const double kbytes = f.alg_b + (nw.on ? d->dom_bytes[1] : 0.0);
     HaloArgs halo{nullptr, nullptr, 0, nullptr};
-    if (put && !fluid) halo = HaloArgs{d->halo_tab.p, d->halo_bcnt.p, d->n_bnd_fused, nullptr};
+    if (put && !fluid) halo = HaloArgs{d->halo_tab.p, d->halo_bcnt.p, f.nb_items, nullptr};
     if (d->cost_buf.p) halo.cost = d->cost_buf.p + d->cost_off[c];
     KTimer kt(d, fluid ? "k_elem3d_fused<fluid>" : (nw.on ? "k_elem3d_fused<solid> + in-kernel Newmark" : "k_elem3d_fused<solid>"), kbytes);
     fused_kernel(f)<<<f.grid, fused_nt(f), f.smem, d->stream>>>(
-        d->desc[c].p + f.first, f.count, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
+        d->desc[c].p + f.first, d->fused_items[c].p, f.nitems, d->plans.p, d->stwpool.p, d->geom.p, d->coef.p, d->attpar.p, d->attstate3d.p,
         fluid ? d->f_field[AX3D_DISPL].p : d->s_field[AX3D_DISPL].p, fluid ? d->f_field[AX3D_STIFF].p : d->s_field[AX3D_STIFF].p,
         f.tile_cap, d->fused_work.p + 2 * which, nw, halo);
 }
@@ -1702,8 +1749,12 @@ int ax3d_halo_connect(ax3d_domain *d, int nneigh, const void *handles, void *con
     {
         bool solid_fused = false;
         for (const FusedLaunch &f : d->fused) solid_fused = solid_fused || f.cls == CLS_S3D;
-        const char *env = getenv("AX3D_NO_INKERNEL_PUT");
-        d->inkernel_put = solid_fused && nneigh <= AX_MAX_NEIGH && !d->halo_sf3d && !(env && atoi(env) != 0);
+        // Opt-in (AX3D_INKERNEL_PUT=1).  Measured on 2 and 4 B200s (cfg4 weak scaling, profiles/r2_scaling.md): the exchange
+        // itself disappears from the step (halo family 0.135 -> 0.036 ms) but the step does not get shorter (0.951 vs 0.941 ms
+        // at N = 4): what a rank waits for at the end of its step is its slower neighbour's compute, not the transfer, and the
+        // fences and boundary-first order cost the element kernel ~1 %.  Default: k_halo_put kernels behind the coupling.
+        const char *env = getenv("AX3D_INKERNEL_PUT");
+        d->inkernel_put = solid_fused && nneigh <= AX_MAX_NEIGH && !d->halo_sf3d && (env && atoi(env) != 0);
         if (d->inkernel_put) {
             HaloTab ht;
             memset(&ht, 0, sizeof(ht));

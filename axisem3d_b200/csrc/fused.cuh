@@ -833,14 +833,18 @@ __device__ __forceinline__ void halo_put_cta(const HaloTab &ht, const float2 *__
 }
 
 // ---------------------------------------------------------------- the kernel   @phase kernel loop
-// grid: persistent, one CTA per SM; block NT compute threads (+ 32 * NWW Newmark threads).  work[0] = next element index
+// Work items: items[w] = (element index << 3) | g -- one row-group pass g of one element (g = 7: every pass of the element in
+// turn).  Passes of one element are independent (each gathers the displacement itself and scatters with RED), so they are
+// scheduled separately: a third of a large element is a finer LPT quantum than the element (ranks whose part of the mesh
+// is a few hundred large elements lose 7 % to the quantisation otherwise, profiles/r2_scaling.md).
+// grid: persistent, one CTA per SM; block NT compute threads (+ 32 * NWW Newmark threads).  work[0] = next item index
 // (starts at gridDim.x), work[1] = number of warps that have finished; the last one re-arms the counters for the next
 // launch (graph replay).  tile_cap: float2 capacity R of the tile region (the per-element offsets twoff / zoff of the
 // descriptors refer to it); the Newmark warps' stage buffers start right behind it.
 #define NW_RING 8   // arrival-code ring (elements finished by the compute warps, not yet posted by Newmark warp 0)
 template <bool FLUID, int NT, int NWW>
 __global__ void __launch_bounds__(NT + 32 * NWW, 1)
-    k_elem3d_fused(const ElemDesc *__restrict__ elems, int nelem, const FftPlan *__restrict__ plans,
+    k_elem3d_fused(const ElemDesc *__restrict__ elems, const int *__restrict__ items, int nitems, const FftPlan *__restrict__ plans,
                    const float2 *__restrict__ stwpool, const float *__restrict__ geom, const float *__restrict__ coef,
                    const float *__restrict__ attpar, float *__restrict__ attstate, const float2 *__restrict__ displ,
                    float2 *__restrict__ stiff, int tile_cap, unsigned *__restrict__ work, const NwArgs nw, const HaloArgs halo) {
@@ -854,7 +858,8 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     __shared__ ElemDesc sE[2];
     __shared__ FftPlan sP[2];
     __shared__ float sGeom[2][9 * AX_NPE];   // geometry (+ trig) of the current / next element, staged with its first gather
-    __shared__ int sIdx[3];   // ring of element indices: current, next, next-next
+    __shared__ int sIdx[3];   // ring of work-item indices: current, next, next-next
+    __shared__ int sCode[3];  // ... and their codes (element << 3 | pass)
     __shared__ unsigned long long sBar[NWARP][NW_NSTAGE];
     __shared__ int sArrCode[NW_RING][AX_NPE];   // ring: pt_nw codes of the elements whose scatter is complete ...
     __shared__ volatile int sArrHead;           // ... up to this count (written by compute thread 0 behind a barrier)
@@ -918,12 +923,19 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                 }
             }
         };
-        int e = blockIdx.x;
+        int e = blockIdx.x;     // work-item index
+        const int nelem = nitems;
         int n_done = 0;     // elements of this CTA whose scatter has been issued (their codes are in the ring)
         if (!FLUID && halo.tab != nullptr && halo.nb == 0 && blockIdx.x == 0) halo_put_cta<NT, NWW>(*halo.tab, displ, stiff, tid);
         if (e < nelem) {
-            load_desc(0, e);
-            if (tid == 0) sIdx[1] = (int)atomicAdd(&work[0], 1u);
+            const int code0 = items[e];
+            load_desc(0, code0 >> 3);
+            if (tid == 0) {
+                sCode[0] = code0;
+                const int nx = (int)atomicAdd(&work[0], 1u);
+                sIdx[1] = nx;
+                sCode[1] = nx < nelem ? items[nx] : 0;
+            }
             cta_sync<NT, NWW>();
             int first_mt = min(sE[0].mt, sE[0].nu + 1);   // modes of the gather tile in flight (first tile of the coming pass)
             gather(sE[0], 0, first_mt, 0);
@@ -935,28 +947,34 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                 cx.TW = smem + E.twoff;
                 cx.Z = smem + E.zoff;
                 const int kn = k == 2 ? 0 : k + 1, knn = kn == 2 ? 0 : kn + 1;   // ring slots of the next two elements
-                // moduli of this element -> L2 while gather/grad/c2r run
+                const int ng = E.ng;
+                const int gsel = sCode[k] & 7, el = sCode[k] >> 3;
+                const int g0 = gsel == 7 ? 0 : gsel, g1 = gsel == 7 ? ng : gsel + 1;
+                // moduli of the points of this item ([k][25][Nr]: rows [5 r0, 5 r1) of every modulus) -> L2 while gather/grad/c2r run
                 {
                     const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
-                    const float *cb = coef + E.coef_off;
-                    const int nline = (ncoef * AX_NPE * E.nr + 31) / 32;
-                    for (int q = tid; q < nline; q += NT) prefetch_l2(cb + (size_t)q * 32);
+                    const int pa = 5 * fused_row_begin(ng, g0), pb = 5 * fused_row_begin(ng, g1);
+                    const int per = ((pb - pa) * E.nr + 31) / 32;          // 128-byte lines per modulus
+                    const float *cb = coef + E.coef_off + (size_t)pa * E.nr;
+                    for (int q = tid; q < ncoef * per; q += NT) {
+                        const int kc = q / per, ln = q - kc * per;
+                        prefetch_l2(cb + (size_t)kc * AX_NPE * E.nr + (size_t)ln * 32);
+                    }
                 }
-                const int ng = E.ng;
                 long long t_el = 0;
                 if (halo.cost != nullptr && tid == 0) t_el = clock64();
-                for (int g = 0; g < ng; ++g) {
-                    const bool last = g + 1 == ng;
+                for (int g = g0; g < g1; ++g) {
+                    const bool last = g + 1 == g1;
                     int next_mt = 0;
                     // next element: descriptor behind the first barrier of the element, displacement (cp.async into the dead U) behind grad
                     auto after_first_sync = [&]() {
-                        if (g != 0) return;
+                        if (g != g0) return;
                         if (nw_on && tid == 0) {   // the previous element's scatter is complete (barrier): hand it to Newmark warp 0
                             __threadfence_block();
                             sArrHead = n_done;
                         }
-                        const int en = sIdx[kn];   // fetched during the previous element
-                        if (en < nelem) load_desc(it ^ 1, en);
+                        const int en = sIdx[kn];   // fetched during the previous item
+                        if (en < nelem) load_desc(it ^ 1, sCode[kn] >> 3);
                         // twiddle tables of this element's plan.  Its TW region may overlap the previous element's Z: written only
                         // now, behind the barrier every thread passes after the previous element's last read of Z; the
                         // barrier behind grad publishes it before the first FFT stage
@@ -973,7 +991,11 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                             gather(E, 0, next_mt, -1);
                             return;
                         }
-                        if (tid == 0) sIdx[knn] = (int)atomicAdd(&work[0], 1u);   // needed one element from now: latency hidden
+                        if (tid == 0) {            // needed one item from now: latency hidden
+                            const int nx = (int)atomicAdd(&work[0], 1u);
+                            sIdx[knn] = nx;
+                            sCode[knn] = nx < nelem ? items[nx] : 0;
+                        }
                         if (sIdx[kn] < nelem) {
                             const ElemDesc &En = sE[it ^ 1];
                             // the first tile of the next element lands in U while this element's TW / Z are live: stay below both
@@ -984,7 +1006,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                     fused_pass<FLUID, NT, NWW>(cx, E, P, g, first_mt, tid, gather, after_first_sync, after_grad);
                     first_mt = next_mt;
                 }
-                if (halo.cost != nullptr && tid == 0) halo.cost[e] = (unsigned)(clock64() - t_el);
+                if (halo.cost != nullptr && tid == 0) atomicAdd(&halo.cost[el], (unsigned)(clock64() - t_el));
                 if (!FLUID && halo.tab != nullptr && E.bnd) {
                     __threadfence();          // this thread's scatter of the element before the count
                     cta_sync<NT, NWW>();

@@ -697,6 +697,14 @@ public:
         check(ax3d_get_nu_wisdom(mDom, nw.data(), (int)nw.size()));
         return nw;
     }
+    // Mesh::measure (Mesh.cpp:530-588): measured cost of every element (microseconds of one SM), the METIS vertex weights of
+    // the second partition pass; element order = domain tags
+    std::vector<double> measureCosts(int repeats = 3) const {
+        finalize();
+        std::vector<double> cost(mElements.size());
+        check(ax3d_measure_costs(mDom, repeats, cost.data(), (int)cost.size()));
+        return cost;
+    }
     void checkStability(double dt, int tstep, double t) const {            // Domain.cpp:237-275
         int ok = 1;
         check(ax3d_check_stability(mDom, &ok));

@@ -365,7 +365,8 @@ def run_ours(args):
         halo = "nccl send/recv (eager steps)"
         if os.environ.get("AX3D_HALO", "peer") == "peer":
             dom.connectHalo(rel["msg"], rank, dist)     # NVLink peer-memory windows; steps replay as CUDA graphs
-            halo = "peer-memory windows over NVLink (k_halo_put / k_halo_wait_add inside the step graph)"
+            halo = "peer-memory windows over NVLink (%s + k_halo_wait_add inside the step graph)" % (
+                "in-kernel put from the solid element kernel" if os.environ.get("AX3D_INKERNEL_PUT", "0") not in ("", "0") else "k_halo_put")
 
     eg, phi, w = global_receivers(mesh)
     mine = register_receivers(dom, rel, eg, phi, w)

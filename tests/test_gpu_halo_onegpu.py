@@ -45,7 +45,11 @@ def _partition(mesh, kind):
     ("blocks4", dict(n_theta=6, n_r=6, nu=3, law="ti", model3d=False, attenuation="cg4")),
     ("strips3", dict(n_theta=9, n_r=5, nu=10, law="aniso", model3d=True, attenuation="full")),
 ])
-def test_same_process_peer_halo_matches_oracle(kind, mesh_kw):
+@pytest.mark.parametrize("inkernel", [False, True], ids=["put_kernels", "inkernel_put"])
+def test_same_process_peer_halo_matches_oracle(kind, mesh_kw, inkernel, monkeypatch):
+    # AX3D_INKERNEL_PUT (read at ax3d_halo_connect): the solid element kernel sends the boundary forces itself (fused.cuh:
+    # halo_put_cta) instead of k_halo_put kernels behind the coupling
+    monkeypatch.setenv("AX3D_INKERNEL_PUT", "1" if inkernel else "0")
     from helpers import build_oracle, build_gpu
     from axisem3d_b200.domain import Domain
     from axisem3d_b200.mesh_synth import SynthMesh
