@@ -30,6 +30,10 @@ for b in blocks:
     short = re.sub(r"\(.*", "", dem).replace("void ", "")
     if not any(h in short for h in HOT):
         continue
+    if "true>" in short and ("k_fft3d_v2" in short or "k_grad3d" in short or "k_quad3d" in short or "k_elem1d" in short):
+        continue          # particle-relabelling instances: same code plus the 9-component branch
+    if "k_fft3d_v2" in short and (", 512," in short or ", 1024," in short):
+        continue          # same body as the 256-thread instance
     ops = collections.Counter()
     n = 0
     for ln in b.splitlines():
