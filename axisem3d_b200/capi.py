@@ -17,7 +17,7 @@ SYMBOLS = [
     "ax3d_run_steps", "ax3d_synchronize", "ax3d_get_point_field", "ax3d_set_point_field",
     "ax3d_get_field_bulk", "ax3d_set_field_bulk", "ax3d_field_size", "ax3d_record_ground_motion",
     "ax3d_launch_count", "ax3d_work_per_step", "ax3d_algorithmic_bytes", "ax3d_enable_timers",
-    "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_kernel_stats", "ax3d_measure_costs", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
+    "ax3d_get_timers", "ax3d_run_steps_timed", "ax3d_run_steps_record", "ax3d_kernel_stats", "ax3d_measure_costs", "ax3d_fft_plan", "ax3d_set_receivers", "ax3d_record", "ax3d_nccl_unique_id",
     "ax3d_halo_export", "ax3d_halo_connect", "ax3d_set_learn_parameters", "ax3d_learn_wisdom", "ax3d_get_nu_wisdom", "ax3d_set_element_prt", "ax3d_add_solid_point_ocean", "ax3d_record_strain", "ax3d_record_curl",
 ]
 
@@ -85,6 +85,7 @@ def load(build_if_missing=True):
     lib.ax3d_run_steps_timed.argtypes = [vp, i, d, pf, pf]
     lib.ax3d_run_steps_record.argtypes = [vp, i, d, pf, pf]
     lib.ax3d_measure_costs.argtypes = [vp, i, pd, i]
+    lib.ax3d_fft_plan.argtypes = [i, pi_, i, pi_]
     lib.ax3d_kernel_stats.argtypes = [vp, i, C.c_char_p, i, pd, C.POINTER(C.c_longlong), pd, pi_, i]
     lib.ax3d_set_receivers.argtypes = [vp, i, pi_, pf, pf]
     lib.ax3d_record.argtypes = [vp, pf]

@@ -300,13 +300,8 @@ struct ax3d_domain {
 static void fail(const std::string &m) { throw std::runtime_error(m); }
 
 // ------------------------------------------------------------------------------------------ FFT plans
-#ifndef AX_PLAN_MAXR2
-#define AX_PLAN_MAXR2 16   // largest power-of-two radix of the FFT plans (16: 32 data registers per butterfly; 8 for kernels compiled for < 96 registers)
-#endif
-static int plan_maxr2() { return AX_PLAN_MAXR2; }
-
 static std::vector<int> choose_radices(int N) {
-    const RadixList rl = choose_radices_ct(N, plan_maxr2());   // fft.cuh: the one definition host and kernels share
+    const RadixList rl = choose_radices_plan(N);   // fft.cuh
     if (rl.n < 0) fail("ax3d::plan || Nr = " + std::to_string(N) + " is not a lucky number (prime factor > 13 or too many stages; PreloopFFTW.cpp:59-99)");
     std::vector<int> r(rl.r, rl.r + rl.n);
     if (r.empty()) r.push_back(1);
@@ -356,20 +351,6 @@ static int get_plan(ax3d_domain *d, int N) {
         }
     }
     pl.stw_len = (int)d->h_stw.size() - pl.stw_base;
-    // the same tables p-major (fused_wp.cuh): T2_s[p * Ls + j] at stw_off[s] + stw2_delta
-    pl.stw2_delta = pl.stw_len;
-    {
-        int L = N;
-        for (int s = 0; s < pl.nstages; ++s) {
-            const int R = pl.radix[s], Ls = L / R;
-            if (Ls > 1) {
-                const size_t src = (size_t)pl.stw_off[s];
-                for (int pp = 0; pp < R; ++pp)
-                    for (int j = 0; j < Ls; ++j) { const float2 w = d->h_stw[src + (size_t)j * R + pp]; d->h_stw.push_back(w); }
-            }
-            L = Ls;
-        }
-    }
     int id = (int)d->h_plans.size();
     d->h_plans.push_back(pl);
     d->h_perm.push_back(perm);
@@ -2429,6 +2410,19 @@ int ax3d_measure_costs(ax3d_domain *d, int repeats, double *cost_us, int nelem) 
     for (size_t e = 0; e < d->elems.size(); ++e) cost_us[e] = acc[e] / repeats;
     d->cost_buf.release();
     d->kstats.clear();
+    API_END
+}
+
+/* The radix sequence the library plans for an azimuthal transform of length nr (host only, no device needed): radices[0 .. *nstages)
+ * in DIF order, their product is nr.  Lucky numbers only (PreloopFFTW.cpp:59-99); fails for a prime factor above 13. */
+int ax3d_fft_plan(int nr, int *radices, int cap, int *nstages) {
+    API_BEGIN
+    if (nr < 1) fail("ax3d::plan || nr must be positive");
+    const RadixList rl = choose_radices_plan(nr);
+    if (rl.n < 0) fail("ax3d::plan || Nr = " + std::to_string(nr) + " is not a lucky number (prime factor > 13 or too many stages; PreloopFFTW.cpp:59-99)");
+    if (rl.n > cap) fail("ax3d::plan || output buffer too small");
+    for (int k = 0; k < rl.n; ++k) radices[k] = rl.r[k];
+    *nstages = rl.n;
     API_END
 }
 

@@ -14,6 +14,9 @@
 //  * one thread owns one radix-R butterfly in registers; passes are separated by __syncthreads().
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <functional>
+#include <vector>
 
 #define AX_MAX_STAGES 10
 
@@ -28,39 +31,51 @@ struct FftPlan {
     // i.e. L_s == R_s).  All tables of one plan are contiguous: [stw_base, stw_base + stw_len).
     int stw_off[AX_MAX_STAGES];
     int stw_base, stw_len;
-    // the same tables once more in p-major order, T2_s[p * (L_s / R_s) + j], for the warp-per-point kernel (fused_wp.cuh: lanes
-    // run over j, so the p-major rows are read conflict-free): table of stage s at stwpool[stw_off[s] + stw2_delta]
-    int stw2_delta;
 };
 
-// Radix sequence of the DIF transform of length N (shared by the host planner and the compile-time specialised
-// kernels, which must agree because phi-dependent arrays are uploaded in the digit-reversed order of this plan):
-// powers of two first (16s, then the 8/4/2 remainder), then odd primes 13, 11, 7, 5, 3 -- so that the LAST DIF
-// stage (stride-1 butterflies) has an odd radix whenever N has an odd factor.  n == 0 marks an unsupported N.
-// maxr2 = 16: powers of two as 16s + remainder (one thread per butterfly, many columns per CTA: fused.cuh, kernels.cuh);
-// maxr2 = 8: as 8s and 4s (2^4 -> 4 4, 2^5 -> 8 4, 2^6 -> 8 8, ...) for the warp-per-point kernel, whose 72-register
-// budget and 3 columns per warp favour small butterflies (fused_wp.cuh).
+// Radix sequence of the DIF transform of length N (host planner; every phi-dependent array is uploaded in the digit-reversed
+// order of this plan, so all kernels of a process share it).  Radices: the primes up to 13, 4, 8, 16 and the composites
+// 6, 9, 10, 12 (DftCT; 14 and 15 would save another 1.5 % of the stages of cfg4 for the two most register-hungry butterflies) -- chosen to minimise the number of stages: each stage is one trip of the whole spectrum
+// through shared memory, one barrier and (all but the last) one twiddle multiplication per sample.  Among the factorisations
+// with the fewest stages the most even one wins (smallest sum of squares); the stages are ordered largest radix first, except
+// that an odd radix, if there is one, goes last (stride-1 butterflies: an odd radix keeps lanes that walk over butterflies of
+// one column on different banks).  n < 0 marks an unsupported N (a prime factor above 13).
 struct RadixList {
     int n;
     int r[AX_MAX_STAGES];
 };
-__host__ __device__ constexpr RadixList choose_radices_ct(int N, int maxr2 = 16) {
+inline RadixList choose_radices_plan(int N) {
+    static const int RAD[13] = {16, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
     RadixList out{0, {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
-    int n = N, e = 0;
-    while (n % 2 == 0 && n > 0) { n /= 2; ++e; }
-    if (maxr2 >= 16) {
-        while (e >= 4) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 16; ++out.n; e -= 4; }
-    } else {
-        while (e > 4 || e == 3) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 8; ++out.n; e -= 3; }
-        while (e >= 2) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 4; ++out.n; e -= 2; }
+    if (N <= 1) return out;
+    // best[d] for every divisor d of N, by increasing d: (stages, sum of squares, first radix)
+    struct Best { int stages; long long sq; int first; };
+    std::vector<int> divs;
+    for (int d = 1; d <= N; ++d)
+        if (N % d == 0) divs.push_back(d);
+    std::vector<Best> best(divs.size(), Best{1 << 20, 0, 0});
+    auto at = [&](int d) { return (size_t)(std::lower_bound(divs.begin(), divs.end(), d) - divs.begin()); };
+    best[0] = Best{0, 0, 0};
+    for (size_t i = 1; i < divs.size(); ++i) {
+        const int d = divs[i];
+        for (int r : RAD) {
+            if (d % r) continue;
+            const Best &sub = best[at(d / r)];
+            if (sub.stages >= (1 << 20)) continue;
+            const Best cand{sub.stages + 1, sub.sq + (long long)r * r, r};
+            if (cand.stages < best[i].stages || (cand.stages == best[i].stages && cand.sq < best[i].sq)) best[i] = cand;
+        }
     }
-    if (e == 3) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 8; ++out.n; }
-    else if (e == 2) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 4; ++out.n; }
-    else if (e == 1) { if (out.n < AX_MAX_STAGES) out.r[out.n] = 2; ++out.n; }
-    const int ps[5] = {13, 11, 7, 5, 3};
-    for (int i = 0; i < 5; ++i)
-        while (n % ps[i] == 0) { if (out.n < AX_MAX_STAGES) out.r[out.n] = ps[i]; ++out.n; n /= ps[i]; }
-    if (n != 1 || out.n > AX_MAX_STAGES) out.n = -1;
+    if (best.back().stages >= (1 << 20) || best.back().stages > AX_MAX_STAGES) { out.n = -1; return out; }
+    std::vector<int> rs;
+    for (int d = N; d > 1; d /= best[at(d)].first) rs.push_back(best[at(d)].first);
+    std::sort(rs.begin(), rs.end(), std::greater<int>());
+    int odd = -1;
+    for (int k = (int)rs.size() - 1; k >= 0; --k)
+        if (rs[k] % 2) { odd = k; break; }          // the smallest odd radix
+    if (odd >= 0) { const int r = rs[odd]; rs.erase(rs.begin() + odd); rs.push_back(r); }
+    out.n = (int)rs.size();
+    for (int k = 0; k < out.n; ++k) out.r[k] = rs[k];
     return out;
 }
 
@@ -239,11 +254,51 @@ struct DftOdd {
         }
     }
 };
+// composite radix R = R1 * R2 in registers (Cooley-Tukey, every index a compile-time constant): R2 transforms of length R1 over
+// a[R2 n1 + n2], the twiddles w_R^(n2 k1) from the constant tables, then R1 transforms of length R2 -> a[k1 + R1 k2].
+// A stage of radix 12 or 10 replaces two stages (4 x 3, 2 x 5): one trip through shared memory, one barrier and one twiddle
+// table less per transform (the planner below minimises the number of stages).
+template <int R1, int R2, int SIGN>
+struct DftCT {
+    static __device__ __forceinline__ void run(float2 (&a)[R1 * R2]) {
+        constexpr int R = R1 * R2;
+        float2 t[R2][R1];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) {
+            float2 c[R1];
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) c[n1] = a[R2 * n1 + n2];
+            Dft<R1, SIGN>::run(c);
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1) {
+                const int m = (n2 * k1) % R;
+                if (m == 0) t[n2][k1] = c[k1];
+                else if (4 * m == R) t[n2][k1] = cmul_i<SIGN>(c[k1]);
+                else if (2 * m == R) t[n2][k1] = make_float2(-c[k1].x, -c[k1].y);
+                else if (4 * m == 3 * R) t[n2][k1] = cmul_i<-SIGN>(c[k1]);
+                else t[n2][k1] = cmul(c[k1], make_float2(c_cos[R][m], SIGN * c_sin[R][m]));
+            }
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            float2 c[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) c[n2] = t[n2][k1];
+            Dft<R2, SIGN>::run(c);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) a[k1 + R1 * k2] = c[k2];
+        }
+    }
+};
 template <int SIGN> struct Dft<3, SIGN> : DftOdd<3, SIGN> {};
 template <int SIGN> struct Dft<5, SIGN> : DftOdd<5, SIGN> {};
 template <int SIGN> struct Dft<7, SIGN> : DftOdd<7, SIGN> {};
 template <int SIGN> struct Dft<11, SIGN> : DftOdd<11, SIGN> {};
 template <int SIGN> struct Dft<13, SIGN> : DftOdd<13, SIGN> {};
+template <int SIGN> struct Dft<6, SIGN> : DftCT<2, 3, SIGN> {};
+template <int SIGN> struct Dft<9, SIGN> : DftCT<3, 3, SIGN> {};
+template <int SIGN> struct Dft<10, SIGN> : DftCT<2, 5, SIGN> {};
+template <int SIGN> struct Dft<12, SIGN> : DftCT<4, 3, SIGN> {};
 
 // ---------------------------------------------------------------- one pass over `ncols` columns
 // z: column c starts at z + c * ldz; tw = W_N table (shared or global); L = current block length.
@@ -296,8 +351,12 @@ __device__ __forceinline__ void fft_pass_dispatch(int R, float2 *z, int ldz, int
         case 3: fft_pass<3, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
         case 4: fft_pass<4, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
         case 5: fft_pass<5, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 6: fft_pass<6, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
         case 7: fft_pass<7, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
         case 8: fft_pass<8, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 9: fft_pass<9, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 10: fft_pass<10, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
+        case 12: fft_pass<12, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
         case 11: fft_pass<11, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
         case 13: fft_pass<13, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;
         case 16: fft_pass<16, SIGN, DIF>(z, ldz, ncols, N, L, tw, tid, nthreads); break;

@@ -50,8 +50,16 @@ __device__ __forceinline__ void cta_sync() {
 
 // ---------------------------------------------------------------- one FFT stage over all columns
 // DIF (c2r, SIGN = +1): butterfly, then twiddle T[j][p].  DIT (r2c, SIGN = -1): conj twiddle, then butterfly.
+#ifndef AX_STAGE_INLINE
+#define AX_STAGE_INLINE 0   // 0: every radix stage is a real function with its own register allocation (B200: cfg4 0.816 vs 0.823 ms per step inlined)
+#endif
+#if AX_STAGE_INLINE
+#define AX_STAGE_ATTR __forceinline__
+#else
+#define AX_STAGE_ATTR __noinline__
+#endif
 template <int R, int SIGN, bool DIF, int NT>
-__device__ __forceinline__ void fused_stage(float2 *__restrict__ z, int N, int L, int ncols, const float2 *__restrict__ T, int tid) {
+__device__ AX_STAGE_ATTR void fused_stage(float2 *__restrict__ z, int N, int L, int ncols, const float2 *__restrict__ T, int tid) {
     const int ldz = fused_ldz(N);
     const int Ls = L / R;
     const int nb = N / R;
@@ -97,8 +105,12 @@ __device__ __forceinline__ void fused_stage_dispatch(int R, float2 *z, int N, in
         case 3: fused_stage<3, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
         case 4: fused_stage<4, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
         case 5: fused_stage<5, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 6: fused_stage<6, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
         case 7: fused_stage<7, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
         case 8: fused_stage<8, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 9: fused_stage<9, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 10: fused_stage<10, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
+        case 12: fused_stage<12, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
         case 11: fused_stage<11, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
         case 13: fused_stage<13, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;
         case 16: fused_stage<16, SIGN, DIF, NT>(z, N, L, ncols, T, tid); break;

@@ -226,6 +226,9 @@ int ax3d_enable_timers(ax3d_domain *dom, int on);
 int ax3d_kernel_stats(ax3d_domain *dom, int index, char *name, int name_cap, double *ms_total, long long *launches,
                       double *bytes_total, int *count, int reset);
 int ax3d_get_timers(ax3d_domain *dom, double out_ms[4], int reset);
+/* The plan of the azimuthal c2r / r2c of length nr that replaces SolverFFTW_N*::initialize's fftwf_plan_many_dft_*
+ * (SolverFFTW_N6.cpp:16-43): radix sequence (2 ... 16, fewest stages) in DIF order.  Host only; no device needed. */
+int ax3d_fft_plan(int nr, int *radices, int cap, int *nstages);
 /* Measured element costs = the reference's cost-measure pass before its second partition (Mesh::measure,
  * Mesh.cpp:412-588: every element's computeStiff is timed, the times become the METIS vertex weights).  Runs
  * Domain::computeStiff `repeats` times with the device clocks on and returns cost_us[element tag] = microseconds of one
