@@ -612,9 +612,9 @@ static void finalize(ax3d_domain *d) {
         // tables below it, the gather tile U = [0, twoff) in front
         auto plan_fused_element = [&](int N, int M, int stw_len, ElemDesc &D) -> bool {
             const int nc = fluid ? 1 : 3, us = nc * AX_NPE;
-            static const int ngs[4] = {1, 2, 3, 5};
+            static const int ngs[5] = {1, 2, 3, 5, 10};
             for (int ng : ngs) {
-                const long long zsz = (long long)npair * 5 * fused_rows_per_group(ng) * fused_ldz(N);
+                const long long zsz = (long long)npair * fused_np_max(ng) * fused_ldz(N);
                 const long long zoff = ((long long)fl.tile_cap - zsz) & ~1ll;
                 const long long twoff = (zoff - ((stw_len + 1) & ~1)) & ~1ll;
                 if (twoff < (long long)us * 16) continue;
@@ -681,10 +681,11 @@ static void finalize(ax3d_domain *d) {
                 for (int k = fl.first; k < fl.first + fl.count; ++k) {
                     const ElemDesc &D = d->h_desc[c][k];
                     const double full = (double)D.nr * std::log2((double)std::max(D.nr, 2)) + 64.0;
-                    if (per_element) { its.push_back(It{((k - fl.first) << 3) | 7, D.bnd != 0, full}); continue; }
+                    if (per_element) { its.push_back(It{((k - fl.first) << 4) | AX_ITEM_ALL, D.bnd != 0, full}); continue; }
                     for (int g = 0; g < D.ng; ++g) {
-                        const int rows = fused_row_begin(D.ng, g + 1) - fused_row_begin(D.ng, g);
-                        its.push_back(It{((k - fl.first) << 3) | g, D.bnd != 0, full * rows / 5.0 + 16.0});
+                        int gp0, gnp;
+                        fused_group(D.ng, g, gp0, gnp);
+                        its.push_back(It{((k - fl.first) << 4) | g, D.bnd != 0, full * gnp / 25.0 + 16.0});
                     }
                 }
                 std::stable_sort(its.begin(), its.end(), [](const It &a, const It &b) {

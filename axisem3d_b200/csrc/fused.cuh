@@ -355,6 +355,19 @@ __host__ __device__ __forceinline__ constexpr int fused_rows_per_group(int ng) {
 __host__ __device__ __forceinline__ constexpr int fused_row_begin(int ng, int g) {
     return g * fused_rows_per_group(ng) < 5 ? g * fused_rows_per_group(ng) : 5;
 }
+// ng = 10: a pass is part of ONE GLL row -- columns 0-2 or 3-4 -- for the longest expansions (a whole row of Nr = 2016 does not
+// fit).  Points of pass g: [p0, p0 + np); most points of any pass of an element with ng passes: fused_np_max(ng).
+#define AX_ITEM_ALL 15        // work-item code (element << 4 | g): g = 15 = every pass of the element in turn
+__host__ __device__ __forceinline__ constexpr int fused_np_max(int ng) { return ng == 10 ? 3 : 5 * fused_rows_per_group(ng); }
+__host__ __device__ __forceinline__ void fused_group(int ng, int g, int &p0, int &np) {
+    if (ng == 10) {
+        p0 = 5 * (g >> 1) + ((g & 1) ? 3 : 0);
+        np = (g & 1) ? 2 : 3;
+    } else {
+        p0 = 5 * fused_row_begin(ng, g);
+        np = 5 * (fused_row_begin(ng, g + 1) - fused_row_begin(ng, g));
+    }
+}
 
 // One pass = one row group of one element.  E, P: descriptor and plan of this element (shared memory).  On entry the
 // first gather tile of this pass (`first_mt` modes) is in flight (cp.async); `after_first_sync` runs behind the first
@@ -373,8 +386,11 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
     const bool nyq = (N & 1) == 0;
     const bool axial = E.axial != 0, tiso = !FLUID && E.tiso != 0;
     const int ng = E.ng;
-    const int r0 = fused_row_begin(ng, g), r1 = fused_row_begin(ng, g + 1);
-    const int p0 = 5 * r0, np = 5 * (r1 - r0);       // points of this pass: [p0, p0 + np)
+    int p0, np;                                       // points of this pass: [p0, p0 + np)
+    fused_group(ng, g, p0, np);
+    const bool partial = ng == 10;                    // part of one GLL row: columns [j0, j1) of row r0
+    const int r0 = p0 / 5, r1 = partial ? r0 + 1 : r0 + np / 5;
+    const int j0 = p0 - 5 * r0, j1 = partial ? j0 + np : 5;
     const int ncols = NPAIR * np, cs = np * ldz;      // column of (pair pr, local point pl) = Z + (pr * np + pl) * ldz
 
     // Static thread mapping of the pass: kpp = NHW / np half-warps share one point of the group and interleave its 16-mode
@@ -467,7 +483,7 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
     // pointwise term r never leaves its registers.
     const float sc = 1.f / (float)N;   // SolverFFTW_N6::computeR2C scaling (SolverFFTW_N6.cpp:47-48)
     const int nchq = (M + 15) >> 4;
-    const int nout = AX_NPE - np;      // points outside the group: xi-partial sums only
+    const int nout = AX_NPE - np;      // points outside the group (full rows): xi-partial sums only
     const int nlive = E.pt_nlive[p], st = E.pt_stride[p];
     float2 *const dst = cx.stiff + (size_t)E.pt_off[p];
     float2 *const zp = Z + pl * ldz;
@@ -513,7 +529,14 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
                         float2 f = r[q][c];
                         const float2 *zx = Z + c * cs + j * ldz + beta;                         // X(k, j), k = r0 .. r1 - 1
                         const float2 *zy = Z + c * cs + (i - r0) * 5 * ldz + N - beta;          // Y(i, k), k = 0 .. 4
-                        if (ng == 1) {
+                        if (partial) {            // one row, columns [j0, j1): X(r0, j) and Y(r0, k), k in [j0, j1), at local index k - j0
+                            const float2 *zr = Z + c * cs - j0 * ldz;
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                if (k == r0) f = cfma(gc.gxi_row[k], zr[j * ldz + beta], f);
+                                if (k >= j0 && k < j1) f = cfma(gc.geta_row[k], zr[k * ldz + N - beta], f);
+                            }
+                        } else if (ng == 1) {
 #pragma unroll
                             for (int k = 0; k < 5; ++k) {
                                 f = cfma(gc.gxi_row[k], zx[k * 5 * ldz], f);
@@ -532,23 +555,37 @@ __device__ __forceinline__ void fused_pass(const FusedCtx<FLUID> &cx, const Elem
                 }
             }
         }
-        // points of the other rows: f(i', j) += sum_{k in group} G_xi(i', k) X(k, j)
-        if (nout) {
+        // points outside the pass: f(i', j) += sum_{k in group} G_xi(i', k) X(k, j); a partial row also owes the rest of its row
+        // the eta-sums f(r0, j') += sum_{k in [j0, j1)} G_eta(j', k) Y(r0, k)
+        const int nout_x = partial ? 4 * np : nout, nout_all = partial ? 4 * np + (5 - np) : nout;
+        if (nout_all) {
             const int nchs = min(QIT * kpp, nchq - c0);
-            for (int it = hw; it < nout * nchs; it += NHW) {
+            for (int it = hw; it < nout_all * nchs; it += NHW) {
                 const int po = it / nchs, ch = it - po * nchs;
-                const int p2 = po < p0 ? po : po + np;          // skip [p0, p0 + np)
+                int p2;
+                const bool xi_target = po < nout_x;
+                if (!partial) p2 = po < p0 ? po : po + np;          // skip [p0, p0 + np)
+                else if (xi_target) { const int ii = po / np; p2 = 5 * (ii < r0 ? ii : ii + 1) + j0 + (po - ii * np); }
+                else { const int q2 = po - nout_x; p2 = 5 * r0 + (q2 < j0 ? q2 : q2 + np); }
                 const int i2 = p2 / 5, j2 = p2 - 5 * i2;
                 const int beta = (c0 + ch) * 16 + t;
                 if (beta < M && !(nyq && beta == nu) && beta < E.pt_nlive[p2]) {
                     const float *Gxi = c_G[axial ? 1 : 0];
+                    const float *Geta = c_G[0];
                     float2 *const dst2 = cx.stiff + (size_t)E.pt_off[p2];
                     const int st2 = E.pt_stride[p2];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         float2 f = czero();
-                        const float2 *zx = Z + c * cs + j2 * ldz + beta;
-                        for (int k = r0; k < r1; ++k) f = cfma(Gxi[i2 * 5 + k], zx[(k - r0) * 5 * ldz], f);
+                        if (!partial) {
+                            const float2 *zx = Z + c * cs + j2 * ldz + beta;
+                            for (int k = r0; k < r1; ++k) f = cfma(Gxi[i2 * 5 + k], zx[(k - r0) * 5 * ldz], f);
+                        } else if (xi_target) {
+                            f = cscale(Z[c * cs + (j2 - j0) * ldz + beta], Gxi[i2 * 5 + r0]);
+                        } else {
+                            const float2 *zy = Z + c * cs + N - beta;
+                            for (int k = j0; k < j1; ++k) f = cfma(Geta[j2 * 5 + k], zy[(k - j0) * ldz], f);
+                        }
                         if (beta == 0) f.y = 0.f;
                         atomicAdd(dst2 + (size_t)c * st2 + beta, make_float2(-f.x, -f.y));
                     }
@@ -845,7 +882,7 @@ __device__ __forceinline__ void halo_put_cta(const HaloTab &ht, const float2 *__
 }
 
 // ---------------------------------------------------------------- the kernel   @phase kernel loop
-// Work items: items[w] = (element index << 3) | g -- one row-group pass g of one element (g = 7: every pass of the element in
+// Work items: items[w] = (element index << 4) | g -- one row-group pass g of one element (g = 15: every pass of the element in
 // turn).  Passes of one element are independent (each gathers the displacement itself and scatters with RED), so they are
 // scheduled separately: a third of a large element is a finer LPT quantum than the element (ranks whose part of the mesh
 // is a few hundred large elements lose 7 % to the quantisation otherwise, profiles/r2_scaling.md).
@@ -871,7 +908,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
     __shared__ FftPlan sP[2];
     __shared__ float sGeom[2][9 * AX_NPE];   // geometry (+ trig) of the current / next element, staged with its first gather
     __shared__ int sIdx[3];   // ring of work-item indices: current, next, next-next
-    __shared__ int sCode[3];  // ... and their codes (element << 3 | pass)
+    __shared__ int sCode[3];  // ... and their codes (element << 4 | pass)
     __shared__ unsigned long long sBar[NWARP][NW_NSTAGE];
     __shared__ int sArrCode[NW_RING][AX_NPE];   // ring: pt_nw codes of the elements whose scatter is complete ...
     __shared__ volatile int sArrHead;           // ... up to this count (written by compute thread 0 behind a barrier)
@@ -941,7 +978,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
         if (!FLUID && halo.tab != nullptr && halo.nb == 0 && blockIdx.x == 0) halo_put_cta<NT, NWW>(*halo.tab, displ, stiff, tid);
         if (e < nelem) {
             const int code0 = items[e];
-            load_desc(0, code0 >> 3);
+            load_desc(0, code0 >> 4);
             if (tid == 0) {
                 sCode[0] = code0;
                 const int nx = (int)atomicAdd(&work[0], 1u);
@@ -960,12 +997,15 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                 cx.Z = smem + E.zoff;
                 const int kn = k == 2 ? 0 : k + 1, knn = kn == 2 ? 0 : kn + 1;   // ring slots of the next two elements
                 const int ng = E.ng;
-                const int gsel = sCode[k] & 7, el = sCode[k] >> 3;
-                const int g0 = gsel == 7 ? 0 : gsel, g1 = gsel == 7 ? ng : gsel + 1;
+                const int gsel = sCode[k] & 15, el = sCode[k] >> 4;
+                const int g0 = gsel == AX_ITEM_ALL ? 0 : gsel, g1 = gsel == AX_ITEM_ALL ? ng : gsel + 1;
                 // moduli of the points of this item ([k][25][Nr]: rows [5 r0, 5 r1) of every modulus) -> L2 while gather/grad/c2r run
                 {
                     const int ncoef = FLUID ? 1 : (E.law == LAW_ISO ? 2 : E.law == LAW_TI ? 5 : 21);
-                    const int pa = 5 * fused_row_begin(ng, g0), pb = 5 * fused_row_begin(ng, g1);
+                    int pa, pn, pb, pm;
+                    fused_group(ng, g0, pa, pn);
+                    fused_group(ng, g1 - 1, pb, pm);
+                    pb += pm;
                     const int per = ((pb - pa) * E.nr + 31) / 32;          // 128-byte lines per modulus
                     const float *cb = coef + E.coef_off + (size_t)pa * E.nr;
                     for (int q = tid; q < ncoef * per; q += NT) {
@@ -986,7 +1026,7 @@ __global__ void __launch_bounds__(NT + 32 * NWW, 1)
                             sArrHead = n_done;
                         }
                         const int en = sIdx[kn];   // fetched during the previous item
-                        if (en < nelem) load_desc(it ^ 1, sCode[kn] >> 3);
+                        if (en < nelem) load_desc(it ^ 1, sCode[kn] >> 4);
                         // twiddle tables of this element's plan.  Its TW region may overlap the previous element's Z: written only
                         // now, behind the barrier every thread passes after the previous element's last read of Z; the
                         // barrier behind grad publishes it before the first FFT stage

@@ -15,9 +15,15 @@ import bench  # noqa: E402
 from axisem3d_b200.domain import Domain  # noqa: E402
 
 rows = {}
-for cfg in ("cfg1", "cfg2", "cfg3", "cfg4"):
-    bench.CFG = cfg
-    m = bench.make_mesh(bench.N_THETA)
+for cfg in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5-shell"):
+    if cfg == "cfg5-shell":      # cfg5's element kind over its whole Nr range: a thin outer shell with the cfg5 order field
+        from axisem3d_b200.mesh_synth import SynthMesh, R_EARTH
+        bench.CFG = "cfg5"
+        m = SynthMesh(n_theta=240, n_r=8, r_in=R_EARTH - 400e3, nu_fn=bench.cfg5_nu, law="aniso", model3d=True, attenuation="cg4",
+                      fluid_layers=(), dtype_coef=np.float32)
+    else:
+        bench.CFG = cfg
+        m = bench.make_mesh(bench.N_THETA)
     dt = m.estimate_dt()
     g = Domain(0)
     rel = m.release(g, dt)

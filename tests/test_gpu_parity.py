@@ -267,13 +267,7 @@ def test_real_mesh_matches_oracle(kw):
     g, _ = build_gpu(m, dt)
     randomize_displ(d, seed=5)
     push_fields(d, g, ("displ",))
-    for it in range(2):
-        d.computeStiff()
-        d.coupleSolidFluid()
-        g.computeStiff()
-        g.coupleSolidFluid()
-        for k, v in compare_field(d, g, "stiff").items():
-            assert v <= TOL_FORCE, (kw, it, k, v)
+    _two_evaluations(d, g, kw)
     # and a time loop with the source, from rest
     d2, _ = build_oracle(m, dt, np.float64)
     g2, _ = build_gpu(m, dt)
@@ -312,3 +306,51 @@ def test_fluid_strain_and_curl_receivers():
     f3 = [e.domain_tag for e in rel3["elements"] if e.kind == "fluid" and e.acoustic.K.shape[0] > 1][:1]
     with pytest.raises(RuntimeError, match="FluidElement::computeStrain"):
         g3.strain(f3, phi[:1], w[:1])
+
+
+@pytest.mark.parametrize("name", ["iso3d_nu1000_split_np1", "ti3d_nu200_split", "cfg4_ragged"])
+def test_split_pipeline_still_matches_oracle(name, monkeypatch):
+    """The fused kernel now takes every element up to Nr ~ 2700 (partial-row passes); the split pipeline (k_grad3d ->
+    k_fft3d_v2 -> k_quad3d, one point per CTA for Nr = 2016) remains for particle relabelling and beyond.  AX3D_NO_FUSED=1
+    (read at finalize) sends every 3D element through it, so that it stays under test."""
+    monkeypatch.setenv("AX3D_NO_FUSED", "1")
+    m = SynthMesh(**CASES[name])
+    dt = m.estimate_dt()
+    d, _ = build_oracle(m, dt, np.float64)
+    g, _ = build_gpu(m, dt)
+    randomize_displ(d, seed=13)
+    push_fields(d, g, ("displ",))
+    _two_evaluations(d, g, name)
+
+
+def _two_evaluations(d, g, tag):
+    """two stiffness evaluations (the second one exercises the memory variables), forces zeroed in between as the Newmark update does"""
+    for it in range(2):
+        d.computeStiff()
+        d.coupleSolidFluid()
+        g.computeStiff()
+        g.coupleSolidFluid()
+        for k, v in compare_field(d, g, "stiff").items():
+            assert v <= TOL_FORCE, (tag, it, k, v)
+        d.S["stiff"][:] = 0
+        d.F["stiff"][:] = 0
+        for fluid in (False, True):
+            a = g.get_bulk("stiff", fluid)
+            if a.size:
+                g.set_bulk("stiff", fluid, np.zeros_like(a))
+
+
+def test_partial_row_passes_cover_mixed_sizes():
+    """Elements of Nr = 2016 (10 partial-row passes), Nr = 1008 (5 passes) and small ones side by side, verbs and graph."""
+    def nu(s, z):
+        if s > 0.9895 * 6371e3 and abs(z) < 40e3:
+            return 1000
+        return 500 if s > 0.97 * 6371e3 and abs(z) < 120e3 else 8
+    m = SynthMesh(n_theta=320, n_r=1, r_in=6371e3 - 80e3, nu_fn=nu, law="aniso", model3d=True, attenuation="cg4", fluid_layers=())
+    dt = m.estimate_dt()
+    d, _ = build_oracle(m, dt, np.float64)
+    g, _ = build_gpu(m, dt)
+    assert m.e_nr.max() == 2016
+    randomize_displ(d, seed=21)
+    push_fields(d, g, ("displ",))
+    _two_evaluations(d, g, "partial rows")
