@@ -612,8 +612,12 @@ static void finalize(ax3d_domain *d) {
         // tables below it, the gather tile U = [0, twoff) in front
         auto plan_fused_element = [&](int N, int M, int stw_len, ElemDesc &D) -> bool {
             const int nc = fluid ? 1 : 3, us = nc * AX_NPE;
+            // ng = 10 (partial-row passes, Nr up to ~2700) is opt-in (AX3D_PARTIAL_ROWS=1): on cfg5 (8 B200s) the split pipeline
+            // with one point per CTA is still ~7 % faster for the Nr > ~1700 elements (summed element time 51.2 vs 54.6 ms)
+            static const bool partial_rows = getenv("AX3D_PARTIAL_ROWS") && atoi(getenv("AX3D_PARTIAL_ROWS")) != 0;
             static const int ngs[5] = {1, 2, 3, 5, 10};
             for (int ng : ngs) {
+                if (ng == 10 && !partial_rows) continue;
                 const long long zsz = (long long)npair * fused_np_max(ng) * fused_ldz(N);
                 const long long zoff = ((long long)fl.tile_cap - zsz) & ~1ll;
                 const long long twoff = (zoff - ((stw_len + 1) & ~1)) & ~1ll;

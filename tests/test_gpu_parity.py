@@ -340,8 +340,10 @@ def _two_evaluations(d, g, tag):
                 g.set_bulk("stiff", fluid, np.zeros_like(a))
 
 
-def test_partial_row_passes_cover_mixed_sizes():
-    """Elements of Nr = 2016 (10 partial-row passes), Nr = 1008 (5 passes) and small ones side by side, verbs and graph."""
+def test_partial_row_passes_cover_mixed_sizes(monkeypatch):
+    """Elements of Nr = 2016 (10 partial-row passes; opt-in, AX3D_PARTIAL_ROWS=1 read at finalize), Nr = 1008 (5 passes) and
+    small ones side by side."""
+    monkeypatch.setenv("AX3D_PARTIAL_ROWS", "1")
     def nu(s, z):
         if s > 0.9895 * 6371e3 and abs(z) < 40e3:
             return 1000
