@@ -98,3 +98,8 @@ inline fftw_plan fftw_plan_many_dft_c2r(int rank, const int *n, int howmany, fft
 }
 inline void fftw_execute(const fftw_plan p) { ax_fftw_run<double>(p); }
 inline void fftw_destroy_plan(fftw_plan p) { delete p; }
+// wisdom (SolverFFTW.cpp:18-64): the stand-in has no planner, so there is nothing to import or export
+inline int fftwf_import_wisdom_from_string(const char *) { return 0; }
+inline int fftw_import_wisdom_from_string(const char *) { return 0; }
+inline int fftwf_export_wisdom_to_filename(const char *) { return 1; }
+inline int fftw_export_wisdom_to_filename(const char *) { return 1; }
