@@ -47,14 +47,25 @@ def _strings(a):
 
 class ExodusMesh:
     def __init__(self, path, nu=2, nu_fn=None, lucky=True, attenuation="cg4", model3d=False, perturb=0.02, fluid3d=False,
-                 dtype_coef=np.float64):
+                 dtype_coef=np.float64, do_kappa=True, volumetric=None, src=None, geodesy=None, ocean_depth=0.0):
         self.path = path
         self.nu, self.nu_fn, self.lucky = nu, nu_fn, bool(lucky)
         self.att_kind = attenuation
+        self.do_kappa = bool(do_kappa)          # ATTENUATION_QKAPPA (AttAxiSEM.cpp:43-50)
+        self.ocean_depth = float(ocean_depth)   # MODEL_3D_OCEAN_LOAD constant$<km> in metres (OceanLoad3D_const; 0 = none)
+        # 3-D volumetric models of inparam.model (volumetric.from_parameters) with the source they are rotated about
+        # (`volumetric` may be a callable(mesh) -> (models, src, geodesy), evaluated once the file's globals are read)
+        self._vol_factory = volumetric if callable(volumetric) else None
+        self.volumetric, self.vol_src, self.vol_geodesy = ([] if callable(volumetric) else list(volumetric or [])), src, geodesy
         self.model3d, self.perturb, self.fluid3d = bool(model3d), float(perturb), bool(fluid3d)
         self.perturb_rho = False
         self.dtype_coef = dtype_coef
         self._read()
+        self.geometric = []                     # 3-D geometric models (relabelling.from_parameters), 4th item of the factory's result
+        if self._vol_factory is not None:
+            res = self._vol_factory(self)
+            self.volumetric, self.vol_src, self.vol_geodesy = res[:3]
+            self.geometric = list(res[3]) if len(res) > 3 else []
         self._auxiliary()
         self._build_quads()
         self._build_points()
@@ -134,6 +145,12 @@ class ExodusMesh:
         self.isotropic = "VP_0" in names
         self.has_att = "QMU_0" in names and "nr_lin_solids" in self.glob
         self.r_outer = self.glob.get("radius", 6371e3)
+        # radial ellipticity profile (ExodusModel.cpp:122-126): row 0 = knots r / R, row 1 = coefficients; used by preloop.Geodesy
+        if "ellipticity" in f:
+            ell = f["ellipticity"].read().astype(np.float64)
+            self.ellip_knots, self.ellip_coeffs = ell[0].copy(), ell[1].copy()
+        else:
+            self.ellip_knots = self.ellip_coeffs = None
         if self.has_att:
             n = int(self.glob["nr_lin_solids"])
             self.sls_w = np.array([self.glob["w_%d" % i] for i in range(n)])
@@ -368,6 +385,27 @@ class ExodusMesh:
                 m["qkp"] = self._interp(self._nodal("QKAPPA", iq), iq)
                 m["qmu"] = self._interp(self._nodal("QMU", iq), iq)
             self.mat.append(m)
+        # 3-D volumetric models (Material::addVolumetric3D): None where no sample of the quad is in range of a model
+        self.vol = [None] * ne
+        if self.volumetric:
+            from . import volumetric as VOL
+            from .preloop import Geodesy
+            geo = self.vol_geodesy or Geodesy(self.r_outer)
+            for iq in range(ne):
+                m, g = self.mat[iq], self.geo[iq]
+                ref1d = {k: m[k].reshape(25) if k in m else np.zeros(25) for k in VOL.KEYS}
+                self.vol[iq] = VOL.apply(self.volumetric, geo, self.vol_src, ref1d, g["s"].reshape(25), g["z"].reshape(25),
+                                         int(self.e_nr[iq]), bool(self.is_fluid[iq]))
+        # particle relabelling (Quad::addGeometric3D -> Relabelling::addUndulation): None where the quad is not displaced
+        self.relab = [None] * ne
+        if self.geometric:
+            from .relabelling import Relabelling
+            from .preloop import Geodesy
+            geo = self.vol_geodesy or Geodesy(self.r_outer)
+            for iq in range(ne):
+                R = Relabelling(self, iq, self.geometric, geo, self.vol_src)
+                if not R.zero:
+                    self.relab[iq] = R
         # integral factor (Quad::formIntegralFactor)
         self.ifact = []
         for iq in range(ne):
@@ -386,16 +424,18 @@ class ExodusMesh:
         self.sf_n = [None] * ng
         self.sf_contrib = {}
         self.p_surface = np.zeros(ng, dtype=bool)
+        self.surf_n = {}
         for iq in range(ne):
             tags, m, f = self.e2g[iq], self.mat[iq], self.ifact[iq]
             for ip in range(5):
                 for jp in range(5):
                     t = tags[ip, jp]
                     rho, vp = self._rho_vp(iq, ip, jp, int(self.p_nr[t]))
+                    jm = 1.0 if self.relab[iq] is None else self.relab[iq].mass_jacobian(ip * 5 + jp)      # Material::computeElementalMass
                     if self.is_fluid[iq]:
-                        self.mass_f[t] += f[ip, jp] / (rho * vp ** 2)
+                        self.mass_f[t] += f[ip, jp] / (rho * vp ** 2) * jm
                     else:
-                        self.mass_s[t] += f[ip, jp] * rho
+                        self.mass_s[t] += f[ip, jp] * rho * jm
             side = int(self.sf_side[iq])
             if side >= 0:
                 for (ip, jp) in CN.EDGE_IJ[side]:
@@ -405,12 +445,16 @@ class ExodusMesh:
                         n = -n
                     if self.sf_n[t] is None:
                         self.sf_n[t] = np.zeros((self.p_nr[t], 3))
-                    self.sf_n[t] += 0.5 * n[None, :]
+                    n = n[None, :] if n.ndim == 1 else n           # [Nr_p][3] under particle relabelling
+                    self.sf_n[t] += 0.5 * n
                     self.sf_contrib.setdefault(int(t), []).append((iq, 0.5 * n))
             side = int(self.surf_side[iq])
             if side >= 0:
                 for (ip, jp) in CN.EDGE_IJ[side]:
                     self.p_surface[tags[ip, jp]] = True
+                    if self.ocean_depth > 0.0:         # GLLPoint::addSurfNormal: the surface area the ocean column stands on
+                        t = tags[ip, jp]
+                        self.surf_n[t] = self.surf_n.get(t, 0.0) + self._normal(iq, side, ip, jp)
         # a synthetic (theta index, radial index) pair per element, for the callers that stride over the mesh
         rc = np.hypot(self.nodes[:, 0].mean(axis=1), self.nodes[:, 1].mean(axis=1))
         tc = np.arctan2(self.nodes[:, 0].mean(axis=1), self.nodes[:, 1].mean(axis=1))
@@ -428,6 +472,10 @@ class ExodusMesh:
 
     def _rho_vp(self, iq, ip, jp, nr):
         m, g = self.mat[iq], self.geo[iq]
+        if self.vol[iq] is not None:           # mRhoMass3D / mVpFluid3D: the quad's samples resampled to the point's Nr
+            from . import volumetric as VOL
+            v = self.vol[iq]
+            return VOL.linear_resampling(nr, v["rho"][:, ip * 5 + jp]), VOL.linear_resampling(nr, v["vpv"][:, ip * 5 + jp])
         p = self._phi_pert(g["s"][ip, jp], g["z"][ip, jp], nr)
         if self.is_fluid[iq] and not self.fluid3d:
             p = np.zeros(nr)
@@ -446,6 +494,10 @@ class ExodusMesh:
         rr = np.hypot(sz[0], sz[1])
         sint, cost = sz[0] / rr, sz[1] / rr
         n = np.array([sint, 0.0, cost])
+        if self.relab[iq] is not None:
+            # nRTZ . Q^T with the tilted normal of the undulated boundary (Relabelling::getSFNormalRTZ), one row per azimuth
+            nrtz = self.relab[iq].sf_normal_rtz(ip * 5 + jp)
+            n = np.stack([nrtz[:, 0] * cost + nrtz[:, 2] * sint, nrtz[:, 1], -nrtz[:, 0] * sint + nrtz[:, 2] * cost], 1)
         wxi = SP.W_GLJ if self.axial[iq] else SP.W_GLL
         wsf = wxi[ip] if side in (0, 2) else SP.W_GLL[jp]
         if self.axial[iq]:
@@ -469,7 +521,17 @@ class ExodusMesh:
             pts = np.stack([g["s"].ravel(), g["z"].ravel()], 1)
             d = np.linalg.norm(pts[:, None, :] - pts[None, :, :], axis=2) + np.eye(25) * 1e300
             vmax = max(m["vpv"].max(), m["vph"].max()) * (1.0 + (0.5 * self.perturb * 1.75 if self.model3d else 0.0))
-            dt = min(dt, courant * d.min() / vmax)
+            hmin = d.min()
+            if self.vol[iq] is not None:       # Material::getVMax on the 3-D samples
+                vmax = max(self.vol[iq]["vpv"].max(), self.vol[iq]["vph"].max())
+            if self.relab[iq] is not None:     # Quad::getDeltaT: min over the azimuthal slices of courant * hmin / vmax
+                hs = self.relab[iq].hmin_slices()
+                if self.vol[iq] is not None:
+                    vs = np.maximum(self.vol[iq]["vpv"].max(axis=1), self.vol[iq]["vph"].max(axis=1))
+                    dt = min(dt, float((courant * hs / vs).min()))
+                    continue
+                hmin = hs.min()
+            dt = min(dt, courant * hmin / vmax)
         return factor * dt
 
     # ------------------------------------------------------------------ release
@@ -485,9 +547,12 @@ class ExodusMesh:
         alpha = np.exp(-w * dt)
         beta = ((1 - alpha) / (w * dt) - alpha) * yd
         gamma = ((alpha - 1) / (w * dt) + 1) * yd
-        kpNo = 1 + 2 * np.log(w1 / w0) / np.pi / Qkp
-        dKp = kpNo / (Qkp / ysum + (1 - fact))
-        kpAtt = kpNo + dKp * fact
+        if self.do_kappa:
+            kpNo = 1 + 2 * np.log(w1 / w0) / np.pi / Qkp
+            dKp = kpNo / (Qkp / ysum + (1 - fact))
+            kpAtt = kpNo + dKp * fact
+        else:
+            dKp, kpAtt, kpNo = np.zeros_like(Qkp), np.ones_like(Qkp), np.ones_like(Qkp)
         muNo = 1 + 2 * np.log(w1 / w0) / np.pi / Qmu
         dMu = muNo / (Qmu / ysum + (1 - fact))
         muAtt = muNo + dMu * fact
@@ -513,7 +578,21 @@ class ExodusMesh:
             if np.ptp(m) <= 1e-12 * np.abs(m).max():
                 return M.Mass1D(np.float32(1.0 / m[0]))
             return M.Mass3D((1.0 / m).astype(np.float32))
-        sp = M.SolidPoint(nr, axial, crds, mk_mass(self.mass_s[t])) if is_s else None
+        sp = None
+        if is_s and self.ocean_depth > 0.0 and int(t) in self.surf_n:
+            # GLLPoint::release, ocean branch (GLLPoint.cpp:57-72): a constant depth over a 1-D mass gives MassOcean1D
+            ms = self.mass_s[t]
+            if np.ptp(ms) > 1e-12 * np.abs(ms).max():
+                raise NotImplementedError("GLLPoint::release || MassOcean3D from the preloop restatement (3-D mass under an ocean)")
+            r = np.hypot(crds[0], crds[1])
+            theta = 0.0 if r < 1e-10 else float(np.arccos(crds[1] / r))
+            sn = np.asarray(self.surf_n[int(t)])
+            if sn.ndim > 1:
+                raise NotImplementedError("GLLPoint::release || ocean load over an undulated surface from the preloop restatement")
+            area = float(np.linalg.norm(sn))
+            sp = M.SolidPoint(nr, axial, crds, M.MassOcean1D(ms[0], 1027.0 * self.ocean_depth * area, theta))
+        elif is_s:
+            sp = M.SolidPoint(nr, axial, crds, mk_mass(self.mass_s[t]))
         fp = M.FluidPoint(nr, axial, crds, mk_mass(self.mass_f[t]), bool(self.p_surface[t])) if is_f else None
         if sp is not None and fp is not None:
             n = self.sf_n[t]
@@ -522,7 +601,7 @@ class ExodusMesh:
                 n_un = np.zeros_like(n)
                 for e, c in self.sf_contrib[int(t)]:
                     if local_mask[e]:
-                        n_un = n_un + c[None, :]
+                        n_un = n_un + c
             mf = self.mass_f[t]
             if np.ptp(mf) <= 1e-12 * np.abs(mf).max() and np.abs(n - n[0]).max() <= 1e-12 * np.abs(n).max():
                 c = M.SFCoupling1D(np.float32(n_un[0, 0]), np.float32(n_un[0, 2]), np.float32(n[0, 0] / mf[0]), np.float32(n[0, 2] / mf[0]))
@@ -539,32 +618,73 @@ class ExodusMesh:
             inv_s[0, :] = 0.0
         grad = M.Gradient(g["J00"] / det, -g["J01"] / det, -g["J10"] / det, g["J11"] / det, inv_s, bool(self.axial[iq]))
         nr = int(self.e_nr[iq])
-        rows = nr if (self.model3d and (not self.is_fluid[iq] or self.fluid3d)) else 1
-        pert = np.zeros((rows, 25))
-        if rows > 1:
-            for ip in range(5):
-                for jp in range(5):
-                    pert[:, ip * 5 + jp] = self._phi_pert(g["s"][ip, jp], g["z"][ip, jp], nr)
-        flat = lambda a: a.reshape(1, 25) * np.ones((rows, 1))
         ff = f.reshape(1, 25)
-        is3d = bool(rows > 1 and np.ptp(pert, axis=0).any())
-        cast = lambda x: np.ascontiguousarray(x if is3d else x[0:1]).astype(self.dtype_coef)
-        rho = flat(m["rho"])
+        vol = self.vol[iq]
+        relab = self.relab[iq]
+        relab3d = relab is not None and not relab.is_par1d()
+        if vol is not None:
+            # 3-D samples from the volumetric models; Quad::releaseSolid / releaseFluid: 1-D element if every property has equal rows
+            from . import volumetric as VOL
+            rows = nr
+            with_att = self.att_kind is not None and self.has_att
+            if self.is_fluid[iq]:
+                is3d = not (VOL.equal_rows(vol["vpv"]) and VOL.equal_rows(vol["rho"]))                       # Material::isFluidPar1D
+            else:
+                is3d = not (all(VOL.equal_rows(vol[k]) for k in ("vpv", "vph", "vsv", "vsh", "rho", "eta")) and
+                            (not with_att or (VOL.equal_rows(vol["qkp"]) and VOL.equal_rows(vol["qmu"]))))   # Material::isSolidPar1D
+            cast = lambda x: np.ascontiguousarray(x if is3d else x[0:1]).astype(self.dtype_coef)
+            rho, vpv, vph, vsv, vsh, eta = (vol[k].copy() for k in ("rho", "vpv", "vph", "vsv", "vsh", "eta"))
+            qkp3, qmu3 = vol["qkp"], vol["qmu"]
+            nrm = np.linalg.norm
+            iso = nrm(vpv - vph) < 1e-10 * nrm(vpv) and nrm(vsv - vsh) < 1e-10 * nrm(vsv) and nrm(eta - 1.0) < 1e-10        # Material::isIsotropic
+        else:
+            rows = nr if ((self.model3d and (not self.is_fluid[iq] or self.fluid3d)) or relab3d) else 1
+            pert = np.zeros((rows, 25))
+            if rows > 1:
+                for ip in range(5):
+                    for jp in range(5):
+                        pert[:, ip * 5 + jp] = self._phi_pert(g["s"][ip, jp], g["z"][ip, jp], nr)
+            flat = lambda a: a.reshape(1, 25) * np.ones((rows, 1))
+            is3d = bool(rows > 1 and (np.ptp(pert, axis=0).any() or relab3d))
+            cast = lambda x: np.ascontiguousarray(x if is3d else x[0:1]).astype(self.dtype_coef)
+            rho = flat(m["rho"])
+            if not self.is_fluid[iq]:
+                vpv, vph = flat(m["vpv"]) * (1 + 0.5 * pert), flat(m["vph"]) * (1 + 0.5 * pert)
+                vsv, vsh = flat(m["vsv"]) * (1 + pert), flat(m["vsh"]) * (1 + pert)
+                eta = flat(m["eta"])
+                if self.has_att:
+                    qkp3, qmu3 = flat(m["qkp"]), flat(m["qmu"])
+            iso = np.allclose(m["vpv"], m["vph"]) and np.allclose(m["vsv"], m["vsh"]) and np.allclose(m["eta"], 1.0)   # Material::isIsotropic
+        # Quad::releaseSolid / releaseFluid: elem1D = material 1-D and relabelling 1-D; PRT from Relabelling::createPRT
+        prt, Jst = None, None
+        if relab is not None:
+            if vol is not None and relab3d:
+                is3d = True
+            Jst = relab.stiff_jacobian()                       # [Nr][25]
+            X = relab.stiff_x()                                # [4][Nr][25]
+            if is3d:
+                prt = M.PRT_3D(np.concatenate([X[k] for k in range(4)], axis=1))
+            else:
+                prt = M.PRT_1D([X[k][0].reshape(5, 5) for k in range(4)])
+            if rows == 1:
+                Jst = Jst[0:1]
+            cast = lambda x: np.ascontiguousarray(x if is3d else x[0:1]).astype(self.dtype_coef)
         if self.is_fluid[iq]:
             K = ff / rho
+            if Jst is not None:
+                K = K * Jst
             ac = M.Acoustic3D(cast(K * np.ones((rows, 1)))) if is3d else M.Acoustic1D(K[0].reshape(5, 5))
-            return M.FluidElement(grad, None, points, ac)
-        vpv, vph = flat(m["vpv"]) * (1 + 0.5 * pert), flat(m["vph"]) * (1 + 0.5 * pert)
-        vsv, vsh = flat(m["vsv"]) * (1 + pert), flat(m["vsh"]) * (1 + pert)
-        eta = flat(m["eta"])
+            return M.FluidElement(grad, prt, points, ac)
         A, C, L, N = rho * vph ** 2 * ff, rho * vpv ** 2 * ff, rho * vsv ** 2 * ff, rho * vsh ** 2 * ff
         F = eta * (A - 2 * L)
+        if Jst is not None:                                    # must do relabelling before attenuation (Material.cpp:322-330)
+            A, C, F, L, N = A * Jst, C * Jst, F * Jst, L * Jst, N * Jst
         att = None
         if self.att_kind is not None and self.has_att:
             kp = (4 * A + C + 4 * F - 4 * N) / 9.0                # Voigt average (Material.cpp:330-333)
             mu = (A + C - 2 * F + 6 * L + 5 * N) / 15.0
             A, C, F, L, N = A - (kp + 4 / 3 * mu), C - (kp + 4 / 3 * mu), F - (kp - 2 / 3 * mu), L - mu, N - mu
-            al, be, ga, dKp, kpAtt, kpNo, dMu, muAtt, muNo = self._att(dt, flat(m["qkp"]), flat(m["qmu"]))
+            al, be, ga, dKp, kpAtt, kpNo, dMu, muAtt, muNo = self._att(dt, qkp3, qmu3)
             nsls = len(al)
             if self.att_kind == "cg4":
                 wc = self._cg4_weights(f)
@@ -575,20 +695,19 @@ class ExodusMesh:
                 for i, k in enumerate(sel):
                     kp[:, k] *= 1 + wc[i] * (kpAtt[:, k] / kpNo[:, k] - 1)
                     mu[:, k] *= 1 + wc[i] * (muAtt[:, k] / muNo[:, k] - 1)
-                att = M.Attenuation3D_CG4(nsls, al, be, ga, dkp, dmu, True) if is3d else \
-                    M.Attenuation1D_CG4(nsls, al, be, ga, nr // 2, dkp[0], dmu[0], True)
+                att = M.Attenuation3D_CG4(nsls, al, be, ga, dkp, dmu, self.do_kappa) if is3d else \
+                    M.Attenuation1D_CG4(nsls, al, be, ga, nr // 2, dkp[0], dmu[0], self.do_kappa)
             else:
                 dkp, dmu = dKp * kp, dMu * mu
                 kp, mu = kp * kpAtt, mu * muAtt
-                att = M.Attenuation3D_Full(nsls, al, be, ga, dkp, dmu, True) if is3d else \
-                    M.Attenuation1D_Full(nsls, al, be, ga, nr // 2, dkp[0].reshape(5, 5), dmu[0].reshape(5, 5), True)
+                att = M.Attenuation3D_Full(nsls, al, be, ga, dkp, dmu, self.do_kappa) if is3d else \
+                    M.Attenuation1D_Full(nsls, al, be, ga, nr // 2, dkp[0].reshape(5, 5), dmu[0].reshape(5, 5), self.do_kappa)
             A, C, F, L, N = A + (kp + 4 / 3 * mu), C + (kp + 4 / 3 * mu), F + (kp - 2 / 3 * mu), L + mu, N + mu
-        iso = np.allclose(m["vpv"], m["vph"]) and np.allclose(m["vsv"], m["vsh"]) and np.allclose(m["eta"], 1.0)   # Material::isIsotropic
         if iso:
             el = (M.Isotropic3D if is3d else M.Isotropic1D)(cast(F), cast(L), att)
         else:
             el = (M.TransverselyIsotropic3D if is3d else M.TransverselyIsotropic1D)(cast(A), cast(C), cast(F), cast(L), cast(N), att)
-        return M.SolidElement(grad, None, points, el)
+        return M.SolidElement(grad, prt, points, el)
 
     def release(self, domain, dt, rank=0, elem_to_proc=None):
         """Mesh::release (Mesh.cpp:177-208)."""

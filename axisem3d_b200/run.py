@@ -1,0 +1,111 @@
+"""`python -m axisem3d_b200.run <run_dir>`: what `./axisem3d` does in a run directory (S/axisem.cpp:12-176), on the CUDA path.
+
+Reads `<run_dir>/input/` unchanged -- inparam.model, inparam.nu, inparam.time_src_recv, inparam.advanced, the Exodus mesh they
+name, CMTSOLUTION (or the point-force file) and STATIONS -- builds the domain through the preloop restatement
+(exodus_mesh.py, preloop.py, volumetric.py), runs the Newmark loop on the GPU (ax3d_run_steps_record: one CUDA graph per step,
+device-side recorder) and writes `<run_dir>/output/stations/<network>.<name>.<RTZ|ENZ|SPZ>.ascii` in the layout of the
+reference's PointwiseIOAscii (S/core/output/pointwise/PointwiseIOAscii.cpp: time and three components per line).
+
+Covered: 1-D background models, the volumetric models of volumetric.py, constant / empirical Nu, CG4 / full attenuation,
+earthquake / point-force sources, a constant ocean load, erf / gauss / ricker source-time functions, geographic / source-centred stations,
+ellipticity mode off / geographic / full (particle relabelling).  Anything else in the input files fails loudly (NotImplementedError) rather than being
+ignored.  There is no CPU fallback: the CUDA library must load and a device must be present.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import preloop as PL
+from . import relabelling as REL
+from . import volumetric as VOL
+from .exodus_mesh import ExodusMesh
+
+
+class Simulation:
+    """Everything axisem_main builds before the time loop, from the input directory alone; `release(domain)` plays
+    Mesh::release, Source::release and ReceiverCollection::release into any object with the Domain verbs."""
+
+    def __init__(self, input_dir):
+        par = self.par = PL.Parameters(input_dir)
+        if par.get("MODEL_PLOT_SLICES_NUM") != "0":
+            raise NotImplementedError("axisem3d_b200.run: MODEL_PLOT_SLICES_NUM != 0 (slice plots are the reference's)")
+        if par.get("MODEL_2D_MODE").lower() != "off":
+            raise NotImplementedError("axisem3d_b200.run: MODEL_2D_MODE " + par.get("MODEL_2D_MODE"))
+        ocean = [x for x in par.get("MODEL_3D_OCEAN_LOAD").split("$") if x != ""]         # OceanLoad3D::buildInparam
+        if ocean[0].lower() == "none":
+            ocean_depth = 0.0
+        elif ocean[0].lower() == "constant":
+            ocean_depth = (float(ocean[1]) if len(ocean) > 1 else 3.0) * 1e3              # OceanLoad3D_const.h: default 3 km
+        else:
+            raise NotImplementedError("axisem3d_b200.run: MODEL_3D_OCEAN_LOAD " + ocean[0] + " (needs the reference's data files)")
+        if par.get("ATTENUATION_SPECFEM_LEGACY", bool):
+            raise NotImplementedError("axisem3d_b200.run: ATTENUATION_SPECFEM_LEGACY (AttSimplex is Fortran in the reference)")
+        if par.get("OUT_STATIONS_WHOLE_SURFACE", bool) or par.get("NU_WISDOM_LEARN", bool):
+            raise NotImplementedError("axisem3d_b200.run: whole-surface output / wisdom learning are driven through the C-ABI verbs, not this runner")
+        nu, nu_fn, lucky = PL.nu_field(par)
+        att = None if not par.get("ATTENUATION", bool) else ("cg4" if par.get("ATTENUATION_CG4", bool) else "full")
+        self.source = PL.Source.from_parameters(par)
+
+        def models(mesh):                       # Volumetric3D / Geometric3D::buildInparam, once the mesh file's globals are known
+            g = PL.Geodesy.from_mesh(mesh, par)
+            return VOL.from_parameters(par, self.source, g), self.source, g, REL.from_parameters(par, g)
+        self.mesh = ExodusMesh(os.path.join(input_dir, par.get("MODEL_1D_EXODUS_MESH_FILE")), nu=nu if nu is not None else 0,
+                               nu_fn=nu_fn, lucky=lucky, attenuation=att, do_kappa=par.get("ATTENUATION_QKAPPA", bool),
+                               volumetric=models, ocean_depth=ocean_depth)
+        self.geodesy = self.mesh.vol_geodesy
+        self.dt = PL.delta_t(par, self.mesh)
+        self.stf, self.shift = PL.stf_from_parameters(par, self.dt)
+        self.receivers = PL.Receivers.from_parameters(par, self.source, self.geodesy).locate(
+            self.mesh, par.get("OUT_STATIONS_DEPTH_REF", bool))
+
+    def release(self, domain):
+        rel = self.mesh.release(domain, self.dt)
+        if self.source is not None:
+            domain.addSourceTerm(self.source.release(self.mesh, self.geodesy, rel["elements"]))
+        return rel
+
+    def times(self):
+        """the time stamp of every recorded sample (Newmark.cpp:27, 64-65: t starts at -shift, recorded before it advances)"""
+        return -self.shift + self.dt * np.arange(len(self.stf))
+
+
+def write_ascii(out_dir, sim, series):
+    """PointwiseIOAscii: one file per station, `time c1 c2 c3` per recorded step."""
+    rc = sim.receivers
+    os.makedirs(out_dir, exist_ok=True)
+    t = sim.times()[::rc.record_interval]
+    for i, key in enumerate(rc.keys):
+        with open(os.path.join(out_dir, "%s.%s.ascii" % (key, rc.components)), "w") as f:
+            for k in range(len(t)):
+                f.write("%.6g %.6g %.6g %.6g\n" % (t[k], series[k, i, 0], series[k, i, 1], series[k, i, 2]))
+
+
+def main(argv=None):
+    argv = sys.argv[1:] if argv is None else argv
+    run_dir = argv[0] if argv else "."
+    from .domain import Domain
+    t0 = time.time()
+    sim = Simulation(os.path.join(run_dir, "input"))
+    dom = Domain(0)
+    rel = sim.release(dom)
+    dom.finalize()
+    sim.receivers.release(dom, rel["elements"])
+    t1 = time.time()
+    series = np.asarray(dom.runStepsRecord(sim.dt, sim.stf))                # [step][receiver][3], SPZ
+    if not dom.checkStability():
+        raise RuntimeError("Domain::checkStability || Simulation has blown up")
+    t2 = time.time()
+    series = sim.receivers.rotate(series)[::sim.receivers.record_interval]
+    write_ascii(os.path.join(run_dir, "output", "stations"), sim, series)
+    print("axisem3d_b200: %d elements, %d points, dt = %.6g s, %d steps, %d stations; preloop %.1f s, time loop %.2f s (%.3f ms / step)"
+          % (len(rel["elements"]), len(rel["points"]), sim.dt, len(sim.stf), len(sim.receivers.keys), t1 - t0, t2 - t1,
+             1e3 * (t2 - t1) / max(len(sim.stf), 1)))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -165,3 +165,107 @@ def read_displacement(path, points):
         res[p.domain_tag] = (s, f)
     assert pos == raw.size, (pos, raw.size)
     return res
+
+
+def parse_dump(raw):
+    """The AX3D serialisation back as plain arrays: {"G", "points": [...], "elements": [...], "sources": [...], "dt", "stf",
+    "receivers": {...} or None}.  Reads what DumpDomain.write produces and what oracle/ref_main_dump.cpp writes from the
+    reference's own Domain (which appends a receiver section)."""
+    raw = bytes(raw)
+    pos = [0]
+
+    def take(dtype, n=1):
+        a = np.frombuffer(raw, dtype=dtype, count=n, offset=pos[0])
+        pos[0] += a.nbytes
+        return a
+
+    def i32():
+        return int(take("<i4")[0])
+
+    assert raw[:4] == b"AX3D"
+    pos[0] = 4
+    res = {"G": (take("<f8", 25).copy(), take("<f8", 25).copy())}
+
+    def mass():
+        n = i32()
+        if n <= -1000000:
+            rows = -1000000 - n
+            return {"ocean": True, "data": take("<f8", 3 if rows == 1 else 5 * rows).copy()}
+        return take("<f4", n).copy()
+
+    pts = []
+    for _ in range(i32()):
+        kind, nr, axial = i32(), i32(), i32()
+        p = {"kind": kind, "nr": nr, "axial": axial, "crds": take("<f8", 2).copy()}
+        if kind == 0:
+            p["mass"] = mass()
+        elif kind == 1:
+            p["mass"] = mass()
+            p["fluidSurf"] = i32()
+        else:
+            p["mass"] = mass()
+            p["mass_fluid"] = mass()
+            p["fluidSurf"] = i32()
+            rows = i32()
+            p["n_un"] = take("<f4", 3 * rows).reshape(3, rows).copy()
+            p["n_as"] = take("<f4", 3 * rows).reshape(3, rows).copy()
+        pts.append(p)
+    res["points"] = pts
+    els = []
+    ncoef = {0: 2, 1: 5, 2: 21}
+    for _ in range(i32()):
+        e = {"fluid": i32(), "axial": i32(), "tags": take("<i4", 25).copy(), "grad": take("<f8", 125).reshape(5, 25).copy()}
+        prt_rows = i32()
+        if prt_rows:
+            e["prt"] = take("<f4", 4 * 25 * prt_rows).reshape(4, 25, prt_rows).copy()
+        if not e["fluid"]:
+            law, rows = i32(), i32()
+            e["law"], e["rows"] = law, rows
+            e["coef"] = take("<f4", ncoef[law] * 25 * rows).reshape(ncoef[law], 25, rows).copy()
+            att = i32()
+            e["att"] = att
+            if att:
+                nsls, do_kappa = i32(), i32()
+                P = 4 if att == 2 else 25
+                e.update(nsls=nsls, doKappa=do_kappa, alpha=take("<f4", nsls).copy(), beta=take("<f4", nsls).copy(),
+                         gamma=take("<f4", nsls).copy(), dkappa=take("<f4", rows * P).reshape(P, rows).copy(),
+                         dmu=take("<f4", rows * P).reshape(P, rows).copy())
+        else:
+            rows = i32()
+            e["rows"] = rows
+            e["K"] = take("<f4", 25 * rows).reshape(25, rows).copy()
+        els.append(e)
+    res["elements"] = els
+    srcs = []
+    for _ in range(i32()):
+        tag = i32()
+        nrow = take("<i4", 25).copy()
+        force = []
+        for k in range(25):
+            c = take("<f4", 2 * 3 * int(nrow[k])).reshape(3, int(nrow[k]), 2)
+            force.append((c[..., 0] + 1j * c[..., 1]).T.copy())          # (nrow, 3)
+        srcs.append({"element": tag, "force": force})
+    res["sources"] = srcs
+    n = i32()
+    res["dt"] = float(take("<f8")[0])
+    res["stf"] = take("<f4", n).copy()
+    res["receivers"] = None
+    if raw[pos[0]:pos[0] + 4] == b"RECV":
+        pos[0] += 4
+        rec = {"shift": float(take("<f8")[0])}
+        nrec = i32()
+        rec["components"] = raw[pos[0]:pos[0] + 3].decode() if nrec else ""
+        pos[0] += 3 if nrec else 0
+        keys, tags, par, w = [], [], [], []
+        for _ in range(nrec):
+            ln = i32()
+            keys.append(raw[pos[0]:pos[0] + ln].decode())
+            pos[0] += ln
+            tags.append(i32())
+            par.append(take("<f8", 6).copy())          # phi, theta, baz, lat, lon, dep
+            w.append(take("<f8", 25).copy())
+        rec.update(keys=keys, element=np.array(tags, dtype=np.int64), par=np.array(par).reshape(-1, 6),
+                   weights=np.array(w).reshape(-1, 25))
+        res["receivers"] = rec
+    assert pos[0] == len(raw), (pos[0], len(raw))
+    return res

@@ -1,0 +1,107 @@
+"""The repo's preloop (Exodus mesh + inparam + CMTSOLUTION + STATIONS -> points, elements, source, STF, receivers) against what
+the REFERENCE's own preloop releases into its Domain on the same files.
+
+tests/golden/main_<case>_domain.bin.xz is the dump written by oracle/_ref/axisem3d_dump: the reference's ExodusModel, Mesh, Quad,
+Material, AttBuilder, GLLPoint, Connectivity, Source, Earthquake, STF and ReceiverCollection classes, compiled unmodified from
+/root/reference (oracle/Makefile.main) and run on template/input.  The comparison is array by array in the serialisation of
+tests/dump_domain.py; integers (point and element order, kinds, tags, Nr) must be identical, floats agree to fp32 rounding of
+the cast at the boundary."""
+import numpy as np
+import pytest
+
+import main_case as MC
+from dump_domain import DumpDomain, parse_dump
+
+TOL_F32 = 3e-7          # one fp32 rounding of an fp64 value computed in a different operation order
+TOL_GEOM = 1e-12        # fp64 quantities: coordinates (relative to the Earth's radius), dt, angles
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="module", params=MC.CASES)
+def pair(request, tmp_path_factory):
+    case = MC.get_case(request.param)
+    d = DumpDomain()
+    case.release(d)
+    path = tmp_path_factory.mktemp("dump") / "ours.bin"
+    d.write(str(path), case.dt, case.stf)
+    ours = parse_dump(open(path, "rb").read())
+    ref = MC.reference_domain(request.param)
+    yield case, ours, ref
+
+
+def test_time_step_and_spectral_constants(pair):
+    case, ours, ref = pair
+    assert abs(case.dt - ref["dt"]) <= TOL_GEOM * ref["dt"]
+    assert _rel(ours["G"][0], ref["G"][0]) < 2e-12 and _rel(ours["G"][1], ref["G"][1]) < 2e-12     # the table has 12 decimals
+
+
+def test_points_match_reference_preloop(pair):
+    case, ours, ref = pair
+    assert len(ours["points"]) == len(ref["points"])
+    worst = {}
+    for i, (p, q) in enumerate(zip(ours["points"], ref["points"])):
+        for k in ("kind", "nr", "axial", "fluidSurf"):
+            assert p.get(k) == q.get(k), (i, k, p.get(k), q.get(k))
+        worst["crds"] = max(worst.get("crds", 0.0), float(np.abs(p["crds"] - q["crds"]).max()) / 6371e3)
+        for k in ("mass", "mass_fluid", "n_un", "n_as"):
+            if k in q:
+                if isinstance(q[k], dict):         # MassOcean1D: (mass, massOcean, theta), recovered from the reference's four fp32 members
+                    assert isinstance(p[k], dict) and p[k]["data"].shape == q[k]["data"].shape, i
+                    a, b = p[k]["data"], q[k]["data"]           # relative for the two masses, absolute for the angle (0 at the pole)
+                    worst["ocean"] = max(worst.get("ocean", 0.0), float(np.abs(a[:2] / b[:2] - 1.0).max()), float(abs(a[2] - b[2])))
+                else:
+                    assert not isinstance(p[k], dict), i
+                    worst[k] = max(worst.get(k, 0.0), _rel(p[k], q[k]))
+    assert worst.pop("crds") < TOL_GEOM, worst
+    assert worst.pop("ocean", 0.0) < 2e-5, worst
+    assert all(v < TOL_F32 for v in worst.values()), worst
+
+
+def test_elements_match_reference_preloop(pair):
+    case, ours, ref = pair
+    assert len(ours["elements"]) == len(ref["elements"])
+    worst, compared = {}, 0
+    for i, (p, q) in enumerate(zip(ours["elements"], ref["elements"])):
+        for k in ("fluid", "axial", "law", "rows", "att", "nsls", "doKappa"):
+            assert p.get(k) == q.get(k), (i, k, p.get(k), q.get(k))
+        assert np.array_equal(p["tags"], q["tags"]), i
+        assert ("prt" in p) == ("prt" in q), i
+        for k in ("grad", "coef", "alpha", "beta", "gamma", "dkappa", "dmu", "K", "prt"):
+            if k in q:
+                assert np.shape(p[k]) == np.shape(q[k]), (i, k)
+                if np.isnan(q[k]).all():                      # "thin" dumps keep the arrays of every n-th element only
+                    continue
+                worst[k] = max(worst.get(k, 0.0), _rel(p[k], q[k]))
+                compared += k in ("coef", "K")
+    assert compared >= len(ref["elements"]) // 8
+    assert all(v < TOL_F32 for v in worst.values()), worst
+
+
+def test_source_and_stf_match_reference_preloop(pair):
+    case, ours, ref = pair
+    assert len(ref["sources"]) == 1 and len(ours["sources"]) == 1
+    a, b = ours["sources"][0], ref["sources"][0]
+    assert a["element"] == b["element"]
+    scale = max(np.abs(f).max() for f in b["force"])
+    for fa, fb in zip(a["force"], b["force"]):
+        assert fa.shape == fb.shape
+        assert np.abs(fa - fb).max() <= TOL_F32 * scale
+    assert len(ours["stf"]) == len(ref["stf"])
+    assert np.abs(ours["stf"] - ref["stf"]).max() <= 1e-6 * np.abs(ref["stf"]).max()
+    assert abs(case.shift - ref["receivers"]["shift"]) <= 1e-9
+
+
+def test_receivers_match_reference_preloop(pair):
+    case, ours, ref = pair
+    rc, R = case.receivers, ref["receivers"]
+    assert rc.keys == R["keys"] and rc.components == R["components"]
+    tags = np.array([case.rel["elements"][int(q)].domain_tag for q in rc.quad])
+    assert np.array_equal(tags, R["element"])
+    got = np.stack([rc.phi, rc.theta, rc.baz, rc.lat, rc.lon, rc.depth], 1)
+    assert np.abs(got - R["par"]).max() < 1e-9
+    assert np.abs(rc.weights - R["weights"]).max() < TOL_F32 * np.abs(R["weights"]).max()
