@@ -56,6 +56,15 @@ CASES = {
     # receivers placed in the undeformed mesh): the reference's own Relabelling / Geometric3D / Ellipticity classes.  Every
     # element is 3-D, so the dump keeps the element arrays of every 6th element only ("thin").
     "ellipticity_prt": dict(steps=300, stride=2, thin=6, par={"MODEL_3D_ELLIPTICITY_MODE": "full"}),
+    # the remaining branches of the source / receiver callers: a point force at the north pole (the pole singularity of
+    # Source::Source), Gaussian source-time function, stations given in source-centred coordinates, SPZ components, no attenuation
+    "pointforce_spz": dict(steps=400, stride=2, thin=100000, par={
+        "SOURCE_TYPE": "point_force", "SOURCE_FILE": "POINTFORCE", "SOURCE_TIME_FUNCTION": "gauss", "SOURCE_STF_HALF_DURATION": "15.0",
+        "OUT_STATIONS_FILE": "STATIONS_SC", "OUT_STATIONS_SYSTEM": "source-centered", "OUT_STATIONS_COMPONENTS": "SPZ",
+        "ATTENUATION": "false"},
+        files={"POINTFORCE": "latitude:   90.0\nlongitude:  10.0\ndepth:      20.0\nFt:         1.0e18\nFp:        -0.5e18\nFr:         2.0e18\n",
+               "STATIONS_SC": "".join("S%02d  SC  %7.3f  %7.3f  0.0  %5.1f\n" % (i, 2.0 + 3.1 * i, (37.0 * i) % 360.0, 0.0 if i % 3 else 25.0 * i)
+                                      for i in range(24))}),
 }
 
 
@@ -81,6 +90,8 @@ def prepare(case, run_dir):
     par["OUT_STATIONS_FORMAT"] = "netcdf"
     par["OPTION_VERBOSE_LEVEL"] = "essential"
     write_overrides(inp, par)
+    for name, text in cfg.get("files", {}).items():
+        open(os.path.join(inp, name), "w").write(text)
     mesh = [f for f in os.listdir(inp) if f.endswith(".e")][0]
     flatten(os.path.join(inp, mesh))
     return par
@@ -120,7 +131,8 @@ def make(case, keep=None):
     stride = cfg["stride"]
     np.savez_compressed(os.path.join(GOLDEN_DIR, "main_%s.npz" % case), time=t[::stride], keys=np.array(keys),
                         seis=seis[:, ::stride].astype(np.float32), stride=stride, steps=cfg["steps"],
-                        par_keys=np.array(sorted(par)), par_vals=np.array([par[k] for k in sorted(par)]))
+                        par_keys=np.array(sorted(par)), par_vals=np.array([par[k] for k in sorted(par)]),
+                        file_names=np.array(sorted(cfg.get("files", {}))), file_texts=np.array([cfg["files"][k] for k in sorted(cfg.get("files", {}))]))
     raw = open(dump_path, "rb").read()
     with lzma.open(os.path.join(GOLDEN_DIR, "main_%s_domain.bin.xz" % case), "wb", preset=9) as f:
         f.write(raw)

@@ -16,13 +16,14 @@ from dump_domain import parse_dump
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 MESH = "AxiSEM_prem_ani_one_crust_50.e"
-CASES = ("cfg1_template", "emp_full_enz", "bubbles_3d", "ellipticity_prt")
+CASES = ("cfg1_template", "emp_full_enz", "bubbles_3d", "ellipticity_prt", "pointforce_spz")
 
 
 def golden(case):
     z = np.load(os.path.join(GOLDEN, "main_%s.npz" % case))
+    files = dict(zip([str(k) for k in z["file_names"]], [str(v) for v in z["file_texts"]])) if "file_names" in z.files else {}
     return dict(time=z["time"], keys=[str(k) for k in z["keys"]], seis=z["seis"], stride=int(z["stride"]), steps=int(z["steps"]),
-                par=dict(zip([str(k) for k in z["par_keys"]], [str(v) for v in z["par_vals"]])))
+                par=dict(zip([str(k) for k in z["par_keys"]], [str(v) for v in z["par_vals"]])), files=files)
 
 
 def reference_domain(case):
@@ -36,7 +37,10 @@ def input_dir(case, tmp=None):
     inp = os.path.join(tmp, "input")
     shutil.copytree(os.path.join(GOLDEN, "template_input"), inp)
     shutil.copy(os.path.join(GOLDEN, MESH), os.path.join(inp, MESH))
-    par = golden(case)["par"]
+    gold = golden(case)
+    par = gold["par"]
+    for name, text in gold["files"].items():           # input files the case adds (a point-force file, a station list)
+        open(os.path.join(inp, name), "w").write(text)
     for name in PL.Parameters.FILES:
         path = os.path.join(inp, name)
         lines = open(path).read().split("\n")

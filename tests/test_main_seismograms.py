@@ -19,7 +19,7 @@ import main_case as MC  # noqa: E402
 TOL = 1e-4
 # the CPU oracle follows only the first steps of every case (long enough for the near stations to carry the body and surface
 # waves); the CUDA test runs all of them (2000 for cfg1_template)
-CPU_STEPS = {"cfg1_template": 400, "emp_full_enz": 200, "bubbles_3d": 200, "ellipticity_prt": 120}
+CPU_STEPS = {"cfg1_template": 400, "emp_full_enz": 200, "bubbles_3d": 120, "ellipticity_prt": 120, "pointforce_spz": 200}
 
 
 def _misfit(got, ref):
@@ -35,13 +35,21 @@ def _misfit(got, ref):
 def test_oracle_seismograms_match_reference_main(name):
     from axisem_oracle import OracleDomain
     from c_oracle import COracle
+    if name == "ellipticity_prt" and not os.environ.get("AX3D_SLOW_TESTS"):
+        # oracle.c has no particle-relabelling path, the numpy oracle needs ~1.2 s per step on this case (2.5 min for the 120
+        # steps the near stations need); run with AX3D_SLOW_TESTS=1 (passes: 1e-6).  The case's preloop arrays are compared
+        # in test_preloop_reference.py and its seismograms, all 300 steps, by the CUDA test below.
+        pytest.skip("slow (numpy oracle, particle relabelling): set AX3D_SLOW_TESTS=1")
     gold = MC.golden(name)
     case = MC.get_case(name)
     if True:
         d = OracleDomain(np.float32)
         rel = case.release(d)
         d.finalize()
-        co = COracle(d)
+        try:
+            co = COracle(d)
+        except NotImplementedError:           # oracle.c has no particle-relabelling path: the numpy oracle steps those cases
+            co = d
         rc = case.receivers
         tags = [rel["elements"][int(q)].domain_tag for q in rc.quad]
         assert len(case.stf) == gold["steps"]
