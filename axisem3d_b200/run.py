@@ -95,7 +95,10 @@ def main(argv=None):
     dom.finalize()
     sim.receivers.release(dom, rel["elements"])
     t1 = time.time()
-    series = np.asarray(dom.runStepsRecord(sim.dt, sim.stf))                # [step][receiver][3], SPZ
+    # ax3d_run_steps_record takes at most 4096 steps per call; 1000 = the reference's OUT_STATIONS_DUMP_INTERVAL default
+    chunk = min(max(sim.par.get("OUT_STATIONS_DUMP_INTERVAL", int), 1), 4096)
+    parts = [np.asarray(dom.runStepsRecord(sim.dt, sim.stf[k:k + chunk])) for k in range(0, len(sim.stf), chunk)]
+    series = np.concatenate(parts, axis=0)                                  # [step][receiver][3], SPZ
     if not dom.checkStability():
         raise RuntimeError("Domain::checkStability || Simulation has blown up")
     t2 = time.time()

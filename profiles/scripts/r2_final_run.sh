@@ -1,0 +1,12 @@
+# the unchanged template run directory (3600 s record = 8274 steps, 128 stations) end to end on the GPU
+mkdir -p gpurun_out
+RUN=/tmp/ax3d_template_run
+rm -rf $RUN && mkdir -p $RUN && cp -r tests/golden/template_input $RUN/input && cp tests/golden/AxiSEM_prem_ani_one_crust_50.e $RUN/input/
+( time timeout 200 python -m axisem3d_b200.run $RUN ) > gpurun_out/r2y_template_run.log 2>&1
+echo "run rc=$?" >> gpurun_out/r2y_template_run.log
+ls $RUN/output/stations | wc -l >> gpurun_out/r2y_template_run.log
+head -2 $RUN/output/stations/II.AAK.RTZ.ascii >> gpurun_out/r2y_template_run.log
+sed -n '2000,2002p' $RUN/output/stations/IU.SSPA.RTZ.ascii >> gpurun_out/r2y_template_run.log
+tail -1 $RUN/output/stations/IU.SSPA.RTZ.ascii >> gpurun_out/r2y_template_run.log
+cp $RUN/output/stations/IU.SSPA.RTZ.ascii gpurun_out/r2y_IU.SSPA.RTZ.ascii
+cat gpurun_out/r2y_template_run.log
