@@ -57,3 +57,43 @@ def test_cpp_driver_matches_oracle(tmp_path):
             assert np.abs(s - ora.get_solid(t, "displ")).max() <= 1e-4 * sscale, t
         if f is not None:
             assert np.abs(f - ora.get_fluid(t, "displ")).max() <= 1e-4 * fscale, t
+
+
+@pytest.mark.gpu
+def test_cpp_driver_replays_the_reference_preloop(tmp_path):
+    """INTEGRATION.md's arrangement end to end: the REFERENCE's own preloop (tests/golden/main_bubbles_3d_domain.bin.xz = what
+    its Mesh / Source / STF release put into its Domain on the template inputs with three 3-D bubble models, dumped by
+    oracle/ref_main_dump.cpp) replayed through the C++ facade classes onto the CUDA path -- no Python preloop in between --
+    against the repo's own preloop + Python binding on the same input directory."""
+    import lzma
+    import struct
+    import main_case as MC
+    from axisem3d_b200.domain import Domain
+    name, nstep = "bubbles_3d", 300
+    raw = lzma.open(os.path.join(MC.GOLDEN, "main_%s_domain.bin.xz" % name), "rb").read()
+    end = raw.rfind(b"RECV")
+    nref = MC.golden(name)["steps"]
+    start = end - (4 + 8 + 4 * nref)
+    n, dt = struct.unpack("<id", raw[start:start + 12])
+    assert n == nref
+    stf = np.frombuffer(raw, dtype="<f4", count=n, offset=start + 12)[:nstep]
+    path, out = os.path.join(str(tmp_path), "ref_domain.bin"), os.path.join(str(tmp_path), "out.bin")
+    with open(path, "wb") as f:
+        f.write(raw[:start] + struct.pack("<id", nstep, dt) + stf.tobytes())
+    r = subprocess.run([build_driver(), path, out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    case = MC.get_case(name)
+    assert abs(case.dt - dt) <= 1e-12 * dt
+    g = Domain(0)
+    rel = case.release(g)
+    g.finalize()
+    g.runSteps(case.dt, case.stf[:nstep])
+    got = read_displacement(out, rel["points"])
+    sscale = max(np.abs(g.get_bulk("displ", False)).max(), 1e-300)
+    fscale = max(np.abs(g.get_bulk("displ", True)).max(), 1e-300)
+    assert sscale > 1e-12
+    for t, (s, f) in got.items():
+        if s is not None:
+            assert np.abs(s - g.get_solid(t, "displ")).max() <= 1e-4 * sscale, t
+        if f is not None:
+            assert np.abs(f - g.get_fluid(t, "displ")).max() <= 1e-4 * fscale, t
