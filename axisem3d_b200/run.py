@@ -62,11 +62,21 @@ class Simulation:
         self.receivers = PL.Receivers.from_parameters(par, self.source, self.geodesy).locate(
             self.mesh, par.get("OUT_STATIONS_DEPTH_REF", bool))
 
-    def release(self, domain):
-        rel = self.mesh.release(domain, self.dt)
+    def release(self, domain, rank=0, elem_to_proc=None):
+        """Mesh::release + Source::release for rank `rank` of the partition `elem_to_proc` (None = one rank holds everything)"""
+        rel = self.mesh.release(domain, self.dt, rank=rank, elem_to_proc=elem_to_proc)
         if self.source is not None:
-            domain.addSourceTerm(self.source.release(self.mesh, self.geodesy, rel["elements"]))
+            st = self.source.release(self.mesh, self.geodesy, rel["elements"], None if elem_to_proc is None else rel["dec"])
+            if st is not None:
+                domain.addSourceTerm(st)
         return rel
+
+    def partition(self, nproc):
+        """The reference's first decomposition pass: METIS k-way on the element dual graph, vertex weight = the element's Nr
+        (Mesh.cpp:88-101, DualGraph.cpp:35-94); deterministic, so every rank computes the same vector."""
+        from . import partition as PT
+        e2p, info = PT.partition_kway(self.mesh.conn, self.mesh.e_nr.astype(np.float64), nproc, imbalance=0.01, ntrials=4)
+        return e2p, info
 
     def times(self):
         """the time stamp of every recorded sample (Newmark.cpp:27, 64-65: t starts at -shift, recorded before it advances)"""
@@ -85,28 +95,71 @@ def write_ascii(out_dir, sim, series):
 
 
 def main(argv=None):
+    """One process per GPU: `python -m axisem3d_b200.run <run_dir>` or, for N GPUs of one node,
+    `python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 -m axisem3d_b200.run <run_dir>` (RANK, WORLD_SIZE,
+    LOCAL_RANK, MASTER_* from the environment).  The halo sum runs over peer-memory windows inside the step graph; the
+    torch.distributed group (gloo) only carries the set-up handles and the station traces gathered on rank 0."""
     argv = sys.argv[1:] if argv is None else argv
     run_dir = argv[0] if argv else "."
     from .domain import Domain
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    dist = None
+    device = local
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        device = local % max(torch.cuda.device_count(), 1)      # ranks may share a device (tests on a one-GPU box)
+        torch.cuda.set_device(device)
+        if not dist.is_initialized():
+            dist.init_process_group("gloo", rank=rank, world_size=world)
     t0 = time.time()
     sim = Simulation(os.path.join(run_dir, "input"))
-    dom = Domain(0)
-    rel = sim.release(dom)
+    dom = Domain(device)
+    e2p = None
+    if world > 1:
+        e2p, _ = sim.partition(world)
+        box = [e2p if rank == 0 else None]
+        dist.broadcast_object_list(box, 0)                      # one partition vector for everybody
+        e2p = box[0]
+    rel = sim.release(dom, rank, e2p)
+    if world > 1:
+        dom.setMessaging(rel["msg"], rank, world, None)
     dom.finalize()
-    sim.receivers.release(dom, rel["elements"])
+    if world > 1:
+        dom.connectHalo(rel["msg"], rank, dist)
+    rc = sim.receivers
+    mine = rc.release(dom, rel["elements"], None if e2p is None else rel["dec"])
     t1 = time.time()
     # ax3d_run_steps_record takes at most 4096 steps per call; 1000 = the reference's OUT_STATIONS_DUMP_INTERVAL default
     chunk = min(max(sim.par.get("OUT_STATIONS_DUMP_INTERVAL", int), 1), 4096)
-    parts = [np.asarray(dom.runStepsRecord(sim.dt, sim.stf[k:k + chunk])) for k in range(0, len(sim.stf), chunk)]
-    series = np.concatenate(parts, axis=0)                                  # [step][receiver][3], SPZ
+    parts = []
+    for k in range(0, len(sim.stf), chunk):
+        if len(mine):
+            parts.append(np.asarray(dom.runStepsRecord(sim.dt, sim.stf[k:k + chunk])))
+        else:                                                   # a rank without stations steps along (same number of exchanges)
+            dom.runSteps(sim.dt, sim.stf[k:k + chunk])
     if not dom.checkStability():
         raise RuntimeError("Domain::checkStability || Simulation has blown up")
+    dom.synchronize()
     t2 = time.time()
-    series = sim.receivers.rotate(series)[::sim.receivers.record_interval]
-    write_ascii(os.path.join(run_dir, "output", "stations"), sim, series)
-    print("axisem3d_b200: %d elements, %d points, dt = %.6g s, %d steps, %d stations; preloop %.1f s, time loop %.2f s (%.3f ms / step)"
-          % (len(rel["elements"]), len(rel["points"]), sim.dt, len(sim.stf), len(sim.receivers.keys), t1 - t0, t2 - t1,
-             1e3 * (t2 - t1) / max(len(sim.stf), 1)))
+    series = np.concatenate(parts, axis=0) if parts else np.zeros((len(sim.stf), 0, 3), np.float32)    # [step][my receivers][3], SPZ
+    series = rc.rotate(series, mine)[::rc.record_interval]
+    if world > 1:
+        everyone = [None] * world if rank == 0 else None
+        dist.gather_object((mine, series), everyone, dst=0)
+        if rank == 0:
+            full = np.zeros((series.shape[0], len(rc.keys), 3), np.float32)
+            for idx, ser in everyone:
+                if len(idx):
+                    full[:, idx] = ser
+            series = full
+        dist.barrier()
+    if rank == 0:
+        write_ascii(os.path.join(run_dir, "output", "stations"), sim, series)
+        print("axisem3d_b200: %d rank(s), %d elements and %d points on rank 0, dt = %.6g s, %d steps, %d stations; preloop %.1f s, "
+              "time loop %.2f s (%.3f ms / step)" % (world, len(rel["elements"]), len(rel["points"]), sim.dt, len(sim.stf), len(rc.keys),
+                                                     t1 - t0, t2 - t1, 1e3 * (t2 - t1) / max(len(sim.stf), 1)))
     return 0
 
 

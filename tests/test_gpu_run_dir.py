@@ -1,0 +1,68 @@
+"""`python -m axisem3d_b200.run <run_dir>`: the reference's template run directory, unchanged, end to end on the CUDA path --
+on one rank and on two ranks (METIS partition, halo sum over peer-memory windows; on a one-GPU box the two rank processes share
+device 0 like tests/test_gpu_multirank.py) -- against the station seismograms of the REFERENCE's whole program
+(tests/golden/main_cfg1_template.npz, oracle/make_golden_main.py)."""
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NSTEP = 600
+TOL = 1e-4          # the ascii station files carry 6 significant digits
+
+
+def _run_dir(tmp_path):
+    import main_case as MC
+    run = os.path.join(str(tmp_path), "run")
+    os.makedirs(run)
+    inp = MC.input_dir("cfg1_template", run)
+    assert inp == os.path.join(run, "input")
+    path = os.path.join(inp, "inparam.advanced")
+    lines = [("DEVELOP_MAX_TIME_STEPS %d" % NSTEP) if ln.split()[:1] == ["DEVELOP_MAX_TIME_STEPS"] else ln for ln in open(path).read().split("\n")]
+    open(path, "w").write("\n".join(lines))
+    return run
+
+
+def _check(run):
+    import main_case as MC
+    gold = MC.golden("cfg1_template")
+    st = os.path.join(run, "output", "stations")
+    got = np.stack([np.loadtxt(os.path.join(st, k + ".ascii")) for k in gold["keys"]])         # [nrec][nstep][1 + 3]
+    assert got.shape[1] == NSTEP
+    n = NSTEP // gold["stride"]
+    assert np.abs(got[0, ::gold["stride"], 0][:n] - gold["time"][:n]).max() < 1e-3
+    a, b = got[:, ::gold["stride"], 1:][:, :n], gold["seis"].astype(np.float64)[:, :n]
+    mis = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    assert mis <= TOL, mis
+
+
+def _worker(rank, world, port, run):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from axisem3d_b200 import run as R
+    assert R.main([run]) == 0
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_run_dir_single_rank(tmp_path):
+    from axisem3d_b200 import run as R
+    run = _run_dir(tmp_path)
+    assert R.main([run]) == 0
+    _check(run)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_run_dir_two_ranks(tmp_path):
+    import torch.multiprocessing as mp
+    run = _run_dir(tmp_path)
+    mp.spawn(_worker, args=(2, 29700 + (os.getpid() % 2000), run), nprocs=2, join=True)
+    _check(run)
+    shutil.rmtree(run, ignore_errors=True)
