@@ -22,6 +22,14 @@ TOL = 1e-4
 CPU_STEPS = {"cfg1_template": 400, "emp_full_enz": 200, "bubbles_3d": 120, "ellipticity_prt": 120, "pointforce_spz": 200}
 
 
+def _log(name, impl, steps, tot, worst):
+    """AX3D_MISFIT_LOG=<file>: keep the measured misfits (profiles/ quotes them)"""
+    path = os.environ.get("AX3D_MISFIT_LOG")
+    if path:
+        with open(path, "a") as f:
+            f.write("%-16s %-12s %5d steps   rel. L2 over all stations %.3e   worst live trace %.3e\n" % (name, impl, steps, tot, worst))
+
+
 def _misfit(got, ref):
     """relative L2 misfit over all stations and components, and the worst single trace among those that carry signal"""
     tot = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
@@ -65,6 +73,7 @@ def test_oracle_seismograms_match_reference_main(name):
         got = rc.rotate(np.array(got)).transpose(1, 0, 2).astype(np.float64)          # [nrec][nt][3]
         assert rc.keys == [k.rsplit(".", 1)[0] for k in gold["keys"]]
         tot, worst = _misfit(got, gold["seis"].astype(np.float64)[:, :got.shape[1]])
+        _log(name, "oracle (CPU)", nstep, tot, worst)
         assert tot <= TOL and worst <= 10 * TOL, (tot, worst)
 
 
@@ -85,4 +94,5 @@ def test_cuda_seismograms_match_reference_main(name):
         assert g.checkStability()
         got = rc.rotate(series)[::gold["stride"]].transpose(1, 0, 2).astype(np.float64)
         tot, worst = _misfit(got, gold["seis"].astype(np.float64))
+        _log(name, "CUDA", gold["steps"], tot, worst)
         assert tot <= TOL and worst <= 10 * TOL, (tot, worst)
