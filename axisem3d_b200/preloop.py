@@ -215,8 +215,14 @@ def nu_field(par, r_outer=6371e3):
         if nu < 0:
             raise RuntimeError("ConstNrField::ConstNrField || Negative Nu.")
         return nu, None, lucky
+    if typ == "wisdom":
+        # WisdomNrField (WisdomNrField.cpp:10-27): Nu from the 4 nearest points of a learning run's wisdom file, times a factor
+        wis = NuWisdom.read(os.path.join(par.input_dir, par.get("NU_WISDOM_REUSE_INPUT")))
+        factor = par.get("NU_WISDOM_REUSE_FACTOR", float)
+        factor = factor if factor > TINY_DOUBLE else 1.0
+        return None, (lambda s, z: int(round(wis.get_nu(s, z, 4) * factor))), lucky
     if typ != "empirical":
-        raise NotImplementedError("NrField::build || NU_TYPE " + typ + " (wisdom / user-defined fields are the reference's)")
+        raise NotImplementedError("NrField::build || NU_TYPE " + typ + " (user-defined fields are compiled into the reference)")
     nu_ref, nu_min = par.get("NU_EMP_REF", int), par.get("NU_EMP_MIN", int)
     sc_s, sc_t, sc_d = (par.get(k, bool) for k in ("NU_EMP_SCALE_AXIS", "NU_EMP_SCALE_THETA", "NU_EMP_SCALE_DEPTH"))
     pow_s, fact_pi = par.get("NU_EMP_POW_AXIS", float), par.get("NU_EMP_FACTOR_PI", float)
@@ -238,6 +244,70 @@ def nu_field(par, r_outer=6371e3):
         return max(nu_min, int(math.ceil(nu)))
 
     return None, nu_fn, lucky
+
+
+# ------------------------------------------------------------------------------------------------------------------ wisdom
+class NuWisdom:
+    """The Nu(s, z) wisdom a learning run leaves behind (NuWisdom.cpp): rows (s, z, learnt Nu, original Nu)."""
+
+    def __init__(self, data):
+        data = np.asarray(data, dtype=np.float64).reshape(len(data), -1)
+        if data.shape[1] == 3:
+            data = np.concatenate([data, data[:, 2:3]], axis=1)
+        if data.shape[1] != 4:
+            raise RuntimeError("NuWisdom::readFromFile || Inconsistent dimensions for wisdom data, must be a matrix of 3 or 4 columns")
+        self.sz = data[:, :2].copy()
+        self.nu_learn = np.round(data[:, 2]).astype(np.int64)
+        self.nu_orign = np.round(data[:, 3]).astype(np.int64)
+
+    @classmethod
+    def read(cls, path):
+        """variable `axisem3d_wisdom` of a NetCDF file: NetCDF-4 / HDF5 (what the reference writes) through h5lite, the
+        classic format (what write() below produces) through scipy"""
+        with open(path, "rb") as f:
+            magic = f.read(8)
+        if magic[:3] == b"CDF":
+            from scipy.io import netcdf_file
+            with netcdf_file(path, "r", mmap=False) as nc:
+                return cls(np.array(nc.variables["axisem3d_wisdom"][:], dtype=np.float64))
+        from . import h5lite
+        return cls(h5lite.File(path)["axisem3d_wisdom"].read())
+
+    def write(self, path):
+        """NuWisdom::writeToFile; classic NetCDF (readable by the reference's NetCDF_Reader through libnetcdf)"""
+        from scipy.io import netcdf_file
+        data = np.concatenate([self.sz, self.nu_learn[:, None].astype(np.float64), self.nu_orign[:, None].astype(np.float64)], axis=1)
+        with netcdf_file(path, "w") as nc:
+            nc.createDimension("ncdim_%d" % len(data), len(data))
+            nc.createDimension("ncdim_4", 4)
+            v = nc.createVariable("axisem3d_wisdom", "d", ("ncdim_%d" % len(data), "ncdim_4"))
+            v[:] = data
+
+    def get_nu(self, s, z, num_samples=4):
+        """NuWisdom::getNu: inverse-distance mean of the learnt Nu of the nearest points (an exact hit wins)"""
+        if len(self.sz) == 0:
+            raise RuntimeError("NuWisdom::getNu || Wisdom is empty.")
+        d = np.hypot(self.sz[:, 0] - s, self.sz[:, 1] - z)
+        k = min(num_samples, len(d))
+        idx = np.argpartition(d, k - 1)[:k]
+        idx = idx[np.argsort(d[idx], kind="stable")]
+        tot = num = 0.0
+        for i in idx:
+            if d[i] < TINY_DOUBLE:
+                return int(self.nu_learn[i])
+            tot += 1.0 / d[i]
+            num += self.nu_learn[i] / d[i]
+        return int(round(num / tot))
+
+    def compression_ratio(self):
+        return float(self.nu_learn.sum()) / float(self.nu_orign.sum())
+
+
+def learn_parameters(par):
+    """LearnParameters (NuWisdom.cpp:134-149) -> (invoked, cutoff, interval, output file name)"""
+    cutoff = min(max(par.get("NU_WISDOM_LEARN_EPSILON", float), 1e-5), 0.1)
+    interval = par.get("NU_WISDOM_LEARN_INTERVAL", int)
+    return par.get("NU_WISDOM_LEARN", bool), cutoff, interval if interval > 0 else 5, par.get("NU_WISDOM_LEARN_OUTPUT")
 
 
 # ------------------------------------------------------------------------------------------------ mapping helpers on a mesh

@@ -6,7 +6,7 @@ name, CMTSOLUTION (or the point-force file) and STATIONS -- builds the domain th
 device-side recorder) and writes `<run_dir>/output/stations/<network>.<name>.<RTZ|ENZ|SPZ>.ascii` in the layout of the
 reference's PointwiseIOAscii (S/core/output/pointwise/PointwiseIOAscii.cpp: time and three components per line).
 
-Covered: 1-D background models, the volumetric models of volumetric.py, constant / empirical Nu, CG4 / full attenuation,
+Covered: 1-D background models, the volumetric models of volumetric.py, constant / empirical / wisdom Nu, wisdom learning, CG4 / full attenuation,
 earthquake / point-force sources, a constant ocean load, erf / gauss / ricker source-time functions, geographic / source-centred stations,
 ellipticity mode off / geographic / full (particle relabelling).  Anything else in the input files fails loudly (NotImplementedError) rather than being
 ignored.  There is no CPU fallback: the CUDA library must load and a device must be present.
@@ -44,8 +44,9 @@ class Simulation:
             raise NotImplementedError("axisem3d_b200.run: MODEL_3D_OCEAN_LOAD " + ocean[0] + " (needs the reference's data files)")
         if par.get("ATTENUATION_SPECFEM_LEGACY", bool):
             raise NotImplementedError("axisem3d_b200.run: ATTENUATION_SPECFEM_LEGACY (AttSimplex is Fortran in the reference)")
-        if par.get("OUT_STATIONS_WHOLE_SURFACE", bool) or par.get("NU_WISDOM_LEARN", bool):
-            raise NotImplementedError("axisem3d_b200.run: whole-surface output / wisdom learning are driven through the C-ABI verbs, not this runner")
+        if par.get("OUT_STATIONS_WHOLE_SURFACE", bool):
+            raise NotImplementedError("axisem3d_b200.run: whole-surface output is driven through the C-ABI verbs, not this runner")
+        self.learn = PL.learn_parameters(par)           # (invoked, cutoff, interval, file): Domain::setLearnParameters
         nu, nu_fn, lucky = PL.nu_field(par)
         att = None if not par.get("ATTENUATION", bool) else ("cg4" if par.get("ATTENUATION_CG4", bool) else "full")
         self.source = PL.Source.from_parameters(par)
@@ -94,6 +95,26 @@ def write_ascii(out_dir, sim, series):
                 f.write("%.6g %.6g %.6g %.6g\n" % (t[k], series[k, i, 0], series[k, i, 1], series[k, i, 2]))
 
 
+def write_wisdom(path, dom, rel, e2p, rank, dist):
+    """Domain::dumpWisdom (Domain.cpp:404-440): (s, z, learnt Nu, Nu) of every point that no lower rank also holds, gathered on
+    rank 0 and written as the `axisem3d_wisdom` variable a later run reads with NU_TYPE wisdom."""
+    nu = dom.getNuWisdom()
+    owned = np.ones(len(rel["points"]), dtype=bool)
+    msg = rel["msg"]
+    for r, pts in zip(msg.mIProcComm, msg.mILocalPoints):
+        if r < rank:
+            owned[np.asarray(pts, dtype=np.int64)] = False                      # Domain::pointInPreviousRank
+    rows = np.array([[p.crds[0], p.crds[1], nu[t], p.nu] for t, p in enumerate(rel["points"]) if owned[t]], dtype=np.float64).reshape(-1, 4)
+    if dist is not None:
+        everyone = [None] * dist.get_world_size() if rank == 0 else None
+        dist.gather_object(rows, everyone, dst=0)
+        if rank == 0:
+            rows = np.concatenate(everyone, axis=0)
+    if rank == 0:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        PL.NuWisdom(rows).write(path)
+
+
 def main(argv=None):
     """One process per GPU: `python -m axisem3d_b200.run <run_dir>` or, for N GPUs of one node,
     `python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 -m axisem3d_b200.run <run_dir>` (RANK, WORLD_SIZE,
@@ -130,6 +151,8 @@ def main(argv=None):
         dom.connectHalo(rel["msg"], rank, dist)
     rc = sim.receivers
     mine = rc.release(dom, rel["elements"], None if e2p is None else rel["dec"])
+    if sim.learn[0]:
+        dom.setLearnParameters(True, sim.learn[1], sim.learn[2])            # Mesh::release (Mesh.cpp:207)
     t1 = time.time()
     # ax3d_run_steps_record takes at most 4096 steps per call; 1000 = the reference's OUT_STATIONS_DUMP_INTERVAL default
     chunk = min(max(sim.par.get("OUT_STATIONS_DUMP_INTERVAL", int), 1), 4096)
@@ -155,6 +178,8 @@ def main(argv=None):
                     full[:, idx] = ser
             series = full
         dist.barrier()
+    if sim.learn[0]:
+        write_wisdom(os.path.join(run_dir, "output", sim.learn[3]), dom, rel, e2p, rank, dist)
     if rank == 0:
         write_ascii(os.path.join(run_dir, "output", "stations"), sim, series)
         print("axisem3d_b200: %d rank(s), %d elements and %d points on rank 0, dt = %.6g s, %d steps, %d stations; preloop %.1f s, "

@@ -65,6 +65,11 @@ CASES = {
         files={"POINTFORCE": "latitude:   90.0\nlongitude:  10.0\ndepth:      20.0\nFt:         1.0e18\nFp:        -0.5e18\nFr:         2.0e18\n",
                "STATIONS_SC": "".join("S%02d  SC  %7.3f  %7.3f  0.0  %5.1f\n" % (i, 2.0 + 3.1 * i, (37.0 * i) % 360.0, 0.0 if i % 3 else 25.0 * i)
                                       for i in range(24))}),
+    # wisdom learning (Domain::learnWisdom / dumpWisdom, Point::learnWisdom): empirical Nu, learn every 5th step with cutoff
+    # 1e-3; the wisdom file the reference writes (s, z, learnt Nu, original Nu per point) is kept next to the traces
+    "wisdom_learn": dict(steps=300, stride=2, thin=100000, par={
+        "NU_TYPE": "empirical", "NU_EMP_REF": "6", "NU_EMP_MIN": "2", "NU_WISDOM_LEARN": "true", "NU_WISDOM_LEARN_EPSILON": "1e-3",
+        "NU_WISDOM_LEARN_INTERVAL": "5", "NU_WISDOM_LEARN_OUTPUT": "learn.nu_wisdom.nc"}),
 }
 
 
@@ -129,10 +134,17 @@ def make(case, keep=None):
     assert keys == keys2 and np.array_equal(t, t2) and seis.tobytes() == seis2.tobytes(), \
         "ref_main_dump.cpp does not mirror axisem_main: the two programs' traces differ"
     stride = cfg["stride"]
+    extra = {}
+    wis = os.path.join(run_dir, "output", par.get("NU_WISDOM_LEARN_OUTPUT", "-") + ".ncflat")
+    if os.path.exists(wis):                                   # NuWisdom::writeToFile: rows (s, z, nu_learn, nu_orign), domain point order
+        w = read_flat(wis)["axisem3d_wisdom"]
+        extra = dict(wisdom_sz=w[:, :2].astype(np.float32), wisdom_nu_learn=np.round(w[:, 2]).astype(np.int16),
+                     wisdom_nu_orign=np.round(w[:, 3]).astype(np.int16))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "main_%s.npz" % case), time=t[::stride], keys=np.array(keys),
                         seis=seis[:, ::stride].astype(np.float32), stride=stride, steps=cfg["steps"],
                         par_keys=np.array(sorted(par)), par_vals=np.array([par[k] for k in sorted(par)]),
-                        file_names=np.array(sorted(cfg.get("files", {}))), file_texts=np.array([cfg["files"][k] for k in sorted(cfg.get("files", {}))]))
+                        file_names=np.array(sorted(cfg.get("files", {}))), file_texts=np.array([cfg["files"][k] for k in sorted(cfg.get("files", {}))]),
+                        **extra)
     raw = open(dump_path, "rb").read()
     with lzma.open(os.path.join(GOLDEN_DIR, "main_%s_domain.bin.xz" % case), "wb", preset=9) as f:
         f.write(raw)

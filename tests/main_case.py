@@ -16,7 +16,7 @@ from dump_domain import parse_dump
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 MESH = "AxiSEM_prem_ani_one_crust_50.e"
-CASES = ("cfg1_template", "emp_full_enz", "bubbles_3d", "ellipticity_prt", "pointforce_spz")
+CASES = ("cfg1_template", "emp_full_enz", "bubbles_3d", "ellipticity_prt", "pointforce_spz", "wisdom_learn")
 
 
 def golden(case):

@@ -66,3 +66,41 @@ def test_run_dir_two_ranks(tmp_path):
     mp.spawn(_worker, args=(2, 29700 + (os.getpid() % 2000), run), nprocs=2, join=True)
     _check(run)
     shutil.rmtree(run, ignore_errors=True)
+
+
+def _set(inp, name, key, value):
+    path = os.path.join(inp, name)
+    lines = [("%s %s" % (key, value)) if ln.split()[:1] == [key] else ln for ln in open(path).read().split("\n")]
+    open(path, "w").write("\n".join(lines))
+
+
+@pytest.mark.gpu
+def test_run_dir_learns_and_reuses_wisdom(tmp_path):
+    """The reference's two-run workflow: a learning run (NU_WISDOM_LEARN true) leaves output/<name>.nu_wisdom.nc behind
+    (Domain::dumpWisdom), a second run reads it as its Nu field (NU_TYPE wisdom, WisdomNrField).  The learnt values are
+    compared with the reference program's own wisdom file (tests/golden/main_wisdom_learn.npz)."""
+    import main_case as MC
+    from axisem3d_b200 import preloop as PL
+    from axisem3d_b200 import run as R
+    import test_wisdom_reference as TW
+    run = os.path.join(str(tmp_path), "learn")
+    os.makedirs(run)
+    inp = MC.input_dir("wisdom_learn", run)
+    assert R.main([run]) == 0
+    wis = PL.NuWisdom.read(os.path.join(run, "output", "learn.nu_wisdom.nc"))
+    sz, learn, orign = TW._gold()
+    assert np.array_equal(wis.nu_orign, orign) and np.abs(wis.sz - sz).max() < 1.0
+    near = np.hypot(sz[:, 0], sz[:, 1] - (6371e3 - 12e3)) < 2500e3
+    assert (wis.nu_learn[near] == learn[near]).all() and float((wis.nu_learn == learn).mean()) >= 0.95
+    # second run: the learnt field as NU_TYPE wisdom
+    run2 = os.path.join(str(tmp_path), "reuse")
+    os.makedirs(run2)
+    inp2 = MC.input_dir("wisdom_learn", run2)
+    shutil.copy(os.path.join(run, "output", "learn.nu_wisdom.nc"), os.path.join(inp2, "learn.nu_wisdom.nc"))
+    _set(inp2, "inparam.nu", "NU_TYPE", "wisdom")
+    _set(inp2, "inparam.nu", "NU_WISDOM_LEARN", "false")
+    _set(inp2, "inparam.nu", "NU_WISDOM_REUSE_INPUT", "learn.nu_wisdom.nc")
+    _set(inp2, "inparam.advanced", "DEVELOP_MAX_TIME_STEPS", "100")
+    assert R.main([run2]) == 0
+    a = np.loadtxt(os.path.join(run2, "output", "stations", "IU.SSPA.RTZ.ascii"))
+    assert a.shape == (100, 4) and np.isfinite(a).all()
