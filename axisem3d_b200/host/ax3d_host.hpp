@@ -20,6 +20,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/axisem3d_b200.h"
@@ -518,6 +519,32 @@ public:
         check(ax3d_record_curl(mDom, 1, &mDomainTag, &phi, weights.data(), curl.data()));
     }
     void forceTIso() {}
+    // the same three with the caller's own matrix types (anything with (i, j) and (i) access, e.g. Eigen's RMatPP / RRow3 / RRow6:
+    // PointwiseRecorder.cpp:73-75, 103-105, 116-118 compile against these unchanged)
+    template <class W, class O, class = decltype(std::declval<const W &>()(0, 0))>
+    void computeGroundMotion(Real phi, const W &weights, O &u_spz) const {
+        RMatPP w;
+        for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) w[i * 5 + j] = (Real)weights(i, j);
+        RRow3 u;
+        computeGroundMotion(phi, w, u);
+        for (int c = 0; c < 3; ++c) u_spz(c) = u[c];
+    }
+    template <class W, class O, class = decltype(std::declval<const W &>()(0, 0))>
+    void computeStrain(Real phi, const W &weights, O &strain) const {
+        RMatPP w;
+        for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) w[i * 5 + j] = (Real)weights(i, j);
+        RRow6 e;
+        computeStrain(phi, w, e);
+        for (int c = 0; c < 6; ++c) strain(c) = e[c];
+    }
+    template <class W, class O, class = decltype(std::declval<const W &>()(0, 0))>
+    void computeCurl(Real phi, const W &weights, O &curl) const {
+        RMatPP w;
+        for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) w[i * 5 + j] = (Real)weights(i, j);
+        RRow3 c3;
+        computeCurl(phi, w, c3);
+        for (int c = 0; c < 3; ++c) curl(c) = c3[c];
+    }
 protected:
     friend class Domain;
     virtual int release(ax3d_domain *dom) = 0;
