@@ -43,7 +43,13 @@ void Domain::setLearnParameters(LearnParameters *lpar) {
     mLearnBound.mCutoff = lpar->mCutoff;
     mLearnBound.mInterval = lpar->mInterval;
     mLearnBound.mFileName = lpar->mFileName;
-    if (lpar->mInvoked) mImpl.setLearnParameters(&mLearnBound);
+    // Mesh::release calls this before Source::release adds the source term (Mesh.cpp:207, axisem.cpp:133-140), and the library's
+    // ax3d_set_learn_parameters finalizes the set-up: the parameters are handed on at the first verb of Newmark::solve
+}
+
+void Domain::resetZero() const {                        // Newmark.cpp:34
+    if (mLearn && mLearn->mInvoked) mImpl.setLearnParameters(const_cast<ax3d::LearnParameters *>(&mLearnBound));
+    mImpl.resetZero();
 }
 
 void Domain::initializeRecorders() const {              // Domain.cpp:193-205
