@@ -46,3 +46,32 @@ def test_no_cpu_fallback_without_a_device():
     rc = lib.ax3d_create(0, ctypes.byref(h))
     assert rc != 0
     assert b"no CUDA device" in lib.ax3d_last_error()
+
+
+def test_drop_in_binary_fails_loudly_without_a_device(tmp_path):
+    """oracle/_ref/axisem3d_gpu (the reference's own main + preloop + recorders over the binding, oracle/Makefile.dropin) runs
+    the reference's whole preloop on the template inputs and then -- on a box without a GPU -- stops in Domain::Domain with the
+    library's error, printed by the reference's own exception handler.  There is no CPU path to fall back to."""
+    import shutil
+    import subprocess
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "axisem3d_gpu")
+    if not os.path.exists(exe) or torch.cuda.is_available():
+        pytest.skip("needs the drop-in binary (built where /root/reference exists) and a box without a CUDA device")
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import main_case as MC
+    from nc_flatten import flatten
+    run = os.path.join(str(tmp_path), "run")
+    os.makedirs(run)
+    inp = MC.input_dir("cfg1_template", run)
+    flatten(os.path.join(inp, MC.MESH))
+    link = os.path.join(run, "axisem3d_gpu")
+    os.symlink(exe, link)
+    r = subprocess.run([link], cwd=run, capture_output=True, text=True, timeout=300)
+    assert "AXISEM3D ABORTED UPON RUNTIME EXCEPTION" in r.stdout and "FROM: Domain::Domain" in r.stdout
+    assert "no CUDA device" in r.stdout
+    assert "Attenuation Builder" in r.stdout            # the reference's preloop ran up to the point where the Domain is created
+    assert not os.path.exists(os.path.join(run, "output", "stations", "axisem3d_synthetics.nc.ncflat"))
+    shutil.rmtree(run, ignore_errors=True)
