@@ -570,6 +570,9 @@ class Receivers:
                     a, b, d = float(strs[2]), float(strs[3]), float(strs[5])
                 except ValueError:
                     continue
+                if any(x.lower() in ("dump_strain", "dump_curl") for x in strs[6:]):
+                    raise NotImplementedError("ReceiverCollection: dump_strain / dump_curl stations are read back through "
+                                              "ax3d_record_strain / ax3d_record_curl by the host, not by this runner (" + strs[0] + ")")
                 names.append(strs[0]); nets.append(strs[1]); c1.append(a); c2.append(b); dep.append(d)
         return names, nets, c1, c2, dep
 

@@ -4,7 +4,8 @@ Reads `<run_dir>/input/` unchanged -- inparam.model, inparam.nu, inparam.time_sr
 name, CMTSOLUTION (or the point-force file) and STATIONS -- builds the domain through the preloop restatement
 (exodus_mesh.py, preloop.py, volumetric.py), runs the Newmark loop on the GPU (ax3d_run_steps_record: one CUDA graph per step,
 device-side recorder) and writes `<run_dir>/output/stations/<network>.<name>.<RTZ|ENZ|SPZ>.ascii` in the layout of the
-reference's PointwiseIOAscii (S/core/output/pointwise/PointwiseIOAscii.cpp: time and three components per line).
+reference's PointwiseIOAscii (S/core/output/pointwise/PointwiseIOAscii.cpp: time and three components per line) and / or
+`axisem3d_synthetics.nc` with the variables of PointwiseIONetCDF, as OUT_STATIONS_FORMAT asks.
 
 Covered: 1-D background models, the volumetric models of volumetric.py, constant / empirical / wisdom Nu, wisdom learning, CG4 / full attenuation,
 earthquake / point-force sources, a constant ocean load, erf / gauss / ricker source-time functions, geographic / source-centred stations,
@@ -95,6 +96,27 @@ def write_ascii(out_dir, sim, series):
                 f.write("%.6g %.6g %.6g %.6g\n" % (t[k], series[k, i, 0], series[k, i, 1], series[k, i, 2]))
 
 
+def write_netcdf(path, sim, series):
+    """PointwiseIONetCDF (S/core/output/pointwise/PointwiseIONetCDF.cpp:83-260): `time_points` [nstep] (double) and one variable
+    `<network>.<name>.<components>` [nstep][3] (float) per station with its latitude / longitude / depth attributes, plus the
+    source location as global attributes.  Written in the classic NetCDF format (scipy); the reference writes NetCDF-4."""
+    from scipy.io import netcdf_file
+    rc = sim.receivers
+    t = sim.times()[::rc.record_interval]
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with netcdf_file(path, "w") as nc:
+        nc.createDimension("ncdim_%d" % len(t), len(t))
+        nc.createDimension("ncdim_3", 3)
+        v = nc.createVariable("time_points", "d", ("ncdim_%d" % len(t),))
+        v[:] = t
+        if sim.source is not None:
+            nc.source_latitude, nc.source_longitude, nc.source_depth = sim.source.lat, sim.source.lon, sim.source.depth
+        for i, key in enumerate(rc.keys):
+            v = nc.createVariable("%s.%s" % (key, rc.components), "f", ("ncdim_%d" % len(t), "ncdim_3"))
+            v[:] = series[:, i, :]
+            v.latitude, v.longitude, v.depth = float(rc.lat[i]), float(rc.lon[i]), float(rc.depth[i])
+
+
 def write_wisdom(path, dom, rel, e2p, rank, dist):
     """Domain::dumpWisdom (Domain.cpp:404-440): (s, z, learnt Nu, Nu) of every point that no lower rank also holds, gathered on
     rank 0 and written as the `axisem3d_wisdom` variable a later run reads with NU_TYPE wisdom."""
@@ -181,7 +203,13 @@ def main(argv=None):
     if sim.learn[0]:
         write_wisdom(os.path.join(run_dir, "output", sim.learn[3]), dom, rel, e2p, rank, dist)
     if rank == 0:
-        write_ascii(os.path.join(run_dir, "output", "stations"), sim, series)
+        fmts = [sim.par.get("OUT_STATIONS_FORMAT", str, k).lower() for k in range(sim.par.size("OUT_STATIONS_FORMAT"))]
+        if any(f not in ("ascii", "netcdf", "netcdf_no_assemble") for f in fmts):
+            raise RuntimeError("ReceiverCollection::buildInparam || Invalid parameter, keyword = OUT_STATIONS_FORMAT.")
+        if "ascii" in fmts or not fmts:
+            write_ascii(os.path.join(run_dir, "output", "stations"), sim, series)
+        if "netcdf" in fmts or "netcdf_no_assemble" in fmts:
+            write_netcdf(os.path.join(run_dir, "output", "stations", "axisem3d_synthetics.nc"), sim, series)
         print("axisem3d_b200: %d rank(s), %d elements and %d points on rank 0, dt = %.6g s, %d steps, %d stations; preloop %.1f s, "
               "time loop %.2f s (%.3f ms / step)" % (world, len(rel["elements"]), len(rel["points"]), sim.dt, len(sim.stf), len(rc.keys),
                                                      t1 - t0, t2 - t1, 1e3 * (t2 - t1) / max(len(sim.stf), 1)))

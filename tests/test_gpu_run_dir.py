@@ -23,7 +23,14 @@ def _run_dir(tmp_path):
     path = os.path.join(inp, "inparam.advanced")
     lines = [("DEVELOP_MAX_TIME_STEPS %d" % NSTEP) if ln.split()[:1] == ["DEVELOP_MAX_TIME_STEPS"] else ln for ln in open(path).read().split("\n")]
     open(path, "w").write("\n".join(lines))
+    _set(inp, "inparam.time_src_recv", "OUT_STATIONS_FORMAT", "ascii netcdf")     # both writers of run.py
     return run
+
+
+def _set(inp, name, key, value):
+    path = os.path.join(inp, name)
+    lines = [("%s %s" % (key, value)) if ln.split()[:1] == [key] else ln for ln in open(path).read().split("\n")]
+    open(path, "w").write("\n".join(lines))
 
 
 def _check(run):
@@ -37,6 +44,15 @@ def _check(run):
     a, b = got[:, ::gold["stride"], 1:][:, :n], gold["seis"].astype(np.float64)[:, :n]
     mis = float(np.linalg.norm(a - b) / np.linalg.norm(b))
     assert mis <= TOL, mis
+    # the NetCDF writer carries the same traces in full fp32
+    from scipy.io import netcdf_file
+    with netcdf_file(os.path.join(st, "axisem3d_synthetics.nc"), "r", mmap=False) as nc:
+        assert np.abs(np.array(nc.variables["time_points"][:]) - got[0, :, 0]).max() < 1e-3
+        k = gold["keys"][len(gold["keys"]) // 2]
+        tr = np.array(nc.variables[k][:], dtype=np.float64)
+        assert tr.shape == (NSTEP, 3)
+        asc = got[gold["keys"].index(k), :, 1:]
+        assert np.abs(tr - asc).max() <= 2e-6 * max(np.abs(asc).max(), 1e-30) + 1e-30
 
 
 def _worker(rank, world, port, run):
@@ -68,12 +84,6 @@ def test_run_dir_two_ranks(tmp_path):
     shutil.rmtree(run, ignore_errors=True)
 
 
-def _set(inp, name, key, value):
-    path = os.path.join(inp, name)
-    lines = [("%s %s" % (key, value)) if ln.split()[:1] == [key] else ln for ln in open(path).read().split("\n")]
-    open(path, "w").write("\n".join(lines))
-
-
 @pytest.mark.gpu
 def test_run_dir_learns_and_reuses_wisdom(tmp_path):
     """The reference's two-run workflow: a learning run (NU_WISDOM_LEARN true) leaves output/<name>.nu_wisdom.nc behind
@@ -101,6 +111,7 @@ def test_run_dir_learns_and_reuses_wisdom(tmp_path):
     _set(inp2, "inparam.nu", "NU_WISDOM_LEARN", "false")
     _set(inp2, "inparam.nu", "NU_WISDOM_REUSE_INPUT", "learn.nu_wisdom.nc")
     _set(inp2, "inparam.advanced", "DEVELOP_MAX_TIME_STEPS", "100")
+    _set(inp2, "inparam.time_src_recv", "OUT_STATIONS_FORMAT", "ascii")
     assert R.main([run2]) == 0
     a = np.loadtxt(os.path.join(run2, "output", "stations", "IU.SSPA.RTZ.ascii"))
     assert a.shape == (100, 4) and np.isfinite(a).all()
