@@ -574,15 +574,19 @@ class ExodusMesh:
         axial = bool(self.p_axis[t])
         is_s, is_f = self.mass_s[t].any(), self.mass_f[t].any()
 
+        def equal_rows(a):                         # XMath::equalRows: every row within 1e-10 (relative, 2-norm) of the first
+            a = np.asarray(a, dtype=np.float64).reshape(len(a), -1)
+            return bool((np.linalg.norm(a - a[0], axis=1) <= 1e-10 * np.linalg.norm(a[0])).all())
+
         def mk_mass(m):
-            if np.ptp(m) <= 1e-12 * np.abs(m).max():
+            if equal_rows(m):
                 return M.Mass1D(np.float32(1.0 / m[0]))
             return M.Mass3D((1.0 / m).astype(np.float32))
         sp = None
         if is_s and self.ocean_depth > 0.0 and int(t) in self.surf_n:
             # GLLPoint::release, ocean branch (GLLPoint.cpp:57-72): a constant depth over a 1-D mass gives MassOcean1D
             ms = self.mass_s[t]
-            if np.ptp(ms) > 1e-12 * np.abs(ms).max():
+            if not equal_rows(ms):
                 raise NotImplementedError("GLLPoint::release || MassOcean3D from the preloop restatement (3-D mass under an ocean)")
             r = np.hypot(crds[0], crds[1])
             theta = 0.0 if r < 1e-10 else float(np.arccos(crds[1] / r))
@@ -603,7 +607,7 @@ class ExodusMesh:
                     if local_mask[e]:
                         n_un = n_un + c
             mf = self.mass_f[t]
-            if np.ptp(mf) <= 1e-12 * np.abs(mf).max() and np.abs(n - n[0]).max() <= 1e-12 * np.abs(n).max():
+            if equal_rows(mf) and equal_rows(n):       # GLLPoint::release: equalRows(mSFNormal_assmble) && equalRows(mMassFluid)
                 c = M.SFCoupling1D(np.float32(n_un[0, 0]), np.float32(n_un[0, 2]), np.float32(n[0, 0] / mf[0]), np.float32(n[0, 2] / mf[0]))
             else:
                 c = M.SFCoupling3D(n_un.astype(np.float32), (n / mf[:, None]).astype(np.float32))

@@ -65,6 +65,11 @@ CASES = {
         files={"POINTFORCE": "latitude:   90.0\nlongitude:  10.0\ndepth:      20.0\nFt:         1.0e18\nFp:        -0.5e18\nFr:         2.0e18\n",
                "STATIONS_SC": "".join("S%02d  SC  %7.3f  %7.3f  0.0  %5.1f\n" % (i, 2.0 + 3.1 * i, (37.0 * i) % 360.0, 0.0 if i % 3 else 25.0 * i)
                                       for i in range(24))}),
+    # full ellipticity seen from a source at the pole: the undulation is axisymmetric, so the relabelling is 1-D (PRT_1D + 1-D
+    # moduli scaled by the Jacobian, Mass1D, SFCoupling1D) -- the other branch of Relabelling::createPRT / Quad::release
+    "ellipticity_pole": dict(steps=200, stride=2, thin=6, par={
+        "MODEL_3D_ELLIPTICITY_MODE": "full", "SOURCE_TYPE": "point_force", "SOURCE_FILE": "POINTFORCE", "ATTENUATION": "false"},
+        files={"POINTFORCE": "latitude:   90.0\nlongitude:  0.0\ndepth:      30.0\nFt:         1.0e18\nFp:         0.0\nFr:         1.0e18\n"}),
     # wisdom learning (Domain::learnWisdom / dumpWisdom, Point::learnWisdom): empirical Nu, learn every 5th step with cutoff
     # 1e-3; the wisdom file the reference writes (s, z, learnt Nu, original Nu per point) is kept next to the traces
     "wisdom_learn": dict(steps=300, stride=2, thin=100000, par={

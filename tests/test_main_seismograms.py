@@ -19,7 +19,7 @@ import main_case as MC  # noqa: E402
 TOL = 1e-4
 # the CPU oracle follows only the first steps of every case (long enough for the near stations to carry the body and surface
 # waves); the CUDA test runs all of them (2000 for cfg1_template)
-CPU_STEPS = {"cfg1_template": 400, "emp_full_enz": 200, "bubbles_3d": 120, "ellipticity_prt": 120, "pointforce_spz": 200, "wisdom_learn": 160}
+CPU_STEPS = {"cfg1_template": 400, "emp_full_enz": 200, "bubbles_3d": 120, "ellipticity_prt": 120, "pointforce_spz": 200, "wisdom_learn": 160, "ellipticity_pole": 100}
 
 
 def _log(name, impl, steps, tot, worst):
@@ -39,7 +39,7 @@ def _misfit(got, ref):
     return tot, float(per.max())
 
 
-@pytest.mark.parametrize("name", MC.CASES)
+@pytest.mark.parametrize("name", MC.CASES + MC.CPU_ONLY_CASES)
 def test_oracle_seismograms_match_reference_main(name):
     from axisem_oracle import OracleDomain
     from c_oracle import COracle

@@ -22,7 +22,7 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-@pytest.fixture(scope="module", params=MC.CASES)
+@pytest.fixture(scope="module", params=MC.CASES + MC.CPU_ONLY_CASES)
 def pair(request, tmp_path_factory):
     case = MC.get_case(request.param)
     d = DumpDomain()
@@ -65,12 +65,23 @@ def test_points_match_reference_preloop(pair):
 def test_elements_match_reference_preloop(pair):
     case, ours, ref = pair
     assert len(ours["elements"]) == len(ref["elements"])
-    worst, compared = {}, 0
+    worst, compared, flips = {}, 0, 0
     for i, (p, q) in enumerate(zip(ours["elements"], ref["elements"])):
-        for k in ("fluid", "axial", "law", "rows", "att", "nsls", "doKappa"):
+        for k in ("fluid", "axial", "law", "att", "nsls", "doKappa"):
             assert p.get(k) == q.get(k), (i, k, p.get(k), q.get(k))
         assert np.array_equal(p["tags"], q["tags"]), i
         assert ("prt" in p) == ("prt" in q), i
+        if p.get("rows") != q.get("rows"):
+            # 1-D or 3-D element is decided by XMath::equalRows on 1e-10: an axisymmetric undulation carries azimuthal rounding
+            # noise of that order (ellipticity_pole: 5e-11), so single elements may fall on the other side.  Their 3-D arrays must
+            # then be azimuthally constant and equal to the 1-D ones.
+            assert 1 in (p["rows"], q["rows"]), (i, p["rows"], q["rows"])
+            flips += 1
+            for k in ("coef", "K", "prt", "dkappa", "dmu"):
+                if k in q and not np.isnan(q[k]).all():
+                    a, b = (p[k], q[k]) if p["rows"] == 1 else (q[k], p[k])
+                    assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), (i, k)
+            continue
         for k in ("grad", "coef", "alpha", "beta", "gamma", "dkappa", "dmu", "K", "prt"):
             if k in q:
                 assert np.shape(p[k]) == np.shape(q[k]), (i, k)
@@ -78,6 +89,7 @@ def test_elements_match_reference_preloop(pair):
                     continue
                 worst[k] = max(worst.get(k, 0.0), _rel(p[k], q[k]))
                 compared += k in ("coef", "K")
+    assert flips <= len(ref["elements"]) // 200
     assert compared >= 1          # thin dumps: at least element 0 carries its arrays (cfg1 / emp / bubbles: every element)
     assert all(v < TOL_F32 for v in worst.values()), worst
 
