@@ -2,7 +2,7 @@
 material of a quad -- what turns a 1-D element into one of the 3-D element kinds of the hot path.
 
     Volumetric3D::buildInparam      S/3d_model/3d_volumetric/Volumetric3D.cpp:23-88
-    Volumetric3D_bubble             S/3d_model/3d_volumetric/simple_shapes/Volumetric3D_bubble.cpp:11-134
+    Volumetric3D_bubble / _cylinder S/3d_model/3d_volumetric/simple_shapes/Volumetric3D_bubble.cpp:11-134, Volumetric3D_cylinder.cpp:11-173
     Material::addVolumetric3D       S/preloop/physics/material/Material.cpp:96-231 (prepare3D: 902-932)
     Quad::computeGeocentricGlobal   S/preloop/mesh/Quad.cpp:468-481
     XMath::linearResampling         S/preloop/utilities/XMath.cpp:161-186
@@ -77,6 +77,65 @@ class Bubble:
         return inside, val
 
 
+class Cylinder:
+    """cylinder$<property>$<ref type>$<value>$<radius km>$<depth1 km>$<lat1>$<lon1>$<depth2 km>$<lat2>$<lon2>
+    [$<source-centred>$<fluid>$<lateral HWHM km>$<top-bottom HWHM km>]  (Volumetric3D_cylinder.cpp:11-173)"""
+
+    def __init__(self, params, src, geodesy: Geodesy):
+        if len(params) < 10:
+            raise RuntimeError("Volumetric3D_cylinder::initialize || Not enough parameters for a cylinder-shaped heterogeneity. Need 10 at least.")
+        names = [p.upper() for p in PROPS]
+        if params[0].upper() not in names:
+            raise RuntimeError("Volumetric3D_cylinder::initialize || Unknown material property, name = " + params[0])
+        self.prop = names.index(params[0].upper())
+        if params[1].lower() not in REF_TYPES:
+            raise RuntimeError("Volumetric3D_cylinder::initialize || Unknown material reference type, type = " + params[1])
+        self.ref = REF_TYPES[params[1].lower()]
+        self.value = float(params[2])
+        self.radius = float(params[3]) * 1e3
+        d1, lat1, lon1 = float(params[4]) * 1e3, float(params[5]), float(params[6])
+        d2, lat2, lon2 = float(params[7]) * 1e3, float(params[8]), float(params[9])
+        src_centred = _bool(params[10]) if len(params) > 10 else False
+        self.fluid = _bool(params[11]) if len(params) > 11 else False
+        self.hwhm_lat = float(params[12]) * 1e3 if len(params) > 12 else -1.0
+        self.hwhm_tb = float(params[13]) * 1e3 if len(params) > 13 else -1.0
+
+        def end(d, lat, lon):
+            if src_centred:
+                rtp = geodesy.rotate_src2glob(np.array([geodesy.r_outer - d, lat * DEGREE, lon * DEGREE]), src.lat, src.lon, src.depth)
+            else:
+                rtp = np.array([geodesy.r_outer - d, geodesy.lat2theta(lat, d), geodesy.lon2phi(lon)])
+            return geodesy.to_cartesian(rtp)
+        self.p1, self.p2 = end(d1, lat1, lon1), end(d2, lat2, lon2)
+        self.length = float(np.linalg.norm(self.p1 - self.p2))
+        if self.hwhm_lat < 0.0:
+            self.hwhm_lat = self.radius * 0.2
+        if self.hwhm_tb < 0.0:
+            self.hwhm_tb = self.length * 0.1
+        if self.ref == 0:
+            self.hwhm_lat = self.hwhm_tb = 0.0
+            self.value *= ABS_SI[self.prop]
+
+    def get(self, r, theta, phi):
+        x = np.stack([r * np.sin(theta) * np.cos(phi), r * np.sin(theta) * np.sin(phi), r * np.cos(theta)], -1)
+        a, b = x - self.p1, x - self.p2
+        dline = np.linalg.norm(np.cross(a, b), axis=-1) / self.length
+        inside = ~(dline > self.radius + 4.0 * self.hwhm_lat)
+        dsurf = np.maximum(dline - self.radius, 0.0)
+        if self.hwhm_lat > 0.0:
+            std = self.hwhm_lat / math.sqrt(2.0 * math.log(2.0))
+            val = self.value * np.exp(-dsurf * dsurf / (std * std * 2.0))
+        else:
+            val = np.full(np.shape(dline), self.value)
+        dmax = np.maximum(np.linalg.norm(a, axis=-1), np.linalg.norm(b, axis=-1))
+        dtb = np.sqrt(np.maximum(dmax * dmax - dline * dline, 0.0)) - self.length
+        inside &= ~(dtb > 4.0 * self.hwhm_tb)
+        if self.hwhm_tb > 0.0:
+            std = self.hwhm_tb / math.sqrt(2.0 * math.log(2.0))
+            val = np.where(dtb > 0.0, val * np.exp(-dtb * dtb / (std * std * 2.0)), val)
+        return inside, val
+
+
 def from_parameters(par: Parameters, src, geodesy):
     """Volumetric3D::buildInparam for the models that need no data files."""
     n = par.get("MODEL_3D_VOLUMETRIC_NUM", int)
@@ -87,6 +146,8 @@ def from_parameters(par: Parameters, src, geodesy):
         strs = [s for s in par.get("MODEL_3D_VOLUMETRIC_LIST", str, i).split("$") if s != ""]
         if strs[0].lower() == "bubble":
             models.append(Bubble(strs[1:], src, geodesy))
+        elif strs[0].lower() == "cylinder":
+            models.append(Cylinder(strs[1:], src, geodesy))
         else:
             raise NotImplementedError("Volumetric3D::buildInparam || model " + strs[0] + " (needs the reference's data files / is not restated)")
     return models

@@ -70,6 +70,11 @@ CASES = {
     "ellipticity_pole": dict(steps=200, stride=2, thin=6, par={
         "MODEL_3D_ELLIPTICITY_MODE": "full", "SOURCE_TYPE": "point_force", "SOURCE_FILE": "POINTFORCE", "ATTENUATION": "false"},
         files={"POINTFORCE": "latitude:   90.0\nlongitude:  0.0\ndepth:      30.0\nFt:         1.0e18\nFp:         0.0\nFr:         1.0e18\n"}),
+    # the second data-free volumetric model: a slanted fast cylinder through the upper mantle next to the source, given in
+    # source-centred coordinates, absolute density in a second, vertical one (Absolute reference type: no decay), Nu = 6
+    "cylinder_3d": dict(steps=120, stride=2, thin=8, par={
+        "NU_CONST": "6", "MODEL_3D_VOLUMETRIC_NUM": "2",
+        "MODEL_3D_VOLUMETRIC_LIST": "cylinder$VP$Ref1D$0.05$150$50$3$20$600$8$60$true cylinder$RHO$Abs$3.1$100$0$35$-70$24$35$-70"}),
     # wisdom learning (Domain::learnWisdom / dumpWisdom, Point::learnWisdom): empirical Nu, learn every 5th step with cutoff
     # 1e-3; the wisdom file the reference writes (s, z, learnt Nu, original Nu per point) is kept next to the traces
     "wisdom_learn": dict(steps=300, stride=2, thin=100000, par={
