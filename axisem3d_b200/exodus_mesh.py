@@ -584,17 +584,19 @@ class ExodusMesh:
             return M.Mass3D((1.0 / m).astype(np.float32))
         sp = None
         if is_s and self.ocean_depth > 0.0 and int(t) in self.surf_n:
-            # GLLPoint::release, ocean branch (GLLPoint.cpp:57-72): a constant depth over a 1-D mass gives MassOcean1D
+            # GLLPoint::release, ocean branch (GLLPoint.cpp:57-72): MassOcean1D where mass, depth and surface normal are the same
+            # on every azimuthal sample, MassOcean3D (per-sample ocean mass and unit normal) otherwise
             ms = self.mass_s[t]
-            if not equal_rows(ms):
-                raise NotImplementedError("GLLPoint::release || MassOcean3D from the preloop restatement (3-D mass under an ocean)")
-            r = np.hypot(crds[0], crds[1])
-            theta = 0.0 if r < 1e-10 else float(np.arccos(crds[1] / r))
-            sn = np.asarray(self.surf_n[int(t)])
-            if sn.ndim > 1:
-                raise NotImplementedError("GLLPoint::release || ocean load over an undulated surface from the preloop restatement")
-            area = float(np.linalg.norm(sn))
-            sp = M.SolidPoint(nr, axial, crds, M.MassOcean1D(ms[0], 1027.0 * self.ocean_depth * area, theta))
+            sn = np.asarray(self.surf_n[int(t)], dtype=np.float64)
+            if equal_rows(ms) and (sn.ndim == 1 or equal_rows(sn)):
+                r = np.hypot(crds[0], crds[1])
+                theta = 0.0 if r < 1e-10 else float(np.arccos(crds[1] / r))
+                area = float(np.linalg.norm(sn if sn.ndim == 1 else sn[0]))
+                sp = M.SolidPoint(nr, axial, crds, M.MassOcean1D(ms[0], 1027.0 * self.ocean_depth * area, theta))
+            else:
+                sn = sn if sn.ndim == 2 else np.repeat(sn[None, :], nr, axis=0)
+                area = np.linalg.norm(sn, axis=1)
+                sp = M.SolidPoint(nr, axial, crds, M.MassOcean3D(ms, 1027.0 * self.ocean_depth * area, sn / area[:, None]))
         elif is_s:
             sp = M.SolidPoint(nr, axial, crds, mk_mass(self.mass_s[t]))
         fp = M.FluidPoint(nr, axial, crds, mk_mass(self.mass_f[t]), bool(self.p_surface[t])) if is_f else None

@@ -81,6 +81,8 @@ CASES = {
     "deep_stations": dict(steps=400, stride=2, thin=100000, par={"OUT_STATIONS_FILE": "STATIONS_DEEP"},
         files={"STATIONS_DEEP": "".join("D%02d  DP  %8.3f  %8.3f  0.0  %9.1f\n" % (i, 37.9 - 1.7 * (i % 9), -77.9 + 4.3 * (i % 7), d)
                                         for i, d in enumerate([0.0, 15e3, 35e3, 3.0e5, 6.6e5, 1.5e6, 2.8e6, 2.95e6, 3.5e6, 4.2e6, 5.0e6, 5.2e6, 5.9e6, 1.0e5, 2.891e6]))}),
+    # an ocean on the ellipsoid: full ellipticity tilts the surface normal with azimuth, so the surface points get MassOcean3D
+    "ocean_on_ellipsoid": dict(steps=200, stride=2, thin=12, par={"MODEL_3D_ELLIPTICITY_MODE": "full", "MODEL_3D_OCEAN_LOAD": "constant$4.0"}),
     # wisdom learning (Domain::learnWisdom / dumpWisdom, Point::learnWisdom): empirical Nu, learn every 5th step with cutoff
     # 1e-3; the wisdom file the reference writes (s, z, learnt Nu, original Nu per point) is kept next to the traces
     "wisdom_learn": dict(steps=300, stride=2, thin=100000, par={

@@ -48,6 +48,7 @@
 #include "Mass1D.h"
 #include "Mass3D.h"
 #include "MassOcean1D.h"
+#include "MassOcean3D.h"
 #include "SFCoupling1D.h"
 #include "SFCoupling3D.h"
 #include "Element.h"
@@ -112,7 +113,22 @@ static void dump_mass(const Mass *m) {
         f64(mass);
         f64(1. / (double)mo->mInvMassZ - mass);
         f64(std::atan2((double)mo->mSint, (double)mo->mCost));
-    } else die("MassOcean3D is not dumped");
+    } else if (const MassOcean3D *m3o = dynamic_cast<const MassOcean3D *>(m)) {
+        // MassOcean3D.cpp:9-16 keeps 1 / mass and normal * sqrt(massOcean / (mass (mass + massOcean))) in fp32; the unit normal,
+        // mass and massOcean the constructor was given are recovered from them: marker, then mass[rows], massOcean[rows], normal
+        // (rows x 3, column-major) as doubles
+        const int rows = (int)m3o->mInvMass.rows();
+        i32(-1000000 - rows);
+        std::vector<double> mass(rows), scal(rows);
+        for (int i = 0; i < rows; ++i) {
+            mass[i] = 1. / (double)m3o->mInvMass(i);
+            scal[i] = std::sqrt((double)m3o->mNormal_scal(i, 0) * m3o->mNormal_scal(i, 0) + (double)m3o->mNormal_scal(i, 1) * m3o->mNormal_scal(i, 1) +
+                                (double)m3o->mNormal_scal(i, 2) * m3o->mNormal_scal(i, 2));
+        }
+        for (int i = 0; i < rows; ++i) f64(mass[i]);
+        for (int i = 0; i < rows; ++i) f64(scal[i] * scal[i] * mass[i] * mass[i] / (1. - scal[i] * scal[i] * mass[i]));
+        for (int c = 0; c < 3; ++c) for (int i = 0; i < rows; ++i) f64((double)m3o->mNormal_scal(i, c) / scal[i]);
+    } else die("unknown Mass class");
 }
 
 static void dump_attenuation(const Attenuation *a, int rows) {

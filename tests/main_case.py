@@ -18,7 +18,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 MESH = "AxiSEM_prem_ani_one_crust_50.e"
 CASES = ("cfg1_template", "emp_full_enz", "bubbles_3d", "ellipticity_prt", "pointforce_spz", "wisdom_learn")
 # cases whose preloop arrays are compared (tests/test_preloop_reference.py) and that the CPU oracle steps, but that have no CUDA test
-CPU_ONLY_CASES = ("ellipticity_pole", "cylinder_3d", "deep_stations")
+CPU_ONLY_CASES = ("ellipticity_pole", "cylinder_3d", "deep_stations", "ocean_on_ellipsoid")
 
 
 def golden(case):

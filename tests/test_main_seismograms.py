@@ -20,7 +20,7 @@ TOL = 1e-4
 # the CPU oracle follows only the first steps of every case (long enough for the near stations to carry the body and surface
 # waves); the CUDA test runs all of them (2000 for cfg1_template)
 CPU_STEPS = {"cfg1_template": 300, "emp_full_enz": 120, "bubbles_3d": 100, "ellipticity_prt": 120, "pointforce_spz": 200, "wisdom_learn": 100,
-             "ellipticity_pole": 60, "cylinder_3d": 80, "deep_stations": 400}
+             "ellipticity_pole": 60, "cylinder_3d": 80, "deep_stations": 400, "ocean_on_ellipsoid": 40}
 
 
 def _log(name, impl, steps, tot, worst):
@@ -44,7 +44,7 @@ def _misfit(got, ref):
 def test_oracle_seismograms_match_reference_main(name):
     from axisem_oracle import OracleDomain
     from c_oracle import COracle
-    if name == "ellipticity_prt" and not os.environ.get("AX3D_SLOW_TESTS"):
+    if name in ("ellipticity_prt", "ocean_on_ellipsoid") and not os.environ.get("AX3D_SLOW_TESTS"):
         # oracle.c has no particle-relabelling path, the numpy oracle needs ~1.2 s per step on this case (2.5 min for the 120
         # steps the near stations need); run with AX3D_SLOW_TESTS=1 (passes: 1e-6).  The case's preloop arrays are compared
         # in test_preloop_reference.py and its seismograms, all 300 steps, by the CUDA test below.

@@ -50,10 +50,15 @@ def test_points_match_reference_preloop(pair):
         worst["crds"] = max(worst.get("crds", 0.0), float(np.abs(p["crds"] - q["crds"]).max()) / 6371e3)
         for k in ("mass", "mass_fluid", "n_un", "n_as"):
             if k in q:
-                if isinstance(q[k], dict):         # MassOcean1D: (mass, massOcean, theta), recovered from the reference's four fp32 members
+                if isinstance(q[k], dict):         # ocean masses, recovered from the fp32 members the reference's classes keep
                     assert isinstance(p[k], dict) and p[k]["data"].shape == q[k]["data"].shape, i
-                    a, b = p[k]["data"], q[k]["data"]           # relative for the two masses, absolute for the angle (0 at the pole)
-                    worst["ocean"] = max(worst.get("ocean", 0.0), float(np.abs(a[:2] / b[:2] - 1.0).max()), float(abs(a[2] - b[2])))
+                    a, b = p[k]["data"], q[k]["data"]
+                    if len(b) == 3:                # MassOcean1D: (mass, massOcean, theta): relative for the masses, absolute for the angle
+                        err = max(float(np.abs(a[:2] / b[:2] - 1.0).max()), float(abs(a[2] - b[2])))
+                    else:                          # MassOcean3D: mass[n], massOcean[n], unit normal [3][n]
+                        n = len(b) // 5
+                        err = max(float(np.abs(a[:2 * n] / b[:2 * n] - 1.0).max()), float(np.abs(a[2 * n:] - b[2 * n:]).max()))
+                    worst["ocean"] = max(worst.get("ocean", 0.0), err)
                 else:
                     assert not isinstance(p[k], dict), i
                     worst[k] = max(worst.get(k, 0.0), _rel(p[k], q[k]))
