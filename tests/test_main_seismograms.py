@@ -20,7 +20,7 @@ TOL = 1e-4
 # the CPU oracle follows only the first steps of every case (long enough for the near stations to carry the body and surface
 # waves); the CUDA test runs all of them (2000 for cfg1_template)
 CPU_STEPS = {"cfg1_template": 300, "emp_full_enz": 120, "bubbles_3d": 100, "ellipticity_prt": 120, "pointforce_spz": 200, "wisdom_learn": 100,
-             "ellipticity_pole": 60, "cylinder_3d": 80, "deep_stations": 400, "ocean_on_ellipsoid": 40}
+             "ellipticity_pole": 60, "cylinder_3d": 80, "deep_stations": 200, "ocean_on_ellipsoid": 40}
 
 
 def _log(name, impl, steps, tot, worst):
