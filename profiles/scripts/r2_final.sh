@@ -6,7 +6,7 @@ timeout 600 python -m pytest tests -m gpu -q --durations=12 -p no:cacheprovider 
 echo "pytest rc=$?" >> gpurun_out/r2x_pytest.log
 tail -25 gpurun_out/r2x_pytest.log
 RUN=/tmp/ax3d_template_run
-rm -rf $RUN && mkdir -p $RUN && cp -r tests/golden/template_input $RUN/input && cp tests/golden/AxiSEM_prem_ani_one_crust_50.e $RUN/input/
+rm -rf $RUN && mkdir -p $RUN && python -c "import json,os,sys; d=json.load(open('tests/golden/template_input.json'))['files']; os.makedirs(sys.argv[1]); [open(os.path.join(sys.argv[1],k),'w').write(v) for k,v in d.items()]" $RUN/input && cp tests/golden/AxiSEM_prem_ani_one_crust_50.e $RUN/input/
 ( time timeout 300 python -m axisem3d_b200.run $RUN ) > gpurun_out/r2x_template_run.log 2>&1
 echo "run rc=$?" >> gpurun_out/r2x_template_run.log
 ls $RUN/output/stations | wc -l >> gpurun_out/r2x_template_run.log

@@ -1,8 +1,9 @@
 """Shared set-up of the "reference main()" cases (tests/golden/main_<case>.npz + main_<case>_domain.bin.xz, written by
-oracle/make_golden_main.py from the reference's whole program): the unchanged template inputs (tests/golden/template_input/ +
+oracle/make_golden_main.py from the reference's whole program): the unchanged template inputs (tests/golden/template_input.json +
 the shipped Exodus mesh) with the case's inparam overrides, run through the repo's preloop (axisem3d_b200/exodus_mesh.py,
 preloop.py) into any domain that offers the Domain verbs (numpy oracle, DumpDomain, CUDA)."""
 import atexit
+import json
 import lzma
 import os
 import shutil
@@ -37,7 +38,9 @@ def input_dir(case, tmp=None):
     """template_input + mesh + the case's overrides in a fresh directory"""
     tmp = tmp or tempfile.mkdtemp(prefix="ax3d_in_")
     inp = os.path.join(tmp, "input")
-    shutil.copytree(os.path.join(GOLDEN, "template_input"), inp)
+    os.makedirs(inp)
+    for fname, text in json.load(open(os.path.join(GOLDEN, "template_input.json")))["files"].items():
+        open(os.path.join(inp, fname), "w").write(text)
     shutil.copy(os.path.join(GOLDEN, MESH), os.path.join(inp, MESH))
     gold = golden(case)
     par = gold["par"]
